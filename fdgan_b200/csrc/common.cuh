@@ -1,0 +1,41 @@
+// Shared helpers for the fdgan_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fdgan_b200.h"
+
+namespace fdg {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);  // cudaGetLastError -> FDG_ECUDA
+
+#define FDG_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      fdg::set_error(__VA_ARGS__);        \
+      return FDG_EINVAL;                  \
+    }                                     \
+  } while (0)
+
+__host__ __device__ inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float prologue_act(float v, float slope) { return v > 0.f ? v : slope * v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// vectorisable view: unit channel stride, 16-byte aligned base and every other stride a multiple of 4 elements
+inline bool vec4_ok(const FdgTensor& t) {
+  return t.p != nullptr && t.sc == 1 && aligned16(t.p) && (t.sn % 4 == 0) && (t.sh % 4 == 0) && (t.sw % 4 == 0);
+}
+
+}  // namespace fdg

@@ -1,0 +1,404 @@
+// HBM-bound kernels of the hot path: BatchNorm bookkeeping, the element-wise halves of the
+// BatchNorm/ReLU/LeakyReLU backward, max pooling, strided copies, weight repacking and fused Adam.
+// All of them stream NHWC rows with 128-bit accesses when the views allow it and reduce per-channel
+// partial sums with warp shuffles before touching global memory.
+#include "common.cuh"
+
+namespace fdg {
+
+// ------------------------------------------------------------------ BatchNorm finalize (forward)
+__global__ void bn_finalize_kernel(FdgBnFinalize p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  float scale, shift;
+  if (p.training) {
+    const double mean = p.stats[c] / p.count;
+    double var = p.stats[p.stats_ld + c] / p.count - mean * mean;  // biased
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + (double)p.eps);
+    scale = (float)((double)p.gamma[c] * invstd);
+    shift = (float)((double)p.beta[c] - mean * (double)p.gamma[c] * invstd);
+    if (p.mean) p.mean[c] = (float)mean;
+    if (p.invstd) p.invstd[c] = (float)invstd;
+    if (p.running_mean) {
+      const double unbiased = p.count > 1.0 ? var * p.count / (p.count - 1.0) : var;
+      p.running_mean[c] = (float)((1.0 - p.momentum) * (double)p.running_mean[c] + p.momentum * mean);
+      p.running_var[c] = (float)((1.0 - p.momentum) * (double)p.running_var[c] + p.momentum * unbiased);
+    }
+  } else {
+    const float invstd = 1.0f / sqrtf(p.running_var[c] + p.eps);
+    scale = p.gamma[c] * invstd;
+    shift = p.beta[c] - p.running_mean[c] * scale;
+    if (p.mean) p.mean[c] = p.running_mean[c];
+    if (p.invstd) p.invstd[c] = invstd;
+  }
+  p.scale[c] = scale;
+  p.shift[c] = shift;
+}
+
+// ------------------------------------------------------------------ BatchNorm finalize (backward)
+// dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  xhat = (x-mu)*invstd
+//    = alpha*dz + beta*x + delta
+__global__ void bn_bwd_finalize_kernel(FdgBnBwdFinalize p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  const double s1 = p.stats[c], s2 = p.stats[p.C + c];  // sum dz, sum dz*x
+  const double mu = p.mean[c], is = p.invstd[c], g = p.gamma[c];
+  const double sum_dz_xhat = (s2 - mu * s1) * is;
+  const double m1 = s1 / p.count, m2 = sum_dz_xhat / p.count;
+  const double alpha = g * is;
+  const double beta = -alpha * m2 * is;
+  const double delta = -alpha * m1 + alpha * m2 * is * mu;
+  p.coef[c] = (float)alpha;
+  p.coef[p.C + c] = (float)beta;
+  p.coef[2 * p.C + c] = (float)delta;
+  if (p.dgamma) p.dgamma[c] = (p.accumulate ? p.dgamma[c] : 0.f) + (float)sum_dz_xhat;
+  if (p.dbeta) p.dbeta[c] = (p.accumulate ? p.dbeta[c] : 0.f) + (float)s1;
+}
+
+// ------------------------------------------------------------------ element-wise backward
+// One warp-wide row of channels per pixel group: thread handles channel group cg (VW channels) for
+// pixels strided by the number of pixel lanes.  Stats mode keeps per-thread partial sums over its pixels
+// and reduces across the pixel lanes of the CTA in shared memory before the fp64 atomics.
+template <int VW>
+__global__ void __launch_bounds__(256) ew_bwd_kernel(FdgEwBwd p, int64_t M, int cgroups, int pix_lanes) {
+  extern __shared__ float sm[];  // stats: [2][pix_lanes][cgroups*VW] partials
+  const int cg = threadIdx.x % cgroups;
+  const int pl = threadIdx.x / cgroups;
+  const int c = (blockIdx.y * cgroups + cg) * VW;
+  const bool cv = c < p.C && pl < pix_lanes;
+  const int HW = p.H * p.W;
+  float sc[VW], sh[VW], ca[VW], cb[VW], cd[VW];
+#pragma unroll
+  for (int u = 0; u < VW; ++u) {
+    const int cc = min(c + u, p.C - 1);
+    sc[u] = p.has_affine ? p.scale[cc] : 1.f;
+    sh[u] = p.has_affine ? p.shift[cc] : 0.f;
+    ca[u] = p.coef ? p.coef[cc] : 1.f;
+    cb[u] = p.coef ? p.coef[p.C + cc] : 0.f;
+    cd[u] = p.coef ? p.coef[2 * p.C + cc] : 0.f;
+  }
+  float s1[VW], s2[VW];
+#pragma unroll
+  for (int u = 0; u < VW; ++u) { s1[u] = 0.f; s2[u] = 0.f; }
+
+  if (cv) {
+    for (int64_t m = (int64_t)blockIdx.x * pix_lanes + pl; m < M; m += (int64_t)gridDim.x * pix_lanes) {
+      const int n = (int)(m / HW);
+      const int rem = (int)(m - (int64_t)n * HW);
+      const int h = rem / p.W, w = rem - h * p.W;
+      const int gh = p.g_gather == FDG_GATHER_UP2 ? h >> 1 : h, gw = p.g_gather == FDG_GATHER_UP2 ? w >> 1 : w;
+      const float* gp = p.g.p + n * p.g.sn + (int64_t)gh * p.g.sh + (int64_t)gw * p.g.sw + (int64_t)c * p.g.sc;
+      const float* xp = p.x.p + n * p.x.sn + (int64_t)h * p.x.sh + (int64_t)w * p.x.sw + (int64_t)c * p.x.sc;
+      float gv[VW], xv[VW];
+      if (VW == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(gp);  // plain load: out may alias g (in-place)
+        const float4 b = __ldg(reinterpret_cast<const float4*>(xp));
+        gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w;
+        xv[0] = b.x; xv[1] = b.y; xv[2] = b.z; xv[3] = b.w;
+      } else {
+        gv[0] = *gp;
+        xv[0] = __ldg(xp);
+      }
+      float o[VW];
+#pragma unroll
+      for (int u = 0; u < VW; ++u) {
+        const float v = fmaf(xv[u], sc[u], sh[u]);
+        const float dz = p.gscale * gv[u] * (v > 0.f ? 1.f : p.slope);
+        s1[u] += dz;
+        s2[u] += dz * xv[u];
+        o[u] = fmaf(ca[u], dz, fmaf(cb[u], xv[u], cd[u]));
+      }
+      if (!p.stats) {
+        float* op = p.out.p + n * p.out.sn + (int64_t)h * p.out.sh + (int64_t)w * p.out.sw + (int64_t)c * p.out.sc;
+        if (VW == 4) {
+          float4 r = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.accumulate) { const float4 old = *reinterpret_cast<const float4*>(op); r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+          *reinterpret_cast<float4*>(op) = r;
+        } else {
+          *op = p.accumulate ? *op + o[0] : o[0];
+        }
+      }
+    }
+  }
+  if (p.stats) {
+    const int CW = cgroups * VW;
+    float* r1 = sm;
+    float* r2 = sm + pix_lanes * CW;
+    if (pl < pix_lanes) {
+#pragma unroll
+      for (int u = 0; u < VW; ++u) {
+        r1[pl * CW + cg * VW + u] = s1[u];
+        r2[pl * CW + cg * VW + u] = s2[u];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CW; i += blockDim.x) {
+      const int cc = blockIdx.y * CW + i;
+      if (cc < p.C) {
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < pix_lanes; ++l) { a += r1[l * CW + i]; b += r2[l * CW + i]; }
+        atomicAdd(p.stats + cc, (double)a);
+        atomicAdd(p.stats + p.C + cc, (double)b);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ max pool 2x2
+__global__ void maxpool2_fwd_kernel(FdgTensor x, FdgTensor y, int64_t total, int OH, int OW, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const float* b = x.p + n * x.sn + (int64_t)(2 * oh) * x.sh + (int64_t)(2 * ow) * x.sw + (int64_t)c * x.sc;
+    const float v = fmaxf(fmaxf(__ldg(b), __ldg(b + x.sw)), fmaxf(__ldg(b + x.sh), __ldg(b + x.sh + x.sw)));
+    y.p[n * y.sn + (int64_t)oh * y.sh + (int64_t)ow * y.sw + (int64_t)c * y.sc] = v;
+  }
+}
+
+__global__ void maxpool2_bwd_kernel(FdgTensor x, FdgTensor gy, FdgTensor gx, int64_t total, int OH, int OW, int C,
+                                    int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const float* b = x.p + n * x.sn + (int64_t)(2 * oh) * x.sh + (int64_t)(2 * ow) * x.sw + (int64_t)c * x.sc;
+    const float v[4] = {__ldg(b), __ldg(b + x.sw), __ldg(b + x.sh), __ldg(b + x.sh + x.sw)};
+    int arg = 0;
+    float best = v[0];
+#pragma unroll
+    for (int d = 1; d < 4; ++d) if (v[d] > best) { best = v[d]; arg = d; }  // first maximum, scan order
+    const float g = __ldg(gy.p + n * gy.sn + (int64_t)oh * gy.sh + (int64_t)ow * gy.sw + (int64_t)c * gy.sc);
+    float* o = gx.p + n * gx.sn + (int64_t)(2 * oh) * gx.sh + (int64_t)(2 * ow) * gx.sw + (int64_t)c * gx.sc;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      float* q = o + (d >> 1) * gx.sh + (d & 1) * gx.sw;
+      const float val = d == arg ? g : 0.f;
+      *q = accumulate ? *q + val : val;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ strided gather-copy with leaky slope
+__global__ void copy4d_kernel(FdgTensor x, FdgTensor y, int64_t total, int H, int W, int C, int gather, float slope,
+                              float scale, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    float v;
+    if (gather == FDG_GATHER_AVGPOOL2) {
+      const float* b = x.p + n * x.sn + (int64_t)(2 * h) * x.sh + (int64_t)(2 * w) * x.sw + (int64_t)c * x.sc;
+      const float v0 = __ldg(b), v1 = __ldg(b + x.sw), v2 = __ldg(b + x.sh), v3 = __ldg(b + x.sh + x.sw);
+      v = 0.25f * ((prologue_act(v0, slope) + prologue_act(v1, slope)) + (prologue_act(v2, slope) + prologue_act(v3, slope)));
+    } else {
+      const int hh = gather == FDG_GATHER_UP2 ? h >> 1 : h, ww = gather == FDG_GATHER_UP2 ? w >> 1 : w;
+      v = prologue_act(__ldg(x.p + n * x.sn + (int64_t)hh * x.sh + (int64_t)ww * x.sw + (int64_t)c * x.sc), slope);
+    }
+    v *= scale;
+    float* o = y.p + n * y.sn + (int64_t)h * y.sh + (int64_t)w * y.sw + (int64_t)c * y.sc;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ out, int64_t n,
+                               int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float yy = y[i];
+    out[i] = g[i] * (act == FDG_ACT_TANH ? (1.f - yy * yy) : yy * (1.f - yy));
+  }
+}
+
+// transposed convolution as a gather (data gradient of a strided conv); one thread per (pixel, ci)
+__global__ void dgrad_strided_kernel(FdgDgradStrided p, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % p.Cin);
+    int64_t r = i / p.Cin;
+    const int x = (int)(r % p.W); r /= p.W;
+    const int y = (int)(r % p.H);
+    const int n = (int)(r / p.H);
+    float acc = 0.f;
+    for (int kr = 0; kr < p.R; ++kr) {
+      const int ty = y + p.pad - kr;
+      if (ty < 0 || ty % p.stride != 0) continue;
+      const int oy = ty / p.stride;
+      if (oy >= p.OH) continue;
+      for (int ks = 0; ks < p.S; ++ks) {
+        const int tx = x + p.pad - ks;
+        if (tx < 0 || tx % p.stride != 0) continue;
+        const int ox = tx / p.stride;
+        if (ox >= p.OW) continue;
+        const float* gp = p.g.p + n * p.g.sn + (int64_t)oy * p.g.sh + (int64_t)ox * p.g.sw;
+        const float* wp = p.w + ((int64_t)ci * p.R + kr) * p.S + ks;
+        for (int co = 0; co < p.Cout; ++co)
+          acc = fmaf(__ldg(gp + (int64_t)co * p.g.sc), __ldg(wp + (int64_t)co * p.Cin * p.R * p.S), acc);
+      }
+    }
+    float* o = p.dx.p + n * p.dx.sn + (int64_t)y * p.dx.sh + (int64_t)x * p.dx.sw + (int64_t)ci * p.dx.sc;
+    *o = p.accumulate ? *o + acc : acc;
+  }
+}
+
+// ------------------------------------------------------------------ weight repack
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, int mode,
+                                   float* __restrict__ out, int out_ld, int64_t total) {
+  // total = K * out_ld over the destination; gather from the source layout
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % out_ld);
+    const int k = (int)(i / out_ld);
+    float v = 0.f;
+    if (mode == 0) {          // [(r,s,ci)][co] <- W[co][ci][r][s]
+      if (n < Cout) {
+        const int tap = k / Cin, ci = k - tap * Cin;
+        v = w[((int64_t)n * Cin + ci) * (R * S) + tap];
+      }
+    } else if (mode == 1) {   // [(r,s,co)][ci] <- W[co][ci][R-1-r][S-1-s]
+      if (n < Cin) {
+        const int tap = k / Cout, co = k - tap * Cout;
+        const int r = tap / S, s = tap - r * S;
+        v = w[((int64_t)co * Cin + n) * (R * S) + (R - 1 - r) * S + (S - 1 - s)];
+      }
+    } else {                  // [(co)][ci] <- W[ci][co]   (ConvTranspose2d 1x1 data gradient)
+      if (n < Cin) v = w[(int64_t)n * Cout + k];
+    }
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ fused Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gr = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gr;
+    const float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+static inline unsigned grid_for(int64_t total, int block) {
+  int64_t g = cdiv64(total, block);
+  const int64_t cap = 148 * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace fdg
+
+using namespace fdg;
+
+extern "C" {
+
+int fdg_bn_finalize(const FdgBnFinalize* p, fdg_stream_t stream) {
+  FDG_REQUIRE(p && p->C > 0 && p->gamma && p->beta && p->scale && p->shift, "fdg_bn_finalize: bad arguments");
+  FDG_REQUIRE(!p->training || (p->stats && p->count > 0), "fdg_bn_finalize: training mode needs stats and count");
+  FDG_REQUIRE(p->training || (p->running_mean && p->running_var), "fdg_bn_finalize: eval mode needs running stats");
+  bn_finalize_kernel<<<cdiv(p->C, 128), 128, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("fdg_bn_finalize");
+}
+
+int fdg_bn_bwd_finalize(const FdgBnBwdFinalize* p, fdg_stream_t stream) {
+  FDG_REQUIRE(p && p->C > 0 && p->stats && p->gamma && p->mean && p->invstd && p->coef && p->count > 0,
+              "fdg_bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<cdiv(p->C, 128), 128, 0, (cudaStream_t)stream>>>(*p);
+  return check_launch("fdg_bn_bwd_finalize");
+}
+
+int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
+  FDG_REQUIRE(p && p->g.p && p->x.p && p->N > 0 && p->H > 0 && p->W > 0 && p->C > 0, "fdg_ew_bwd: bad arguments");
+  FDG_REQUIRE(p->stats || p->out.p, "fdg_ew_bwd: neither stats nor out given");
+  FDG_REQUIRE(!p->has_affine || (p->scale && p->shift), "fdg_ew_bwd: affine without scale/shift");
+  FDG_REQUIRE(p->g_gather == FDG_GATHER_DIRECT || p->g_gather == FDG_GATHER_UP2, "fdg_ew_bwd: bad gather");
+  const bool vec = vec4_ok(p->g) && vec4_ok(p->x) && (p->stats || vec4_ok(p->out)) && (p->C % 4 == 0);
+  const int VW = vec ? 4 : 1;
+  const int groups_total = cdiv(p->C, VW);
+  const int cgroups = groups_total < 64 ? groups_total : 64;   // channel groups per CTA
+  const int pix_lanes = 256 / cgroups;
+  const int64_t M = (int64_t)p->N * p->H * p->W;
+  int64_t gx = cdiv64(M, (int64_t)pix_lanes * 8);
+  const int gy = cdiv(groups_total, cgroups);
+  const int64_t cap = (148 * 8) / gy + 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  const size_t smem = p->stats ? sizeof(float) * 2 * pix_lanes * cgroups * VW : 0;
+  dim3 grid((unsigned)gx, gy);
+  if (vec) ew_bwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+  else ew_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+  return check_launch("fdg_ew_bwd");
+}
+
+int fdg_maxpool2_fwd(const FdgTensor* x, const FdgTensor* y, int N, int OH, int OW, int C, fdg_stream_t stream) {
+  FDG_REQUIRE(x && y && x->p && y->p && N > 0 && OH > 0 && OW > 0 && C > 0, "fdg_maxpool2_fwd: bad arguments");
+  const int64_t total = (int64_t)N * OH * OW * C;
+  maxpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y, total, OH, OW, C);
+  return check_launch("fdg_maxpool2_fwd");
+}
+
+int fdg_maxpool2_bwd(const FdgTensor* x, const FdgTensor* gy, const FdgTensor* gx, int N, int OH, int OW, int C,
+                     int accumulate, fdg_stream_t stream) {
+  FDG_REQUIRE(x && gy && gx && x->p && gy->p && gx->p && N > 0 && OH > 0 && OW > 0 && C > 0,
+              "fdg_maxpool2_bwd: bad arguments");
+  const int64_t total = (int64_t)N * OH * OW * C;
+  maxpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *gy, *gx, total, OH, OW, C, accumulate);
+  return check_launch("fdg_maxpool2_bwd");
+}
+
+int fdg_copy4d(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int C, int gather, float slope, float scale,
+               int accumulate, fdg_stream_t stream) {
+  FDG_REQUIRE(x && y && x->p && y->p && N > 0 && H > 0 && W > 0 && C > 0, "fdg_copy4d: bad arguments");
+  FDG_REQUIRE(gather >= 0 && gather <= 2, "fdg_copy4d: bad gather mode");
+  const int64_t total = (int64_t)N * H * W * C;
+  copy4d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y, total, H, W, C, gather, slope, scale, accumulate);
+  return check_launch("fdg_copy4d");
+}
+
+int fdg_act_bwd(const float* g, const float* y, float* out, int64_t n, int act, fdg_stream_t stream) {
+  FDG_REQUIRE(g && y && out && n > 0 && (act == FDG_ACT_TANH || act == FDG_ACT_SIGMOID), "fdg_act_bwd: bad arguments");
+  act_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(g, y, out, n, act);
+  return check_launch("fdg_act_bwd");
+}
+
+int fdg_conv2d_dgrad_strided(const FdgDgradStrided* p, fdg_stream_t stream) {
+  FDG_REQUIRE(p && p->g.p && p->w && p->dx.p, "fdg_conv2d_dgrad_strided: null pointer");
+  FDG_REQUIRE(p->N > 0 && p->OH > 0 && p->OW > 0 && p->Cout > 0 && p->Cin > 0 && p->R > 0 && p->S > 0 && p->stride > 0 &&
+                  p->H > 0 && p->W > 0, "fdg_conv2d_dgrad_strided: bad extents");
+  FDG_REQUIRE(p->OH == (p->H + 2 * p->pad - p->R) / p->stride + 1 && p->OW == (p->W + 2 * p->pad - p->S) / p->stride + 1,
+              "fdg_conv2d_dgrad_strided: OH/OW inconsistent");
+  const int64_t total = (int64_t)p->N * p->H * p->W * p->Cin;
+  dgrad_strided_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(*p, total);
+  return check_launch("fdg_conv2d_dgrad_strided");
+}
+
+int fdg_pack_weight(const float* w, int Cout, int Cin, int R, int S, int mode, float* out, int out_ld,
+                    fdg_stream_t stream) {
+  FDG_REQUIRE(w && out && Cout > 0 && Cin > 0 && R > 0 && S > 0 && mode >= 0 && mode <= 2, "fdg_pack_weight: bad arguments");
+  const int K = mode == 0 ? R * S * Cin : (mode == 1 ? R * S * Cout : Cout);
+  const int ncols = mode == 0 ? Cout : Cin;
+  FDG_REQUIRE(out_ld >= ncols, "fdg_pack_weight: out_ld too small");
+  FDG_REQUIRE(mode != 2 || (R == 1 && S == 1), "fdg_pack_weight: mode 2 is 1x1 only");
+  const int64_t total = (int64_t)K * out_ld;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, R, S, mode, out, out_ld, total);
+  return check_launch("fdg_pack_weight");
+}
+
+int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, fdg_stream_t stream) {
+  FDG_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "fdg_adam_flat: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                  bc1, sqrtf(bc2), grad_scale);
+  return check_launch("fdg_adam_flat");
+}
+
+}  // extern "C"

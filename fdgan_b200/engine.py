@@ -1,0 +1,573 @@
+"""Forward / backward executors of the three networks on the hot path.
+
+Each executor walks the network once and enqueues fdgan_b200 kernels (ops.py) on the current CUDA
+stream.  Design points (DESIGN.md has the long form):
+
+  * activations are NHWC fp32; every DenseNet block owns ONE pre-allocated concat buffer and the
+    producing convolutions write their 32 new channels in place (no torch.cat, models/densenet.py:181,242);
+  * BatchNorm never runs as a pass: batch statistics come out of the producer's epilogue (fp64 sums),
+    ``bn_finalize`` turns them into per-channel scale/shift, and the consumer applies normalise+ReLU in
+    its operand loader.  Statistics of a concat channel are computed once and shared by every later norm1;
+  * avg-pool / nearest-upsample are folded into loaders and stores (gather / store modes);
+  * backward = data-gradient convolutions (same kernel, flipped weights), weight-gradient GEMMs over the
+    pixel dimension, and two light element-wise passes per BatchNorm (reduce, then apply).
+
+Reference semantics followed: FDGAN.forward models/dehaze1113.py:758-801, BottleneckBlockdy :268-275,
+TransitionBlockdy :366-370, D :188-230, Vgg16.forward myutils/vgg16.py:27-49, torchvision dense
+layer/transition (spec copy models/densenet.py:179-242).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, GATHER_AVGPOOL2, GATHER_DIRECT, GATHER_UP2,
+                  STORE_ACCUM, STORE_NORMAL, STORE_UP2, View)
+
+GROWTH = 32
+BOTTLENECK = 128
+
+
+class BNRun:
+    """Per-forward state of one BatchNorm: scale/shift applied by the consumer, mean/invstd for backward."""
+
+    __slots__ = ("mod", "C", "count", "scale", "shift", "mean", "invstd")
+
+    def __init__(self, mod, C, count, buf):
+        self.mod, self.C, self.count = mod, C, count
+        self.scale, self.shift, self.mean, self.invstd = buf[0:C], buf[C:2 * C], buf[2 * C:3 * C], buf[3 * C:4 * C]
+
+
+class _Pool:
+    """Bump allocator over one zero-initialised torch buffer (small per-forward scratch: BN stats, BN vectors)."""
+
+    def __init__(self, n, dtype, device):
+        self.buf = torch.zeros(n, dtype=dtype, device=device)
+        self.off = 0
+
+    def take(self, n, align=4):
+        self.off = (self.off + align - 1) // align * align
+        t = self.buf[self.off:self.off + n]
+        assert t.numel() == n, "scratch pool exhausted"
+        self.off += n
+        return t
+
+
+def _bn_run(mod, stats, stats_ld, C, count, training, fpool, nbt_list):
+    run = BNRun(mod, C, count, fpool.take(4 * C))
+    track = training and mod.track_running_stats
+    ops.bn_finalize(stats, stats_ld, C, count, mod.weight, mod.bias, mod.eps, mod.momentum,
+                    mod.running_mean if track else None, mod.running_var if track else None,
+                    training, run.scale, run.shift, run.mean, run.invstd)
+    if track:
+        nbt_list.append(mod.num_batches_tracked)
+    return run
+
+
+def _bn_bwd(g: View, x: View, run: BNRun, out: View, dpool, grads, prefix, *, slope=0.0, accumulate=False,
+            g_gather=GATHER_DIRECT, gscale=1.0):
+    """BatchNorm + (Leaky)ReLU backward: out (=|+=) dL/dx given g = dL/d(act(bn(x)))."""
+    C = run.C
+    st = dpool.take(2 * C)
+    ops.ew_bwd(g, x, stats=st, scale=run.scale, shift=run.shift, slope=slope, g_gather=g_gather, gscale=gscale)
+    coef = torch.empty(3 * C, dtype=torch.float32, device=x.base.device)
+    dgamma = grads.get(prefix + ".weight") if grads is not None else None
+    dbeta = grads.get(prefix + ".bias") if grads is not None else None
+    ops.bn_bwd_finalize(st, C, run.count, run.mod.weight, run.mean, run.invstd, coef, dgamma, dbeta, accumulate=True)
+    ops.ew_bwd(g, x, out=out, scale=run.scale, shift=run.shift, slope=slope, coef=coef, accumulate=accumulate,
+               g_gather=g_gather, gscale=gscale)
+
+
+# ======================================================================================================
+# Generator
+# ======================================================================================================
+
+
+class GCtx:
+    pass
+
+
+def _dense_block_fwd(block, prefix, n_layers, c_in, X: View, S, training, fpool, spool, nbt, saved):
+    N, H, W, Ctot = X.N, X.H, X.W, X.C
+    count = N * H * W
+    layers = []
+    for i in range(n_layers):
+        lyr = getattr(block, "denselayer%d" % (i + 1))
+        cin = c_in + GROWTH * i
+        bn1 = _bn_run(lyr.norm1, S, Ctot, cin, count, training, fpool, nbt)
+        T = View.alloc(N, H, W, BOTTLENECK, X.base.device)
+        ST = spool.take(2 * BOTTLENECK) if training else None
+        w1, ld1 = ops.pack_weight(lyr.conv1.weight, 0)
+        ops.conv2d(X.ch(0, cin), w1, ld1, 1, 1, 1, 0, BOTTLENECK, T, scale=bn1.scale, shift=bn1.shift, slope=0.0,
+                   stats=ST, stats_ld=BOTTLENECK)
+        bn2 = _bn_run(lyr.norm2, ST, BOTTLENECK, BOTTLENECK, count, training, fpool, nbt)
+        w2, ld2 = ops.pack_weight(lyr.conv2.weight, 0)
+        ops.conv2d(T, w2, ld2, 3, 3, 1, 1, GROWTH, X.ch(cin, cin + GROWTH), scale=bn2.scale, shift=bn2.shift,
+                   slope=0.0, stats=(S.data_ptr() + 8 * cin) if training else None, stats_ld=Ctot)
+        layers.append((T, bn1, bn2))
+    saved[prefix] = layers
+
+
+def _transition_fwd(tr, X: View, S, y: View, ystats, ystats_ld, training, fpool, nbt):
+    bn = _bn_run(tr.norm, S, X.C, X.C, X.N * X.H * X.W, training, fpool, nbt)
+    w, ld = ops.pack_weight(tr.conv.weight, 0)
+    ops.conv2d(X, w, ld, 1, 1, 1, 0, y.C, y, gather=GATHER_AVGPOOL2, scale=bn.scale, shift=bn.shift, slope=0.0,
+               stats=ystats, stats_ld=ystats_ld)
+    return bn
+
+
+def generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
+    """FDGAN.forward (models/dehaze1113.py:758-801).  x: [B,3,H,W] fp32 CUDA (any strides) -> [B,3,H',W']."""
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("FDGAN expects a [B,3,H,W] input, got %s" % (tuple(x.shape),))
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError("fdgan_b200 runs on CUDA fp32 tensors only (no CPU fallback); got %s %s" % (x.device, x.dtype))
+    B, _, H1, W1 = x.shape
+    H2, W2 = H1 // 2, W1 // 2
+    H3, W3 = H2 // 2, W2 // 2
+    H4, W4 = H3 // 2, W3 // 2
+    if H4 < 1 or W4 < 1 or 2 * H4 != H3 or 2 * W4 != W3:
+        # same condition under which the reference's torch.cat([x4, x2]) (dehaze1113.py:786) succeeds
+        raise RuntimeError("FDGAN: input %dx%d is not supported: floor(H/4) must equal 2*floor(H/8)" % (H1, W1))
+    dev = x.device
+    ctx = GCtx()
+    saved = {}
+    nbt = []
+    fpool = _Pool(4 * 60000, torch.float32, dev)          # BN scale/shift/mean/invstd vectors
+    spool = _Pool(2 * (256 + 512 + 1024) + 42 * 256 + 1024, torch.float64, dev)  # BN statistics (zero-initialised)
+    xin = View.from_nchw(x)
+
+    # ---- stem: x0 = relu0(conv_refin1(x)) written straight into block 1's concat buffer
+    X1 = View.alloc(B, H1, W1, 256, dev)
+    S1 = spool.take(2 * 256)
+    w, ld = ops.pack_weight(m.conv_refin1.weight, 0)
+    ops.conv2d(xin, w, ld, 3, 3, 1, 1, 64, X1.ch(0, 64), bias=m.conv_refin1.bias, act=ACT_RELU,
+               stats=S1 if training else None, stats_ld=256)
+    # ---- x01 = conv_refin2(avg_pool2d(x0, 2)) -> first 32 channels of the conv_refine4 input
+    C4 = View.alloc(B, H2, W2, 160, dev)
+    w, ld = ops.pack_weight(m.conv_refin2.weight, 0)
+    ops.conv2d(X1.ch(0, 64), w, ld, 1, 1, 1, 0, 32, C4.ch(0, 32), gather=GATHER_AVGPOOL2, bias=m.conv_refin2.bias)
+    # ---- dense_block1 + trans_block1
+    _dense_block_fwd(m.dense_block1, "dense_block1", 6, 64, X1, S1, training, fpool, spool, nbt, saved)
+    bn_t1 = _transition_fwd(m.trans_block1, X1, S1, C4.ch(32, 160), None, 0, training, fpool, nbt)
+    # ---- x10 = conv_refine4(cat[x01, x1])
+    X2 = View.alloc(B, H2, W2, 512, dev)
+    S2 = spool.take(2 * 512)
+    w, ld = ops.pack_weight(m.conv_refine4.weight, 0)
+    ops.conv2d(C4, w, ld, 3, 3, 1, 1, 128, X2.ch(0, 128), bias=m.conv_refine4.bias,
+               stats=S2 if training else None, stats_ld=512)
+    _dense_block_fwd(m.dense_block2, "dense_block2", 12, 128, X2, S2, training, fpool, spool, nbt, saved)
+    X3 = View.alloc(B, H3, W3, 1024, dev)
+    S3 = spool.take(2 * 1024)
+    bn_t2 = _transition_fwd(m.trans_block2, X2, S2, X3.ch(0, 256), S3 if training else None, 1024, training, fpool, nbt)
+    _dense_block_fwd(m.dense_block3, "dense_block3", 24, 256, X3, S3, training, fpool, spool, nbt, saved)
+    C6 = View.alloc(B, H4, W4, 640, dev)
+    bn_t3 = _transition_fwd(m.trans_block3, X3, S3, C6.ch(0, 512), None, 0, training, fpool, nbt)
+    # ---- x22 = conv_refin5(avg_pool2d(x2, 2))
+    w, ld = ops.pack_weight(m.conv_refin5.weight, 0)
+    ops.conv2d(X3.ch(0, 256), w, ld, 1, 1, 1, 0, 128, C6.ch(512, 640), gather=GATHER_AVGPOOL2, bias=m.conv_refin5.bias)
+    # ---- decoder level 4: conv_refin6 -> BottleneckBlockdy(512,256) -> TransitionBlockdy(768,128)
+    D4 = View.alloc(B, H4, W4, 768, dev)
+    w, ld = ops.pack_weight(m.conv_refin6.weight, 0)
+    ops.conv2d(C6, w, ld, 3, 3, 1, 1, 512, D4.ch(0, 512), bias=m.conv_refin6.bias, act=ACT_RELU)  # in-place ReLU of Bdy
+    T4 = View.alloc(B, H4, W4, 1024, dev)
+    w, ld = ops.pack_weight(m.dense_block4.conv1.weight, 0)
+    ops.conv2d(D4.ch(0, 512), w, ld, 1, 1, 1, 0, 1024, T4)
+    w, ld = ops.pack_weight(m.dense_block4.conv2.weight, 0)
+    ops.conv2d(T4, w, ld, 3, 3, 1, 1, 256, D4.ch(512, 768), slope=0.0)
+    X42 = View.alloc(B, H3, W3, 512, dev)  # [relu(x4) | relu(x2) | block-5 growth]
+    ops.conv2d(D4, m.trans_block4.conv1.weight, 128, 1, 1, 1, 0, 128, X42.ch(0, 128), slope=0.0, act=ACT_RELU,
+               store=STORE_UP2)
+    ops.copy4d(X3.ch(0, 256), X42.ch(128, 384), slope=0.0)
+    # ---- decoder level 5
+    T5 = View.alloc(B, H3, W3, 512, dev)
+    w, ld = ops.pack_weight(m.dense_block5.conv1.weight, 0)
+    ops.conv2d(X42.ch(0, 384), w, ld, 1, 1, 1, 0, 512, T5)
+    w, ld = ops.pack_weight(m.dense_block5.conv2.weight, 0)
+    ops.conv2d(T5, w, ld, 3, 3, 1, 1, 128, X42.ch(384, 512), slope=0.0)
+    Hd2, Wd2 = 2 * H3, 2 * W3
+    D6 = View.alloc(B, Hd2, Wd2, 96, dev)   # [relu(x5) | block-6 growth]
+    ops.conv2d(X42, m.trans_block5.conv1.weight, 64, 1, 1, 1, 0, 64, D6.ch(0, 64), slope=0.0, act=ACT_RELU,
+               store=STORE_UP2)
+    # ---- decoder level 6
+    T6 = View.alloc(B, Hd2, Wd2, 128, dev)
+    w, ld = ops.pack_weight(m.dense_block6.conv1.weight, 0)
+    ops.conv2d(D6.ch(0, 64), w, ld, 1, 1, 1, 0, 128, T6)
+    w, ld = ops.pack_weight(m.dense_block6.conv2.weight, 0)
+    ops.conv2d(T6, w, ld, 3, 3, 1, 1, 32, D6.ch(64, 96), slope=0.0)
+    Hd1, Wd1 = 2 * Hd2, 2 * Wd2
+    X6 = View.alloc(B, Hd1, Wd1, 16, dev)
+    ops.conv2d(D6, m.trans_block6.conv1.weight, 16, 1, 1, 1, 0, 16, X6, slope=0.0, store=STORE_UP2)
+    # ---- head: tanh(conv_refin3(x6)), NCHW output
+    out = torch.empty((B, 3, Hd1, Wd1), dtype=torch.float32, device=dev)
+    w, ld = ops.pack_weight(m.conv_refin3.weight, 0)
+    ops.conv2d(X6, w, ld, 3, 3, 1, 1, 3, View.from_nchw(out), bias=m.conv_refin3.bias, act=ACT_TANH)
+    if nbt:
+        torch._foreach_add_(nbt, 1)
+    if not need_ctx:
+        return out, None
+    ctx.x, ctx.out = x, out
+    ctx.X1, ctx.C4, ctx.X2, ctx.X3, ctx.C6, ctx.D4, ctx.T4 = X1, C4, X2, X3, C6, D4, T4
+    ctx.X42, ctx.T5, ctx.D6, ctx.T6, ctx.X6 = X42, T5, D6, T6, X6
+    ctx.bn_t1, ctx.bn_t2, ctx.bn_t3 = bn_t1, bn_t2, bn_t3
+    ctx.saved = saved
+    ctx.keep = (fpool, spool)
+    ctx.training = training
+    return out, ctx
+
+
+def _conv_dgrad_w(weight):
+    """[K=(r,s,co)][N=ci] operand for the data gradient of a stride-1 conv; 1x1 weights are used as they are."""
+    co, ci, R, S = weight.shape
+    if R == 1 and S == 1:
+        return weight, ci
+    return ops.pack_weight(weight, 1)
+
+
+def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, grads, dpool):
+    N, H, W = X.N, X.H, X.W
+    dev = X.base.device
+    dA2 = View.alloc(N, H, W, BOTTLENECK, dev)
+    cmax = c_in + GROWTH * (n_layers - 1)
+    dA1buf = torch.empty(N * H * W * cmax, dtype=torch.float32, device=dev)
+    for i in reversed(range(n_layers)):
+        lyr = getattr(block, "denselayer%d" % (i + 1))
+        p = "%s.denselayer%d" % (prefix, i + 1)
+        cin = c_in + GROWTH * i
+        T, bn1, bn2 = layers[i]
+        g2 = dX.ch(cin, cin + GROWTH)
+        ops.wgrad(T, g2, 3, 3, 1, 1, grads[p + ".conv2.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.0)
+        wd, ldd = _conv_dgrad_w(lyr.conv2.weight)
+        ops.conv2d(g2, wd, ldd, 3, 3, 1, 1, BOTTLENECK, dA2)
+        _bn_bwd(dA2, T, bn2, dA2, dpool, grads, p + ".norm2")                      # dA2 <- dL/d(conv1 output), in place
+        ops.wgrad(X.ch(0, cin), dA2, 1, 1, 1, 0, grads[p + ".conv1.weight"], scale=bn1.scale, shift=bn1.shift, slope=0.0)
+        dA1 = View.nhwc(dA1buf, N, H, W, cin)
+        ops.conv2d(dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dA1)
+        _bn_bwd(dA1, X.ch(0, cin), bn1, dX.ch(0, cin), dpool, grads, p + ".norm1", accumulate=True)
+
+
+def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dpool):
+    """torchvision transition backward; g = dL/d(output) at the pooled resolution; accumulates into dX."""
+    ops.wgrad(X, g, 1, 1, 1, 0, grads[prefix + ".conv.weight"], gather=GATHER_AVGPOOL2, scale=bn.scale, shift=bn.shift,
+              slope=0.0)
+    dP = View.alloc(g.N, g.H, g.W, X.C, X.base.device)
+    ops.conv2d(g, tr.conv.weight, X.C, 1, 1, 1, 0, X.C, dP)
+    if (X.H, X.W) != (2 * g.H, 2 * g.W):
+        raise RuntimeError("fdgan_b200 backward needs even feature-map sizes at every transition (got %dx%d)" % (X.H, X.W))
+    _bn_bwd(dP, X, bn, dX, dpool, grads, prefix + ".norm", accumulate=True, g_gather=GATHER_UP2, gscale=0.25)
+
+
+def _bdy_bwd(blk, prefix, Dv: View, dD: View, T: View, c_in, grads):
+    """BottleneckBlockdy backward.  Dv = [relu(x) | conv2 out]; dD holds dL/dDv (already masked by Dv > 0);
+    on return dD[:, :c_in] is dL/d(pre-ReLU x)."""
+    c_out = Dv.C - c_in
+    g = dD.ch(c_in, Dv.C)
+    ops.wgrad(T, g, 3, 3, 1, 1, grads[prefix + ".conv2.weight"], slope=0.0)
+    dT = View.alloc(T.N, T.H, T.W, T.C, T.base.device)
+    wd, ldd = _conv_dgrad_w(blk.conv2.weight)
+    ops.conv2d(g, wd, ldd, 3, 3, 1, 1, T.C, dT, e=T, eslope=0.0)
+    ops.wgrad(Dv.ch(0, c_in), dT, 1, 1, 1, 0, grads[prefix + ".conv1.weight"])
+    ops.conv2d(dT, blk.conv1.weight, c_in, 1, 1, 1, 0, c_in, dD.ch(0, c_in), e=Dv.ch(0, c_in), eslope=0.0,
+               store=STORE_ACCUM)
+    del c_out
+
+
+def _tdy_bwd(tr, prefix, Dv: View, dD: View, gUp: View, grads):
+    """TransitionBlockdy backward: gUp = dL/d(upsampled output); writes dD = dL/dDv masked by Dv > 0."""
+    c_out = gUp.C
+    dU = View.alloc(Dv.N, Dv.H, Dv.W, c_out, Dv.base.device)
+    ops.copy4d(gUp, dU, gather=GATHER_AVGPOOL2, scale=4.0)              # adjoint of nearest x2
+    ops.wgrad(Dv, dU, 1, 1, 1, 0, grads[prefix + ".conv1.weight"], slope=0.0, transposed=True)
+    wd, ldd = ops.pack_weight(tr.conv1.weight, 2)
+    ops.conv2d(dU, wd, ldd, 1, 1, 1, 0, Dv.C, dD, e=Dv, eslope=0.0)
+
+
+def generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: bool):
+    """Backward of generator_forward.  ``grads`` maps parameter names to pre-zeroed fp32 tensors that the
+    kernels accumulate into.  Returns dL/dx (NCHW) or None."""
+    if not ctx.training:
+        raise RuntimeError("fdgan_b200: backward through FDGAN in eval() mode is not implemented (the reference always "
+                           "runs BatchNorm on batch statistics, README.md:38)")
+    if grads is None:
+        grads = _NoGrads()
+    dev = dout.device
+    B = ctx.out.shape[0]
+    dpool = _Pool(2 * 60000, torch.float64, dev)
+    X1, C4, X2, X3, C6, D4, T4 = ctx.X1, ctx.C4, ctx.X2, ctx.X3, ctx.C6, ctx.D4, ctx.T4
+    X42, T5, D6, T6, X6 = ctx.X42, ctx.T5, ctx.D6, ctx.T6, ctx.X6
+    # ---- head
+    dpre = torch.empty_like(ctx.out)
+    ops.act_bwd(dout.contiguous(), ctx.out, dpre, ACT_TANH)
+    gpre = View.from_nchw(dpre)
+    ops.wgrad(X6, gpre, 3, 3, 1, 1, grads["conv_refin3.weight"], dbias=grads["conv_refin3.bias"])
+    dX6 = View.alloc(X6.N, X6.H, X6.W, 16, dev)
+    wd, ldd = _conv_dgrad_w(m.conv_refin3.weight)
+    ops.conv2d(gpre, wd, ldd, 3, 3, 1, 1, 16, dX6)
+    # ---- level 6
+    dD6 = View.alloc(D6.N, D6.H, D6.W, 96, dev)
+    _tdy_bwd(m.trans_block6, "trans_block6", D6, dD6, dX6, grads)
+    _bdy_bwd(m.dense_block6, "dense_block6", D6, dD6, T6, 64, grads)
+    # ---- level 5
+    dX42 = View.alloc(X42.N, X42.H, X42.W, 512, dev)
+    _tdy_bwd(m.trans_block5, "trans_block5", X42, dX42, dD6.ch(0, 64), grads)
+    _bdy_bwd(m.dense_block5, "dense_block5", X42, dX42, T5, 384, grads)
+    # gradient buffers of the encoder blocks (zero-initialised, everything accumulates)
+    dX3 = View.alloc(X3.N, X3.H, X3.W, 1024, dev, zero=True)
+    ops.copy4d(dX42.ch(128, 384), dX3.ch(0, 256), accumulate=True)       # x2 skip (already masked by relu(x2) > 0)
+    # ---- level 4
+    dD4 = View.alloc(D4.N, D4.H, D4.W, 768, dev)
+    _tdy_bwd(m.trans_block4, "trans_block4", D4, dD4, dX42.ch(0, 128), grads)
+    _bdy_bwd(m.dense_block4, "dense_block4", D4, dD4, T4, 512, grads)
+    g6 = dD4.ch(0, 512)                                                   # dL/d(conv_refin6 pre-ReLU output)
+    ops.wgrad(C6, g6, 3, 3, 1, 1, grads["conv_refin6.weight"], dbias=grads["conv_refin6.bias"])
+    dC6 = View.alloc(C6.N, C6.H, C6.W, 640, dev)
+    wd, ldd = _conv_dgrad_w(m.conv_refin6.weight)
+    ops.conv2d(g6, wd, ldd, 3, 3, 1, 1, 640, dC6)
+    # ---- conv_refin5 branch (x22)
+    g5 = dC6.ch(512, 640)
+    ops.wgrad(X3.ch(0, 256), g5, 1, 1, 1, 0, grads["conv_refin5.weight"], gather=GATHER_AVGPOOL2,
+              dbias=grads["conv_refin5.bias"])
+    dP = View.alloc(g5.N, g5.H, g5.W, 256, dev)
+    ops.conv2d(g5, m.conv_refin5.weight, 256, 1, 1, 1, 0, 256, dP)
+    ops.copy4d(dP, dX3.ch(0, 256), gather=GATHER_UP2, scale=0.25, accumulate=True)
+    # ---- encoder level 3
+    _transition_bwd(m.trans_block3, "trans_block3", X3, dX3, dC6.ch(0, 512), ctx.bn_t3, grads, dpool)
+    _dense_block_bwd(m.dense_block3, "dense_block3", 24, 256, X3, dX3, ctx.saved["dense_block3"], grads, dpool)
+    # ---- encoder level 2
+    dX2 = View.alloc(X2.N, X2.H, X2.W, 512, dev, zero=True)
+    _transition_bwd(m.trans_block2, "trans_block2", X2, dX2, dX3.ch(0, 256), ctx.bn_t2, grads, dpool)
+    _dense_block_bwd(m.dense_block2, "dense_block2", 12, 128, X2, dX2, ctx.saved["dense_block2"], grads, dpool)
+    g4 = dX2.ch(0, 128)
+    ops.wgrad(C4, g4, 3, 3, 1, 1, grads["conv_refine4.weight"], dbias=grads["conv_refine4.bias"])
+    dC4 = View.alloc(C4.N, C4.H, C4.W, 160, dev)
+    wd, ldd = _conv_dgrad_w(m.conv_refine4.weight)
+    ops.conv2d(g4, wd, ldd, 3, 3, 1, 1, 160, dC4)
+    # ---- encoder level 1
+    dX1 = View.alloc(X1.N, X1.H, X1.W, 256, dev, zero=True)
+    _transition_bwd(m.trans_block1, "trans_block1", X1, dX1, dC4.ch(32, 160), ctx.bn_t1, grads, dpool)
+    g2 = dC4.ch(0, 32)
+    ops.wgrad(X1.ch(0, 64), g2, 1, 1, 1, 0, grads["conv_refin2.weight"], gather=GATHER_AVGPOOL2,
+              dbias=grads["conv_refin2.bias"])
+    dP = View.alloc(g2.N, g2.H, g2.W, 64, dev)
+    ops.conv2d(g2, m.conv_refin2.weight, 64, 1, 1, 1, 0, 64, dP)
+    if (X1.H, X1.W) != (2 * dP.H, 2 * dP.W):
+        raise RuntimeError("fdgan_b200 backward needs an even input size (got %dx%d)" % (X1.H, X1.W))
+    ops.copy4d(dP, dX1.ch(0, 64), gather=GATHER_UP2, scale=0.25, accumulate=True)
+    _dense_block_bwd(m.dense_block1, "dense_block1", 6, 64, X1, dX1, ctx.saved["dense_block1"], grads, dpool)
+    # ---- stem: x0 = relu(conv_refin1(x)) stored post-ReLU
+    g0 = dX1.ch(0, 64)
+    ops.ew_bwd(g0, X1.ch(0, 64), out=g0, slope=0.0)
+    xin = View.from_nchw(ctx.x)
+    ops.wgrad(xin, g0, 3, 3, 1, 1, grads["conv_refin1.weight"], dbias=grads["conv_refin1.bias"])
+    if not need_dx:
+        return None
+    dx = torch.empty((B, 3, xin.H, xin.W), dtype=torch.float32, device=dev)
+    wd, ldd = _conv_dgrad_w(m.conv_refin1.weight)
+    ops.conv2d(g0, wd, ldd, 3, 3, 1, 1, 3, View.from_nchw(dx))
+    return dx
+
+
+# ======================================================================================================
+# Fusion-discriminator
+# ======================================================================================================
+
+
+class DCtx:
+    pass
+
+
+def discriminator_forward(m, z: torch.Tensor, training: bool, need_ctx: bool):
+    """D.forward (models/dehaze1113.py:188-230): z [B,nc,H,W] -> sigmoid patch map [B,1,H/2-2,W/2-2]."""
+    if z.dim() != 4 or z.shape[1] != m.nc:
+        raise ValueError("D expects a [B,%d,H,W] input, got %s" % (m.nc, tuple(z.shape)))
+    if not z.is_cuda or z.dtype != torch.float32:
+        raise RuntimeError("fdgan_b200 runs on CUDA fp32 tensors only (no CPU fallback)")
+    dev = z.device
+    nf = m.nf
+    B, _, H, W = z.shape
+    zin = View.from_nchw(z)
+    l1, l2, l3, l4, l5 = m.layer_params()
+    fpool = _Pool(4 * 6 * nf + 64, torch.float32, dev)
+    spool = _Pool(2 * 6 * nf + 16, torch.float64, dev)
+    nbt = []
+    H1, W1 = (H + 2 - 4) // 2 + 1, (W + 2 - 4) // 2 + 1
+    if H1 < 3 or W1 < 3:
+        raise RuntimeError("D: input %dx%d too small" % (H, W))
+    Y1 = View.alloc(B, H1, W1, nf, dev)
+    w, ld = ops.pack_weight(l1.weight, 0)
+    ops.conv2d(zin, w, ld, 4, 4, 2, 1, nf, Y1)
+    Y2 = View.alloc(B, H1, W1, 2 * nf, dev)
+    S2 = spool.take(4 * nf)
+    w, ld = ops.pack_weight(l2.conv.weight, 0)
+    ops.conv2d(Y1, w, ld, 3, 3, 1, 1, 2 * nf, Y2, slope=0.2, stats=S2 if training else None, stats_ld=2 * nf)
+    bn2 = _bn_run(l2.bn, S2, 2 * nf, 2 * nf, B * H1 * W1, training, fpool, nbt)
+    Y3 = View.alloc(B, H1, W1, 4 * nf, dev)
+    S3 = spool.take(8 * nf)
+    w, ld = ops.pack_weight(l3.conv.weight, 0)
+    ops.conv2d(Y2, w, ld, 3, 3, 1, 1, 4 * nf, Y3, scale=bn2.scale, shift=bn2.shift, slope=0.2,
+               stats=S3 if training else None, stats_ld=4 * nf)
+    bn3 = _bn_run(l3.bn, S3, 4 * nf, 4 * nf, B * H1 * W1, training, fpool, nbt)
+    Y4 = View.alloc(B, H1 - 1, W1 - 1, 8 * nf, dev)
+    w, ld = ops.pack_weight(l4.weight, 0)
+    ops.conv2d(Y3, w, ld, 4, 4, 1, 1, 8 * nf, Y4, scale=bn3.scale, shift=bn3.shift, slope=0.2)
+    out = torch.empty((B, 1, H1 - 2, W1 - 2), dtype=torch.float32, device=dev)
+    w, ld = ops.pack_weight(l5.weight, 0)
+    ops.conv2d(Y4, w, ld, 4, 4, 1, 1, 1, View.from_nchw(out), slope=0.2, act=ACT_SIGMOID)
+    if nbt:
+        torch._foreach_add_(nbt, 1)
+    if not need_ctx:
+        return out, None
+    ctx = DCtx()
+    ctx.z, ctx.out, ctx.Y1, ctx.Y2, ctx.Y3, ctx.Y4, ctx.bn2, ctx.bn3 = z, out, Y1, Y2, Y3, Y4, bn2, bn3
+    ctx.keep = (fpool, spool)
+    ctx.training = training
+    return out, ctx
+
+
+class _NoGrads(dict):
+    """grads mapping used when a network's parameters are frozen: every lookup yields None."""
+
+    def __getitem__(self, k):
+        return None
+
+    def get(self, k, default=None):
+        return None
+
+
+def discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bool):
+    if not ctx.training:
+        raise RuntimeError("fdgan_b200: backward through D in eval() mode is not implemented")
+    need_w = grads is not None
+    if grads is None:
+        grads = _NoGrads()
+    dev = dout.device
+    nf = m.nf
+    l1, l2, l3, l4, l5 = m.layer_params()
+    dpool = _Pool(2 * 6 * nf + 16, torch.float64, dev)
+    Y1, Y2, Y3, Y4, bn2, bn3 = ctx.Y1, ctx.Y2, ctx.Y3, ctx.Y4, ctx.bn2, ctx.bn3
+    dpre = torch.empty_like(ctx.out)
+    ops.act_bwd(dout.contiguous(), ctx.out, dpre, ACT_SIGMOID)
+    g5 = View.from_nchw(dpre)
+    if need_w:
+        ops.wgrad(Y4, g5, 4, 4, 1, 1, grads["main.layer5.conv.weight"], slope=0.2)
+    dY4 = View.alloc(Y4.N, Y4.H, Y4.W, Y4.C, dev)
+    wd, ldd = ops.pack_weight(l5.weight, 1)
+    ops.conv2d(g5, wd, ldd, 4, 4, 1, 2, Y4.C, dY4, e=Y4, eslope=0.2)
+    if need_w:
+        ops.wgrad(Y3, dY4, 4, 4, 1, 1, grads["main.layer4.conv.weight"], scale=bn3.scale, shift=bn3.shift, slope=0.2)
+    dY3 = View.alloc(Y3.N, Y3.H, Y3.W, Y3.C, dev)
+    wd, ldd = ops.pack_weight(l4.weight, 1)
+    ops.conv2d(dY4, wd, ldd, 4, 4, 1, 2, Y3.C, dY3)
+    _bn_bwd(dY3, Y3, bn3, dY3, dpool, grads if need_w else None, "main.layer3.layer3.bn", slope=0.2)
+    if need_w:
+        ops.wgrad(Y2, dY3, 3, 3, 1, 1, grads["main.layer3.layer3.conv.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.2)
+    dY2 = View.alloc(Y2.N, Y2.H, Y2.W, Y2.C, dev)
+    wd, ldd = ops.pack_weight(l3.conv.weight, 1)
+    ops.conv2d(dY3, wd, ldd, 3, 3, 1, 1, Y2.C, dY2)
+    _bn_bwd(dY2, Y2, bn2, dY2, dpool, grads if need_w else None, "main.layer2.layer2.bn", slope=0.2)
+    if need_w:
+        ops.wgrad(Y1, dY2, 3, 3, 1, 1, grads["main.layer2.layer2.conv.weight"], slope=0.2)
+    dY1 = View.alloc(Y1.N, Y1.H, Y1.W, Y1.C, dev)
+    wd, ldd = ops.pack_weight(l2.conv.weight, 1)
+    ops.conv2d(dY2, wd, ldd, 3, 3, 1, 1, Y1.C, dY1, e=Y1, eslope=0.2)
+    zin = View.from_nchw(ctx.z)
+    if need_w:
+        ops.wgrad(zin, dY1, 4, 4, 2, 1, grads["main.layer1.conv.weight"])
+    if not need_dx:
+        return None
+    # channels-last memory, returned as a logical NCHW tensor
+    dzv = View.alloc(zin.N, zin.H, zin.W, zin.C, dev)
+    ops.dgrad_strided(dY1, l1.weight, 2, 1, dzv)
+    return dzv.as_nchw()
+
+
+# ======================================================================================================
+# VGG16 feature extractor
+# ======================================================================================================
+
+VGG_STAGES = (("conv1_1", "conv1_2"), ("conv2_1", "conv2_2"), ("conv3_1", "conv3_2", "conv3_3"),
+              ("conv4_1", "conv4_2", "conv4_3"))
+
+
+class VCtx:
+    pass
+
+
+def vgg_forward(m, x: torch.Tensor, need_ctx: bool):
+    """Vgg16.forward (myutils/vgg16.py:27-49) -> [relu1_2, relu2_2, relu3_3, relu4_3] as NCHW-shaped views."""
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("Vgg16 expects a [B,3,H,W] input, got %s" % (tuple(x.shape),))
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError("fdgan_b200 runs on CUDA fp32 tensors only (no CPU fallback)")
+    dev = x.device
+    B, _, H, W = x.shape
+    cur = View.from_nchw(x)
+    feats, acts = [], []
+    for si, stage in enumerate(VGG_STAGES):
+        if si > 0:
+            pooled = View.alloc(B, cur.H // 2, cur.W // 2, cur.C, dev)
+            if pooled.H < 1 or pooled.W < 1:
+                raise RuntimeError("Vgg16: input %dx%d too small" % (H, W))
+            ops.maxpool2_fwd(cur, pooled)
+            cur = pooled
+        stage_acts = [cur]
+        for name in stage:
+            conv = getattr(m, name)
+            cout = conv.weight.shape[0]
+            y = View.alloc(B, cur.H, cur.W, cout, dev)
+            w, ld = ops.pack_weight(conv.weight, 0)
+            ops.conv2d(cur, w, ld, 3, 3, 1, 1, cout, y, bias=conv.bias, act=ACT_RELU)
+            cur = y
+            stage_acts.append(y)
+        acts.append(stage_acts)
+        feats.append(cur)
+    outs = [f.as_nchw() for f in feats]
+    if not need_ctx:
+        return outs, None
+    ctx = VCtx()
+    ctx.x, ctx.acts, ctx.feats = x, acts, feats
+    return outs, ctx
+
+
+def vgg_backward(m, ctx: VCtx, gouts, grads, need_dx: bool):
+    """gouts: 4 tensors or None (NCHW-shaped, any strides).  grads: dict for weight/bias gradients or None
+    (frozen extractor: data gradient only)."""
+    dev = ctx.x.device
+    need_w = grads is not None
+    g_next = None  # gradient w.r.t. the pooled input of the following stage
+    for si in reversed(range(len(VGG_STAGES))):
+        stage = VGG_STAGES[si]
+        acts = ctx.acts[si]
+        top = acts[-1]
+        if g_next is None and gouts[si] is None:
+            continue
+        dF = View.alloc(top.N, top.H, top.W, top.C, dev, zero=True)
+        if gouts[si] is not None:
+            ops.copy4d(View.from_nchw(gouts[si]), dF, accumulate=True)
+        if g_next is not None:
+            ops.maxpool2_bwd(top, g_next, dF, accumulate=True)
+        ops.ew_bwd(dF, top, out=dF, slope=0.0)       # ReLU mask of the stage output
+        g = dF
+        for li in reversed(range(len(stage))):
+            name = stage[li]
+            conv = getattr(m, name)
+            xin = acts[li]
+            if need_w:
+                ops.wgrad(xin, g, 3, 3, 1, 1, grads[name + ".weight"], dbias=grads[name + ".bias"])
+            first = (si == 0 and li == 0)
+            if first and not need_dx:
+                g = None
+                break
+            wd, ldd = ops.pack_weight(conv.weight, 1)
+            if first:
+                dx = torch.empty_like(ctx.x, memory_format=torch.contiguous_format)
+                ops.conv2d(g, wd, ldd, 3, 3, 1, 1, 3, View.from_nchw(dx))
+                return dx
+            gi = View.alloc(xin.N, xin.H, xin.W, xin.C, dev)
+            if li > 0:
+                ops.conv2d(g, wd, ldd, 3, 3, 1, 1, xin.C, gi, e=xin, eslope=0.0)   # fused ReLU mask of the producer
+            else:
+                ops.conv2d(g, wd, ldd, 3, 3, 1, 1, xin.C, gi)                       # pooled input: mask applied after un-pooling
+            g = gi
+        g_next = g
+    return None

@@ -1,0 +1,226 @@
+"""Typed Python wrappers over the C ABI (one function per entry point of include/fdgan_b200.h).
+
+PyTorch is used for device memory and streams only: every function enqueues hand-written sm_100a
+kernels on ``torch.cuda.current_stream()``; nothing here computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, GATHER_AVGPOOL2, GATHER_DIRECT, GATHER_UP2,  # noqa: F401
+                   IMPL_AUTO, IMPL_SIMT, IMPL_UMMA, STORE_ACCUM, STORE_NORMAL, STORE_UP2)
+
+_byref = C.byref
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int | None:
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+class View:
+    """A strided fp32 [N,H,W,C] view of device memory (element strides sn, sh, sw, sc).  ``base`` keeps the
+    owning torch tensor alive."""
+
+    __slots__ = ("base", "ptr", "N", "H", "W", "C", "sn", "sh", "sw", "sc")
+
+    def __init__(self, base, ptr, N, H, W, Cc, sn, sh, sw, sc):
+        self.base, self.ptr = base, ptr
+        self.N, self.H, self.W, self.C = N, H, W, Cc
+        self.sn, self.sh, self.sw, self.sc = sn, sh, sw, sc
+
+    @staticmethod
+    def nhwc(buf: torch.Tensor, N, H, W, Ctot) -> "View":
+        assert buf.dtype == torch.float32 and buf.is_cuda and buf.is_contiguous()
+        assert buf.numel() >= N * H * W * Ctot, (buf.numel(), N, H, W, Ctot)
+        return View(buf, buf.data_ptr(), N, H, W, Ctot, H * W * Ctot, W * Ctot, Ctot, 1)
+
+    @staticmethod
+    def alloc(N, H, W, Ctot, device, zero=False) -> "View":
+        f = torch.zeros if zero else torch.empty
+        return View.nhwc(f(N * H * W * Ctot, dtype=torch.float32, device=device), N, H, W, Ctot)
+
+    @staticmethod
+    def from_nchw(t: torch.Tensor) -> "View":
+        """A logical-NCHW torch tensor with arbitrary strides (contiguous NCHW, channels_last, slices ...)."""
+        assert t.dim() == 4 and t.dtype == torch.float32 and t.is_cuda
+        n, c, h, w = t.shape
+        sn, sc, sh, sw = t.stride()
+        return View(t, t.data_ptr(), n, h, w, c, sn, sh, sw, sc)
+
+    def ch(self, c0, c1) -> "View":
+        assert 0 <= c0 < c1 <= self.C
+        return View(self.base, self.ptr + 4 * c0 * self.sc, self.N, self.H, self.W, c1 - c0, self.sn, self.sh, self.sw, self.sc)
+
+    def ft(self) -> L.FdgTensor:
+        return L.FdgTensor(self.ptr, self.sn, self.sh, self.sw, self.sc)
+
+    def as_nchw(self) -> torch.Tensor:
+        """torch view with logical shape [N,C,H,W] over the same memory (no copy)."""
+        off = (self.ptr - self.base.data_ptr()) // 4
+        return torch.as_strided(self.base, (self.N, self.C, self.H, self.W), (self.sn, self.sc, self.sh, self.sw),
+                                self.base.storage_offset() + off)
+
+
+_NULLT = L.FdgTensor(None, 0, 0, 0, 0)
+
+
+def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_DIRECT, scale=None, shift=None,
+           slope=1.0, bias=None, act=ACT_NONE, e: View | None = None, eslope=0.0, store=STORE_NORMAL, stats=None,
+           stats_ld=0, alpha=1.0, impl=IMPL_AUTO, w_umma=None):
+    """fdg_conv2d.  ``w`` is the packed [K][w_ld] operand (tensor or pointer)."""
+    if gather == GATHER_AVGPOOL2:
+        H, W = x.H // 2, x.W // 2
+    elif gather == GATHER_UP2:
+        H, W = 2 * x.H, 2 * x.W
+    else:
+        H, W = x.H, x.W
+    OH = (H + 2 * pad - R) // stride + 1
+    OW = (W + 2 * pad - S) // stride + 1
+    mul = 2 if store == STORE_UP2 else 1
+    if (y.N, y.H, y.W, y.C) != (x.N, mul * OH, mul * OW, Cout):
+        raise ValueError("conv2d: output view %s does not match %s" % ((y.N, y.H, y.W, y.C), (x.N, mul * OH, mul * OW, Cout)))
+    if e is not None and (e.N, e.H, e.W, e.C) != (x.N, OH, OW, Cout):
+        raise ValueError("conv2d: mask view shape mismatch")
+    d = L.FdgConv(
+        x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
+        _ptr(w), w_ld, R, S, stride, pad, Cout, OH, OW, _ptr(bias), act,
+        e.ft() if e is not None else _NULLT, eslope, y.ft(), store, _ptr(stats), stats_ld, alpha, impl, _ptr(w_umma))
+    L.check(L.lib.fdg_conv2d(_byref(d), _stream()), "conv2d")
+
+
+def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scale=None, shift=None, slope=1.0,
+          transposed=False, dbias=None):
+    """fdg_conv2d_wgrad: dw (+)= A^T g in the parameter's own layout (dw must be pre-zeroed or accumulating).
+    ``dw is None`` (frozen parameter) skips the launch."""
+    if dw is None:
+        return
+    if gather == GATHER_AVGPOOL2:
+        H, W = x.H // 2, x.W // 2
+    elif gather == GATHER_UP2:
+        H, W = 2 * x.H, 2 * x.W
+    else:
+        H, W = x.H, x.W
+    OH = (H + 2 * pad - R) // stride + 1
+    OW = (W + 2 * pad - S) // stride + 1
+    if (g.N, g.H, g.W) != (x.N, OH, OW):
+        raise ValueError("wgrad: gradient view %s does not match output extent %s" % ((g.N, g.H, g.W), (x.N, OH, OW)))
+    d = L.FdgWgrad(x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
+                   g.ft(), R, S, stride, pad, g.C, OH, OW, _ptr(dw), 1 if transposed else 0, _ptr(dbias))
+    L.check(L.lib.fdg_conv2d_wgrad(_byref(d), _stream()), "conv2d_wgrad")
+
+
+def pack_weight(w: torch.Tensor, mode: int) -> tuple[torch.Tensor, int]:
+    """fdg_pack_weight.  mode 0: OIHW -> [(r,s,ci)][co]; 1: OIHW -> flipped [(r,s,co)][ci]; 2: [Cin][Cout] -> [co][ci]."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    if mode == 2:
+        cin, cout, R, S = w.shape
+    else:
+        cout, cin, R, S = w.shape
+    K = R * S * cin if mode == 0 else (R * S * cout if mode == 1 else cout)
+    ncols = cout if mode == 0 else cin
+    ld = (ncols + 3) // 4 * 4
+    out = torch.empty(K * ld, dtype=torch.float32, device=w.device)
+    L.check(L.lib.fdg_pack_weight(w.data_ptr(), cout, cin, R, S, mode, out.data_ptr(), ld, _stream()), "pack_weight")
+    return out, ld
+
+
+def bn_finalize(stats, stats_ld, Cc, count, gamma, beta, eps, momentum, running_mean, running_var, training,
+                scale, shift, mean=None, invstd=None):
+    d = L.FdgBnFinalize(_ptr(stats), stats_ld, Cc, float(count), _ptr(gamma), _ptr(beta), eps, momentum,
+                        _ptr(running_mean), _ptr(running_var), 1 if training else 0, _ptr(scale), _ptr(shift),
+                        _ptr(mean), _ptr(invstd))
+    L.check(L.lib.fdg_bn_finalize(_byref(d), _stream()), "bn_finalize")
+
+
+def ew_bwd(g: View, x: View, *, out: View | None = None, stats=None, g_gather=GATHER_DIRECT, gscale=1.0, scale=None,
+           shift=None, slope=0.0, coef=None, accumulate=False):
+    if g_gather == GATHER_UP2:
+        assert (g.N, g.H, g.W, g.C) == (x.N, x.H // 2, x.W // 2, x.C), "ew_bwd: pooled gradient extent mismatch"
+    else:
+        assert (g.N, g.H, g.W, g.C) == (x.N, x.H, x.W, x.C), "ew_bwd: gradient extent mismatch"
+    if out is not None:
+        assert (out.N, out.H, out.W, out.C) == (x.N, x.H, x.W, x.C)
+    d = L.FdgEwBwd(g.ft(), g_gather, gscale, x.ft(), x.N, x.H, x.W, x.C, 1 if scale is not None else 0,
+                   _ptr(scale), _ptr(shift), slope, _ptr(coef), out.ft() if out is not None else _NULLT,
+                   1 if accumulate else 0, _ptr(stats))
+    L.check(L.lib.fdg_ew_bwd(_byref(d), _stream()), "ew_bwd")
+
+
+def bn_bwd_finalize(stats, Cc, count, gamma, mean, invstd, coef, dgamma=None, dbeta=None, accumulate=True):
+    d = L.FdgBnBwdFinalize(_ptr(stats), Cc, float(count), _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(coef),
+                           _ptr(dgamma), _ptr(dbeta), 1 if accumulate else 0)
+    L.check(L.lib.fdg_bn_bwd_finalize(_byref(d), _stream()), "bn_bwd_finalize")
+
+
+def maxpool2_fwd(x: View, y: View):
+    assert (y.N, y.H, y.W, y.C) == (x.N, x.H // 2, x.W // 2, x.C)
+    xt, yt = x.ft(), y.ft()
+    L.check(L.lib.fdg_maxpool2_fwd(_byref(xt), _byref(yt), y.N, y.H, y.W, y.C, _stream()), "maxpool2_fwd")
+
+
+def maxpool2_bwd(x: View, gy: View, gx: View, accumulate=True):
+    assert (gy.N, gy.H, gy.W, gy.C) == (x.N, x.H // 2, x.W // 2, x.C) and (gx.H, gx.W, gx.C) == (x.H, x.W, x.C)
+    xt, gyt, gxt = x.ft(), gy.ft(), gx.ft()
+    L.check(L.lib.fdg_maxpool2_bwd(_byref(xt), _byref(gyt), _byref(gxt), gy.N, gy.H, gy.W, gy.C,
+                                   1 if accumulate else 0, _stream()), "maxpool2_bwd")
+
+
+def copy4d(x: View, y: View, *, gather=GATHER_DIRECT, slope=1.0, scale=1.0, accumulate=False):
+    if gather == GATHER_AVGPOOL2:
+        exp = (x.N, x.H // 2, x.W // 2, x.C)
+    elif gather == GATHER_UP2:
+        exp = (x.N, 2 * x.H, 2 * x.W, x.C)
+    else:
+        exp = (x.N, x.H, x.W, x.C)
+    assert (y.N, y.H, y.W, y.C) == exp, ("copy4d extent mismatch", (y.N, y.H, y.W, y.C), exp)
+    xt, yt = x.ft(), y.ft()
+    L.check(L.lib.fdg_copy4d(_byref(xt), _byref(yt), y.N, y.H, y.W, y.C, gather, slope, scale,
+                             1 if accumulate else 0, _stream()), "copy4d")
+
+
+def act_bwd(g: torch.Tensor, y: torch.Tensor, out: torch.Tensor, act: int):
+    assert g.is_contiguous() and y.is_contiguous() and out.is_contiguous() and g.numel() == y.numel() == out.numel()
+    L.check(L.lib.fdg_act_bwd(g.data_ptr(), y.data_ptr(), out.data_ptr(), g.numel(), act, _stream()), "act_bwd")
+
+
+def dgrad_strided(g: View, w: torch.Tensor, stride, pad, dx: View, accumulate=False):
+    cout, cin, R, S = w.shape
+    assert g.C == cout and dx.C == cin and w.is_contiguous()
+    d = L.FdgDgradStrided(g.ft(), g.N, g.H, g.W, cout, w.data_ptr(), cin, R, S, stride, pad, dx.ft(), dx.H, dx.W,
+                          1 if accumulate else 0)
+    L.check(L.lib.fdg_conv2d_dgrad_strided(_byref(d), _stream()), "conv2d_dgrad_strided")
+
+
+def colsum(x: View, out: torch.Tensor, accumulate=False):
+    xt = x.ft()
+    L.check(L.lib.fdg_colsum(_byref(xt), x.N, x.H, x.W, x.C, out.data_ptr(), 1 if accumulate else 0, _stream()), "colsum")
+
+
+def freq_concat_fwd(x: View, z: View):
+    assert x.C == 3 and z.C == 9 and (x.N, x.H, x.W) == (z.N, z.H, z.W)
+    xt, zt = x.ft(), z.ft()
+    L.check(L.lib.fdg_freq_concat_fwd(_byref(xt), _byref(zt), x.N, x.H, x.W, _stream()), "freq_concat_fwd")
+
+
+def freq_concat_bwd(dz: View, dx: View, scratch: torch.Tensor):
+    assert dz.C == 9 and dx.C == 3 and scratch.numel() >= dx.N * 3 * dx.H * dx.W
+    a, b = dz.ft(), dx.ft()
+    L.check(L.lib.fdg_freq_concat_bwd(_byref(a), _byref(b), scratch.data_ptr(), dx.N, dx.H, dx.W, _stream()), "freq_concat_bwd")
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    L.check(L.lib.fdg_adam_flat(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
+                                lr, beta1, beta2, eps, step, grad_scale, _stream()), "adam_flat")

@@ -1,0 +1,254 @@
+/*
+ * fdgan_b200 -- C ABI of the B200-native FD-GAN hot path.
+ *
+ * The reference (WeilanAnnn/FD-GAN) has no FFI: its boundary is the torch.nn.Module
+ * API (demo.py:73,132).  The Python modules in fdgan_b200/ mirror that surface and
+ * call the entry points below through ctypes; every entry point replaces a PyTorch
+ * library call the reference makes on the path.  Citations are into /root/reference.
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, a negative FDG_E* code otherwise; fdg_last_error() gives
+ *     the message (thread-local).  Never throws, never allocates, never synchronises.
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch), fp32 unless
+ *     stated; work is enqueued on the cudaStream_t passed last (as void*).
+ *   - activations are addressed with explicit element strides (n, h, w, c) so that
+ *     NCHW images, NHWC feature maps and channel slices of a dense-block concat
+ *     buffer are all expressible; the fast paths need c-stride 1 and 16-byte alignment.
+ */
+#ifndef FDGAN_B200_H_
+#define FDGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDG_OK 0
+#define FDG_EINVAL (-1)   /* bad argument / unsupported shape */
+#define FDG_ECUDA (-2)    /* CUDA runtime error at launch */
+#define FDG_ENOSUPPORT (-3)
+
+typedef void* fdg_stream_t; /* cudaStream_t */
+
+/* A strided 4-D activation view: element (n,h,w,c) lives at p[n*sn + h*sh + w*sw + c*sc]. */
+typedef struct FdgTensor {
+  float* p;
+  int64_t sn, sh, sw, sc;
+} FdgTensor;
+
+/* gather modes of the conv A-operand (what the loader does instead of a separate pass) */
+#define FDG_GATHER_DIRECT 0
+#define FDG_GATHER_AVGPOOL2 1 /* logical pixel = mean of the 2x2 physical block, AFTER the prologue: replaces
+                                 F.avg_pool2d(x,2) (models/dehaze1113.py:763,780) and the AvgPool2d of the
+                                 torchvision transition (models/densenet.py:221), commuted in front of its 1x1 conv */
+#define FDG_GATHER_UP2 2      /* logical pixel (y,x) reads physical (y/2,x/2): F.upsample_nearest (dehaze1113.py:370) */
+
+/* activations of the conv epilogue */
+#define FDG_ACT_NONE 0
+#define FDG_ACT_RELU 1    /* relu0 (dehaze1113.py:760), F.relu (vgg16.py:28-47) */
+#define FDG_ACT_TANH 2    /* dehaze1113.py:799 */
+#define FDG_ACT_SIGMOID 3 /* dehaze1113.py:223 */
+
+/* store modes */
+#define FDG_STORE_NORMAL 0
+#define FDG_STORE_UP2 1   /* write each output pixel to its 2x2 nearest-neighbour block (TransitionBlockdy, dehaze1113.py:370) */
+#define FDG_STORE_ACCUM 2 /* y += result (gradient accumulation into a dense-block gradient buffer) */
+
+/*
+ * fdg_conv2d: implicit-GEMM convolution y = act(conv(prologue(gather(x)), W) + bias).
+ * Replaces nn.Conv2d / nn.ConvTranspose2d(1x1) / F.conv2d on the path (dehaze1113.py:744-755,
+ * 262-266,363; torchvision _DenseLayer conv1/conv2 restated at models/densenet.py:193-198;
+ * D convs dehaze1113.py:196-222; vgg16.py:9-22) and, with flipped weights, their data gradients.
+ *   prologue:  v = has_affine ? x*scale[c] + shift[c] : x ;  a = v > 0 ? v : slope*v
+ *              (slope 1 = identity, 0 = ReLU, 0.2 = LeakyReLU; affine = BatchNorm apply, dehaze1113.py:40 /
+ *              torchvision norm1/norm2).  Zero padding is applied AFTER the prologue.
+ *   epilogue:  *alpha, +bias, activation, optional multiply by (e > 0 ? 1 : eslope) with e a second
+ *              tensor of the output's shape (ReLU/LeakyReLU backward mask), optional per-channel
+ *              sum / sum-of-squares of the stored values accumulated in fp64 (BatchNorm batch statistics).
+ */
+typedef struct FdgConv {
+  FdgTensor x;          /* physical input */
+  int N, H, W, Cin;     /* logical input extent seen by the filter (after gather) */
+  int gather;
+  int has_affine;
+  const float* scale;   /* [Cin] */
+  const float* shift;   /* [Cin] */
+  float slope;
+  const float* w;       /* packed weights [R*S*Cin][w_ld], k = (r*S + s)*Cin + ci */
+  int w_ld;
+  int R, S, stride, pad;
+  int Cout, OH, OW;
+  const float* bias;    /* [Cout] or NULL */
+  int act;
+  FdgTensor e;          /* epilogue mask source or p == NULL */
+  float eslope;
+  FdgTensor y;          /* output (for FDG_STORE_UP2 the physical output is 2OH x 2OW) */
+  int store;
+  double* stats;        /* sums at stats[c], sums of squares at stats[stats_ld + c] (c < Cout); or NULL */
+  int stats_ld;
+  float alpha;          /* result scale applied before the bias (4 = adjoint of nearest x2 through FDG_GATHER_AVGPOOL2) */
+  int impl;             /* 0 auto, 1 force SIMT fp32, 2 force tcgen05 (error if unsupported) */
+  const void* w_umma;   /* tcgen05 operand image of the weights (fdg_pack_weight_umma) or NULL */
+} FdgConv;
+
+int fdg_conv2d(const FdgConv* p, fdg_stream_t stream);
+
+/*
+ * fdg_conv2d_wgrad: weight gradient dW[k][co] (+)= sum_pixels a[pixel][k] * g[pixel][co] with the same
+ * A-operand (gather + prologue) as fdg_conv2d and g = gradient w.r.t. the conv output.  Written straight
+ * into the PyTorch parameter layout: OIHW (nn.Conv2d) or, for transposed=1, [Cin][Cout] (ConvTranspose2d 1x1).
+ * Replaces autograd's conv backward-weight for every conv listed above.  dw must be zeroed by the caller
+ * unless it is accumulating (split-K partial sums are added atomically).
+ */
+typedef struct FdgWgrad {
+  FdgTensor x;
+  int N, H, W, Cin;
+  int gather;
+  int has_affine;
+  const float* scale;
+  const float* shift;
+  float slope;
+  FdgTensor g;          /* [N, OH, OW, Cout] */
+  int R, S, stride, pad;
+  int Cout, OH, OW;
+  float* dw;
+  int transposed;
+  float* dbias;         /* [Cout] (+)= sum_pixels g, or NULL */
+} FdgWgrad;
+
+int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream);
+
+/* Weight repacking (PyTorch layout -> GEMM operand [K][N]).
+ *   mode 0: OIHW          -> [(r,s,ci)][co]           forward of nn.Conv2d
+ *   mode 1: OIHW          -> [(r,s,co)][ci], flipped  data gradient of a stride-1 nn.Conv2d
+ *   mode 2: [Cin][Cout]   -> [(co)][ci]               data gradient of ConvTranspose2d 1x1
+ * (forward of ConvTranspose2d 1x1 and data gradient of a 1x1 nn.Conv2d use the parameter as is.) */
+int fdg_pack_weight(const float* w, int Cout, int Cin, int R, int S, int mode, float* out, int out_ld,
+                    fdg_stream_t stream);
+
+/*
+ * BatchNorm2d training-mode bookkeeping (nn.BatchNorm2d as used at README.md:38: always batch statistics).
+ * fdg_bn_finalize: stats (fp64 sum, sumsq over count elements per channel) -> scale = gamma*invstd,
+ * shift = beta - mean*scale, saved mean/invstd; updates running_mean/var (momentum, unbiased variance)
+ * when running_mean != NULL.  With training == 0 scale/shift come from the running statistics.
+ */
+typedef struct FdgBnFinalize {
+  const double* stats; /* [2*stats_ld]: sums at [c], sums of squares at [stats_ld + c] */
+  int stats_ld;
+  int C;
+  double count;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float momentum;
+  float* running_mean; /* may be NULL */
+  float* running_var;
+  int training;
+  float* scale;        /* out [C] */
+  float* shift;        /* out [C] */
+  float* mean;         /* out [C] or NULL */
+  float* invstd;       /* out [C] or NULL */
+} FdgBnFinalize;
+
+int fdg_bn_finalize(const FdgBnFinalize* p, fdg_stream_t stream);
+
+/*
+ * fdg_ew_bwd: the element-wise half of BatchNorm+ReLU / ReLU / LeakyReLU backward.
+ *   v  = has_affine ? x*scale[c] + shift[c] : x
+ *   dz = gscale * g * (v > 0 ? 1 : slope)            (g optionally read through FDG_GATHER_UP2: avg-pool adjoint)
+ *   if stats != NULL:  stats[c] += dz, stats[C + c] += dz*x      (fp64; BatchNorm backward reductions), no store
+ *   else:              out (=|+=) coef ? coef[c]*dz + coef[C+c]*x + coef[2C+c] : dz
+ */
+typedef struct FdgEwBwd {
+  FdgTensor g;
+  int g_gather;        /* FDG_GATHER_DIRECT or FDG_GATHER_UP2 */
+  float gscale;
+  FdgTensor x;
+  int N, H, W, C;      /* extent of x / out */
+  int has_affine;
+  const float* scale;
+  const float* shift;
+  float slope;
+  const float* coef;   /* [3*C] alpha, beta, delta or NULL */
+  FdgTensor out;
+  int accumulate;
+  double* stats;       /* [2*C] or NULL */
+} FdgEwBwd;
+
+int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream);
+
+/* BatchNorm backward finalize: from sum(dz), sum(dz*x) -> coef (alpha, beta, delta) such that
+ * dx = alpha*dz + beta*x + delta, and dgamma/dbeta (+)=. */
+typedef struct FdgBnBwdFinalize {
+  const double* stats; /* [2*C] */
+  int C;
+  double count;
+  const float* gamma;
+  const float* mean;
+  const float* invstd;
+  float* coef;         /* out [3*C] */
+  float* dgamma;       /* (+)= or NULL */
+  float* dbeta;
+  int accumulate;
+} FdgBnBwdFinalize;
+
+int fdg_bn_bwd_finalize(const FdgBnBwdFinalize* p, fdg_stream_t stream);
+
+/* 2x2 max pooling (F.max_pool2d(h, 2, 2), vgg16.py:31,36,42) and its gradient (routed to the first maximum). */
+int fdg_maxpool2_fwd(const FdgTensor* x, const FdgTensor* y, int N, int OH, int OW, int C, fdg_stream_t stream);
+int fdg_maxpool2_bwd(const FdgTensor* x, const FdgTensor* gy, const FdgTensor* gx, int N, int OH, int OW, int C,
+                     int accumulate, fdg_stream_t stream);
+
+/* Strided gather-copy y (=|+=) scale * gather(leaky(x, slope)); N,H,W,C are the extents of y.  Places trans_block2's
+ * output into the decoder concat (dehaze1113.py:786, slope 0: the in-place ReLU of BottleneckBlockdy), and is the adjoint
+ * of nearest x2 (gather AVGPOOL2, scale 4) and of avg-pool (gather UP2, scale 0.25) in the backward pass. */
+int fdg_copy4d(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int C, int gather, float slope, float scale,
+               int accumulate, fdg_stream_t stream);
+
+/* out = g * act'(y) for contiguous arrays: act = FDG_ACT_TANH (1 - y^2) or FDG_ACT_SIGMOID (y (1 - y)). */
+int fdg_act_bwd(const float* g, const float* y, float* out, int64_t n, int act, fdg_stream_t stream);
+
+/* Data gradient of a strided nn.Conv2d (the 4x4 stride-2 first layer of D, dehaze1113.py:196), i.e. a transposed
+ * convolution evaluated as a gather: dx[n,y,x,ci] (=|+=) sum_{r,s,co} g[n,(y+pad-r)/stride,(x+pad-s)/stride,co] W[co,ci,r,s]. */
+typedef struct FdgDgradStrided {
+  FdgTensor g;
+  int N, OH, OW, Cout;
+  const float* w;      /* OIHW parameter */
+  int Cin, R, S, stride, pad;
+  FdgTensor dx;
+  int H, W;
+  int accumulate;
+} FdgDgradStrided;
+
+int fdg_conv2d_dgrad_strided(const FdgDgradStrided* p, fdg_stream_t stream);
+
+/* per-channel column sum: out[c] (+)= sum over (n,h,w) of x (bias gradients). */
+int fdg_colsum(const FdgTensor* x, int N, int H, int W, int C, float* out, int accumulate, fdg_stream_t stream);
+
+/*
+ * Frequency decomposition feeding the Fusion-discriminator (loss.pyc Blur@L122-151 with the
+ * 15x15 sigma=3 kernel of @L153-162, Laplacian@L245-301; concat per facades/network.png):
+ *   z[:, 0:3] = x ; z[:, 3:6] = gauss15x15(reflect_pad7((x - mean)/std)) ; z[:, 6:9] = 3x3 [1..;1 -8 1;..] zero pad.
+ * x is [N,3,H,W] (any strides), z is [N,9,H,W] (any strides).  bwd is the exact adjoint: dx = dz0 + Blur^T dz1 + Lap dz2.
+ */
+int fdg_freq_concat_fwd(const FdgTensor* x, const FdgTensor* z, int N, int H, int W, fdg_stream_t stream);
+int fdg_freq_concat_bwd(const FdgTensor* dz, const FdgTensor* dx, float* scratch /* N*3*H*W floats */, int N, int H,
+                        int W, fdg_stream_t stream);
+
+/* Fused Adam over a flat fp32 buffer (torch.optim.Adam arithmetic; --lrG/--lrD 2e-4, --beta1 0.5: demo.py:43-46).
+ * grad_scale multiplies the gradient first (1/world_size after the NCCL sum). */
+int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, fdg_stream_t stream);
+
+/* diagnostics */
+const char* fdg_last_error(void);
+int fdg_version(void);
+/* number of kernels this library has launched from this process (all threads); bench.py reports the delta */
+int64_t fdg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDGAN_B200_H_ */

@@ -1,0 +1,219 @@
+"""GPU parity of the reference-facing modules (FDGAN, D, Vgg16, Blur/Laplacian) against the CPU oracle
+and the golden vectors generated from the real reference (tests/golden, oracle/make_golden.py).
+
+Tolerance: the north star asks for <= 1e-3 max-abs fp32 on outputs; the fp32 SIMT path is held to 2e-4
+(range-relative) and gradients to 2e-3 relative to their scale."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fdgan_oracle as O
+from oracle.make_golden import G_GRAD_KEYS, G_STAT_KEYS
+from tests.util import assert_sample_close, golden, maxabs, seeded
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 2e-4
+GRAD_RTOL = 2e-3
+
+
+def _fdgan(seed=0):
+    import fdgan_b200
+    net = fdgan_b200.FDGAN()
+    net.load_state_dict(O.make_fdgan_state(seed))
+    return net.cuda().train()
+
+
+@pytest.mark.parametrize("batch,tag", [(1, "b1_32"), (2, "b2_32")])
+def test_fdgan_matches_reference_golden(batch, tag):
+    g = golden("fdgan_" + tag)
+    net = _fdgan()
+    x = seeded((batch, 3, 32, 32), 5).cuda().requires_grad_(True)
+    r = seeded((batch, 3, 32, 32), 6, -1.0, 1.0).cuda()
+    y = net(x)
+    assert tuple(y.shape) == (batch, 3, 32, 32)
+    rng = float(g["y"].max() - g["y"].min()) / 2
+    assert maxabs(y, g["y"]) <= OUT_TOL * max(1.0, rng)
+    (y * r).sum().backward()
+    assert maxabs(x.grad, g["dx"]) <= GRAD_RTOL * max(1.0, float(np.abs(g["dx"]).max()))
+    params = dict(net.named_parameters())
+    for k in G_GRAD_KEYS:
+        assert_sample_close(params[k].grad, g["grad:" + k], GRAD_RTOL, 1e-5, k)
+    sd = net.state_dict()
+    for k in G_STAT_KEYS:
+        assert maxabs(sd[k], g["stat:" + k]) <= 1e-4, k
+    unused = [k for k, p in params.items() if p.grad is None]
+    assert len(unused) == int(g["n_unused"]) == 117
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 48), (1, 3, 40, 72)])
+def test_fdgan_forward_backward_vs_oracle(shape):
+    net = _fdgan(seed=3)
+    sd = O.make_fdgan_state(3)
+    for k in O.fdgan_used_param_names():
+        sd[k].requires_grad_(True)
+    x = seeded(shape, 11)
+    r = seeded(shape, 12, -1.0, 1.0)
+    xo = x.clone().requires_grad_(True)
+    yo = O.fdgan_forward(sd, xo, True, True)
+    (yo * r).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    y = net(xd)
+    assert maxabs(y, yo) <= OUT_TOL
+    (y * r.cuda()).sum().backward()
+    assert maxabs(xd.grad, xo.grad) <= GRAD_RTOL * max(1.0, float(xo.grad.abs().max()))
+    worst = 0.0
+    for k, p in net.named_parameters():
+        if sd[k].grad is None:
+            assert p.grad is None, k
+            continue
+        scale = max(1e-3, float(sd[k].grad.abs().max()))
+        worst = max(worst, maxabs(p.grad, sd[k].grad) / scale)
+        assert maxabs(p.grad, sd[k].grad) <= GRAD_RTOL * scale + 1e-5, k
+    # BatchNorm running statistics follow nn.BatchNorm2d
+    for k, v in net.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            assert maxabs(v, sd[k]) <= 1e-4, k
+    print("worst relative parameter-gradient error", worst)
+
+
+def test_fdgan_inference_paths_and_errors():
+    net = _fdgan()
+    x = seeded((1, 3, 32, 32), 5).cuda()
+    with torch.no_grad():
+        y1 = net(x)
+    g = golden("fdgan_b1_32")
+    assert maxabs(y1, g["y"]) <= OUT_TOL
+    # channels-last / non-contiguous inputs give the same answer
+    y2 = net(x.contiguous(memory_format=torch.channels_last).detach())
+    assert maxabs(y2, y1) <= 1e-6
+    # eval() uses running statistics like nn.BatchNorm2d
+    sd = O.make_fdgan_state(0)
+    net2 = _fdgan().eval()
+    with torch.no_grad():
+        ye = net2(x)
+        yo = O.fdgan_forward(sd, x.cpu(), False, False)
+    assert maxabs(ye, yo) <= OUT_TOL
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 100, 100, device="cuda"))   # floor(H/4) != 2 floor(H/8), as in the reference
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 32, 32))                     # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 4, 32, 32, device="cuda"))
+
+
+def test_fdgan_checkpoint_key_remap():
+    import fdgan_b200
+    sd = O.make_fdgan_state(0)
+    legacy = {}
+    for k, v in sd.items():
+        if "num_batches_tracked" in k:
+            continue   # PyTorch 0.3 checkpoints do not have it
+        for a, b in (("norm1.", "norm.1."), ("norm2.", "norm.2."), ("conv1.", "conv.1."), ("conv2.", "conv.2.")):
+            if "denselayer" in k:
+                k = k.replace(a, b)
+        legacy["module." + k] = v
+    net = fdgan_b200.FDGAN()
+    net.load_state_dict(legacy)
+    for k, v in net.state_dict().items():
+        if "num_batches_tracked" not in k:
+            assert torch.equal(v, sd[k]), k
+
+
+@pytest.mark.parametrize("nf", [36, 64])
+def test_discriminator_matches_reference_golden(nf):
+    import fdgan_b200
+    g = golden("d_nf%d" % nf)
+    net = fdgan_b200.D(9, nf)
+    net.load_state_dict(O.make_d_state(9, nf, 1))
+    net = net.cuda().train()
+    x = seeded((2, 9, 32, 32), 7, -1.0, 1.0).cuda().requires_grad_(True)
+    y = net(x)
+    assert tuple(y.shape) == (2, 1, 14, 14)
+    assert maxabs(y, g["y"]) <= 1e-5
+    r = seeded(tuple(y.shape), 8, -1.0, 1.0).cuda()
+    (y * r).sum().backward()
+    assert maxabs(x.grad, g["dx"]) <= GRAD_RTOL * max(1e-3, float(np.abs(g["dx"]).max()))
+    params = dict(net.named_parameters())
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert_sample_close(params[k[5:]].grad, g[k], GRAD_RTOL, 1e-6, k)
+    sd = net.state_dict()
+    for k in g.files:
+        if k.startswith("stat:"):
+            assert maxabs(sd[k[5:]], g[k]) <= 1e-5, k
+
+
+def test_discriminator_frozen_and_larger_shape_vs_oracle():
+    import fdgan_b200
+    net = fdgan_b200.D(9, 36)
+    dsd = O.make_d_state(9, 36, 1)
+    net.load_state_dict(dsd)
+    net = net.cuda().train()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    x = seeded((2, 9, 64, 80), 7, -1.0, 1.0)
+    xo = x.clone().requires_grad_(True)
+    yo = O.d_forward(dsd, xo, True, False)
+    yo.sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    y = net(xd)
+    assert tuple(y.shape) == (2, 1, 30, 38)
+    assert maxabs(y, yo) <= 1e-5
+    y.sum().backward()
+    assert maxabs(xd.grad, xo.grad) <= GRAD_RTOL * max(1e-4, float(xo.grad.abs().max()))
+    assert all(p.grad is None for p in net.parameters())
+
+
+def test_vgg16_matches_reference_golden():
+    import fdgan_b200
+    g = golden("vgg16")
+    net = fdgan_b200.Vgg16()
+    net.load_state_dict(O.make_vgg_state(2))
+    net = net.cuda()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    x = seeded((2, 3, 16, 16), 9).cuda().requires_grad_(True)
+    feats = net(x)
+    assert [tuple(f.shape) for f in feats] == [(2, 64, 16, 16), (2, 128, 8, 8), (2, 256, 4, 4), (2, 512, 2, 2)]
+    loss = 0
+    for i, f in enumerate(feats):
+        assert_sample_close(f, g["f%d" % i], 1e-5, 1e-5, "relu%d" % i)
+        loss = loss + (f * seeded(tuple(f.shape), 10 + i, -1.0, 1.0).cuda()).sum()
+    loss.backward()
+    assert maxabs(x.grad, g["dx"]) <= GRAD_RTOL * max(1.0, float(np.abs(g["dx"]).max()))
+
+
+def test_vgg16_subset_of_outputs_and_weight_grads_vs_oracle():
+    import fdgan_b200
+    vsd = O.make_vgg_state(2)
+    for v in vsd.values():
+        v.requires_grad_(True)
+    net = fdgan_b200.Vgg16()
+    net.load_state_dict({k: v.detach() for k, v in vsd.items()})
+    net = net.cuda()
+    x = seeded((1, 3, 24, 40), 9)
+    xo = x.clone().requires_grad_(True)
+    fo = O.vgg16_forward(vsd, xo)
+    (fo[1] ** 2).mean().backward()        # only relu2_2 enters the loss
+    xd = x.cuda().requires_grad_(True)
+    fd = net(xd)
+    (fd[1] ** 2).mean().backward()
+    assert maxabs(xd.grad, xo.grad) <= GRAD_RTOL * max(1e-6, float(xo.grad.abs().max()))
+    params = dict(net.named_parameters())
+    for k in ("conv1_1.weight", "conv1_2.bias", "conv2_2.weight"):
+        assert maxabs(params[k].grad, vsd[k].grad) <= GRAD_RTOL * max(1e-6, float(vsd[k].grad.abs().max())), k
+    assert params["conv3_1.weight"].grad is None or float(params["conv3_1.weight"].grad.abs().max()) == 0.0
+
+
+def test_blur_laplacian_modules():
+    import fdgan_b200
+    from fdgan_b200 import loss as L
+    x = seeded((2, 3, 24, 30), 30)
+    assert maxabs(L.blur(x.cuda()), O.blur(x)) <= 1e-5
+    assert maxabs(L.laplace_filter(x.cuda()), O.laplacian(x)) <= 1e-5
+    assert maxabs(fdgan_b200.freq_concat(x.cuda()), O.freq_concat(x)) <= 1e-5
+    with pytest.raises(ValueError):
+        L.laplace_filter(x[0].cuda())
+    with pytest.raises(NotImplementedError):
+        L.Blur(l=7)

@@ -1,0 +1,294 @@
+"""GPU parity of every C-ABI entry point against plain torch fp32/fp64 CPU arithmetic (unit level).
+All calls go through the C ABI (fdgan_b200.ops -> ctypes -> libfdgan_b200.so)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import maxabs, seeded
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from fdgan_b200 import ops
+    return ops
+
+
+def cl(t):
+    """NCHW logical tensor in channels-last memory on the GPU."""
+    return t.cuda().contiguous(memory_format=torch.channels_last)
+
+
+def ref_prologue(x, scale, shift, slope):
+    v = x if scale is None else x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    return torch.where(v > 0, v, slope * v)
+
+
+CONV_CASES = [
+    # Cin, Cout, R, stride, pad, H, W, gather, affine, slope, bias, act, store, stats, mask
+    (128, 32, 3, 1, 1, 12, 20, 0, True, 0.0, False, 0, 0, True, False),    # K1 dense-layer conv2
+    (96, 128, 1, 1, 0, 9, 7, 0, True, 0.0, False, 0, 0, True, False),      # K2 dense-layer conv1
+    (64, 32, 1, 1, 0, 10, 12, 1, False, 1.0, True, 0, 0, False, False),    # conv_refin2 (avg-pool gather)
+    (256, 128, 1, 1, 0, 8, 8, 1, True, 0.0, False, 0, 0, True, False),     # transition
+    (3, 64, 3, 1, 1, 11, 13, 0, False, 1.0, True, 1, 0, True, False),      # conv_refin1 (K=27)
+    (16, 3, 3, 1, 1, 10, 10, 0, False, 1.0, True, 2, 0, False, False),     # conv_refin3 + tanh
+    (160, 128, 3, 1, 1, 6, 6, 0, False, 1.0, True, 0, 0, True, False),     # conv_refine4
+    (96, 16, 1, 1, 0, 5, 6, 0, False, 0.0, False, 0, 1, False, False),     # TransitionBlockdy (up2 store)
+    (64, 64, 1, 1, 0, 5, 6, 0, False, 0.0, False, 1, 1, False, False),     # up2 store + relu epilogue
+    (9, 36, 4, 2, 1, 16, 18, 0, False, 1.0, False, 0, 0, False, False),    # D layer 1
+    (36, 72, 3, 1, 1, 8, 9, 0, False, 0.2, False, 0, 0, True, False),      # D layer 2
+    (144, 288, 4, 1, 1, 8, 9, 0, True, 0.2, False, 0, 0, False, False),    # D layer 4
+    (288, 1, 4, 1, 1, 7, 8, 0, False, 0.2, False, 3, 0, False, False),     # D layer 5 + sigmoid
+    (32, 128, 3, 1, 1, 7, 9, 0, False, 1.0, False, 0, 0, False, True),     # dgrad-like with ReLU mask epilogue
+    (128, 72, 1, 1, 0, 6, 5, 0, False, 1.0, False, 0, 2, False, True),     # accumulate store + mask
+    (16, 24, 1, 1, 0, 4, 6, 2, False, 1.0, False, 0, 0, False, False),     # up2 gather
+    (64, 600, 3, 1, 1, 4, 4, 0, False, 1.0, True, 1, 0, False, False),     # wide N (several N tiles), VGG-like
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("nchw_in", [False, True])
+def test_conv2d(case, nchw_in):
+    ops = _ops()
+    Cin, Cout, R, stride, pad, H, W, gather, affine, slope, bias, act, store, stats, mask = case
+    N = 2
+    ph, pw = (2 * H, 2 * W) if gather == 1 else ((H + 1) // 2, (W + 1) // 2) if gather == 2 else (H, W)
+    if gather == 2:
+        H, W = 2 * ph, 2 * pw
+    x = seeded((N, Cin, ph, pw), 1, -1.0, 1.0)
+    w = seeded((Cout, Cin, R, R), 2, -1.0, 1.0) / math.sqrt(Cin * R * R)
+    b = seeded((Cout,), 3, -0.5, 0.5) if bias else None
+    sc = seeded((Cin,), 4, 0.5, 1.5) if affine else None
+    sh = seeded((Cin,), 5, -0.3, 0.3) if affine else None
+    # ---- reference (CPU, fp64)
+    a = ref_prologue(x.double(), sc.double() if affine else None, sh.double() if affine else None, slope)
+    if gather == 1:
+        a = F.avg_pool2d(a, 2)
+    elif gather == 2:
+        a = F.interpolate(a, scale_factor=2, mode="nearest")
+    y = F.conv2d(a, w.double(), b.double() if bias else None, stride=stride, padding=pad)
+    y = {0: lambda t: t, 1: torch.relu, 2: torch.tanh, 3: torch.sigmoid}[act](y)
+    OH, OW = y.shape[-2:]
+    e = seeded((N, Cout, OH, OW), 6, -1.0, 1.0) if mask else None
+    if mask:
+        y = y * torch.where(e.double() > 0, 1.0, 0.3)
+    ysum, ysq = y.sum((0, 2, 3)), (y * y).sum((0, 2, 3))
+    if store == 1:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    y0 = seeded(tuple(y.shape), 7, -1.0, 1.0)
+    if store == 2:
+        y = y + y0.double()
+    # ---- device
+    xd = x.cuda() if nchw_in else cl(x)
+    wp, ld = ops.pack_weight(w.cuda(), 0)
+    yd = cl(y0.clone())
+    st = torch.zeros(2 * Cout + 6, dtype=torch.float64, device="cuda") if stats else None
+    ops.conv2d(ops.View.from_nchw(xd), wp, ld, R, R, stride, pad, Cout, ops.View.from_nchw(yd), gather=gather,
+               scale=sc.cuda() if affine else None, shift=sh.cuda() if affine else None, slope=slope,
+               bias=b.cuda() if bias else None, act=act, e=ops.View.from_nchw(cl(e)) if mask else None, eslope=0.3,
+               store=store, stats=st, stats_ld=Cout + 3, impl=ops.IMPL_SIMT)
+    torch.cuda.synchronize()
+    assert maxabs(yd, y) <= 2e-5
+    if stats:
+        assert maxabs(st[:Cout], ysum) <= 1e-3 and maxabs(st[Cout + 3:2 * Cout + 3], ysq) <= 1e-3
+
+
+def test_conv2d_nchw_output_and_errors():
+    ops = _ops()
+    x = seeded((1, 16, 9, 9), 1, -1, 1)
+    w = seeded((3, 16, 3, 3), 2, -1, 1) / 12
+    y = torch.empty(1, 3, 9, 9, device="cuda")
+    wp, ld = ops.pack_weight(w.cuda(), 0)
+    ops.conv2d(ops.View.from_nchw(cl(x)), wp, ld, 3, 3, 1, 1, 3, ops.View.from_nchw(y), impl=ops.IMPL_SIMT)
+    assert maxabs(y, F.conv2d(x, w, padding=1)) <= 1e-5
+    with pytest.raises(ValueError):
+        ops.conv2d(ops.View.from_nchw(cl(x)), wp, ld, 3, 3, 1, 1, 4, ops.View.from_nchw(y))
+    with pytest.raises(RuntimeError):  # C ABI rejects an inconsistent descriptor (w_ld < Cout)
+        ops.conv2d(ops.View.from_nchw(cl(x)), wp, 2, 3, 3, 1, 1, 3, ops.View.from_nchw(y))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pack_weight(mode):
+    ops = _ops()
+    if mode == 2:
+        w = seeded((24, 10, 1, 1), 1)
+        want = w[:, :, 0, 0].t()                      # [co][ci]
+    else:
+        w = seeded((10, 24, 3, 3), 1)
+        if mode == 0:
+            want = w.permute(2, 3, 1, 0).reshape(9 * 24, 10)
+        else:
+            want = w.flip(2, 3).permute(2, 3, 0, 1).reshape(9 * 10, 24)
+    out, ld = ops.pack_weight(w.cuda(), mode)
+    got = out.view(-1, ld)[:, :want.shape[1]]
+    assert maxabs(got, want) == 0.0
+    assert float(out.view(-1, ld)[:, want.shape[1]:].abs().sum()) == 0.0
+
+
+WGRAD_CASES = [
+    # Cin, Cout, R, stride, pad, H, W, gather, affine, slope, transposed, dbias
+    (128, 32, 3, 1, 1, 12, 10, 0, True, 0.0, False, False),
+    (96, 128, 1, 1, 0, 9, 7, 0, True, 0.0, False, False),
+    (256, 128, 1, 1, 0, 6, 6, 1, True, 0.0, False, False),
+    (3, 64, 3, 1, 1, 9, 11, 0, False, 1.0, False, True),
+    (96, 16, 1, 1, 0, 7, 5, 0, False, 0.0, True, False),
+    (9, 36, 4, 2, 1, 16, 14, 0, False, 1.0, False, False),
+    (144, 288, 4, 1, 1, 7, 7, 0, True, 0.2, False, False),
+    (160, 130, 3, 1, 1, 5, 6, 0, False, 1.0, False, True),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad(case):
+    ops = _ops()
+    Cin, Cout, R, stride, pad, H, W, gather, affine, slope, transposed, dbias = case
+    N = 3
+    ph, pw = (2 * H, 2 * W) if gather == 1 else (H, W)
+    x = seeded((N, Cin, ph, pw), 1, -1, 1).double()
+    sc = seeded((Cin,), 4, 0.5, 1.5).double() if affine else None
+    sh = seeded((Cin,), 5, -0.3, 0.3).double() if affine else None
+    a = ref_prologue(x, sc, sh, slope)
+    if gather == 1:
+        a = F.avg_pool2d(a, 2)
+    w = torch.zeros(Cout, Cin, R, R, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(a, w, stride=stride, padding=pad)
+    g = seeded(tuple(y.shape), 8, -1, 1).double()
+    (y * g).sum().backward()
+    want = w.grad
+    if transposed:
+        want = want[:, :, 0, 0].t().reshape(Cin, Cout, 1, 1)
+    dw = torch.zeros(tuple(want.shape), device="cuda")
+    db = torch.zeros(Cout, device="cuda") if dbias else None
+    nchw_small = Cin < 16
+    xd = x.float().cuda() if nchw_small else cl(x.float())
+    ops.wgrad(ops.View.from_nchw(xd), ops.View.from_nchw(cl(g.float())), R, R, stride, pad, dw, gather=gather,
+              scale=sc.float().cuda() if affine else None, shift=sh.float().cuda() if affine else None, slope=slope,
+              transposed=transposed, dbias=db)
+    assert maxabs(dw, want) <= 2e-4 * max(1.0, float(want.abs().max()))
+    if dbias:
+        assert maxabs(db, g.sum((0, 2, 3))) <= 1e-3
+
+
+def test_bn_finalize_and_backward_pieces():
+    ops = _ops()
+    N, C, H, W = 3, 20, 6, 5
+    x = seeded((N, C, H, W), 1, -2, 3).double().requires_grad_(True)
+    gamma = seeded((C,), 2, 0.5, 1.5).double().requires_grad_(True)
+    beta = seeded((C,), 3, -0.5, 0.5).double().requires_grad_(True)
+    rm, rv = seeded((C,), 4, -0.1, 0.1).double(), seeded((C,), 5, 0.5, 1.5).double()
+    rm0, rv0 = rm.clone(), rv.clone()
+    y = F.leaky_relu(F.batch_norm(x, rm, rv, gamma, beta, True, 0.1, 1e-5), 0.2)
+    g = seeded((N, C, H, W), 6, -1, 1).double()
+    (y * g).sum().backward()
+    # device: stats -> finalize -> bwd stats -> bwd finalize -> apply
+    xd = cl(x.detach().float())
+    st = torch.stack([x.detach().sum((0, 2, 3)), (x.detach() ** 2).sum((0, 2, 3))]).reshape(-1).cuda()
+    buf = torch.zeros(4 * C, device="cuda")
+    rmd, rvd = rm0.float().cuda(), rv0.float().cuda()
+    ops.bn_finalize(st, C, C, N * H * W, gamma.detach().float().cuda(), beta.detach().float().cuda(), 1e-5, 0.1, rmd, rvd,
+                    True, buf[:C], buf[C:2 * C], buf[2 * C:3 * C], buf[3 * C:])
+    assert maxabs(rmd, rm) <= 1e-6 and maxabs(rvd, rv) <= 1e-6
+    xv, gv = ops.View.from_nchw(xd), ops.View.from_nchw(cl(g.float()))
+    st2 = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    ops.ew_bwd(gv, xv, stats=st2, scale=buf[:C], shift=buf[C:2 * C], slope=0.2)
+    coef = torch.empty(3 * C, device="cuda")
+    dgm, dbt = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.bn_bwd_finalize(st2, C, N * H * W, gamma.detach().float().cuda(), buf[2 * C:3 * C], buf[3 * C:], coef, dgm, dbt)
+    base = seeded((N, C, H, W), 9, -1, 1)
+    outd = cl(base.clone())
+    ops.ew_bwd(gv, xv, out=ops.View.from_nchw(outd), scale=buf[:C], shift=buf[C:2 * C], slope=0.2, coef=coef, accumulate=True)
+    assert maxabs(outd, x.grad + base.double()) <= 2e-5
+    assert maxabs(dgm, gamma.grad) <= 1e-4 and maxabs(dbt, beta.grad) <= 1e-4
+    # eval mode uses the running statistics
+    ops.bn_finalize(None, 0, C, 1, gamma.detach().float().cuda(), beta.detach().float().cuda(), 1e-5, 0.1, rmd, rvd, False,
+                    buf[:C], buf[C:2 * C])
+    want = gamma.detach() / torch.sqrt(rv + 1e-5)
+    assert maxabs(buf[:C], want) <= 1e-5
+
+
+def test_ew_bwd_pooled_gradient_scalar_path():
+    ops = _ops()
+    N, C, H, W = 2, 9, 6, 8   # C=9: scalar path
+    x = seeded((N, C, H, W), 1, -1, 1)
+    g = seeded((N, C, H // 2, W // 2), 2, -1, 1)
+    out = torch.zeros(N, C, H, W, device="cuda")
+    ops.ew_bwd(ops.View.from_nchw(g.cuda()), ops.View.from_nchw(x.cuda()), out=ops.View.from_nchw(out), slope=0.0,
+               g_gather=ops.GATHER_UP2, gscale=0.25)
+    want = 0.25 * F.interpolate(g, scale_factor=2, mode="nearest") * (x > 0)
+    assert maxabs(out, want) <= 1e-6
+
+
+def test_maxpool_copy_colsum_actbwd():
+    ops = _ops()
+    x = seeded((2, 12, 9, 10), 1, -1, 1).requires_grad_(True)
+    y = F.max_pool2d(x, 2, 2)
+    g = seeded(tuple(y.shape), 2, -1, 1)
+    (y * g).sum().backward()
+    xd = cl(x.detach())
+    yd = cl(torch.zeros_like(y))
+    ops.maxpool2_fwd(ops.View.from_nchw(xd), ops.View.from_nchw(yd))
+    assert maxabs(yd, y) == 0.0
+    gx = cl(torch.zeros_like(x))
+    ops.maxpool2_bwd(ops.View.from_nchw(xd), ops.View.from_nchw(cl(g)), ops.View.from_nchw(gx), accumulate=True)
+    assert maxabs(gx, x.grad) == 0.0
+    # copy4d: adjoint of nearest x2 and of avg-pool
+    a = seeded((2, 8, 6, 6), 3, -1, 1)
+    o = cl(torch.zeros(2, 8, 3, 3))
+    ops.copy4d(ops.View.from_nchw(cl(a)), ops.View.from_nchw(o), gather=ops.GATHER_AVGPOOL2, scale=4.0)
+    assert maxabs(o, 4 * F.avg_pool2d(a, 2)) <= 1e-6
+    o2 = cl(torch.ones(2, 8, 12, 12))
+    ops.copy4d(ops.View.from_nchw(cl(a)), ops.View.from_nchw(o2), gather=ops.GATHER_UP2, scale=0.25, slope=0.0, accumulate=True)
+    assert maxabs(o2, 1 + 0.25 * F.interpolate(torch.relu(a), scale_factor=2, mode="nearest")) <= 1e-6
+    cs = torch.zeros(8, device="cuda")
+    ops.colsum(ops.View.from_nchw(cl(a)), cs)
+    assert maxabs(cs, a.sum((0, 2, 3))) <= 1e-4
+    yv, gv = torch.tanh(seeded((1000,), 4, -2, 2)), seeded((1000,), 5, -1, 1)
+    od = torch.empty(1000, device="cuda")
+    ops.act_bwd(gv.cuda(), yv.cuda(), od, ops.ACT_TANH)
+    assert maxabs(od, gv * (1 - yv * yv)) <= 1e-6
+    ops.act_bwd(gv.cuda(), yv.abs().cuda(), od, ops.ACT_SIGMOID)
+    assert maxabs(od, gv * yv.abs() * (1 - yv.abs())) <= 1e-6
+
+
+def test_dgrad_strided():
+    ops = _ops()
+    x = seeded((2, 9, 16, 18), 1, -1, 1).requires_grad_(True)
+    w = seeded((36, 9, 4, 4), 2, -1, 1) / 12
+    y = F.conv2d(x, w, stride=2, padding=1)
+    g = seeded(tuple(y.shape), 3, -1, 1)
+    (y * g).sum().backward()
+    dx = torch.zeros(2, 9, 16, 18, device="cuda")
+    ops.dgrad_strided(ops.View.from_nchw(cl(g)), w.cuda(), 2, 1, ops.View.from_nchw(dx))
+    assert maxabs(dx, x.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 40, 56), (1, 3, 8, 9), (1, 3, 33, 65)])
+def test_freq_concat_fwd_bwd(shape):
+    from fdgan_b200.loss import freq_concat
+    from oracle import fdgan_oracle as O
+    x = seeded(shape, 1).requires_grad_(True)
+    z = O.freq_concat(x)
+    g = seeded(tuple(z.shape), 2, -1, 1)
+    (z * g).sum().backward()
+    xd = x.detach().cuda().requires_grad_(True)
+    zd = freq_concat(xd)
+    assert tuple(zd.shape) == tuple(z.shape)
+    assert maxabs(zd, z) <= 1e-5
+    (zd * g.cuda()).sum().backward()
+    assert maxabs(xd.grad, x.grad) <= 1e-4
+
+
+def test_adam_flat():
+    ops = _ops()
+    p = seeded((1000,), 1, -1, 1)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=2e-4, betas=(0.5, 0.999))
+    pd, m, v = p.cuda(), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
+    for step in range(1, 4):
+        g = seeded((1000,), 10 + step, -1, 1)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_flat(pd, (2 * g).cuda(), m, v, 2e-4, 0.5, 0.999, 1e-8, step, grad_scale=0.5)
+    assert maxabs(pd, ref.detach()) <= 1e-6
