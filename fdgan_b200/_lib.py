@@ -23,6 +23,7 @@ GATHER_DIRECT, GATHER_AVGPOOL2, GATHER_UP2 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 STORE_NORMAL, STORE_UP2, STORE_ACCUM = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
+LOSS_L1, LOSS_MSE, LOSS_BCE = 0, 1, 2
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -106,6 +107,9 @@ _SIGS = {
     "fdg_freq_concat_fwd": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_bwd": ([_P(FdgTensor), _P(FdgTensor), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_adam_flat": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p], C.c_int),
+    "fdg_loss_grad": ([C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
+    "fdg_profile_enable": ([C.c_int], C.c_int),
+    "fdg_profile_collect": ([C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
     "fdg_last_error": ([], C.c_char_p),
     "fdg_version": ([], C.c_int),
     "fdg_launch_count": ([], C.c_int64),
@@ -127,3 +131,17 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib.fdg_launch_count())
+
+
+PROF_FAMILIES = ("conv_simt_f32", "conv_tcgen05", "wgrad", "ew_bwd", "freq", "other")
+
+
+def profile_enable(on: bool) -> None:
+    lib.fdg_profile_enable(1 if on else 0)
+
+
+def profile_collect() -> dict:
+    n = len(PROF_FAMILIES)
+    ms, fl, by, ln = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+    check(lib.fdg_profile_collect(ms, fl, by, ln), "profile_collect")
+    return {PROF_FAMILIES[i]: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(ln[i])) for i in range(n)}

@@ -1,6 +1,8 @@
 // Error reporting, launch accounting and version of the fdgan_b200 C ABI.
 #include <atomic>
 #include <cstdarg>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -28,9 +30,61 @@ int check_launch(const char* what) {
   return FDG_OK;
 }
 
+// ---------------------------------------------------------------- per-launch event profiling
+struct ProfRec { int family; double flops, bytes; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::atomic<int> g_prof_on{0};
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(int family, double flops, double bytes, cudaStream_t stream) : idx(-1), st(stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{family, flops, bytes, prof_event(), prof_event()};
+  cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+  idx = (int)g_prof_recs.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[idx].b, st);
+}
+
 }  // namespace fdg
 
 extern "C" {
+
+int fdg_profile_enable(int on) {
+  fdg::g_prof_on.store(on ? 1 : 0);
+  return FDG_OK;
+}
+
+// Sums the recorded launches per family (ms, algorithmic flops, algorithmic bytes, launch count) and clears them.
+// Arrays have FDG_PROF_FAMILIES entries.  Synchronises on the recorded events.
+int fdg_profile_collect(double* ms, double* flops, double* bytes, int64_t* launches) {
+  std::lock_guard<std::mutex> lk(fdg::g_prof_mu);
+  for (int f = 0; f < fdg::PF_COUNT; ++f) { ms[f] = 0; flops[f] = 0; bytes[f] = 0; launches[f] = 0; }
+  for (auto& r : fdg::g_prof_recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms[r.family] += t; flops[r.family] += r.flops; bytes[r.family] += r.bytes; launches[r.family] += 1;
+    }
+    fdg::g_prof_pool.push_back(r.a);
+    fdg::g_prof_pool.push_back(r.b);
+  }
+  fdg::g_prof_recs.clear();
+  cudaGetLastError();
+  return FDG_OK;
+}
 
 const char* fdg_last_error(void) { return fdg::g_err; }
 

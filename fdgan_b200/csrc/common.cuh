@@ -12,6 +12,15 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);  // cudaGetLastError -> FDG_ECUDA
 
+// optional per-launch CUDA-event timing (bench.py's live roofline measurement); families of kernels
+enum ProfFamily { PF_CONV_SIMT = 0, PF_CONV_UMMA = 1, PF_WGRAD = 2, PF_EW = 3, PF_FREQ = 4, PF_OTHER = 5, PF_COUNT = 6 };
+struct ProfScope {
+  int idx;
+  cudaStream_t st;
+  ProfScope(int family, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
+
 #define FDG_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

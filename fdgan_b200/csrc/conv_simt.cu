@@ -288,6 +288,9 @@ __global__ void __launch_bounds__(NT, 2) conv_simt_kernel(const __grid_constant_
 template <int BN>
 static int launch_simt(const ConvArgs& a, bool vec, cudaStream_t st) {
   dim3 grid((unsigned)cdiv64(a.M, BM), (unsigned)cdiv(a.c.Cout, BN));
+  const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
+  ProfScope prof(PF_CONV_SIMT, 2.0 * (double)a.M * a.Ktot * a.c.Cout,
+                 4.0 * ((double)a.M * a.c.Cout + gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
   if (vec) conv_simt_kernel<BN, true><<<grid, NT, 0, st>>>(a);
   else conv_simt_kernel<BN, false><<<grid, NT, 0, st>>>(a);
   return check_launch("fdg_conv2d[simt]");

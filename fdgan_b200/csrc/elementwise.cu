@@ -287,6 +287,42 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// ------------------------------------------------------------------ fused loss value + gradient
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, float target,
+                                                        int kind, int64_t n, float scale, float* __restrict__ grad,
+                                                        int accumulate, double* loss) {
+  float part = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float av = a[i];
+    float l, g;
+    if (kind == FDG_LOSS_L1) {
+      const float d = av - b[i];
+      l = fabsf(d);
+      g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    } else if (kind == FDG_LOSS_MSE) {
+      const float d = av - b[i];
+      l = d * d;
+      g = 2.f * d;
+    } else {
+      const float la = fmaxf(logf(av), -100.f), l1a = fmaxf(log1pf(-av), -100.f);
+      l = -(target * la + (1.f - target) * l1a);
+      g = (av - target) / fmaxf(av * (1.f - av), 1e-12f);
+    }
+    part += l;
+    if (grad) grad[i] = (accumulate ? grad[i] : 0.f) + scale * g;
+  }
+  part = warp_sum(part);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(loss, (double)t * (double)scale);
+  }
+}
+
 static inline unsigned grid_for(int64_t total, int block) {
   int64_t g = cdiv64(total, block);
   const int64_t cap = 148 * 16;
@@ -332,6 +368,8 @@ int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
   if (gx < 1) gx = 1;
   const size_t smem = p->stats ? sizeof(float) * 2 * pix_lanes * cgroups * VW : 0;
   dim3 grid((unsigned)gx, gy);
+  ProfScope prof(PF_EW, 4.0 * (double)M * p->C, 4.0 * (double)M * p->C * (p->stats ? 2.0 : (p->accumulate ? 4.0 : 3.0)),
+                 (cudaStream_t)stream);
   if (vec) ew_bwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   else ew_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   return check_launch("fdg_ew_bwd");
@@ -389,6 +427,14 @@ int fdg_pack_weight(const float* w, int Cout, int Cin, int R, int S, int mode, f
   const int64_t total = (int64_t)K * out_ld;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, R, S, mode, out, out_ld, total);
   return check_launch("fdg_pack_weight");
+}
+
+int fdg_loss_grad(const float* a, const float* b, float target, int kind, int64_t n, float scale, float* grad,
+                  int accumulate, double* loss, fdg_stream_t stream) {
+  FDG_REQUIRE(a && loss && n > 0 && kind >= 0 && kind <= 2, "fdg_loss_grad: bad arguments");
+  FDG_REQUIRE(kind == FDG_LOSS_BCE || b, "fdg_loss_grad: L1/MSE need a second operand");
+  loss_grad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, target, kind, n, scale, grad, accumulate, loss);
+  return check_launch("fdg_loss_grad");
 }
 
 int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

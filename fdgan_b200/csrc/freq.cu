@@ -149,6 +149,7 @@ extern "C" int fdg_freq_concat_fwd(const FdgTensor* x, const FdgTensor* z, int N
   FDG_REQUIRE(H > FR && W > FR, "fdg_freq_concat_fwd: reflection padding 7 needs H, W > 7 (got %d x %d)", H, W);
   static const Gauss15 gk = make_gauss();
   dim3 grid(cdiv(W, FT), cdiv(H, FT), N * 3);
+  ProfScope prof(PF_FREQ, 2.0 * 234.0 * 3.0 * N * H * W, 48.0 * (double)N * H * W, (cudaStream_t)stream);
   freq_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*x, *z, H, W, gk);
   return check_launch("fdg_freq_concat_fwd");
 }

@@ -221,11 +221,16 @@ extern "C" int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream) {
   a.m_per_split = cdiv64(cdiv64(a.M, splits), WPM) * WPM;
   splits = cdiv64(a.M, a.m_per_split);
   dim3 grid(cdiv(a.Ktot, WTK), cdiv(p->Cout, WTC), (unsigned)splits);
+  int rc;
+  {
+  ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * a.Ktot * p->Cout,
+                 4.0 * ((double)a.M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);
   if (a.avec && a.gvec) wgrad_simt_kernel<true, true><<<grid, WNT, 0, st>>>(a);
   else if (a.avec) wgrad_simt_kernel<true, false><<<grid, WNT, 0, st>>>(a);
   else if (a.gvec) wgrad_simt_kernel<false, true><<<grid, WNT, 0, st>>>(a);
   else wgrad_simt_kernel<false, false><<<grid, WNT, 0, st>>>(a);
-  int rc = check_launch("fdg_conv2d_wgrad");
+  rc = check_launch("fdg_conv2d_wgrad");
+  }
   if (rc != FDG_OK) return rc;
   if (p->dbias) {
     return fdg_colsum(&p->g, p->N, p->OH, p->OW, p->Cout, p->dbias, 1, stream);

@@ -522,10 +522,9 @@ def vgg_forward(m, x: torch.Tensor, need_ctx: bool):
         acts.append(stage_acts)
         feats.append(cur)
     outs = [f.as_nchw() for f in feats]
-    if not need_ctx:
-        return outs, None
     ctx = VCtx()
-    ctx.x, ctx.acts, ctx.feats = x, acts, feats
+    ctx.feats = feats                      # the four NHWC feature buffers (always returned)
+    ctx.x, ctx.acts = (x, acts) if need_ctx else (None, None)
     return outs, ctx
 
 

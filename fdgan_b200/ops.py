@@ -224,3 +224,13 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, gra
     assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
     L.check(L.lib.fdg_adam_flat(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
                                 lr, beta1, beta2, eps, step, grad_scale, _stream()), "adam_flat")
+
+
+LOSS_L1, LOSS_MSE, LOSS_BCE = L.LOSS_L1, L.LOSS_MSE, L.LOSS_BCE
+
+
+def loss_grad(kind, a: torch.Tensor, b, n, scale, loss: torch.Tensor, grad=None, accumulate=False, target=0.0):
+    """fdg_loss_grad over the first ``n`` floats of the (identically laid out) buffers a and b."""
+    assert loss.dtype == torch.float64 and loss.numel() == 1
+    L.check(L.lib.fdg_loss_grad(_ptr(a), _ptr(b), target, kind, n, scale, _ptr(grad), 1 if accumulate else 0,
+                                loss.data_ptr(), _stream()), "loss_grad")

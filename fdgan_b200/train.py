@@ -1,0 +1,141 @@
+"""The FD-GAN training step on fdgan_b200 kernels (the reference's train.py is not in its tree; this follows
+the reconstruction in SURVEY 3.3 from demo.py:43-46 flags, misc.py helpers, loss.pyc and facades/network.png).
+
+    fake = G(hazy)
+    D step:  lossD = BCE(D([clean,LF,HF]), 1) + BCE(D([fake.detach(),LF,HF]), 0);  Adam(D)
+    G step:  lossG = w_l1 L1(fake, clean) + w_perc sum_k MSE(vgg_k(fake), vgg_k(clean)) + w_adv BCE(D([fake,LF,HF]), 1);  Adam(G)
+
+The step drives the network executors directly (no autograd graph): loss values and their gradients come from
+one fused kernel each, parameter gradients land in ONE flat fp32 buffer per network, which is all-reduced once
+(NCCL over NVLink when world_size > 1) and consumed by a fused flat Adam.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import dist as fdist
+from . import engine, ops
+from .ops import View
+
+DEFAULT_WEIGHTS = dict(l1=1.0, perc=0.5, adv=0.01)
+
+
+class FlatState:
+    """Used parameters of one network re-homed into a single flat fp32 buffer (16-byte aligned slices), with a
+    flat gradient buffer of the same layout (views by parameter name) and flat Adam moments."""
+
+    def __init__(self, module):
+        named = module._used_named_parameters()
+        dev = named[0][1].device
+        offs, off = [], 0
+        for _n, p in named:
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.n = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad_views = {}
+        for (n, p), o in zip(named, offs):
+            v = self.flat[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            self.grad_views[n] = self.grad[o:o + p.numel()].view(p.shape)
+        self.step = 0
+        self.module = module
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def adam(self, lr, beta1, beta2, eps, grad_scale):
+        self.step += 1
+        ops.adam_flat(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, self.step, grad_scale)
+
+
+class GANTrainer:
+    def __init__(self, netG, netD, vgg, lr=2e-4, betas=(0.5, 0.999), eps=1e-8, weights=None, perc_layers=(1, 3),
+                 process_group=None):
+        self.G, self.D, self.V = netG, netD, vgg
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.w = dict(DEFAULT_WEIGHTS)
+        if weights:
+            self.w.update(weights)
+        self.perc_layers = tuple(perc_layers)
+        self.group = process_group
+        self.world = fdist.world_size(process_group)
+        self.sG, self.sD = FlatState(netG), FlatState(netD)
+        fdist.broadcast_flat_(self.sG.flat, 0, process_group)
+        fdist.broadcast_flat_(self.sD.flat, 0, process_group)
+        dev = self.sG.flat.device
+        self.loss_buf = torch.zeros(4, dtype=torch.float64, device=dev)   # lossD, weighted l1 / perceptual / adversarial terms of lossG
+        self.last = {}
+
+    # ------------------------------------------------------------------
+    def step(self, hazy: torch.Tensor, clean: torch.Tensor, sync_losses: bool = True):
+        """One D update and one G update on this rank's shard.  hazy, clean: [b,3,H,W] fp32 CUDA."""
+        G, D, V = self.G, self.D, self.V
+        dev = hazy.device
+        lb = self.loss_buf
+        lb.zero_()
+        b1, b2 = self.betas
+        gscale = 1.0 / self.world
+
+        fake, gctx = engine.generator_forward(G, hazy, True, True)
+        B, _, H, W = fake.shape
+        if tuple(clean.shape) != tuple(fake.shape):
+            raise ValueError("clean %s does not match G(hazy) %s" % (tuple(clean.shape), tuple(fake.shape)))
+        clean = clean.contiguous()
+        z_real = View.alloc(B, H, W, 9, dev)
+        z_fake = View.alloc(B, H, W, 9, dev)
+        ops.freq_concat_fwd(View.from_nchw(clean), z_real)
+        ops.freq_concat_fwd(View.from_nchw(fake), z_fake)
+
+        # ---------------- D step
+        self.sD.zero_grad()
+        pr, ctx_r = engine.discriminator_forward(D, z_real.as_nchw(), True, True)
+        pf, ctx_f = engine.discriminator_forward(D, z_fake.as_nchw(), True, True)
+        n_p = pr.numel()
+        dpr, dpf = torch.empty_like(pr), torch.empty_like(pf)
+        ops.loss_grad(ops.LOSS_BCE, pr, None, n_p, 1.0 / n_p, lb[0:1], dpr, target=1.0)
+        ops.loss_grad(ops.LOSS_BCE, pf, None, n_p, 1.0 / n_p, lb[0:1], dpf, target=0.0)
+        engine.discriminator_backward(D, ctx_r, dpr, self.sD.grad_views, False)
+        engine.discriminator_backward(D, ctx_f, dpf, self.sD.grad_views, False)
+        del ctx_r, ctx_f
+        fdist.allreduce_flat_(self.sD.grad, self.group)
+        self.sD.adam(self.lr, b1, b2, self.eps, gscale)
+
+        # ---------------- G step (D frozen: data gradient only)
+        self.sG.zero_grad()
+        pf2, ctx_f2 = engine.discriminator_forward(D, z_fake.as_nchw(), True, True)
+        dpf2 = torch.empty_like(pf2)
+        ops.loss_grad(ops.LOSS_BCE, pf2, None, n_p, self.w["adv"] / n_p, lb[3:4], dpf2, target=1.0)
+        dz = engine.discriminator_backward(D, ctx_f2, dpf2, None, True)
+        del ctx_f2
+        dfake = torch.empty_like(fake)
+        scratch = torch.empty(B * 3 * H * W, dtype=torch.float32, device=dev)
+        ops.freq_concat_bwd(View.from_nchw(dz), View.from_nchw(dfake), scratch)
+        n_img = fake.numel()
+        ops.loss_grad(ops.LOSS_L1, fake, clean, n_img, self.w["l1"] / n_img, lb[1:2], dfake, accumulate=True)
+        if self.w["perc"] != 0.0 and self.perc_layers:
+            _fo, vctx = engine.vgg_forward(V, fake, True)
+            _co, cctx = engine.vgg_forward(V, clean, False)
+            gouts = [None, None, None, None]
+            for k in self.perc_layers:
+                fk, ck = vctx.feats[k], cctx.feats[k]
+                n_k = fk.N * fk.H * fk.W * fk.C
+                gk = View.alloc(fk.N, fk.H, fk.W, fk.C, dev)
+                ops.loss_grad(ops.LOSS_MSE, fk.base, ck.base, n_k, self.w["perc"] / n_k, lb[2:3], gk.base)
+                gouts[k] = gk.as_nchw()
+            dxv = engine.vgg_backward(V, vctx, gouts, None, True)
+            del vctx, cctx
+            ops.copy4d(View.from_nchw(dxv), View.from_nchw(dfake), accumulate=True)
+        engine.generator_backward(G, gctx, dfake, self.sG.grad_views, False)
+        del gctx
+        fdist.allreduce_flat_(self.sG.grad, self.group)
+        self.sG.adam(self.lr, b1, b2, self.eps, gscale)
+
+        if sync_losses:
+            v = lb.tolist()    # the step's device->host read; slots 1..3 hold the WEIGHTED generator terms
+            self.last = dict(loss_d=v[0], l1_weighted=v[1], perc_weighted=v[2], adv_weighted=v[3], loss_g=v[1] + v[2] + v[3])
+        return fake

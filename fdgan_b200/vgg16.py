@@ -23,7 +23,7 @@ class _VggFn(torch.autograd.Function):
     def forward(ctx, mod, x, *params):
         need = any(ctx.needs_input_grad[1:])
         outs, ectx = engine.vgg_forward(mod, x, need)
-        ctx.mod, ctx.ectx = mod, ectx
+        ctx.mod, ctx.ectx = mod, (ectx if need else None)
         return tuple(outs)
 
     @staticmethod

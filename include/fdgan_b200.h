@@ -242,6 +242,25 @@ int fdg_freq_concat_bwd(const FdgTensor* dz, const FdgTensor* dx, float* scratch
 int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int step, float grad_scale, fdg_stream_t stream);
 
+/* Fused scalar loss + its gradient over flat arrays (the training step never builds an autograd graph for these):
+ *   kind FDG_LOSS_L1:  loss += scale * sum |a-b|        grad (=|+=) scale * sign(a-b)       (F.l1_loss, mean folded into scale)
+ *   kind FDG_LOSS_MSE: loss += scale * sum (a-b)^2      grad (=|+=) 2 scale (a-b)           (F.mse_loss on VGG features)
+ *   kind FDG_LOSS_BCE: loss += scale * sum -[t log a + (1-t) log(1-a)], logs clamped at -100 like torch;
+ *                      grad (=|+=) scale * (a-t) / max(a (1-a), 1e-12)                      (nn.BCELoss against the constant target t;
+ *                      D ends in a Sigmoid, dehaze1113.py:223)
+ * loss is a device double accumulated atomically; grad may be NULL (value only). */
+#define FDG_LOSS_L1 0
+#define FDG_LOSS_MSE 1
+#define FDG_LOSS_BCE 2
+int fdg_loss_grad(const float* a, const float* b, float target, int kind, int64_t n, float scale, float* grad,
+                  int accumulate, double* loss, fdg_stream_t stream);
+
+/* Live per-launch timing for bench.py's roofline: when enabled every entry point brackets its kernel with CUDA events
+ * on the launching stream; collect() sums elapsed ms, algorithmic flops / bytes and launches per kernel family. */
+#define FDG_PROF_FAMILIES 6 /* 0 conv fp32 SIMT, 1 conv tcgen05, 2 weight gradient, 3 element-wise backward, 4 frequency, 5 other */
+int fdg_profile_enable(int on);
+int fdg_profile_collect(double* ms, double* flops, double* bytes, int64_t* launches);
+
 /* diagnostics */
 const char* fdg_last_error(void);
 int fdg_version(void);

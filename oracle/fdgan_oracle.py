@@ -18,7 +18,7 @@ What each function follows (paths relative to /root/reference):
                            L122-162 / L205-304 recovered in SURVEY Appendix B) --
                            bytecode only, "parity unpinned"
   * ``ssim``               models/pytorch_ssim/__init__.py:7-37
-  * ``train_step``         RECONSTRUCTED; the reference has no train.py
+  * ``train_step``         RECONSTRUCTED; the reference has no train.py -- parity unpinned
 
 BatchNorm always uses batch statistics when ``train=True`` (README.md:38, demo.py
 never calls .eval()).
@@ -395,33 +395,56 @@ def ssim(img1, img2, window_size=11):
 # reconstructed training step
 # --------------------------------------------------------------------------------------
 
-DEFAULT_LOSS_WEIGHTS = dict(l1=1.0, ssim=1.0, perc=0.5, adv=0.01)
+DEFAULT_LOSS_WEIGHTS = dict(l1=1.0, ssim=0.0, perc=0.5, adv=0.01)
 
 
 def _bce(p, target):
     return F.binary_cross_entropy(p, torch.full_like(p, target))
 
 
-def train_losses(g_sd, d_sd, v_sd, hazy, clean, weights=None, perc_layers=(1, 3), update_running=True):
-    """One reconstructed FD-GAN iteration's two losses (no optimiser): returns
-    (lossD, lossG, fake).  D step sees fake.detach(); G step back-propagates through
-    blur/laplace, D (parameters treated as constants) and the frozen VGG."""
+def d_param_names(d_sd):
+    return [k for k, v in d_sd.items() if v.is_floating_point() and "running" not in k]
+
+
+def train_step(g_sd, d_sd, v_sd, hazy, clean, state_g, state_d, weights=None, perc_layers=(1, 3), lr=2e-4,
+               betas=(0.5, 0.999)):
+    """One reconstructed FD-GAN iteration: D update on (clean, fake.detach()), then G update
+    through blur/laplace, the UPDATED D (parameters constant) and the frozen VGG.  Mutates g_sd / d_sd.
+    Returns (losses dict, D gradients, G gradients)."""
     wts = dict(DEFAULT_LOSS_WEIGHTS)
     if weights:
         wts.update(weights)
-    fake = fdgan_forward(g_sd, hazy, True, update_running)
+    g_names, d_names = fdgan_used_param_names(), d_param_names(d_sd)
+    for k in g_names:
+        g_sd[k].requires_grad_(True)
+    for k in d_names:
+        d_sd[k].requires_grad_(True)
+    fake = fdgan_forward(g_sd, hazy, True, True)
     real_in = freq_concat(clean)
     fake_in_d = freq_concat(fake.detach())
-    loss_d = _bce(d_forward(d_sd, real_in, True, update_running), 1.0) + \
-        _bce(d_forward(d_sd, fake_in_d, True, update_running), 0.0)
+    loss_d = _bce(d_forward(d_sd, real_in, True, True), 1.0) + _bce(d_forward(d_sd, fake_in_d, True, True), 0.0)
+    grads_d = torch.autograd.grad(loss_d, [d_sd[k] for k in d_names])
+    adam_step([d_sd[k] for k in d_names], grads_d, state_d, lr, betas)
     d_const = OrderedDict((k, v.detach()) for k, v in d_sd.items())
-    fake_in = freq_concat(fake)
-    loss_g = wts["l1"] * F.l1_loss(fake, clean) + wts["ssim"] * (1 - ssim(fake, clean))
-    fv, cv = vgg16_forward(v_sd, fake), vgg16_forward(v_sd, clean)
-    for k in perc_layers:
-        loss_g = loss_g + wts["perc"] * F.mse_loss(fv[k], cv[k].detach())
-    loss_g = loss_g + wts["adv"] * _bce(d_forward(d_const, fake_in, True, update_running), 1.0)
-    return loss_d, loss_g, fake
+    l1 = F.l1_loss(fake, clean)
+    loss_g = wts["l1"] * l1
+    parts = {"l1_weighted": float(wts["l1"] * l1)}
+    if wts["ssim"] != 0.0:
+        loss_g = loss_g + wts["ssim"] * (1 - ssim(fake, clean))
+    perc = 0.0
+    if wts["perc"] != 0.0 and perc_layers:
+        v_const = OrderedDict((k, v.detach()) for k, v in v_sd.items())
+        fv, cv = vgg16_forward(v_const, fake), vgg16_forward(v_const, clean)
+        for k in perc_layers:
+            perc = perc + F.mse_loss(fv[k], cv[k].detach())
+        loss_g = loss_g + wts["perc"] * perc
+    adv = _bce(d_forward(d_const, freq_concat(fake), True, True), 1.0)
+    loss_g = loss_g + wts["adv"] * adv
+    grads_g = torch.autograd.grad(loss_g, [g_sd[k] for k in g_names])
+    adam_step([g_sd[k] for k in g_names], grads_g, state_g, lr, betas)
+    parts.update(loss_d=float(loss_d), loss_g=float(loss_g), perc_weighted=float(wts["perc"] * perc),
+                 adv_weighted=float(wts["adv"] * adv))
+    return parts, dict(zip(d_names, grads_d)), dict(zip(g_names, grads_g)), fake.detach()
 
 
 def adam_step(params, grads, state, lr=2e-4, betas=(0.5, 0.999), eps=1e-8):

@@ -1,0 +1,53 @@
+"""GPU parity of the training step (fdgan_b200.train.GANTrainer) against the oracle's reconstructed step."""
+import pytest
+import torch
+
+from oracle import fdgan_oracle as O
+from tests.util import grad_close, maxabs, seeded
+
+pytestmark = pytest.mark.gpu
+
+
+def _nets():
+    import fdgan_b200
+    G, D, V = fdgan_b200.FDGAN(), fdgan_b200.D(9, 36), fdgan_b200.Vgg16()
+    G.load_state_dict(O.make_fdgan_state(0))
+    D.load_state_dict(O.make_d_state(9, 36, 1))
+    V.load_state_dict(O.make_vgg_state(2))
+    return G.cuda().train(), D.cuda().train(), V.cuda()
+
+
+@pytest.mark.parametrize("batch,hw", [(1, 32), (2, 48)])
+def test_train_step_matches_oracle(batch, hw):
+    from fdgan_b200.train import GANTrainer
+    G, D, V = _nets()
+    tr = GANTrainer(G, D, V)
+    g_sd, d_sd, v_sd = O.make_fdgan_state(0), O.make_d_state(9, 36, 1), O.make_vgg_state(2)
+    sg, sdd = {}, {}
+    hazy, clean = seeded((batch, 3, hw, hw), 5), seeded((batch, 3, hw, hw), 6)
+    for it in range(2):
+        parts, gd, gg, fake_o = O.train_step(g_sd, d_sd, v_sd, hazy, clean, sg, sdd)
+        fake = tr.step(hazy.cuda(), clean.cuda())
+        assert maxabs(fake, fake_o) <= (2e-4 if it == 0 else 5e-3)
+        for k in ("loss_d", "loss_g", "l1_weighted", "perc_weighted", "adv_weighted"):
+            assert abs(tr.last[k] - parts[k]) <= 2e-3 * max(1.0, abs(parts[k])), (it, k, tr.last[k], parts[k])
+        if it == 0:
+            for k, g in gd.items():
+                grad_close(tr.sD.grad_views[k], g, "D " + k)
+            worst = 0.0
+            for k, g in gg.items():
+                l2, _ = grad_close(tr.sG.grad_views[k], g, "G " + k, rel_l2=3e-2, rel_max=1e-1)
+                worst = max(worst, l2)
+            print("worst G-gradient rel-L2", worst)
+    # parameters moved by Adam exactly like the oracle's (first step: lr * sign-like update)
+    moved = maxabs(dict(D.named_parameters())["main.layer5.conv.weight"], d_sd["main.layer5.conv.weight"])
+    assert moved <= 2e-4
+
+
+def test_trainer_uses_flat_buffers():
+    from fdgan_b200.train import GANTrainer
+    G, D, V = _nets()
+    tr = GANTrainer(G, D, V)
+    for n, p in G._used_named_parameters():
+        assert p.data_ptr() >= tr.sG.flat.data_ptr() and p.data_ptr() < tr.sG.flat.data_ptr() + 4 * tr.sG.n
+    assert tr.sG.n >= 11803155 and tr.sD.n >= 790416

@@ -38,3 +38,16 @@ def maxabs(a, b):
     a = torch.as_tensor(a).detach().double().cpu()
     b = torch.as_tensor(b).detach().double().cpu()
     return float((a - b).abs().max())
+
+
+def grad_close(got, want, what="", rel_l2=2e-2, rel_max=5e-2):
+    """Gradient parity for B >= 2.  The reference itself is chaotic there: its own fp32 and fp64 CPU runs differ by
+    ~0.5 % in relative L2 and ~1 % of the max in max-abs (ReLU masks flip on near-zero pre-activations, measured with
+    oracle/fdgan_oracle.py), so gradients are held to a relative-L2 bound plus a loose max-abs bound."""
+    a = torch.as_tensor(got).detach().double().cpu().reshape(-1)
+    b = torch.as_tensor(want).detach().double().cpu().reshape(-1)
+    nb = float(b.norm())
+    l2 = float((a - b).norm()) / max(nb, 1e-12)
+    mx = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-12)
+    assert l2 <= rel_l2 and mx <= rel_max, "%s: rel-L2 %.3e (<= %.1e), rel-max %.3e (<= %.1e)" % (what, l2, rel_l2, mx, rel_max)
+    return l2, mx
