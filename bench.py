@@ -223,6 +223,11 @@ def run_ours(args):
     value = world * B * args.steps / (ms_total / 1e3)
     clocks = clk.summary()
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "unit": UNIT, "ms_per_step": ms_step, "gpu_launches": int(launches),
+                              "steps": args.steps, "clocks": clocks}))
+        return 0
     # ---- e2e: pinned host inputs -> H2D, step, loss scalars D2H, all inside the timed region
     barrier()
     ev0.record()
@@ -313,6 +318,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (weak scaling)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="value leg only (used under ncu): no e2e / profiled / CPU passes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -428,7 +428,7 @@ def train_step(g_sd, d_sd, v_sd, hazy, clean, state_g, state_d, weights=None, pe
     d_const = OrderedDict((k, v.detach()) for k, v in d_sd.items())
     l1 = F.l1_loss(fake, clean)
     loss_g = wts["l1"] * l1
-    parts = {"l1_weighted": float(wts["l1"] * l1)}
+    parts = {"l1_weighted": float(wts["l1"] * l1.detach())}
     if wts["ssim"] != 0.0:
         loss_g = loss_g + wts["ssim"] * (1 - ssim(fake, clean))
     perc = 0.0
@@ -442,8 +442,9 @@ def train_step(g_sd, d_sd, v_sd, hazy, clean, state_g, state_d, weights=None, pe
     loss_g = loss_g + wts["adv"] * adv
     grads_g = torch.autograd.grad(loss_g, [g_sd[k] for k in g_names])
     adam_step([g_sd[k] for k in g_names], grads_g, state_g, lr, betas)
-    parts.update(loss_d=float(loss_d), loss_g=float(loss_g), perc_weighted=float(wts["perc"] * perc),
-                 adv_weighted=float(wts["adv"] * adv))
+    parts.update(loss_d=float(loss_d.detach()), loss_g=float(loss_g.detach()),
+                 perc_weighted=float(wts["perc"] * (perc.detach() if torch.is_tensor(perc) else perc)),
+                 adv_weighted=float(wts["adv"] * adv.detach()))
     return parts, dict(zip(d_names, grads_d)), dict(zip(g_names, grads_g)), fake.detach()
 
 
