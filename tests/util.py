@@ -40,12 +40,14 @@ def maxabs(a, b):
     return float((a - b).abs().max())
 
 
-def grad_close(got, want, what="", rel_l2=2e-2, rel_max=5e-2):
+def grad_close(got, want, what="", rel_l2=2e-2, rel_max=5e-2, abs_floor=2e-6):
     """Gradient parity for B >= 2.  The reference itself is chaotic there: its own fp32 and fp64 CPU runs differ by
     ~0.5 % in relative L2 and ~1 % of the max in max-abs (ReLU masks flip on near-zero pre-activations, measured with
     oracle/fdgan_oracle.py), so gradients are held to a relative-L2 bound plus a loose max-abs bound."""
     a = torch.as_tensor(got).detach().double().cpu().reshape(-1)
     b = torch.as_tensor(want).detach().double().cpu().reshape(-1)
+    if float((a - b).abs().max()) <= abs_floor:
+        return 0.0, 0.0      # analytically-zero gradients (a bias in front of a BatchNorm) are rounding noise on both sides
     nb = float(b.norm())
     l2 = float((a - b).norm()) / max(nb, 1e-12)
     mx = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-12)
