@@ -36,7 +36,7 @@ def test_train_step_matches_oracle(batch, hw):
                 grad_close(tr.sD.grad_views[k], g, "D " + k)
             worst = 0.0
             for k, g in gg.items():
-                l2, _ = grad_close(tr.sG.grad_views[k], g, "G " + k, rel_l2=3e-2, rel_max=1e-1)
+                l2, _ = grad_close(tr.sG.grad_views[k], g, "G " + k)
                 worst = max(worst, l2)
             print("worst G-gradient rel-L2", worst)
     # parameters moved by Adam exactly like the oracle's (first step: lr * sign-like update)
