@@ -95,6 +95,8 @@ _SIGS = {
     "fdg_conv2d": ([_P(FdgConv), C.c_void_p], C.c_int),
     "fdg_conv2d_wgrad": ([_P(FdgWgrad), C.c_void_p], C.c_int),
     "fdg_pack_weight": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
+    "fdg_umma_weight_bytes": ([C.c_int, C.c_int, C.c_int], C.c_int64),
+    "fdg_pack_weight_umma": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_bn_finalize": ([_P(FdgBnFinalize), C.c_void_p], C.c_int),
     "fdg_ew_bwd": ([_P(FdgEwBwd), C.c_void_p], C.c_int),
     "fdg_bn_bwd_finalize": ([_P(FdgBnBwdFinalize), C.c_void_p], C.c_int),

@@ -1,7 +1,478 @@
-// tcgen05 implicit-GEMM path of fdg_conv2d (placeholder until the kernel lands: reports "unsupported").
-#include "common.cuh"
+// fdg_conv2d, tcgen05 (5th-gen tensor core) implicit-GEMM path for sm_100a.
+//
+//   D[128 pixels x NT channels] (fp32, TMEM) += A[128 x 64] (bf16, smem) * B[NT x 64]^T (bf16, smem)   per K chunk
+//
+// * Split precision: every fp32 operand value is split hi = bf16(x), lo = bf16(x - hi) and each K chunk
+//   issues three MMAs per 16-deep slice (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM accumulator, i.e.
+//   ~16 operand mantissa bits (plain bf16/tf32 operands miss the 1e-3 parity bar).
+// * A operand: the activations are fp32 NHWC in HBM and need the consumer-side prologue (BatchNorm
+//   scale/shift + ReLU/LeakyReLU, avg-pool / nearest-upsample gather, zero padding AFTER the prologue),
+//   which TMA cannot apply -- so 8 loader warps read 128-bit, transform in registers, split, and store the
+//   bf16 hi/lo tiles into shared memory in the canonical K-major SWIZZLE_128B layout, then
+//   fence.proxy.async + mbarrier.arrive.  K order = (filter tap, 64-channel chunk).
+// * B operand: weights are pre-split and pre-swizzled by fdg_pack_weight_umma into the exact shared-memory
+//   image of every (N tile, K chunk), so one 1-D bulk TMA (cp.async.bulk, mbarrier complete_tx) per stage
+//   brings hi and lo.
+// * One elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=NT, K=16); tcgen05.commit
+//   releases the smem stage / publishes the accumulator.  Epilogue warps read TMEM with tcgen05.ld
+//   (32x32b.x32), apply alpha/bias/activation/mask, reduce the per-channel BatchNorm statistics with a
+//   butterfly of warp shuffles and store 128-bit rows.
+#include <cuda_bf16.h>
+
+#include "aop.cuh"
 
 namespace fdg {
-int conv2d_umma_supported(const FdgConv* p) { (void)p; return 0; }
-int conv2d_umma(const FdgConv* p, cudaStream_t st) { (void)p; (void)st; set_error("tcgen05 conv path not built"); return FDG_ENOSUPPORT; }
+
+constexpr int UM = 128;          // pixels per tile (UMMA M)
+constexpr int UKC = 64;          // K elements per chunk (128 B of bf16 = one swizzle row)
+constexpr int ULOAD_WARPS = 8;
+constexpr int UTHREADS = (ULOAD_WARPS + 1) * 32;   // + 1 control warp (MMA issue, B bulk copies, TMEM alloc)
+constexpr int A_TILE_BYTES = UM * 128;             // one bf16 [128 x 64] tile
+
+struct UmmaArgs {
+  FdgConv c;
+  AOp ao;
+  int64_t M;
+  int cchunks;   // ceil(Cin / 64)
+  int nchunks;   // taps * cchunks
+  int yvec;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
+// SBO(1024 B >> 4)<<32 | version 1 <<46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 pair -> packed bf16x2 (lo half = first element) and the residual pair
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ float epi_act_u(float v, int act) {
+  switch (act) {
+    case FDG_ACT_RELU: return fmaxf(v, 0.f);
+    case FDG_ACT_TANH: return tanhf(v);
+    case FDG_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// column sums of a 32-lane x 32-column register tile: afterwards lane l holds the sum of column l in v[0]
+__device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(UTHREADS, (NT <= 64 ? 2 : 1)) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
+  constexpr int B_TILE_BYTES = NT * 128;
+  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sred[2][NT];
+
+  const FdgConv& p = a.c;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
+  const int64_t m0 = (int64_t)blockIdx.x * UM;
+  const int ntile = blockIdx.y;
+  const int OHW = p.OH * p.OW;
+
+  if (t == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), ULOAD_WARPS * 32 + 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_acc), 1);
+    fence_barrier_init();
+  }
+  if (t < NT) { sred[0][t] = 0.f; sred[1][t] = 0.f; }
+  if (warp == ULOAD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < ULOAD_WARPS) {
+    // =============================================================== A loaders
+    // thread handles the 16-byte bf16 chunk j (8 channels) of rows rbase + 32*i, i = 0..3
+    const int j = t & 7, rbase = t >> 3;
+    int pn[4], piy[4], pix[4];
+    bool pv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + rbase + 32 * i;
+      pv[i] = m < a.M;
+      const int64_t mm = pv[i] ? m : 0;
+      pn[i] = (int)(mm / OHW);
+      const int rem = (int)(mm - (int64_t)pn[i] * OHW);
+      const int oy = rem / p.OW, ox = rem - oy * p.OW;
+      piy[i] = oy * p.stride - p.pad;
+      pix[i] = ox * p.stride - p.pad;
+    }
+    for (int kc = 0; kc < a.nchunks; ++kc) {
+      const int s = kc % STAGES;
+      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+      const int tap = kc / a.cchunks;
+      const int c = (kc - tap * a.cchunks) * UKC + j * 8;
+      const int r = tap / p.S, sx = tap - r * p.S;
+      // issue the global loads before waiting for the stage to drain
+      float4 v0[4], v1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int iy = piy[i] + r, ix = pix[i] + sx;
+        v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v1[i] = v0[i];
+        if (pv[i] && c < p.Cin && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          v0[i] = fetch4(a.ao, pn[i], iy, ix, c);
+          v1[i] = fetch4(a.ao, pn[i], iy, ix, c + 4);
+        }
+      }
+      mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = rbase + 32 * i;
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+        uint32_t h[4], l[4];
+        split2(v0[i].x, v0[i].y, h[0], l[0]);
+        split2(v0[i].z, v0[i].w, h[1], l[1]);
+        split2(v1[i].x, v1[i].y, h[2], l[2]);
+        split2(v1[i].z, v1[i].w, h[3], l[3]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bar_full[s]));
+    }
+  } else if (lane == 0) {
+    // =============================================================== control thread: B bulk copies + MMA issue
+    const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)ntile * a.nchunks * (2 * B_TILE_BYTES);
+    constexpr uint32_t idesc = umma_idesc_bf16(UM, NT);
+    const int pre = a.nchunks < STAGES ? a.nchunks : STAGES;
+    for (int kc = 0; kc < pre; ++kc) {                       // prologue: fill the ring with weight tiles
+      const uint32_t bar = smem_u32(&bar_full[kc]);
+      mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
+      bulk_g2s(smem_base + kc * STAGE_BYTES + 2 * A_TILE_BYTES, wimg + (size_t)kc * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+    }
+    for (int kc = 0; kc < a.nchunks; ++kc) {
+      const int s = kc % STAGES;
+      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+      mbar_wait(smem_u32(&bar_full[s]), ph);
+      tc_fence_after();
+      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+      const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t aa = term == 2 ? a_lo : a_hi;
+        const uint32_t bb = term == 1 ? b_lo : b_hi;
+#pragma unroll
+        for (int k4 = 0; k4 < UKC / 16; ++k4) {
+          umma_bf16(tmem_base, umma_desc_k128(aa + k4 * 32), umma_desc_k128(bb + k4 * 32), idesc,
+                    (kc > 0 || term > 0 || k4 > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(smem_u32(&bar_empty[s]));                  // frees this stage when the MMAs above retire
+      // refill the stage of the PREVIOUS chunk (its MMAs retire while this chunk's run) with the weights of chunk kc-1+STAGES
+      const int pj = kc - 1, nk = pj + STAGES;
+      if (pj >= 0 && nk < a.nchunks) {
+        const int ps = pj % STAGES;
+        mbar_wait(smem_u32(&bar_empty[ps]), (uint32_t)(pj / STAGES) & 1u);
+        const uint32_t bar = smem_u32(&bar_full[ps]);
+        mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
+        bulk_g2s(smem_base + ps * STAGE_BYTES + 2 * A_TILE_BYTES, wimg + (size_t)nk * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+      }
+    }
+    umma_commit(smem_u32(&bar_acc));
+  }
+
+  // =============================================================== epilogue (warps 0..3: TMEM lane quarter = warp)
+  if (warp < 4) {
+    mbar_wait(smem_u32(&bar_acc), 0);
+    tc_fence_after();
+    const int64_t m = m0 + warp * 32 + lane;
+    const bool mv = m < a.M;
+    int n = 0, oy = 0, ox = 0;
+    if (mv) {
+      n = (int)(m / OHW);
+      const int rem = (int)(m - (int64_t)n * OHW);
+      oy = rem / p.OW;
+      ox = rem - oy * p.OW;
+    }
+    const int cbase = ntile * NT;
+#pragma unroll 1
+    for (int g = 0; g < NT / 32; ++g) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32), v);
+      const int c0 = cbase + g * 32;
+      if (c0 >= p.Cout) break;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const int c = c0 + u;
+        float r = v[u] * p.alpha;
+        if (mv && c < p.Cout) {
+          if (p.bias) r += __ldg(p.bias + c);
+          r = epi_act_u(r, p.act);
+          if (p.e.p) {
+            const float ev = __ldg(p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + (int64_t)c * p.e.sc);
+            r *= (ev > 0.f ? 1.f : p.eslope);
+          }
+        } else {
+          r = 0.f;
+        }
+        v[u] = r;
+      }
+      if (mv) {
+        const bool full = c0 + 32 <= p.Cout;
+        const int reps = p.store == FDG_STORE_UP2 ? 4 : 1;
+        for (int d = 0; d < reps; ++d) {
+          const int yy = p.store == FDG_STORE_UP2 ? 2 * oy + (d >> 1) : oy, xx = p.store == FDG_STORE_UP2 ? 2 * ox + (d & 1) : ox;
+          float* yp = p.y.p + n * p.y.sn + (int64_t)yy * p.y.sh + (int64_t)xx * p.y.sw + (int64_t)c0 * p.y.sc;
+          if (a.yvec && full) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              if (p.store == FDG_STORE_ACCUM) {
+                const float4 old = *reinterpret_cast<const float4*>(yp + 4 * q);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(yp + 4 * q) = o;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (c0 + u < p.Cout) {
+                float* q1 = yp + (int64_t)u * p.y.sc;
+                *q1 = p.store == FDG_STORE_ACCUM ? *q1 + v[u] : v[u];
+              }
+          }
+        }
+      }
+      if (p.stats) {
+        float sq[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) sq[u] = v[u] * v[u];
+        const float s1 = butterfly_colsum(v, lane);
+        const float s2 = butterfly_colsum(sq, lane);
+        atomicAdd(&sred[0][g * 32 + lane], s1);
+        atomicAdd(&sred[1][g * 32 + lane], s2);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (p.stats && t < NT) {
+    const int c = ntile * NT + t;
+    if (c < p.Cout) {
+      atomicAdd(p.stats + c, (double)sred[0][t]);
+      atomicAdd(p.stats + p.stats_ld + c, (double)sred[1][t]);
+    }
+  }
+  if (warp == ULOAD_WARPS) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight image
+// out[(ntile, kchunk)] = [hi: NT rows x 128 B, SWIZZLE_128B][lo: same]; source = fp32 [K][ld] GEMM operand
+__global__ void pack_umma_kernel(const float* __restrict__ w, int ld, int taps, int Cin, int Cout, int NT, int cchunks,
+                                 uint8_t* __restrict__ out, int64_t total_pairs) {
+  // one thread per (ntile, kchunk, row n, 16-byte chunk j): 8 consecutive k of one output channel
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pairs; i += (int64_t)gridDim.x * blockDim.x) {
+    const int jj = (int)(i & 7);
+    int64_t r = i >> 3;
+    const int nrow = (int)(r % NT); r /= NT;
+    const int nchunks = taps * cchunks;
+    const int kc = (int)(r % nchunks);
+    const int nt = (int)(r / nchunks);
+    const int tap = kc / cchunks;
+    const int cbase = (kc - tap * cchunks) * UKC + jj * 8;
+    const int co = nt * NT + nrow;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float f[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int ci = cbase + 2 * e + q;
+        f[q] = (co < Cout && ci < Cin) ? w[((int64_t)tap * Cin + ci) * ld + co] : 0.f;
+      }
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(f[0], f[1]);
+      const float2 hf = __bfloat1622float2(hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(f[0] - hf.x, f[1] - hf.y);
+      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    uint8_t* base = out + ((int64_t)nt * nchunks + kc) * (2 * NT * 128);
+    const int off = nrow * 128 + ((jj ^ (nrow & 7)) << 4);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(base + NT * 128 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+static inline int umma_ntile(int Cout) { return Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256)); }
+
+int conv2d_umma_supported(const FdgConv* p) {
+  if (!p->w_umma) return 0;
+  if (p->Cin % 8 != 0 || p->Cin < 32 || p->Cout < 16) return 0;
+  AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
+  if (!aop_vec_ok(ao, p->Cin)) return 0;
+  return 1;
+}
+
+template <int NT, int STAGES>
+static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("fdg_conv2d[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
+      return FDG_ECUDA;
+    }
+    attr_done = true;
+  }
+  dim3 grid((unsigned)cdiv64(a.M, UM), (unsigned)cdiv(a.c.Cout, NT));
+  const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
+  ProfScope prof(PF_CONV_UMMA, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
+                 4.0 * ((double)a.M * a.c.Cout + gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
+  conv_umma_kernel<NT, STAGES><<<grid, UTHREADS, smem, st>>>(a);
+  return check_launch("fdg_conv2d[tcgen05]");
+}
+
+int conv2d_umma(const FdgConv* p, cudaStream_t st) {
+  UmmaArgs a;
+  a.c = *p;
+  a.ao = AOp{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
+  a.M = (int64_t)p->N * p->OH * p->OW;
+  a.cchunks = cdiv(p->Cin, UKC);
+  a.nchunks = p->R * p->S * a.cchunks;
+  a.yvec = vec4_ok(p->y);
+  switch (umma_ntile(p->Cout)) {
+    case 32: return launch_umma<32, 2>(a, st);    // 81 KB: two CTAs per SM
+    case 64: return launch_umma<64, 2>(a, st);    // 97 KB: two CTAs per SM
+    case 128: return launch_umma<128, 3>(a, st);
+    default: return launch_umma<256, 2>(a, st);
+  }
+}
+
 }  // namespace fdg
+
+using namespace fdg;
+
+extern "C" int64_t fdg_umma_weight_bytes(int taps, int Cin, int Cout) {
+  const int NT = umma_ntile(Cout);
+  return (int64_t)cdiv(Cout, NT) * taps * cdiv(Cin, UKC) * 2 * NT * 128;
+}
+
+extern "C" int fdg_pack_weight_umma(const float* w, int w_ld, int taps, int Cin, int Cout, void* out, fdg_stream_t stream) {
+  FDG_REQUIRE(w && out && taps > 0 && Cin > 0 && Cout > 0 && w_ld >= Cout, "fdg_pack_weight_umma: bad arguments");
+  FDG_REQUIRE(aligned16(out), "fdg_pack_weight_umma: output must be 16-byte aligned");
+  const int NT = umma_ntile(Cout);
+  const int cch = cdiv(Cin, UKC);
+  const int64_t total = (int64_t)cdiv(Cout, NT) * taps * cch * NT * 8;
+  int64_t g = cdiv64(total, 256);
+  if (g > 148 * 8) g = 148 * 8;
+  pack_umma_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, w_ld, taps, Cin, Cout, NT, cch, (uint8_t*)out, total);
+  return check_launch("fdg_pack_weight_umma");
+}

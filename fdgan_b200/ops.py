@@ -74,6 +74,23 @@ class View:
 
 _NULLT = L.FdgTensor(None, 0, 0, 0, 0)
 
+# tcgen05 path switch: True = every eligible convolution runs on the tensor cores (bf16x3 split, fp32 accumulate);
+# False = fp32 SIMT everywhere (used by tests to compare the two paths).
+USE_UMMA = True
+
+
+def umma_eligible(x: View, Cout: int) -> bool:
+    return (x.C % 8 == 0 and x.C >= 32 and Cout >= 16 and x.sc == 1 and x.ptr % 16 == 0 and x.sn % 4 == 0 and
+            x.sh % 4 == 0 and x.sw % 4 == 0)
+
+
+def pack_weight_umma(w, w_ld: int, taps: int, Cin: int, Cout: int, device) -> torch.Tensor:
+    """fdg_pack_weight_umma: bf16 hi/lo, pre-swizzled per-stage images of the GEMM-form weight w[K][w_ld]."""
+    nbytes = int(L.lib.fdg_umma_weight_bytes(taps, Cin, Cout))
+    out = torch.empty(nbytes // 4, dtype=torch.int32, device=device)
+    L.check(L.lib.fdg_pack_weight_umma(_ptr(w), w_ld, taps, Cin, Cout, out.data_ptr(), _stream()), "pack_weight_umma")
+    return out
+
 
 def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_DIRECT, scale=None, shift=None,
            slope=1.0, bias=None, act=ACT_NONE, e: View | None = None, eslope=0.0, store=STORE_NORMAL, stats=None,
@@ -92,6 +109,8 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
         raise ValueError("conv2d: output view %s does not match %s" % ((y.N, y.H, y.W, y.C), (x.N, mul * OH, mul * OW, Cout)))
     if e is not None and (e.N, e.H, e.W, e.C) != (x.N, OH, OW, Cout):
         raise ValueError("conv2d: mask view shape mismatch")
+    if w_umma is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and umma_eligible(x, Cout):
+        w_umma = pack_weight_umma(w, w_ld, R * S, x.C, Cout, x.base.device)
     d = L.FdgConv(
         x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
         _ptr(w), w_ld, R, S, stride, pad, Cout, OH, OW, _ptr(bias), act,

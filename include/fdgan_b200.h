@@ -128,6 +128,12 @@ int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream);
 int fdg_pack_weight(const float* w, int Cout, int Cin, int R, int S, int mode, float* out, int out_ld,
                     fdg_stream_t stream);
 
+/* tcgen05 operand image of a GEMM-form weight w[K = taps*Cin][w_ld] (the output of fdg_pack_weight, or a 1x1 parameter
+ * used as is): bf16 hi/lo split, pre-swizzled (SWIZZLE_128B, K-major) per (N tile, 64-deep K chunk) so that the conv
+ * kernel fetches each stage with one bulk TMA copy.  fdg_umma_weight_bytes gives the size of `out` (16-byte aligned). */
+int64_t fdg_umma_weight_bytes(int taps, int Cin, int Cout);
+int fdg_pack_weight_umma(const float* w, int w_ld, int taps, int Cin, int Cout, void* out, fdg_stream_t stream);
+
 /*
  * BatchNorm2d training-mode bookkeeping (nn.BatchNorm2d as used at README.md:38: always batch statistics).
  * fdg_bn_finalize: stats (fp64 sum, sumsq over count elements per channel) -> scale = gamma*invstd,
