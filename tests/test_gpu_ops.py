@@ -45,14 +45,24 @@ CONV_CASES = [
     (128, 72, 1, 1, 0, 6, 5, 0, False, 1.0, False, 0, 2, False, True),     # accumulate store + mask
     (16, 24, 1, 1, 0, 4, 6, 2, False, 1.0, False, 0, 0, False, False),     # up2 gather
     (64, 600, 3, 1, 1, 4, 4, 0, False, 1.0, True, 1, 0, False, False),     # wide N (several N tiles), VGG-like
+    (1024, 256, 3, 1, 1, 9, 11, 0, False, 0.0, False, 0, 0, False, False), # dense_block4.conv2 (K = 9216)
+    (224, 128, 1, 1, 0, 33, 31, 0, True, 0.0, False, 0, 0, True, False),   # ragged M (tail tile), padded K chunk
+    (128, 32, 3, 1, 1, 64, 64, 0, True, 0.0, False, 0, 0, True, False),    # many tiles + statistics
+    (512, 128, 3, 1, 1, 8, 8, 0, False, 0.0, False, 0, 2, False, True),    # dense_block5.conv2 dgrad-style accumulate
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("nchw_in", [False, True])
-def test_conv2d(case, nchw_in):
+@pytest.mark.parametrize("variant", ["simt_nhwc", "simt_nchw", "tcgen05"])
+def test_conv2d(case, variant):
+    """fdg_conv2d against fp64 torch on every shape family of the path, through both kernels: the fp32 SIMT path
+    (2e-5) and the tcgen05 bf16x3 path (5e-5; ~16 operand mantissa bits, fp32 accumulation in TMEM)."""
     ops = _ops()
     Cin, Cout, R, stride, pad, H, W, gather, affine, slope, bias, act, store, stats, mask = case
+    nchw_in = variant == "simt_nchw"
+    impl = ops.IMPL_UMMA if variant == "tcgen05" else ops.IMPL_SIMT
+    if variant == "tcgen05" and not (Cin % 8 == 0 and Cin >= 32 and Cout >= 16):
+        pytest.skip("shape not covered by the tcgen05 path (runs on the SIMT kernel)")
     N = 2
     ph, pw = (2 * H, 2 * W) if gather == 1 else ((H + 1) // 2, (W + 1) // 2) if gather == 2 else (H, W)
     if gather == 2:
@@ -88,9 +98,9 @@ def test_conv2d(case, nchw_in):
     ops.conv2d(ops.View.from_nchw(xd), wp, ld, R, R, stride, pad, Cout, ops.View.from_nchw(yd), gather=gather,
                scale=sc.cuda() if affine else None, shift=sh.cuda() if affine else None, slope=slope,
                bias=b.cuda() if bias else None, act=act, e=ops.View.from_nchw(cl(e)) if mask else None, eslope=0.3,
-               store=store, stats=st, stats_ld=Cout + 3, impl=ops.IMPL_SIMT)
+               store=store, stats=st, stats_ld=Cout + 3, impl=impl)
     torch.cuda.synchronize()
-    assert maxabs(yd, y) <= 2e-5
+    assert maxabs(yd, y) <= (5e-5 if variant == "tcgen05" else 2e-5)
     if stats:
         assert maxabs(st[:Cout], ysum) <= 1e-3 and maxabs(st[Cout + 3:2 * Cout + 3], ysq) <= 1e-3
 
