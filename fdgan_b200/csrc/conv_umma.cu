@@ -155,7 +155,7 @@ __device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int NT, int STAGES>
-__global__ void __launch_bounds__(UTHREADS, (NT <= 64 ? 2 : 1)) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
+__global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
@@ -449,8 +449,8 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
   a.nchunks = p->R * p->S * a.cchunks;
   a.yvec = vec4_ok(p->y);
   switch (umma_ntile(p->Cout)) {
-    case 32: return launch_umma<32, 2>(a, st);    // 81 KB: two CTAs per SM
-    case 64: return launch_umma<64, 2>(a, st);    // 97 KB: two CTAs per SM
+    case 32: return launch_umma<32, 5>(a, st);    // 5 x 40 KB
+    case 64: return launch_umma<64, 4>(a, st);    // 4 x 48 KB
     case 128: return launch_umma<128, 3>(a, st);
     default: return launch_umma<256, 2>(a, st);
   }

@@ -102,7 +102,8 @@ def test_conv2d(case, variant):
     torch.cuda.synchronize()
     assert maxabs(yd, y) <= (5e-5 if variant == "tcgen05" else 2e-5)
     if stats:
-        assert maxabs(st[:Cout], ysum) <= 1e-3 and maxabs(st[Cout + 3:2 * Cout + 3], ysq) <= 1e-3
+        tol = 2e-6 * float(N * OH * OW) + 1e-3   # fp32 partial sums over the tile, fp64 across tiles
+        assert maxabs(st[:Cout], ysum) <= tol and maxabs(st[Cout + 3:2 * Cout + 3], ysq) <= tol
 
 
 def test_conv2d_nchw_output_and_errors():
