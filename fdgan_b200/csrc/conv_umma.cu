@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
 
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), ULOAD_WARPS * 32 + 1);
+      mbar_init(smem_u32(&bar_full[s]), ULOAD_WARPS + 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
     // =============================================================== A loaders
     // thread handles the 16-byte bf16 chunk j (8 channels) of rows rbase + 32*i, i = 0..3
     const int j = t & 7, rbase = t >> 3;
+    const bool direct = p.gather == FDG_GATHER_DIRECT;
     int pn[4], piy[4], pix[4];
+    const float* rowp[4];
     bool pv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -208,23 +210,45 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
       const int oy = rem / p.OW, ox = rem - oy * p.OW;
       piy[i] = oy * p.stride - p.pad;
       pix[i] = ox * p.stride - p.pad;
+      rowp[i] = p.x.p + pn[i] * p.x.sn + (int64_t)piy[i] * p.x.sh + (int64_t)pix[i] * p.x.sw + j * 8;   // only dereferenced when in range
     }
+    int s = 0, r = 0, sx = 0, cc = 0;
+    uint32_t ph = 0;
     for (int kc = 0; kc < a.nchunks; ++kc) {
-      const int s = kc % STAGES;
-      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-      const int tap = kc / a.cchunks;
-      const int c = (kc - tap * a.cchunks) * UKC + j * 8;
-      const int r = tap / p.S, sx = tap - r * p.S;
+      const int c = cc * UKC + j * 8;
       // issue the global loads before waiting for the stage to drain
       float4 v0[4], v1[4];
+      const int64_t toff = (int64_t)r * p.x.sh + (int64_t)sx * p.x.sw + cc * UKC;
+      float4 sc0, sc1, sh0, sh1;
+      const bool cvalid = c < p.Cin;
+      if (direct && p.has_affine && cvalid) {
+        sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
+        sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int iy = piy[i] + r, ix = pix[i] + sx;
         v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         v1[i] = v0[i];
-        if (pv[i] && c < p.Cin && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-          v0[i] = fetch4(a.ao, pn[i], iy, ix, c);
-          v1[i] = fetch4(a.ao, pn[i], iy, ix, c + 4);
+        if (pv[i] && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          if (direct) {
+            v0[i] = ld4(rowp[i] + toff);
+            v1[i] = ld4(rowp[i] + toff + 4);
+            if (p.has_affine) {
+              v0[i].x = fmaf(v0[i].x, sc0.x, sh0.x); v0[i].y = fmaf(v0[i].y, sc0.y, sh0.y);
+              v0[i].z = fmaf(v0[i].z, sc0.z, sh0.z); v0[i].w = fmaf(v0[i].w, sc0.w, sh0.w);
+              v1[i].x = fmaf(v1[i].x, sc1.x, sh1.x); v1[i].y = fmaf(v1[i].y, sc1.y, sh1.y);
+              v1[i].z = fmaf(v1[i].z, sc1.z, sh1.z); v1[i].w = fmaf(v1[i].w, sc1.w, sh1.w);
+            }
+            const float sl = p.slope;
+            v0[i].x = prologue_act(v0[i].x, sl); v0[i].y = prologue_act(v0[i].y, sl);
+            v0[i].z = prologue_act(v0[i].z, sl); v0[i].w = prologue_act(v0[i].w, sl);
+            v1[i].x = prologue_act(v1[i].x, sl); v1[i].y = prologue_act(v1[i].y, sl);
+            v1[i].z = prologue_act(v1[i].z, sl); v1[i].w = prologue_act(v1[i].w, sl);
+          } else {
+            v0[i] = fetch4(a.ao, pn[i], iy, ix, c);
+            v1[i] = fetch4(a.ao, pn[i], iy, ix, c + 4);
+          }
         }
       }
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
@@ -241,8 +265,11 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
       }
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&bar_full[s]));
+      fence_proxy_async();          // make this thread's generic-proxy stores visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));   // one arrival per loader warp
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+      if (++cc == a.cchunks) { cc = 0; if (++sx == p.S) { sx = 0; ++r; } }
     }
   } else if (lane == 0) {
     // =============================================================== control thread: B bulk copies + MMA issue

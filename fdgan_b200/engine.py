@@ -56,8 +56,9 @@ class _Pool:
 def _bn_run(mod, stats, stats_ld, C, count, training, fpool, nbt_list):
     run = BNRun(mod, C, count, fpool.take(4 * C))
     track = training and mod.track_running_stats
+    use_running = track or not training
     ops.bn_finalize(stats, stats_ld, C, count, mod.weight, mod.bias, mod.eps, mod.momentum,
-                    mod.running_mean if track else None, mod.running_var if track else None,
+                    mod.running_mean if use_running else None, mod.running_var if use_running else None,
                     training, run.scale, run.shift, run.mean, run.invstd)
     if track:
         nbt_list.append(mod.num_batches_tracked)

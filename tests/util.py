@@ -47,6 +47,10 @@ def maxabs(a, b):
     return float((a - b).abs().max())
 
 
+# parameters whose gradient is analytically zero (a bias feeding only BatchNorms): both sides hold rounding noise
+ZERO_GRAD_PARAMS = ("conv_refine4.bias",)
+
+
 def grad_close(got, want, what="", rel_l2=3e-2, rel_max=0.25, abs_floor=2e-6):
     """Gradient parity for B >= 2.  The reference itself is chaotic there: its own fp32 and fp64 CPU runs differ by
     ~0.5 % in relative L2 and ~1 % of the max in max-abs (ReLU masks flip on near-zero pre-activations, measured with
@@ -54,6 +58,9 @@ def grad_close(got, want, what="", rel_l2=3e-2, rel_max=0.25, abs_floor=2e-6):
     sanity bound.  Exactness of every backward kernel is established separately, at 2e-5, by tests/test_gpu_ops.py."""
     a = torch.as_tensor(got).detach().double().cpu().reshape(-1)
     b = torch.as_tensor(want).detach().double().cpu().reshape(-1)
+    if any(z in what for z in ZERO_GRAD_PARAMS):
+        assert float(a.abs().max()) <= 1e-3, "%s: analytically-zero gradient is %.3e" % (what, float(a.abs().max()))
+        return 0.0, 0.0
     if float((a - b).abs().max()) <= abs_floor:
         return 0.0, 0.0      # analytically-zero gradients (a bias in front of a BatchNorm) are rounding noise on both sides
     nb = float(b.norm())
