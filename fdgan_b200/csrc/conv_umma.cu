@@ -129,6 +129,8 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 __device__ __forceinline__ float epi_act_u(float v, int act) {
   switch (act) {
     case FDG_ACT_RELU: return fmaxf(v, 0.f);
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float sred[2][NT];
+  __shared__ float sred[2][4][NT];
 
   const FdgConv& p = a.c;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
     mbar_init(smem_u32(&bar_acc), 1);
     fence_barrier_init();
   }
-  if (t < NT) { sred[0][t] = 0.f; sred[1][t] = 0.f; }
+  for (int i = t; i < 2 * 4 * NT; i += UTHREADS) (&sred[0][0][0])[i] = 0.f;
   if (warp == ULOAD_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS)
                  : "memory");
@@ -212,19 +214,12 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
       pix[i] = ox * p.stride - p.pad;
       rowp[i] = p.x.p + pn[i] * p.x.sn + (int64_t)piy[i] * p.x.sh + (int64_t)pix[i] * p.x.sw + j * 8;   // only dereferenced when in range
     }
-    int s = 0, r = 0, sx = 0, cc = 0;
-    uint32_t ph = 0;
-    for (int kc = 0; kc < a.nchunks; ++kc) {
+    // issue the global loads of one K chunk into registers (raw values for the direct gather; the pooled /
+    // upsampled gathers apply the prologue inside fetch4 because it has to precede the averaging)
+    auto issue = [&](float4 (&v0)[4], float4 (&v1)[4], int r, int sx, int cc) {
       const int c = cc * UKC + j * 8;
-      // issue the global loads before waiting for the stage to drain
-      float4 v0[4], v1[4];
-      const int64_t toff = (int64_t)r * p.x.sh + (int64_t)sx * p.x.sw + cc * UKC;
-      float4 sc0, sc1, sh0, sh1;
       const bool cvalid = c < p.Cin;
-      if (direct && p.has_affine && cvalid) {
-        sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
-        sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
-      }
+      const int64_t toff = (int64_t)r * p.x.sh + (int64_t)sx * p.x.sw + cc * UKC;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int iy = piy[i] + r, ix = pix[i] + sx;
@@ -234,21 +229,35 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
           if (direct) {
             v0[i] = ld4(rowp[i] + toff);
             v1[i] = ld4(rowp[i] + toff + 4);
-            if (p.has_affine) {
-              v0[i].x = fmaf(v0[i].x, sc0.x, sh0.x); v0[i].y = fmaf(v0[i].y, sc0.y, sh0.y);
-              v0[i].z = fmaf(v0[i].z, sc0.z, sh0.z); v0[i].w = fmaf(v0[i].w, sc0.w, sh0.w);
-              v1[i].x = fmaf(v1[i].x, sc1.x, sh1.x); v1[i].y = fmaf(v1[i].y, sc1.y, sh1.y);
-              v1[i].z = fmaf(v1[i].z, sc1.z, sh1.z); v1[i].w = fmaf(v1[i].w, sc1.w, sh1.w);
-            }
-            const float sl = p.slope;
-            v0[i].x = prologue_act(v0[i].x, sl); v0[i].y = prologue_act(v0[i].y, sl);
-            v0[i].z = prologue_act(v0[i].z, sl); v0[i].w = prologue_act(v0[i].w, sl);
-            v1[i].x = prologue_act(v1[i].x, sl); v1[i].y = prologue_act(v1[i].y, sl);
-            v1[i].z = prologue_act(v1[i].z, sl); v1[i].w = prologue_act(v1[i].w, sl);
           } else {
             v0[i] = fetch4(a.ao, pn[i], iy, ix, c);
             v1[i] = fetch4(a.ao, pn[i], iy, ix, c + 4);
           }
+        }
+      }
+    };
+    // prologue (direct gather), bf16 hi/lo split and swizzled store of one K chunk into stage s
+    auto finish = [&](float4 (&v0)[4], float4 (&v1)[4], int r, int sx, int cc, int s, uint32_t ph) {
+      const int c = cc * UKC + j * 8;
+      if (direct) {
+        const bool cvalid = c < p.Cin;
+        float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+        if (p.has_affine && cvalid) {
+          sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
+          sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
+        }
+        const float sl = p.slope;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int iy = piy[i] + r, ix = pix[i] + sx;
+          const bool ok = pv[i] && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          float4 a0 = v0[i], a1 = v1[i];
+          a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
+          a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
+          a1.x = prologue_act(fmaf(a1.x, sc1.x, sh1.x), sl); a1.y = prologue_act(fmaf(a1.y, sc1.y, sh1.y), sl);
+          a1.z = prologue_act(fmaf(a1.z, sc1.z, sh1.z), sl); a1.w = prologue_act(fmaf(a1.w, sc1.w, sh1.w), sl);
+          v0[i] = ok ? a0 : make_float4(0.f, 0.f, 0.f, 0.f);     // zero padding is applied AFTER the prologue
+          v1[i] = ok ? a1 : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
@@ -268,8 +277,24 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
       fence_proxy_async();          // make this thread's generic-proxy stores visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));   // one arrival per loader warp
+    };
+    // two chunks of loads are always in flight per thread (register double buffering)
+    int lr = 0, lsx = 0, lcc = 0;    // coordinates of the next chunk to load
+    int fr = 0, fsx = 0, fcc = 0;    // coordinates of the next chunk to finish
+    int s = 0;
+    uint32_t ph = 0;
+    auto adv = [&](int& r, int& sx, int& cc) { if (++cc == a.cchunks) { cc = 0; if (++sx == p.S) { sx = 0; ++r; } } };
+    float4 A0[4], A1[4], B0[4], B1[4];
+    issue(A0, A1, lr, lsx, lcc); adv(lr, lsx, lcc);
+    for (int kc = 0; kc < a.nchunks; kc += 2) {
+      if (kc + 1 < a.nchunks) { issue(B0, B1, lr, lsx, lcc); adv(lr, lsx, lcc); }
+      finish(A0, A1, fr, fsx, fcc, s, ph); adv(fr, fsx, fcc);
       if (++s == STAGES) { s = 0; ph ^= 1u; }
-      if (++cc == a.cchunks) { cc = 0; if (++sx == p.S) { sx = 0; ++r; } }
+      if (kc + 1 < a.nchunks) {
+        if (kc + 2 < a.nchunks) { issue(A0, A1, lr, lsx, lcc); adv(lr, lsx, lcc); }
+        finish(B0, B1, fr, fsx, fcc, s, ph); adv(fr, fsx, fcc);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
     }
   } else if (lane == 0) {
     // =============================================================== control thread: B bulk copies + MMA issue
@@ -326,48 +351,84 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
       ox = rem - oy * p.OW;
     }
     const int cbase = ntile * NT;
+    const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
 #pragma unroll 1
     for (int g = 0; g < NT / 32; ++g) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32), v);
       const int c0 = cbase + g * 32;
       if (c0 >= p.Cout) break;
+      const int nvalid = p.Cout - c0 < 32 ? p.Cout - c0 : 32;
+      const bool full = nvalid == 32;
+      // ---- alpha, bias
+      if (p.bias) {
+        if (full) {
 #pragma unroll
-      for (int u = 0; u < 32; ++u) {
-        const int c = c0 + u;
-        float r = v[u] * p.alpha;
-        if (mv && c < p.Cout) {
-          if (p.bias) r += __ldg(p.bias + c);
-          r = epi_act_u(r, p.act);
-          if (p.e.p) {
-            const float ev = __ldg(p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + (int64_t)c * p.e.sc);
-            r *= (ev > 0.f ? 1.f : p.eslope);
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = ld4(p.bias + c0 + 4 * q);
+            v[4 * q] = fmaf(v[4 * q], p.alpha, b.x); v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, b.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, b.z); v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, b.w);
           }
         } else {
-          r = 0.f;
+#pragma unroll
+          for (int u = 0; u < 32; ++u) v[u] = fmaf(v[u], p.alpha, u < nvalid ? __ldg(p.bias + c0 + u) : 0.f);
         }
-        v[u] = r;
+      } else if (p.alpha != 1.f) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] *= p.alpha;
+      }
+      // ---- activation (uniform switch hoisted out of the element loop)
+      if (p.act == FDG_ACT_RELU) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = fmaxf(v[u], 0.f);
+      } else if (p.act == FDG_ACT_TANH) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = tanhf(v[u]);
+      } else if (p.act == FDG_ACT_SIGMOID) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = 1.f / (1.f + expf(-v[u]));
+      }
+      // ---- ReLU / LeakyReLU backward mask from a second tensor
+      if (p.e.p && mv) {
+        const float* ep = p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + (int64_t)c0 * p.e.sc;
+        if (evec && full) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 ev = ld4(ep + 4 * q);
+            v[4 * q] *= ev.x > 0.f ? 1.f : p.eslope; v[4 * q + 1] *= ev.y > 0.f ? 1.f : p.eslope;
+            v[4 * q + 2] *= ev.z > 0.f ? 1.f : p.eslope; v[4 * q + 3] *= ev.w > 0.f ? 1.f : p.eslope;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+            if (u < nvalid) v[u] *= __ldg(ep + (int64_t)u * p.e.sc) > 0.f ? 1.f : p.eslope;
+        }
+      }
+      if (!mv || !full) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) if (!mv || u >= nvalid) v[u] = 0.f;
       }
       if (mv) {
-        const bool full = c0 + 32 <= p.Cout;
         const int reps = p.store == FDG_STORE_UP2 ? 4 : 1;
         for (int d = 0; d < reps; ++d) {
           const int yy = p.store == FDG_STORE_UP2 ? 2 * oy + (d >> 1) : oy, xx = p.store == FDG_STORE_UP2 ? 2 * ox + (d & 1) : ox;
           float* yp = p.y.p + n * p.y.sn + (int64_t)yy * p.y.sh + (int64_t)xx * p.y.sw + (int64_t)c0 * p.y.sc;
           if (a.yvec && full) {
+            if (p.store == FDG_STORE_ACCUM) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-              if (p.store == FDG_STORE_ACCUM) {
+              for (int q = 0; q < 8; ++q) {
                 const float4 old = *reinterpret_cast<const float4*>(yp + 4 * q);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q] + old.x, v[4 * q + 1] + old.y, v[4 * q + 2] + old.z, v[4 * q + 3] + old.w);
               }
-              *reinterpret_cast<float4*>(yp + 4 * q) = o;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
           } else {
 #pragma unroll
             for (int u = 0; u < 32; ++u)
-              if (c0 + u < p.Cout) {
+              if (u < nvalid) {
                 float* q1 = yp + (int64_t)u * p.y.sc;
                 *q1 = p.store == FDG_STORE_ACCUM ? *q1 + v[u] : v[u];
               }
@@ -380,8 +441,8 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
         for (int u = 0; u < 32; ++u) sq[u] = v[u] * v[u];
         const float s1 = butterfly_colsum(v, lane);
         const float s2 = butterfly_colsum(sq, lane);
-        atomicAdd(&sred[0][g * 32 + lane], s1);
-        atomicAdd(&sred[1][g * 32 + lane], s2);
+        sred[0][warp][g * 32 + lane] = s1;      // per-warp partial column sums, combined after the barrier
+        sred[1][warp][g * 32 + lane] = s2;
       }
     }
     tc_fence_before();
@@ -390,8 +451,8 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
   if (p.stats && t < NT) {
     const int c = ntile * NT + t;
     if (c < p.Cout) {
-      atomicAdd(p.stats + c, (double)sred[0][t]);
-      atomicAdd(p.stats + p.stats_ld + c, (double)sred[1][t]);
+      atomicAdd(p.stats + c, (double)((sred[0][0][t] + sred[0][1][t]) + (sred[0][2][t] + sred[0][3][t])));
+      atomicAdd(p.stats + p.stats_ld + c, (double)((sred[1][0][t] + sred[1][1][t]) + (sred[1][2][t] + sred[1][3][t])));
     }
   }
   if (warp == ULOAD_WARPS) {
