@@ -156,34 +156,47 @@ __device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// Persistent, warp-specialised: grid = min(#tiles, #SMs) CTAs of 13 warps
+//   warps 0..7   A loaders (thread 0 also issues the bulk-TMA copy of each stage's weight tile)
+//   warp  8      control: one thread issues tcgen05.mma / tcgen05.commit; the warp owns the TMEM allocation
+//   warps 9..12  epilogue: TMEM -> registers -> global, overlapped with the next tile's main loop through
+//                two TMEM accumulator buffers
+// The shared-memory ring and the loaders' register double buffer run straight across tile boundaries.
+constexpr int UEPI_WARP0 = ULOAD_WARPS + 1;
+constexpr int UTHREADS_P = (ULOAD_WARPS + 1 + 4) * 32;
+
 template <int NT, int STAGES>
-__global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
+__global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+  constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
-  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sred[2][4][NT];
 
   const FdgConv& p = a.c;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
-  const int64_t m0 = (int64_t)blockIdx.x * UM;
-  const int ntile = blockIdx.y;
   const int OHW = p.OH * p.OW;
+  const int m_tiles = (int)((a.M + UM - 1) / UM);
+  const int n_tiles = (p.Cout + NT - 1) / NT;
+  const int total_tiles = m_tiles * n_tiles;
 
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), ULOAD_WARPS + 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_acc), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_acc_full[b]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[b]), 4);
+    }
     fence_barrier_init();
   }
-  for (int i = t; i < 2 * 4 * NT; i += UTHREADS) (&sred[0][0][0])[i] = 0.f;
   if (warp == ULOAD_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS)
                  : "memory");
@@ -199,33 +212,44 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
     // thread handles the 16-byte bf16 chunk j (8 channels) of rows rbase + 32*i, i = 0..3
     const int j = t & 7, rbase = t >> 3;
     const bool direct = p.gather == FDG_GATHER_DIRECT;
+    // ---- load cursor: (tile, chunk) of the next chunk to fetch, with the tile's pixel coordinates
+    int l_tile = blockIdx.x, l_kc = 0, l_r = 0, l_sx = 0, l_cc = 0, l_nt = 0;
     int pn[4], piy[4], pix[4];
     const float* rowp[4];
-    bool pv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t m = m0 + rbase + 32 * i;
-      pv[i] = m < a.M;
-      const int64_t mm = pv[i] ? m : 0;
-      pn[i] = (int)(mm / OHW);
-      const int rem = (int)(mm - (int64_t)pn[i] * OHW);
-      const int oy = rem / p.OW, ox = rem - oy * p.OW;
-      piy[i] = oy * p.stride - p.pad;
-      pix[i] = ox * p.stride - p.pad;
-      rowp[i] = p.x.p + pn[i] * p.x.sn + (int64_t)piy[i] * p.x.sh + (int64_t)pix[i] * p.x.sw + j * 8;   // only dereferenced when in range
-    }
-    // issue the global loads of one K chunk into registers (raw values for the direct gather; the pooled /
-    // upsampled gathers apply the prologue inside fetch4 because it has to precede the averaging)
-    auto issue = [&](float4 (&v0)[4], float4 (&v1)[4], int r, int sx, int cc) {
-      const int c = cc * UKC + j * 8;
-      const bool cvalid = c < p.Cin;
-      const int64_t toff = (int64_t)r * p.x.sh + (int64_t)sx * p.x.sw + cc * UKC;
+    uint32_t pvmask = 0;
+    auto set_tile = [&](int tile) {
+      const int mt = tile % m_tiles;
+      l_nt = tile / m_tiles;
+      pvmask = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int iy = piy[i] + r, ix = pix[i] + sx;
+        const int64_t m = (int64_t)mt * UM + rbase + 32 * i;
+        const bool v = m < a.M;
+        pvmask |= (v ? 1u : 0u) << i;
+        const int64_t mm = v ? m : 0;
+        pn[i] = (int)(mm / OHW);
+        const int rem = (int)(mm - (int64_t)pn[i] * OHW);
+        const int oy = rem / p.OW, ox = rem - oy * p.OW;
+        piy[i] = oy * p.stride - p.pad;
+        pix[i] = ox * p.stride - p.pad;
+        rowp[i] = p.x.p + pn[i] * p.x.sn + (int64_t)piy[i] * p.x.sh + (int64_t)pix[i] * p.x.sw + j * 8;  // dereferenced only in range
+      }
+    };
+    // issue the global loads of the cursor's chunk into registers (raw values for the direct gather; the pooled /
+    // upsampled gathers apply the prologue inside fetch4 because it has to precede the averaging); returns metadata
+    // (bits 0..3 in-range mask, bits 8.. channel-chunk index, bits 16.. weight-tile index) and advances the cursor
+    auto issue = [&](float4 (&v0)[4], float4 (&v1)[4]) -> uint32_t {
+      const int c = l_cc * UKC + j * 8;
+      const bool cvalid = c < p.Cin;
+      const int64_t toff = (int64_t)l_r * p.x.sh + (int64_t)l_sx * p.x.sw + l_cc * UKC;
+      uint32_t ok = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int iy = piy[i] + l_r, ix = pix[i] + l_sx;
         v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         v1[i] = v0[i];
-        if (pv[i] && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+        if (((pvmask >> i) & 1u) && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          ok |= 1u << i;
           if (direct) {
             v0[i] = ld4(rowp[i] + toff);
             v1[i] = ld4(rowp[i] + toff + 4);
@@ -235,22 +259,28 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
           }
         }
       }
+      const uint32_t meta = ok | ((uint32_t)l_cc << 8) | ((uint32_t)(l_nt * a.nchunks + l_kc) << 16);
+      if (++l_cc == a.cchunks) { l_cc = 0; if (++l_sx == p.S) { l_sx = 0; ++l_r; } }
+      if (++l_kc == a.nchunks) {
+        l_kc = 0; l_r = 0; l_sx = 0; l_cc = 0;
+        l_tile += gridDim.x;
+        if (l_tile < total_tiles) set_tile(l_tile);
+      }
+      return meta;
     };
     // prologue (direct gather), bf16 hi/lo split and swizzled store of one K chunk into stage s
-    auto finish = [&](float4 (&v0)[4], float4 (&v1)[4], int r, int sx, int cc, int s, uint32_t ph) {
-      const int c = cc * UKC + j * 8;
+    auto finish = [&](float4 (&v0)[4], float4 (&v1)[4], uint32_t meta, int s, uint32_t ph) {
       if (direct) {
-        const bool cvalid = c < p.Cin;
+        const int c = (int)((meta >> 8) & 0xffu) * UKC + j * 8;
         float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
-        if (p.has_affine && cvalid) {
+        if (p.has_affine && c < p.Cin) {
           sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
           sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
         }
         const float sl = p.slope;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int iy = piy[i] + r, ix = pix[i] + sx;
-          const bool ok = pv[i] && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          const bool ok = (meta >> i) & 1u;
           float4 a0 = v0[i], a1 = v1[i];
           a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
           a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
@@ -262,6 +292,12 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
       }
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
       const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+      if (t == 0) {   // this stage's weight tile (hi + lo) through the bulk-copy engine
+        const uint32_t bar = smem_u32(&bar_full[s]);
+        mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
+        bulk_g2s(a_lo + A_TILE_BYTES, reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)(meta >> 16) * (2 * B_TILE_BYTES),
+                 2 * B_TILE_BYTES, bar);
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = rbase + 32 * i;
@@ -278,183 +314,205 @@ __global__ void __launch_bounds__(UTHREADS, 1) conv_umma_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));   // one arrival per loader warp
     };
-    // two chunks of loads are always in flight per thread (register double buffering)
-    int lr = 0, lsx = 0, lcc = 0;    // coordinates of the next chunk to load
-    int fr = 0, fsx = 0, fcc = 0;    // coordinates of the next chunk to finish
-    int s = 0;
-    uint32_t ph = 0;
-    auto adv = [&](int& r, int& sx, int& cc) { if (++cc == a.cchunks) { cc = 0; if (++sx == p.S) { sx = 0; ++r; } } };
-    float4 A0[4], A1[4], B0[4], B1[4];
-    issue(A0, A1, lr, lsx, lcc); adv(lr, lsx, lcc);
-    for (int kc = 0; kc < a.nchunks; kc += 2) {
-      if (kc + 1 < a.nchunks) { issue(B0, B1, lr, lsx, lcc); adv(lr, lsx, lcc); }
-      finish(A0, A1, fr, fsx, fcc, s, ph); adv(fr, fsx, fcc);
-      if (++s == STAGES) { s = 0; ph ^= 1u; }
-      if (kc + 1 < a.nchunks) {
-        if (kc + 2 < a.nchunks) { issue(A0, A1, lr, lsx, lcc); adv(lr, lsx, lcc); }
-        finish(B0, B1, fr, fsx, fcc, s, ph); adv(fr, fsx, fcc);
+    int my_tiles = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
+    const int total_chunks = my_tiles * a.nchunks;
+    if (total_chunks > 0) {
+      set_tile(l_tile);
+      int s = 0;
+      uint32_t ph = 0;
+      float4 A0[4], A1[4], B0[4], B1[4];
+      uint32_t metaA, metaB = 0;
+      metaA = issue(A0, A1);
+      for (int q = 0; q < total_chunks; q += 2) {       // two chunks of loads in flight per thread
+        if (q + 1 < total_chunks) metaB = issue(B0, B1);
+        finish(A0, A1, metaA, s, ph);
         if (++s == STAGES) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else if (lane == 0) {
-    // =============================================================== control thread: B bulk copies + MMA issue
-    const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)ntile * a.nchunks * (2 * B_TILE_BYTES);
-    constexpr uint32_t idesc = umma_idesc_bf16(UM, NT);
-    const int pre = a.nchunks < STAGES ? a.nchunks : STAGES;
-    for (int kc = 0; kc < pre; ++kc) {                       // prologue: fill the ring with weight tiles
-      const uint32_t bar = smem_u32(&bar_full[kc]);
-      mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
-      bulk_g2s(smem_base + kc * STAGE_BYTES + 2 * A_TILE_BYTES, wimg + (size_t)kc * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
-    }
-    for (int kc = 0; kc < a.nchunks; ++kc) {
-      const int s = kc % STAGES;
-      const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-      mbar_wait(smem_u32(&bar_full[s]), ph);
-      tc_fence_after();
-      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-      const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
-#pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t aa = term == 2 ? a_lo : a_hi;
-        const uint32_t bb = term == 1 ? b_lo : b_hi;
-#pragma unroll
-        for (int k4 = 0; k4 < UKC / 16; ++k4) {
-          umma_bf16(tmem_base, umma_desc_k128(aa + k4 * 32), umma_desc_k128(bb + k4 * 32), idesc,
-                    (kc > 0 || term > 0 || k4 > 0) ? 1u : 0u);
+        if (q + 1 < total_chunks) {
+          if (q + 2 < total_chunks) metaA = issue(A0, A1);
+          finish(B0, B1, metaB, s, ph);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
-      umma_commit(smem_u32(&bar_empty[s]));                  // frees this stage when the MMAs above retire
-      // refill the stage of the PREVIOUS chunk (its MMAs retire while this chunk's run) with the weights of chunk kc-1+STAGES
-      const int pj = kc - 1, nk = pj + STAGES;
-      if (pj >= 0 && nk < a.nchunks) {
-        const int ps = pj % STAGES;
-        mbar_wait(smem_u32(&bar_empty[ps]), (uint32_t)(pj / STAGES) & 1u);
-        const uint32_t bar = smem_u32(&bar_full[ps]);
-        mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
-        bulk_g2s(smem_base + ps * STAGE_BYTES + 2 * A_TILE_BYTES, wimg + (size_t)nk * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+    }
+  } else if (warp == ULOAD_WARPS) {
+    // =============================================================== control thread: MMA issue
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(UM, NT);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        mbar_wait(smem_u32(&bar_acc_empty[b]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * NT);
+        for (int kc = 0; kc < a.nchunks; ++kc) {
+          mbar_wait(smem_u32(&bar_full[s]), ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t aa = term == 2 ? a_lo : a_hi;
+            const uint32_t bb = term == 1 ? b_lo : b_hi;
+#pragma unroll
+            for (int k4 = 0; k4 < UKC / 16; ++k4) {
+              umma_bf16(d_tmem, umma_desc_k128(aa + k4 * 32), umma_desc_k128(bb + k4 * 32), idesc,
+                        (kc > 0 || term > 0 || k4 > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&bar_empty[s]));                // frees this stage when the MMAs above retire
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(smem_u32(&bar_acc_full[b]));               // accumulator of this tile complete
       }
     }
-    umma_commit(smem_u32(&bar_acc));
-  }
-
-  // =============================================================== epilogue (warps 0..3: TMEM lane quarter = warp)
-  if (warp < 4) {
-    mbar_wait(smem_u32(&bar_acc), 0);
-    tc_fence_after();
-    const int64_t m = m0 + warp * 32 + lane;
-    const bool mv = m < a.M;
-    int n = 0, oy = 0, ox = 0;
-    if (mv) {
-      n = (int)(m / OHW);
-      const int rem = (int)(m - (int64_t)n * OHW);
-      oy = rem / p.OW;
-      ox = rem - oy * p.OW;
-    }
-    const int cbase = ntile * NT;
+  } else {
+    // =============================================================== epilogue warps (TMEM lane quarter = warp & 3)
+    const int quarter = warp & 3;
     const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
-#pragma unroll 1
-    for (int g = 0; g < NT / 32; ++g) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32), v);
-      const int c0 = cbase + g * 32;
-      if (c0 >= p.Cout) break;
-      const int nvalid = p.Cout - c0 < 32 ? p.Cout - c0 : 32;
-      const bool full = nvalid == 32;
-      // ---- alpha, bias
-      if (p.bias) {
-        if (full) {
+    float acc1[NT / 32], acc2[NT / 32];     // running per-channel sums of this lane's column (BatchNorm statistics)
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 b = ld4(p.bias + c0 + 4 * q);
-            v[4 * q] = fmaf(v[4 * q], p.alpha, b.x); v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, b.y);
-            v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, b.z); v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, b.w);
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 32; ++u) v[u] = fmaf(v[u], p.alpha, u < nvalid ? __ldg(p.bias + c0 + u) : 0.f);
-        }
-      } else if (p.alpha != 1.f) {
-#pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] *= p.alpha;
-      }
-      // ---- activation (uniform switch hoisted out of the element loop)
-      if (p.act == FDG_ACT_RELU) {
-#pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] = fmaxf(v[u], 0.f);
-      } else if (p.act == FDG_ACT_TANH) {
-#pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] = tanhf(v[u]);
-      } else if (p.act == FDG_ACT_SIGMOID) {
-#pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] = 1.f / (1.f + expf(-v[u]));
-      }
-      // ---- ReLU / LeakyReLU backward mask from a second tensor
-      if (p.e.p && mv) {
-        const float* ep = p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + (int64_t)c0 * p.e.sc;
-        if (evec && full) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 ev = ld4(ep + 4 * q);
-            v[4 * q] *= ev.x > 0.f ? 1.f : p.eslope; v[4 * q + 1] *= ev.y > 0.f ? 1.f : p.eslope;
-            v[4 * q + 2] *= ev.z > 0.f ? 1.f : p.eslope; v[4 * q + 3] *= ev.w > 0.f ? 1.f : p.eslope;
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 32; ++u)
-            if (u < nvalid) v[u] *= __ldg(ep + (int64_t)u * p.e.sc) > 0.f ? 1.f : p.eslope;
-        }
-      }
-      if (!mv || !full) {
-#pragma unroll
-        for (int u = 0; u < 32; ++u) if (!mv || u >= nvalid) v[u] = 0.f;
-      }
+    for (int g = 0; g < NT / 32; ++g) { acc1[g] = 0.f; acc2[g] = 0.f; }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile % m_tiles, ntile = tile / m_tiles;
+      const int b = it & 1;
+      mbar_wait(smem_u32(&bar_acc_full[b]), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      const int64_t m = (int64_t)mt * UM + quarter * 32 + lane;
+      const bool mv = m < a.M;
+      int n = 0, oy = 0, ox = 0;
       if (mv) {
-        const int reps = p.store == FDG_STORE_UP2 ? 4 : 1;
-        for (int d = 0; d < reps; ++d) {
-          const int yy = p.store == FDG_STORE_UP2 ? 2 * oy + (d >> 1) : oy, xx = p.store == FDG_STORE_UP2 ? 2 * ox + (d & 1) : ox;
-          float* yp = p.y.p + n * p.y.sn + (int64_t)yy * p.y.sh + (int64_t)xx * p.y.sw + (int64_t)c0 * p.y.sc;
-          if (a.yvec && full) {
-            if (p.store == FDG_STORE_ACCUM) {
+        n = (int)(m / OHW);
+        const int rem = (int)(m - (int64_t)n * OHW);
+        oy = rem / p.OW;
+        ox = rem - oy * p.OW;
+      }
+      const int cbase = ntile * NT;
+#pragma unroll
+      for (int g = 0; g < NT / 32; ++g) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * NT + g * 32), v);
+        const int c0 = cbase + g * 32;
+        if (c0 < p.Cout) {
+          const int nvalid = p.Cout - c0 < 32 ? p.Cout - c0 : 32;
+          const bool full = nvalid == 32;
+          // ---- alpha, bias
+          if (p.bias) {
+            if (full) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const float4 old = *reinterpret_cast<const float4*>(yp + 4 * q);
-                *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q] + old.x, v[4 * q + 1] + old.y, v[4 * q + 2] + old.z, v[4 * q + 3] + old.w);
+                const float4 bb = ld4(p.bias + c0 + 4 * q);
+                v[4 * q] = fmaf(v[4 * q], p.alpha, bb.x); v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, bb.y);
+                v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, bb.z); v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, bb.w);
               }
             } else {
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int u = 0; u < 32; ++u) v[u] = fmaf(v[u], p.alpha, u < nvalid ? __ldg(p.bias + c0 + u) : 0.f);
             }
-          } else {
+          } else if (p.alpha != 1.f) {
 #pragma unroll
-            for (int u = 0; u < 32; ++u)
-              if (u < nvalid) {
-                float* q1 = yp + (int64_t)u * p.y.sc;
-                *q1 = p.store == FDG_STORE_ACCUM ? *q1 + v[u] : v[u];
+            for (int u = 0; u < 32; ++u) v[u] *= p.alpha;
+          }
+          // ---- activation (uniform switch hoisted out of the element loop)
+          if (p.act == FDG_ACT_RELU) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = fmaxf(v[u], 0.f);
+          } else if (p.act == FDG_ACT_TANH) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = tanhf(v[u]);
+          } else if (p.act == FDG_ACT_SIGMOID) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = 1.f / (1.f + expf(-v[u]));
+          }
+          // ---- ReLU / LeakyReLU backward mask from a second tensor
+          if (p.e.p && mv) {
+            const float* ep = p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + (int64_t)c0 * p.e.sc;
+            if (evec && full) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 ev = ld4(ep + 4 * q);
+                v[4 * q] *= ev.x > 0.f ? 1.f : p.eslope; v[4 * q + 1] *= ev.y > 0.f ? 1.f : p.eslope;
+                v[4 * q + 2] *= ev.z > 0.f ? 1.f : p.eslope; v[4 * q + 3] *= ev.w > 0.f ? 1.f : p.eslope;
               }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 32; ++u)
+                if (u < nvalid) v[u] *= __ldg(ep + (int64_t)u * p.e.sc) > 0.f ? 1.f : p.eslope;
+            }
+          }
+          if (!mv || !full) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) if (!mv || u >= nvalid) v[u] = 0.f;
+          }
+          if (mv) {
+            const int reps = p.store == FDG_STORE_UP2 ? 4 : 1;
+            for (int d = 0; d < reps; ++d) {
+              const int yy = p.store == FDG_STORE_UP2 ? 2 * oy + (d >> 1) : oy, xx = p.store == FDG_STORE_UP2 ? 2 * ox + (d & 1) : ox;
+              float* yp = p.y.p + n * p.y.sn + (int64_t)yy * p.y.sh + (int64_t)xx * p.y.sw + (int64_t)c0 * p.y.sc;
+              if (a.yvec && full) {
+                if (p.store == FDG_STORE_ACCUM) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 old = *reinterpret_cast<const float4*>(yp + 4 * q);
+                    *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q] + old.x, v[4 * q + 1] + old.y, v[4 * q + 2] + old.z, v[4 * q + 3] + old.w);
+                  }
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int u = 0; u < 32; ++u)
+                  if (u < nvalid) {
+                    float* q1 = yp + (int64_t)u * p.y.sc;
+                    *q1 = p.store == FDG_STORE_ACCUM ? *q1 + v[u] : v[u];
+                  }
+              }
+            }
+          }
+          if (p.stats) {
+            float sq[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) sq[u] = v[u] * v[u];
+            acc1[g] += butterfly_colsum(v, lane);
+            acc2[g] += butterfly_colsum(sq, lane);
           }
         }
       }
+      // release the accumulator buffer to the MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));
+      // statistics are per output-channel tile: flush when the next tile of this CTA belongs to another one
       if (p.stats) {
-        float sq[32];
+        const int next = tile + gridDim.x;
+        if (next >= total_tiles || next / m_tiles != ntile) {
 #pragma unroll
-        for (int u = 0; u < 32; ++u) sq[u] = v[u] * v[u];
-        const float s1 = butterfly_colsum(v, lane);
-        const float s2 = butterfly_colsum(sq, lane);
-        sred[0][warp][g * 32 + lane] = s1;      // per-warp partial column sums, combined after the barrier
-        sred[1][warp][g * 32 + lane] = s2;
+          for (int g = 0; g < NT / 32; ++g) {
+            sred[0][quarter][g * 32 + lane] = acc1[g];
+            sred[1][quarter][g * 32 + lane] = acc2[g];
+            acc1[g] = 0.f; acc2[g] = 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
+          const int et = t - UEPI_WARP0 * 32;
+          for (int cidx = et; cidx < NT; cidx += 128) {
+            const int c = ntile * NT + cidx;
+            if (c < p.Cout) {
+              atomicAdd(p.stats + c, (double)((sred[0][0][cidx] + sred[0][1][cidx]) + (sred[0][2][cidx] + sred[0][3][cidx])));
+              atomicAdd(p.stats + p.stats_ld + c, (double)((sred[1][0][cidx] + sred[1][1][cidx]) + (sred[1][2][cidx] + sred[1][3][cidx])));
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
       }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
-  if (p.stats && t < NT) {
-    const int c = ntile * NT + t;
-    if (c < p.Cout) {
-      atomicAdd(p.stats + c, (double)((sred[0][0][t] + sred[0][1][t]) + (sred[0][2][t] + sred[0][3][t])));
-      atomicAdd(p.stats + p.stats_ld + c, (double)((sred[1][0][t] + sred[1][1][t]) + (sred[1][2][t] + sred[1][3][t])));
-    }
-  }
   if (warp == ULOAD_WARPS) {
     __syncwarp();
     tc_fence_after();
@@ -520,11 +578,18 @@ static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
     }
     attr_done = true;
   }
-  dim3 grid((unsigned)cdiv64(a.M, UM), (unsigned)cdiv(a.c.Cout, NT));
+  const int64_t tiles = cdiv64(a.M, UM) * cdiv(a.c.Cout, NT);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));
   const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
   ProfScope prof(PF_CONV_UMMA, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  conv_umma_kernel<NT, STAGES><<<grid, UTHREADS, smem, st>>>(a);
+  conv_umma_kernel<NT, STAGES><<<grid, UTHREADS_P, smem, st>>>(a);
   return check_launch("fdg_conv2d[tcgen05]");
 }
 
