@@ -179,6 +179,11 @@ __global__ void colsum_kernel(FdgTensor x, int64_t M, int HW, int W, int C, floa
 
 }  // namespace fdg
 
+namespace fdg {
+int wgrad_umma_supported(const FdgWgrad* p);
+int wgrad_umma(const FdgWgrad* p, cudaStream_t st);
+}  // namespace fdg
+
 using namespace fdg;
 
 extern "C" int fdg_colsum(const FdgTensor* x, int N, int H, int W, int C, float* out, int accumulate,
@@ -205,6 +210,16 @@ extern "C" int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream) {
   FDG_REQUIRE(!p->transposed || (p->R == 1 && p->S == 1), "fdg_conv2d_wgrad: transposed layout is 1x1 only");
   FDG_REQUIRE(!p->has_affine || (p->scale && p->shift), "fdg_conv2d_wgrad: affine prologue without scale/shift");
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->impl != 1) {
+    const int ok = wgrad_umma_supported(p);
+    if (p->impl == 2 && !ok) { set_error("fdg_conv2d_wgrad: impl=tcgen05 requested but shape/layout unsupported"); return FDG_ENOSUPPORT; }
+    if (ok) {
+      const int rc = wgrad_umma(p, st);
+      if (rc != FDG_OK) return rc;
+      if (p->dbias) return fdg_colsum(&p->g, p->N, p->OH, p->OW, p->Cout, p->dbias, 1, stream);
+      return FDG_OK;
+    }
+  }
   WgradArgs a;
   a.c = *p;
   a.ao = AOp{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};

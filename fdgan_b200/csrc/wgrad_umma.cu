@@ -1,0 +1,308 @@
+// fdg_conv2d_wgrad, tcgen05 path:  dW[k][co] += sum_pixels a[pixel][k] * g[pixel][co]
+//
+// GEMM with the PIXEL index as the contraction dimension.  One CTA owns a (filter tap, 128-channel block,
+// NT-wide output-channel tile) of dW and a contiguous range of pixels (split-K over pixels across CTAs); it keeps
+// the fp32 [128 x NT] partial result in TMEM for its whole lifetime and adds it to global memory once at the end.
+//   * A operand = the conv input after the consumer prologue (BatchNorm scale/shift + ReLU/LeakyReLU, pooled /
+//     upsampled gather, zero padding), B operand = the output gradient; both are fp32 NHWC in HBM, channel-
+//     contiguous, i.e. MN-major for this GEMM, so the loaders store [pixel][64 channels] rows of 128 bytes into the
+//     canonical MN-major SWIZZLE_128B layout and the MMA runs with a_major = b_major = MN.
+//   * bf16 hi/lo split of both operands, three MMAs per 16-pixel slice (hi*hi + hi*lo + lo*hi), fp32 accumulate.
+//   * 16 loader warps with a two-chunk register double buffer keep global loads in flight; one thread issues
+//     tcgen05.mma; mbarrier ring of STAGES chunks of 64 pixels.
+#include "aop.cuh"
+#include "umma.cuh"
+
+namespace fdg {
+
+constexpr int WU_K = 128;                 // channel rows per tile (MMA M)
+constexpr int WU_P = 64;                  // pixels per chunk
+constexpr int WU_LOAD_WARPS = 16;
+constexpr int WU_THREADS = (WU_LOAD_WARPS + 1) * 32;
+constexpr int WU_BLK = WU_P * 128;        // one [64 pixels x 64 channels] bf16 block = 8 KB
+constexpr int WU_A_BYTES = 2 * WU_BLK;    // 128 channels = two blocks
+
+struct WUArgs {
+  FdgWgrad c;
+  AOp ao;
+  int64_t M;
+  int cblocks;       // ceil(Cin / 128)
+  int co_tiles;      // ceil(Cout / NT)
+  int tiles;         // taps * cblocks * co_tiles
+  int64_t m_per_split;
+};
+
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs a) {
+  constexpr int G_BYTES = (NT / 64) * WU_BLK;
+  constexpr int STAGE_BYTES = 2 * WU_A_BYTES + 2 * G_BYTES;
+  constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+  constexpr int GQ = NT / 64;             // 8-channel gradient chunks per loader thread
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t tmem_base_s;
+
+  const FdgWgrad& p = a.c;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int tile = blockIdx.x % a.tiles, split = blockIdx.x / a.tiles;
+  const int cot = tile % a.co_tiles;
+  const int cb = (tile / a.co_tiles) % a.cblocks;
+  const int tap = tile / (a.co_tiles * a.cblocks);
+  const int fr = tap / p.S, fs = tap - fr * p.S;
+  const int64_t mbeg = (int64_t)split * a.m_per_split;
+  const int64_t mend = mbeg + a.m_per_split < a.M ? mbeg + a.m_per_split : a.M;
+  const int nchunks = mbeg < mend ? (int)((mend - mbeg + WU_P - 1) / WU_P) : 0;
+  const int OHW = p.OH * p.OW;
+
+  if (t == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), WU_LOAD_WARPS);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_acc), 1);
+    fence_barrier_init();
+  }
+  if (warp == WU_LOAD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < WU_LOAD_WARPS && nchunks > 0) {
+    // =============================================================== loaders
+    // thread: pixel row pr of the chunk; 8-channel chunks seg and seg+8 of the A block pair; gradient chunks seg + 8q
+    const int pr = t >> 3, seg = t & 7;
+    const bool direct = p.gather == FDG_GATHER_DIRECT;
+    // running pixel coordinates of (chunk base + pr)
+    int pn, poy, pox;
+    {
+      const int64_t m = mbeg + pr;
+      const int64_t mm = m < a.M ? m : 0;
+      pn = (int)(mm / OHW);
+      const int rem = (int)(mm - (int64_t)pn * OHW);
+      poy = rem / p.OW;
+      pox = rem - poy * p.OW;
+    }
+    int64_t lm = mbeg + pr;        // pixel index of the next chunk to load
+    const int ca0 = cb * WU_K + seg * 8, ca1 = ca0 + 64;     // A channels of this thread
+    const int cg0 = cot * NT + seg * 8;                       // first gradient channel of this thread
+
+    auto issue = [&](float4 (&av)[4], float4 (&gv)[2 * GQ]) -> uint32_t {
+      uint32_t ok = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 2 * GQ; ++i) gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lm < mend) {
+        const int iy = poy * p.stride - p.pad + fr, ix = pox * p.stride - p.pad + fs;
+        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          if (direct) {
+            const float* xp = p.x.p + pn * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw;
+            if (ca0 < p.Cin) { av[0] = ld4(xp + ca0); av[1] = ld4(xp + ca0 + 4); ok |= 1u; }
+            if (ca1 < p.Cin) { av[2] = ld4(xp + ca1); av[3] = ld4(xp + ca1 + 4); ok |= 2u; }
+          } else {
+            if (ca0 < p.Cin) { av[0] = fetch4(a.ao, pn, iy, ix, ca0); av[1] = fetch4(a.ao, pn, iy, ix, ca0 + 4); ok |= 1u; }
+            if (ca1 < p.Cin) { av[2] = fetch4(a.ao, pn, iy, ix, ca1); av[3] = fetch4(a.ao, pn, iy, ix, ca1 + 4); ok |= 2u; }
+          }
+        }
+        const float* gp = p.g.p + pn * p.g.sn + (int64_t)poy * p.g.sh + (int64_t)pox * p.g.sw;
+#pragma unroll
+        for (int q = 0; q < GQ; ++q) {
+          const int c = cg0 + 64 * q;
+          if (c < p.Cout) { gv[2 * q] = ld4(gp + c); gv[2 * q + 1] = ld4(gp + c + 4); }
+        }
+      }
+      // advance the pixel cursor by one chunk
+      lm += WU_P;
+      pox += WU_P;
+      while (pox >= p.OW) { pox -= p.OW; if (++poy == p.OH) { poy = 0; ++pn; } }
+      return ok;
+    };
+    auto finish = [&](float4 (&av)[4], float4 (&gv)[2 * GQ], uint32_t ok, int s, uint32_t ph) {
+      if (direct) {
+        const float sl = p.slope;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = h ? ca1 : ca0;
+          if ((ok >> h) & 1u) {
+            float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+            if (p.has_affine) {
+              sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
+              sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
+            }
+            float4& a0 = av[2 * h];
+            float4& a1 = av[2 * h + 1];
+            a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
+            a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
+            a1.x = prologue_act(fmaf(a1.x, sc1.x, sh1.x), sl); a1.y = prologue_act(fmaf(a1.y, sc1.y, sh1.y), sl);
+            a1.z = prologue_act(fmaf(a1.z, sc1.z, sh1.z), sl); a1.w = prologue_act(fmaf(a1.w, sc1.w, sh1.w), sl);
+          }
+        }
+      }
+      mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + WU_A_BYTES;
+      const uint32_t g_hi = a_lo + WU_A_BYTES, g_lo = g_hi + G_BYTES;
+      const uint32_t roff = (uint32_t)pr * 128u + (uint32_t)((seg ^ (pr & 7)) << 4);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t hi[4], lo[4];
+        split2(av[2 * h].x, av[2 * h].y, hi[0], lo[0]);
+        split2(av[2 * h].z, av[2 * h].w, hi[1], lo[1]);
+        split2(av[2 * h + 1].x, av[2 * h + 1].y, hi[2], lo[2]);
+        split2(av[2 * h + 1].z, av[2 * h + 1].w, hi[3], lo[3]);
+        const uint32_t off = (uint32_t)h * WU_BLK + roff;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+      }
+#pragma unroll
+      for (int q = 0; q < GQ; ++q) {
+        uint32_t hi[4], lo[4];
+        split2(gv[2 * q].x, gv[2 * q].y, hi[0], lo[0]);
+        split2(gv[2 * q].z, gv[2 * q].w, hi[1], lo[1]);
+        split2(gv[2 * q + 1].x, gv[2 * q + 1].y, hi[2], lo[2]);
+        split2(gv[2 * q + 1].z, gv[2 * q + 1].w, hi[3], lo[3]);
+        const uint32_t off = (uint32_t)q * WU_BLK + roff;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+    };
+
+    int s = 0;
+    uint32_t ph = 0;
+    float4 A0[4], G0[2 * GQ], A1[4], G1[2 * GQ];
+    uint32_t ok0, ok1 = 0;
+    ok0 = issue(A0, G0);
+    for (int q = 0; q < nchunks; q += 2) {
+      if (q + 1 < nchunks) ok1 = issue(A1, G1);
+      finish(A0, G0, ok0, s, ph);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+      if (q + 1 < nchunks) {
+        if (q + 2 < nchunks) ok0 = issue(A0, G0);
+        finish(A1, G1, ok1, s, ph);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
+    // =============================================================== MMA issue
+    constexpr uint32_t idesc = umma_idesc_bf16_mn(WU_K, NT);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kc = 0; kc < nchunks; ++kc) {
+      mbar_wait(smem_u32(&bar_full[s]), ph);
+      tc_fence_after();
+      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + WU_A_BYTES;
+      const uint32_t g_hi = a_lo + WU_A_BYTES, g_lo = g_hi + G_BYTES;
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t aa = term == 2 ? a_lo : a_hi;
+        const uint32_t gg = term == 1 ? g_lo : g_hi;
+#pragma unroll
+        for (int k16 = 0; k16 < WU_P / 16; ++k16) {
+          // 16 pixels = two 8-row swizzle atoms (SBO 1024 B); 64-channel blocks are WU_BLK bytes apart (LBO)
+          umma_bf16(tmem_base, umma_desc_mn128(aa + k16 * 2048, WU_BLK, 1024), umma_desc_mn128(gg + k16 * 2048, WU_BLK, 1024), idesc,
+                    (kc > 0 || term > 0 || k16 > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(smem_u32(&bar_empty[s]));
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    umma_commit(smem_u32(&bar_acc));
+  }
+
+  // =============================================================== epilogue: TMEM -> atomicAdd into the parameter layout
+  if (warp < 4 && nchunks > 0) {
+    mbar_wait(smem_u32(&bar_acc), 0);
+    tc_fence_after();
+    const int ci = cb * WU_K + warp * 32 + lane;
+    const int RS = p.R * p.S;
+#pragma unroll 1
+    for (int g = 0; g < NT / 32; ++g) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32), v);
+      if (ci < p.Cin) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const int co = cot * NT + g * 32 + u;
+          if (co < p.Cout) {
+            const int64_t idx = p.transposed ? (int64_t)ci * p.Cout + co : ((int64_t)co * p.Cin + ci) * RS + tap;
+            atomicAdd(p.dw + idx, v[u]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == WU_LOAD_WARPS) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+static inline int wu_ntile(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256); }
+
+int wgrad_umma_supported(const FdgWgrad* p) {
+  if (p->Cin % 8 != 0 || p->Cin < 32 || p->Cout % 8 != 0 || p->Cout < 16) return 0;
+  AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
+  if (!aop_vec_ok(ao, p->Cin)) return 0;
+  if (!vec4_ok(p->g)) return 0;
+  return 1;
+}
+
+template <int NT, int STAGES>
+static int launch_wu(WUArgs& a, cudaStream_t st) {
+  constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * (NT / 64) * WU_BLK) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("fdg_conv2d_wgrad[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
+      return FDG_ECUDA;
+    }
+    attr_done = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  a.co_tiles = cdiv(a.c.Cout, NT);
+  a.tiles = a.c.R * a.c.S * a.cblocks * a.co_tiles;
+  // split the pixels so that about one wave of CTAs covers the chip; every split is a whole number of chunks
+  int64_t splits = a.tiles >= num_sms ? 1 : num_sms / a.tiles;
+  const int64_t max_splits = cdiv64(a.M, 4 * WU_P);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  a.m_per_split = cdiv64(cdiv64(a.M, splits), WU_P) * WU_P;
+  splits = cdiv64(a.M, a.m_per_split);
+  ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
+                 4.0 * ((double)a.M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
+  wgrad_umma_kernel<NT, STAGES><<<(unsigned)(a.tiles * splits), WU_THREADS, smem, st>>>(a);
+  return check_launch("fdg_conv2d_wgrad[tcgen05]");
+}
+
+int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
+  WUArgs a;
+  a.c = *p;
+  a.ao = AOp{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
+  a.M = (int64_t)p->N * p->OH * p->OW;
+  a.cblocks = cdiv(p->Cin, WU_K);
+  switch (wu_ntile(p->Cout)) {
+    case 64: return launch_wu<64, 4>(a, st);      // 4 x 48 KB
+    case 128: return launch_wu<128, 3>(a, st);    // 3 x 64 KB
+    default: return launch_wu<256, 2>(a, st);     // 2 x 96 KB
+  }
+}
+
+}  // namespace fdg

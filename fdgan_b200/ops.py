@@ -119,7 +119,7 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
 
 
 def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scale=None, shift=None, slope=1.0,
-          transposed=False, dbias=None):
+          transposed=False, dbias=None, impl=None):
     """fdg_conv2d_wgrad: dw (+)= A^T g in the parameter's own layout (dw must be pre-zeroed or accumulating).
     ``dw is None`` (frozen parameter) skips the launch."""
     if dw is None:
@@ -135,7 +135,8 @@ def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scal
     if (g.N, g.H, g.W) != (x.N, OH, OW):
         raise ValueError("wgrad: gradient view %s does not match output extent %s" % ((g.N, g.H, g.W), (x.N, OH, OW)))
     d = L.FdgWgrad(x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
-                   g.ft(), R, S, stride, pad, g.C, OH, OW, _ptr(dw), 1 if transposed else 0, _ptr(dbias))
+                   g.ft(), R, S, stride, pad, g.C, OH, OW, _ptr(dw), 1 if transposed else 0, _ptr(dbias),
+                   (IMPL_AUTO if USE_UMMA else IMPL_SIMT) if impl is None else impl)
     L.check(L.lib.fdg_conv2d_wgrad(_byref(d), _stream()), "conv2d_wgrad")
 
 

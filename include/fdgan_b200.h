@@ -116,6 +116,7 @@ typedef struct FdgWgrad {
   float* dw;
   int transposed;
   float* dbias;         /* [Cout] (+)= sum_pixels g, or NULL */
+  int impl;             /* 0 auto, 1 force SIMT fp32, 2 force tcgen05 (error if unsupported) */
 } FdgWgrad;
 
 int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream);

@@ -148,13 +148,22 @@ WGRAD_CASES = [
     (9, 36, 4, 2, 1, 16, 14, 0, False, 1.0, False, False),
     (144, 288, 4, 1, 1, 7, 7, 0, True, 0.2, False, False),
     (160, 130, 3, 1, 1, 5, 6, 0, False, 1.0, False, True),
+    (160, 136, 3, 1, 1, 9, 11, 0, False, 1.0, False, True),      # two channel blocks (padded), two co tiles at NT=128? (136 -> NT 256)
+    (64, 32, 1, 1, 0, 40, 24, 1, False, 1.0, False, True),       # conv_refin2 (avg-pool gather), many pixel chunks
+    (1024, 256, 3, 1, 1, 6, 5, 0, False, 0.0, False, False),     # dense_block4.conv2
+    (512, 64, 1, 1, 0, 12, 12, 0, False, 0.0, True, False),      # trans_block5 (ConvTranspose layout)
+    (128, 32, 3, 1, 1, 33, 29, 0, True, 0.0, False, False),      # K1 with ragged pixel count
 ]
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
-def test_wgrad(case):
+@pytest.mark.parametrize("variant", ["simt", "tcgen05"])
+def test_wgrad(case, variant):
     ops = _ops()
     Cin, Cout, R, stride, pad, H, W, gather, affine, slope, transposed, dbias = case
+    if variant == "tcgen05" and not (Cin % 8 == 0 and Cin >= 32 and Cout % 8 == 0 and Cout >= 16):
+        pytest.skip("shape not covered by the tcgen05 weight-gradient path (runs on the SIMT kernel)")
+    impl = ops.IMPL_UMMA if variant == "tcgen05" else ops.IMPL_SIMT
     N = 3
     ph, pw = (2 * H, 2 * W) if gather == 1 else (H, W)
     x = seeded((N, Cin, ph, pw), 1, -1, 1).double()
@@ -176,7 +185,7 @@ def test_wgrad(case):
     xd = x.float().cuda() if nchw_small else cl(x.float())
     ops.wgrad(ops.View.from_nchw(xd), ops.View.from_nchw(cl(g.float())), R, R, stride, pad, dw, gather=gather,
               scale=sc.float().cuda() if affine else None, shift=sh.float().cuda() if affine else None, slope=slope,
-              transposed=transposed, dbias=db)
+              transposed=transposed, dbias=db, impl=impl)
     assert maxabs(dw, want) <= 2e-4 * max(1.0, float(want.abs().max()))
     if dbias:
         assert maxabs(db, g.sum((0, 2, 3))) <= 1e-3
