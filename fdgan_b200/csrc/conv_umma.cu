@@ -24,7 +24,7 @@ namespace fdg {
 
 constexpr int UM = 128;          // pixels per tile (UMMA M)
 constexpr int UKC = 64;          // K elements per chunk (128 B of bf16 = one swizzle row)
-constexpr int ULOAD_WARPS = 8;
+constexpr int ULOAD_WARPS = 16;
 constexpr int UTHREADS = (ULOAD_WARPS + 1) * 32;   // + 1 control warp (MMA issue, B bulk copies, TMEM alloc)
 constexpr int A_TILE_BYTES = UM * 128;             // one bf16 [128 x 64] tile
 
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sred[2][4][NT];
+  __shared__ float ep_tile[4][32][33];     // per-epilogue-warp transpose tile for the BatchNorm statistics
 
   const FdgConv& p = a.c;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -115,21 +116,23 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
 
   if (warp < ULOAD_WARPS) {
     // =============================================================== A loaders
-    // thread handles the 16-byte bf16 chunk j (8 channels) of rows rbase + 32*i, i = 0..3
+    // thread handles the 16-byte bf16 chunk j (8 channels) of rows rbase + 64*i, i = 0..1
+    constexpr int RPT = UM * 8 / (ULOAD_WARPS * 32);   // rows per thread
+    constexpr int RSTEP = ULOAD_WARPS * 4;             // row stride between them
     const int j = t & 7, rbase = t >> 3;
     const bool direct = p.gather == FDG_GATHER_DIRECT;
     // ---- load cursor: (tile, chunk) of the next chunk to fetch, with the tile's pixel coordinates
     int l_tile = blockIdx.x, l_kc = 0, l_r = 0, l_sx = 0, l_cc = 0, l_nt = 0;
-    int pn[4], piy[4], pix[4];
-    const float* rowp[4];
+    int pn[RPT], piy[RPT], pix[RPT];
+    const float* rowp[RPT];
     uint32_t pvmask = 0;
     auto set_tile = [&](int tile) {
       const int mt = tile % m_tiles;
       l_nt = tile / m_tiles;
       pvmask = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t m = (int64_t)mt * UM + rbase + 32 * i;
+      for (int i = 0; i < RPT; ++i) {
+        const int64_t m = (int64_t)mt * UM + rbase + RSTEP * i;
         const bool v = m < a.M;
         pvmask |= (v ? 1u : 0u) << i;
         const int64_t mm = v ? m : 0;
@@ -144,13 +147,13 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     // issue the global loads of the cursor's chunk into registers (raw values for the direct gather; the pooled /
     // upsampled gathers apply the prologue inside fetch4 because it has to precede the averaging); returns metadata
     // (bits 0..3 in-range mask, bits 8.. channel-chunk index, bits 16.. weight-tile index) and advances the cursor
-    auto issue = [&](float4 (&v0)[4], float4 (&v1)[4]) -> uint32_t {
+    auto issue = [&](float4 (&v0)[RPT], float4 (&v1)[RPT]) -> uint32_t {
       const int c = l_cc * UKC + j * 8;
       const bool cvalid = c < p.Cin;
       const int64_t toff = (int64_t)l_r * p.x.sh + (int64_t)l_sx * p.x.sw + l_cc * UKC;
       uint32_t ok = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RPT; ++i) {
         const int iy = piy[i] + l_r, ix = pix[i] + l_sx;
         v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         v1[i] = v0[i];
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       return meta;
     };
     // prologue (direct gather), bf16 hi/lo split and swizzled store of one K chunk into stage s
-    auto finish = [&](float4 (&v0)[4], float4 (&v1)[4], uint32_t meta, int s, uint32_t ph) {
+    auto finish = [&](float4 (&v0)[RPT], float4 (&v1)[RPT], uint32_t meta, int s, uint32_t ph) {
       if (direct) {
         const int c = (int)((meta >> 8) & 0xffu) * UKC + j * 8;
         float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
         }
         const float sl = p.slope;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RPT; ++i) {
           const bool ok = (meta >> i) & 1u;
           float4 a0 = v0[i], a1 = v1[i];
           a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
@@ -205,8 +208,8 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
                  2 * B_TILE_BYTES, bar);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = rbase + 32 * i;
+      for (int i = 0; i < RPT; ++i) {
+        const int row = rbase + RSTEP * i;
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
         uint32_t h[4], l[4];
         split2(v0[i].x, v0[i].y, h[0], l[0]);
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       set_tile(l_tile);
       int s = 0;
       uint32_t ph = 0;
-      float4 A0[4], A1[4], B0[4], B1[4];
+      float4 A0[RPT], A1[RPT], B0[RPT], B1[RPT];
       uint32_t metaA, metaB = 0;
       metaA = issue(A0, A1);
       for (int q = 0; q < total_chunks; q += 2) {       // two chunks of loads in flight per thread
@@ -381,11 +384,20 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
             }
           }
           if (p.stats) {
-            float sq[32];
+            // column sums through a padded shared-memory transpose: lane l ends up with the sums of column l
 #pragma unroll
-            for (int u = 0; u < 32; ++u) sq[u] = v[u] * v[u];
-            acc1[g] += butterfly_colsum(v, lane);
-            acc2[g] += butterfly_colsum(sq, lane);
+            for (int u = 0; u < 32; ++u) ep_tile[quarter][u][lane] = v[u];
+            __syncwarp();
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const float xv = ep_tile[quarter][lane][rr];
+              s1 += xv;
+              s2 = fmaf(xv, xv, s2);
+            }
+            __syncwarp();
+            acc1[g] += s1;
+            acc2[g] += s2;
           }
         }
       }

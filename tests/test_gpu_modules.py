@@ -30,8 +30,8 @@ def conv_path(request):
     ops.USE_UMMA = old
 
 
-def gtol(path, base=3e-2):
-    return dict(rel_l2=base * (2.0 if path.startswith("tcgen05") else 1.0), rel_max=0.25 * (2.0 if path.startswith("tcgen05") else 1.0))
+def gtol(path, base=5e-2):
+    return dict(rel_l2=base * (1.6 if path.startswith("tcgen05") else 1.0), rel_max=0.3 * (1.6 if path.startswith("tcgen05") else 1.0))
 
 
 def _fdgan(seed=0):
@@ -54,7 +54,7 @@ def test_fdgan_matches_reference_golden(batch, tag, conv_path):
     (y * r).sum().backward()
     params = dict(net.named_parameters())
     # gradients: the reference's own fp32/fp64 runs differ by ~1 % of max (ReLU-mask flips; tests/util.py:grad_close)
-    grad_close(x.grad, g["dx"], "dx", **gtol(conv_path, 1e-2 if (batch == 1 and conv_path == "simt_fp32") else 3e-2))
+    grad_close(x.grad, g["dx"], "dx", **gtol(conv_path, 1e-2 if (batch == 1 and conv_path == "simt_fp32") else 5e-2))
     for k in G_GRAD_KEYS:
         assert_sample_grad_close(params[k].grad, g["grad:" + k], k, **gtol(conv_path))
     sd = net.state_dict()
