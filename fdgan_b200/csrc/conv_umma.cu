@@ -24,7 +24,7 @@ namespace fdg {
 
 constexpr int UM = 128;          // pixels per tile (UMMA M)
 constexpr int UKC = 64;          // K elements per chunk (128 B of bf16 = one swizzle row)
-constexpr int ULOAD_WARPS = 16;
+constexpr int ULOAD_WARPS = 8;
 constexpr int UTHREADS = (ULOAD_WARPS + 1) * 32;   // + 1 control warp (MMA issue, B bulk copies, TMEM alloc)
 constexpr int A_TILE_BYTES = UM * 128;             // one bf16 [128 x 64] tile
 
@@ -71,10 +71,13 @@ __device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
 constexpr int UEPI_WARP0 = ULOAD_WARPS + 1;
 constexpr int UTHREADS_P = (ULOAD_WARPS + 1 + 4) * 32;
 
-template <int NT, int STAGES>
+// DEPTH > 0: the loaders fetch through cp.async into a thread-private shared-memory staging ring (DEPTH chunks in
+// flight, no registers tied up by loads in flight); DEPTH == 0: two-chunk register double buffer.
+template <int NT, int STAGES, int DEPTH>
 __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int STAGING_BYTES = UM * UKC * 4;          // one raw fp32 chunk
   constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
@@ -230,17 +233,86 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       set_tile(l_tile);
       int s = 0;
       uint32_t ph = 0;
-      float4 A0[RPT], A1[RPT], B0[RPT], B1[RPT];
-      uint32_t metaA, metaB = 0;
-      metaA = issue(A0, A1);
-      for (int q = 0; q < total_chunks; q += 2) {       // two chunks of loads in flight per thread
-        if (q + 1 < total_chunks) metaB = issue(B0, B1);
-        finish(A0, A1, metaA, s, ph);
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
-        if (q + 1 < total_chunks) {
-          if (q + 2 < total_chunks) metaA = issue(A0, A1);
-          finish(B0, B1, metaB, s, ph);
+      if (DEPTH > 0) {
+        // ---- cp.async staging: slot d of this thread = RPT rows x 32 bytes, laid out [d][row i][thread]
+        constexpr int NLT = ULOAD_WARPS * 32;
+        const uint32_t stg = smem_base + STAGES * STAGE_BYTES + (uint32_t)t * 32u;
+        __shared__ uint32_t meta_s[DEPTH > 0 ? DEPTH : 1][ULOAD_WARPS * 32];
+        auto issue_async = [&](int d) {
+          const int c = l_cc * UKC + j * 8;
+          const bool cvalid = c < p.Cin;
+          const int64_t toff = (int64_t)l_r * p.x.sh + (int64_t)l_sx * p.x.sw + l_cc * UKC;
+          uint32_t ok = 0;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int iy = piy[i] + l_r, ix = pix[i] + l_sx;
+            const bool v = ((pvmask >> i) & 1u) && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            const uint32_t dst = stg + (uint32_t)((d * RPT + i) * NLT) * 32u;
+            if (direct) {
+              if (v) {
+                ok |= 1u << i;
+                const float* src = rowp[i] + toff;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 4) : "memory");
+              }
+            } else {
+              float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+              if (v) { ok |= 1u << i; f0 = fetch4(a.ao, pn[i], iy, ix, c); f1 = fetch4(a.ao, pn[i], iy, ix, c + 4); }
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f0.x), "f"(f0.y), "f"(f0.z), "f"(f0.w) : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
+            }
+          }
+          meta_s[d][t] = ok | ((uint32_t)l_cc << 8) | ((uint32_t)(l_nt * a.nchunks + l_kc) << 16);
+          if (++l_cc == a.cchunks) { l_cc = 0; if (++l_sx == p.S) { l_sx = 0; ++l_r; } }
+          if (++l_kc == a.nchunks) {
+            l_kc = 0; l_r = 0; l_sx = 0; l_cc = 0;
+            l_tile += gridDim.x;
+            if (l_tile < total_tiles) set_tile(l_tile);
+          }
+        };
+        int dl = 0, df = 0;     // staging slots of the next chunk to load / to finish
+#pragma unroll 1
+        for (int q = 0; q < DEPTH - 1; ++q) {
+          if (q < total_chunks) issue_async(dl);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (++dl == DEPTH) dl = 0;
+        }
+#pragma unroll 1
+        for (int q = 0; q < total_chunks; ++q) {
+          if (q + DEPTH - 1 < total_chunks) issue_async(dl);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (++dl == DEPTH) dl = 0;
+          asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");
+          const uint32_t meta = meta_s[df][t];
+          float4 v0[RPT], v1[RPT];
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const uint32_t src = stg + (uint32_t)((df * RPT + i) * NLT) * 32u;
+            if ((meta >> i) & 1u) {
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0[i].x), "=f"(v0[i].y), "=f"(v0[i].z), "=f"(v0[i].w) : "r"(src) : "memory");
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1[i].x), "=f"(v1[i].y), "=f"(v1[i].z), "=f"(v1[i].w) : "r"(src + 16) : "memory");
+            } else {
+              v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              v1[i] = v0[i];
+            }
+          }
+          finish(v0, v1, meta, s, ph);
+          if (++df == DEPTH) df = 0;
           if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      } else {
+        float4 A0[RPT], A1[RPT], B0[RPT], B1[RPT];
+        uint32_t metaA, metaB = 0;
+        metaA = issue(A0, A1);
+        for (int q = 0; q < total_chunks; q += 2) {       // two chunks of loads in flight per thread
+          if (q + 1 < total_chunks) metaB = issue(B0, B1);
+          finish(A0, A1, metaA, s, ph);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          if (q + 1 < total_chunks) {
+            if (q + 2 < total_chunks) metaA = issue(A0, A1);
+            finish(B0, B1, metaB, s, ph);
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
         }
       }
     }
@@ -485,12 +557,12 @@ int conv2d_umma_supported(const FdgConv* p) {
   return 1;
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int DEPTH>
 static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + 1024;
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + DEPTH * (UM * UKC * 4) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -507,7 +579,7 @@ static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
   ProfScope prof(PF_CONV_UMMA, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  conv_umma_kernel<NT, STAGES><<<grid, UTHREADS_P, smem, st>>>(a);
+  conv_umma_kernel<NT, STAGES, DEPTH><<<grid, UTHREADS_P, smem, st>>>(a);
   return check_launch("fdg_conv2d[tcgen05]");
 }
 
@@ -520,10 +592,10 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
   a.nchunks = p->R * p->S * a.cchunks;
   a.yvec = vec4_ok(p->y);
   switch (umma_ntile(p->Cout)) {
-    case 32: return launch_umma<32, 5>(a, st);    // 5 x 40 KB
-    case 64: return launch_umma<64, 4>(a, st);    // 4 x 48 KB
-    case 128: return launch_umma<128, 3>(a, st);
-    default: return launch_umma<256, 2>(a, st);
+    case 32: return launch_umma<32, 2, 3>(a, st);     // ring 2 x 40 KB + staging 3 x 32 KB
+    case 64: return launch_umma<64, 2, 3>(a, st);     // ring 2 x 48 KB + staging 3 x 32 KB
+    case 128: return launch_umma<128, 2, 2>(a, st);   // ring 2 x 64 KB + staging 2 x 32 KB
+    default: return launch_umma<256, 2, 0>(a, st);    // ring 2 x 96 KB, register double buffer
   }
 }
 
