@@ -27,6 +27,7 @@ constexpr int UKC = 64;          // K elements per chunk (128 B of bf16 = one sw
 constexpr int ULOAD_WARPS = 8;
 constexpr int UTHREADS = (ULOAD_WARPS + 1) * 32;   // + 1 control warp (MMA issue, B bulk copies, TMEM alloc)
 constexpr int A_TILE_BYTES = UM * 128;             // one bf16 [128 x 64] tile
+constexpr int UMAX_AFF = 1024;                     // input channels whose scale/shift are cached in shared memory
 
 struct UmmaArgs {
   FdgConv c;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   __shared__ uint32_t tmem_base_s;
   __shared__ float sred[2][4][NT];
   __shared__ float ep_tile[4][32][33];     // per-epilogue-warp transpose tile for the BatchNorm statistics
+  __shared__ __align__(16) float aff_s[2][UMAX_AFF];   // BatchNorm scale / shift of the input channels (when they fit)
 
   const FdgConv& p = a.c;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -111,6 +113,10 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const bool aff_smem = p.has_affine && p.Cin <= UMAX_AFF;
+  if (aff_smem) {
+    for (int i = t; i < p.Cin; i += UTHREADS_P) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
   }
   tc_fence_before();
   __syncthreads();
@@ -184,22 +190,43 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     auto finish = [&](float4 (&v0)[RPT], float4 (&v1)[RPT], uint32_t meta, int s, uint32_t ph) {
       if (direct) {
         const int c = (int)((meta >> 8) & 0xffu) * UKC + j * 8;
-        float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
-        if (p.has_affine && c < p.Cin) {
-          sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
-          sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
-        }
         const float sl = p.slope;
+        if (p.has_affine) {
+          float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+          if (c < p.Cin) {
+            if (aff_smem) {
+              sc0 = *reinterpret_cast<const float4*>(&aff_s[0][c]); sc1 = *reinterpret_cast<const float4*>(&aff_s[0][c + 4]);
+              sh0 = *reinterpret_cast<const float4*>(&aff_s[1][c]); sh1 = *reinterpret_cast<const float4*>(&aff_s[1][c + 4]);
+            } else {
+              sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
+              sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
+            }
+          }
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const bool ok = (meta >> i) & 1u;
-          float4 a0 = v0[i], a1 = v1[i];
-          a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
-          a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
-          a1.x = prologue_act(fmaf(a1.x, sc1.x, sh1.x), sl); a1.y = prologue_act(fmaf(a1.y, sc1.y, sh1.y), sl);
-          a1.z = prologue_act(fmaf(a1.z, sc1.z, sh1.z), sl); a1.w = prologue_act(fmaf(a1.w, sc1.w, sh1.w), sl);
-          v0[i] = ok ? a0 : make_float4(0.f, 0.f, 0.f, 0.f);     // zero padding is applied AFTER the prologue
-          v1[i] = ok ? a1 : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < RPT; ++i) {
+            v0[i].x = fmaf(v0[i].x, sc0.x, sh0.x); v0[i].y = fmaf(v0[i].y, sc0.y, sh0.y);
+            v0[i].z = fmaf(v0[i].z, sc0.z, sh0.z); v0[i].w = fmaf(v0[i].w, sc0.w, sh0.w);
+            v1[i].x = fmaf(v1[i].x, sc1.x, sh1.x); v1[i].y = fmaf(v1[i].y, sc1.y, sh1.y);
+            v1[i].z = fmaf(v1[i].z, sc1.z, sh1.z); v1[i].w = fmaf(v1[i].w, sc1.w, sh1.w);
+          }
+        }
+        if (sl == 0.f) {            // ReLU
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            v0[i].x = fmaxf(v0[i].x, 0.f); v0[i].y = fmaxf(v0[i].y, 0.f); v0[i].z = fmaxf(v0[i].z, 0.f); v0[i].w = fmaxf(v0[i].w, 0.f);
+            v1[i].x = fmaxf(v1[i].x, 0.f); v1[i].y = fmaxf(v1[i].y, 0.f); v1[i].z = fmaxf(v1[i].z, 0.f); v1[i].w = fmaxf(v1[i].w, 0.f);
+          }
+        } else if (sl != 1.f) {     // LeakyReLU
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            v0[i].x = prologue_act(v0[i].x, sl); v0[i].y = prologue_act(v0[i].y, sl); v0[i].z = prologue_act(v0[i].z, sl); v0[i].w = prologue_act(v0[i].w, sl);
+            v1[i].x = prologue_act(v1[i].x, sl); v1[i].y = prologue_act(v1[i].y, sl); v1[i].z = prologue_act(v1[i].z, sl); v1[i].w = prologue_act(v1[i].w, sl);
+          }
+        }
+        if (p.has_affine) {         // zero padding is applied AFTER the prologue (a shifted zero is not zero)
+#pragma unroll
+          for (int i = 0; i < RPT; ++i)
+            if (!((meta >> i) & 1u)) { v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i]; }
         }
       }
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
