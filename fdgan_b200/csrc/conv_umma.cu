@@ -578,7 +578,7 @@ static inline int umma_ntile(int Cout) { return Cout <= 32 ? 32 : (Cout <= 64 ? 
 
 int conv2d_umma_supported(const FdgConv* p) {
   if (!p->w_umma) return 0;
-  if (p->Cin % 8 != 0 || p->Cin < 32 || p->Cout < 16) return 0;
+  if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
   AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   if (!aop_vec_ok(ao, p->Cin)) return 0;
   return 1;

@@ -30,9 +30,12 @@ struct WUArgs {
   int co_tiles;      // ceil(Cout / NT)
   int tiles;         // taps * cblocks * co_tiles
   int64_t m_per_split;
+  int gvec;          // gradient rows loadable as float4 (unit channel stride, aligned, Cout % 8 == 0)
 };
 
-template <int NT, int STAGES>
+// DEPTH > 0: loads go through cp.async into a thread-private staging ring (DEPTH chunks in flight);
+// DEPTH == 0: two-chunk register double buffer.
+template <int NT, int STAGES, int DEPTH>
 __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs a) {
   constexpr int G_BYTES = (NT / 64) * WU_BLK;
   constexpr int STAGE_BYTES = 2 * WU_A_BYTES + 2 * G_BYTES;
@@ -93,6 +96,17 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
     int64_t lm = mbeg + pr;        // pixel index of the next chunk to load
     const int ca0 = cb * WU_K + seg * 8, ca1 = ca0 + 64;     // A channels of this thread
     const int cg0 = cot * NT + seg * 8;                       // first gradient channel of this thread
+    // BatchNorm scale/shift of this thread's 16 input channels (constant for the whole kernel)
+    float4 scv[4], shv[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = h ? ca1 : ca0;
+      const bool v = p.has_affine && c < p.Cin;
+      scv[2 * h] = v ? ld4(p.scale + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      scv[2 * h + 1] = v ? ld4(p.scale + c + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+      shv[2 * h] = v ? ld4(p.shift + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      shv[2 * h + 1] = v ? ld4(p.shift + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     auto issue = [&](float4 (&av)[4], float4 (&gv)[2 * GQ]) -> uint32_t {
       uint32_t ok = 0;
@@ -116,7 +130,16 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
 #pragma unroll
         for (int q = 0; q < GQ; ++q) {
           const int c = cg0 + 64 * q;
-          if (c < p.Cout) { gv[2 * q] = ld4(gp + c); gv[2 * q + 1] = ld4(gp + c + 4); }
+          if (c < p.Cout) {
+            if (a.gvec) { gv[2 * q] = ld4(gp + c); gv[2 * q + 1] = ld4(gp + c + 4); }
+            else {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = c + e < p.Cout ? __ldg(gp + (int64_t)(c + e) * p.g.sc) : 0.f;
+              gv[2 * q] = make_float4(f[0], f[1], f[2], f[3]);
+              gv[2 * q + 1] = make_float4(f[4], f[5], f[6], f[7]);
+            }
+          }
         }
       }
       // advance the pixel cursor by one chunk
@@ -130,13 +153,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
         const float sl = p.slope;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int c = h ? ca1 : ca0;
           if ((ok >> h) & 1u) {
-            float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
-            if (p.has_affine) {
-              sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
-              sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
-            }
+            const float4 sc0 = scv[2 * h], sc1 = scv[2 * h + 1], sh0 = shv[2 * h], sh1 = shv[2 * h + 1];
             float4& a0 = av[2 * h];
             float4& a1 = av[2 * h + 1];
             a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
@@ -179,17 +197,111 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
 
     int s = 0;
     uint32_t ph = 0;
-    float4 A0[4], G0[2 * GQ], A1[4], G1[2 * GQ];
-    uint32_t ok0, ok1 = 0;
-    ok0 = issue(A0, G0);
-    for (int q = 0; q < nchunks; q += 2) {
-      if (q + 1 < nchunks) ok1 = issue(A1, G1);
-      finish(A0, G0, ok0, s, ph);
-      if (++s == STAGES) { s = 0; ph ^= 1u; }
-      if (q + 1 < nchunks) {
-        if (q + 2 < nchunks) ok0 = issue(A0, G0);
-        finish(A1, G1, ok1, s, ph);
+    if (DEPTH > 0) {
+      constexpr int NLT = WU_LOAD_WARPS * 32;
+      constexpr int PIECES = 4 + 2 * GQ;       // 16-byte pieces per thread per chunk
+      const uint32_t stg = smem_base + STAGES * STAGE_BYTES + (uint32_t)t * 16u;
+      __shared__ uint32_t meta_s[DEPTH > 0 ? DEPTH : 1][WU_LOAD_WARPS * 32];
+      auto slot = [&](int d, int k) -> uint32_t { return stg + (uint32_t)((d * PIECES + k) * NLT) * 16u; };
+      auto issue_async = [&](int d) {
+        uint32_t ok = 0;
+        if (lm < mend) {
+          const int iy = poy * p.stride - p.pad + fr, ix = pox * p.stride - p.pad + fs;
+          if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+            if (direct) {
+              const float* xp = p.x.p + pn * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw;
+              if (ca0 < p.Cin) {
+                ok |= 1u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 0)), "l"(xp + ca0) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 1)), "l"(xp + ca0 + 4) : "memory");
+              }
+              if (ca1 < p.Cin) {
+                ok |= 2u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 2)), "l"(xp + ca1) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 3)), "l"(xp + ca1 + 4) : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int c = h ? ca1 : ca0;
+                if (c < p.Cin) {
+                  ok |= 1u << h;
+                  const float4 f0 = fetch4(a.ao, pn, iy, ix, c), f1 = fetch4(a.ao, pn, iy, ix, c + 4);
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 2 * h)), "f"(f0.x), "f"(f0.y), "f"(f0.z), "f"(f0.w) : "memory");
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 2 * h + 1)), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
+                }
+              }
+            }
+          }
+          const float* gp = p.g.p + pn * p.g.sn + (int64_t)poy * p.g.sh + (int64_t)pox * p.g.sw;
+#pragma unroll
+          for (int q = 0; q < GQ; ++q) {
+            const int c = cg0 + 64 * q;
+            if (c < p.Cout) {
+              ok |= 4u << q;
+              if (a.gvec) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 4 + 2 * q)), "l"(gp + c) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 5 + 2 * q)), "l"(gp + c + 4) : "memory");
+              } else {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = c + e < p.Cout ? __ldg(gp + (int64_t)(c + e) * p.g.sc) : 0.f;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 4 + 2 * q)), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 5 + 2 * q)), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+              }
+            }
+          }
+        }
+        meta_s[d][t] = ok;
+        lm += WU_P;
+        pox += WU_P;
+        while (pox >= p.OW) { pox -= p.OW; if (++poy == p.OH) { poy = 0; ++pn; } }
+      };
+      auto lds4 = [&](uint32_t addr) -> float4 {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+        return v;
+      };
+      int dl = 0, df = 0;
+#pragma unroll 1
+      for (int q = 0; q < DEPTH - 1; ++q) {
+        if (q < nchunks) issue_async(dl);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++dl == DEPTH) dl = 0;
+      }
+#pragma unroll 1
+      for (int q = 0; q < nchunks; ++q) {
+        if (q + DEPTH - 1 < nchunks) issue_async(dl);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++dl == DEPTH) dl = 0;
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");
+        const uint32_t ok = meta_s[df][t];
+        float4 av[4], gv[2 * GQ];
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        av[0] = (ok & 1u) ? lds4(slot(df, 0)) : z4; av[1] = (ok & 1u) ? lds4(slot(df, 1)) : z4;
+        av[2] = (ok & 2u) ? lds4(slot(df, 2)) : z4; av[3] = (ok & 2u) ? lds4(slot(df, 3)) : z4;
+#pragma unroll
+        for (int g = 0; g < GQ; ++g) {
+          gv[2 * g] = (ok & (4u << g)) ? lds4(slot(df, 4 + 2 * g)) : z4;
+          gv[2 * g + 1] = (ok & (4u << g)) ? lds4(slot(df, 5 + 2 * g)) : z4;
+        }
+        finish(av, gv, ok & 3u, s, ph);
+        if (++df == DEPTH) df = 0;
         if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    } else {
+      float4 A0[4], G0[2 * GQ], A1[4], G1[2 * GQ];
+      uint32_t ok0, ok1 = 0;
+      ok0 = issue(A0, G0);
+      for (int q = 0; q < nchunks; q += 2) {
+        if (q + 1 < nchunks) ok1 = issue(A1, G1);
+        finish(A0, G0, ok0, s, ph);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        if (q + 1 < nchunks) {
+          if (q + 2 < nchunks) ok0 = issue(A0, G0);
+          finish(A1, G1, ok1, s, ph);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
@@ -253,19 +365,18 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
 static inline int wu_ntile(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256); }
 
 int wgrad_umma_supported(const FdgWgrad* p) {
-  if (p->Cin % 8 != 0 || p->Cin < 32 || p->Cout % 8 != 0 || p->Cout < 16) return 0;
+  if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
   AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   if (!aop_vec_ok(ao, p->Cin)) return 0;
-  if (!vec4_ok(p->g)) return 0;
   return 1;
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, int DEPTH>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * (NT / 64) * WU_BLK) + 1024;
+  constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * (NT / 64) * WU_BLK) + DEPTH * (WU_LOAD_WARPS * 32) * (4 + 2 * (NT / 64)) * 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d_wgrad[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -288,7 +399,7 @@ static int launch_wu(WUArgs& a, cudaStream_t st) {
   splits = cdiv64(a.M, a.m_per_split);
   ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  wgrad_umma_kernel<NT, STAGES><<<(unsigned)(a.tiles * splits), WU_THREADS, smem, st>>>(a);
+  wgrad_umma_kernel<NT, STAGES, DEPTH><<<(unsigned)(a.tiles * splits), WU_THREADS, smem, st>>>(a);
   return check_launch("fdg_conv2d_wgrad[tcgen05]");
 }
 
@@ -298,10 +409,11 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   a.ao = AOp{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   a.M = (int64_t)p->N * p->OH * p->OW;
   a.cblocks = cdiv(p->Cin, WU_K);
+  a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   switch (wu_ntile(p->Cout)) {
-    case 64: return launch_wu<64, 4>(a, st);      // 4 x 48 KB
-    case 128: return launch_wu<128, 3>(a, st);    // 3 x 64 KB
-    default: return launch_wu<256, 2>(a, st);     // 2 x 96 KB
+    case 64: return launch_wu<64, 2, 2>(a, st);      // ring 2 x 48 KB + staging 2 x 48 KB
+    case 128: return launch_wu<128, 1, 2>(a, st);    // ring 64 KB + staging 2 x 64 KB
+    default: return launch_wu<256, 2, 0>(a, st);     // ring 2 x 96 KB, register double buffer
   }
 }
 

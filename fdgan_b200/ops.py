@@ -80,7 +80,7 @@ USE_UMMA = True
 
 
 def umma_eligible(x: View, Cout: int) -> bool:
-    return (x.C % 8 == 0 and x.C >= 32 and Cout >= 16 and x.sc == 1 and x.ptr % 16 == 0 and x.sn % 4 == 0 and
+    return (x.C % 8 == 0 and x.C >= 16 and Cout >= 1 and x.sc == 1 and x.ptr % 16 == 0 and x.sn % 4 == 0 and
             x.sh % 4 == 0 and x.sw % 4 == 0)
 
 
