@@ -17,6 +17,8 @@
 //   releases the smem stage / publishes the accumulator.  Epilogue warps read TMEM with tcgen05.ld
 //   (32x32b.x32), apply alpha/bias/activation/mask, reduce the per-channel BatchNorm statistics with a
 //   butterfly of warp shuffles and store 128-bit rows.
+#include <cstdlib>
+
 #include "aop.cuh"
 #include "umma.cuh"
 
@@ -574,7 +576,11 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, int ld, int taps, 
   }
 }
 
-static inline int umma_ntile(int Cout) { return Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256)); }
+static inline int umma_ntile(int Cout) {
+  static const int cap = [] { const char* e = getenv("FDG_UMMA_NT_CAP"); return e ? atoi(e) : 128; }();
+  const int nt = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+  return nt > cap ? cap : nt;
+}
 
 int conv2d_umma_supported(const FdgConv* p) {
   if (!p->w_umma) return 0;

@@ -10,6 +10,8 @@
 //   * bf16 hi/lo split of both operands, three MMAs per 16-pixel slice (hi*hi + hi*lo + lo*hi), fp32 accumulate.
 //   * 16 loader warps with a two-chunk register double buffer keep global loads in flight; one thread issues
 //     tcgen05.mma; mbarrier ring of STAGES chunks of 64 pixels.
+#include <cstdlib>
+
 #include "aop.cuh"
 #include "umma.cuh"
 
@@ -26,9 +28,9 @@ struct WUArgs {
   FdgWgrad c;
   AOp ao;
   int64_t M;
-  int cblocks;       // ceil(Cin / 128)
+  int kblocks;       // ceil(R*S*Cin / 128): blocks of the flattened (tap, channel) index
   int co_tiles;      // ceil(Cout / NT)
-  int tiles;         // taps * cblocks * co_tiles
+  int tiles;         // kblocks * co_tiles
   int64_t m_per_split;
   int gvec;          // gradient rows loadable as float4 (unit channel stride, aligned, Cout % 8 == 0)
 };
@@ -52,9 +54,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int tile = blockIdx.x % a.tiles, split = blockIdx.x / a.tiles;
   const int cot = tile % a.co_tiles;
-  const int cb = (tile / a.co_tiles) % a.cblocks;
-  const int tap = tile / (a.co_tiles * a.cblocks);
-  const int fr = tap / p.S, fs = tap - fr * p.S;
+  const int kb = tile / a.co_tiles;
+  const int Ktot = p.R * p.S * p.Cin;
   const int64_t mbeg = (int64_t)split * a.m_per_split;
   const int64_t mend = mbeg + a.m_per_split < a.M ? mbeg + a.m_per_split : a.M;
   const int nchunks = mbeg < mend ? (int)((mend - mbeg + WU_P - 1) / WU_P) : 0;
@@ -94,7 +95,12 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       pox = rem - poy * p.OW;
     }
     int64_t lm = mbeg + pr;        // pixel index of the next chunk to load
-    const int ca0 = cb * WU_K + seg * 8, ca1 = ca0 + 64;     // A channels of this thread
+    // this thread's two 8-channel A chunks in the flattened k = tap*Cin + ci index (Cin % 8 == 0: a chunk never
+    // straddles a tap); each has its own filter tap, i.e. its own shifted source pixel
+    const int k0 = kb * WU_K + seg * 8, k1 = k0 + 64;
+    const int tap0 = k0 < Ktot ? k0 / p.Cin : 0, tap1 = k1 < Ktot ? k1 / p.Cin : 0;
+    const int ca0 = k0 < Ktot ? k0 - tap0 * p.Cin : p.Cin, ca1 = k1 < Ktot ? k1 - tap1 * p.Cin : p.Cin;   // >= Cin: chunk is padding
+    const int fr0 = tap0 / p.S, fs0 = tap0 - fr0 * p.S, fr1 = tap1 / p.S, fs1 = tap1 - fr1 * p.S;
     const int cg0 = cot * NT + seg * 8;                       // first gradient channel of this thread
     // BatchNorm scale/shift of this thread's 16 input channels (constant for the whole kernel)
     float4 scv[4], shv[4];
@@ -115,15 +121,18 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
 #pragma unroll
       for (int i = 0; i < 2 * GQ; ++i) gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (lm < mend) {
-        const int iy = poy * p.stride - p.pad + fr, ix = pox * p.stride - p.pad + fs;
-        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-          if (direct) {
-            const float* xp = p.x.p + pn * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw;
-            if (ca0 < p.Cin) { av[0] = ld4(xp + ca0); av[1] = ld4(xp + ca0 + 4); ok |= 1u; }
-            if (ca1 < p.Cin) { av[2] = ld4(xp + ca1); av[3] = ld4(xp + ca1 + 4); ok |= 2u; }
-          } else {
-            if (ca0 < p.Cin) { av[0] = fetch4(a.ao, pn, iy, ix, ca0); av[1] = fetch4(a.ao, pn, iy, ix, ca0 + 4); ok |= 1u; }
-            if (ca1 < p.Cin) { av[2] = fetch4(a.ao, pn, iy, ix, ca1); av[3] = fetch4(a.ao, pn, iy, ix, ca1 + 4); ok |= 2u; }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = h ? ca1 : ca0;
+          const int iy = poy * p.stride - p.pad + (h ? fr1 : fr0), ix = pox * p.stride - p.pad + (h ? fs1 : fs0);
+          if (c < p.Cin && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+            ok |= 1u << h;
+            if (direct) {
+              const float* xp = p.x.p + pn * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw + c;
+              av[2 * h] = ld4(xp); av[2 * h + 1] = ld4(xp + 4);
+            } else {
+              av[2 * h] = fetch4(a.ao, pn, iy, ix, c); av[2 * h + 1] = fetch4(a.ao, pn, iy, ix, c + 4);
+            }
           }
         }
         const float* gp = p.g.p + pn * p.g.sn + (int64_t)poy * p.g.sh + (int64_t)pox * p.g.sw;
@@ -206,30 +215,20 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       auto issue_async = [&](int d) {
         uint32_t ok = 0;
         if (lm < mend) {
-          const int iy = poy * p.stride - p.pad + fr, ix = pox * p.stride - p.pad + fs;
-          if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-            if (direct) {
-              const float* xp = p.x.p + pn * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw;
-              if (ca0 < p.Cin) {
-                ok |= 1u;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 0)), "l"(xp + ca0) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 1)), "l"(xp + ca0 + 4) : "memory");
-              }
-              if (ca1 < p.Cin) {
-                ok |= 2u;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 2)), "l"(xp + ca1) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 3)), "l"(xp + ca1 + 4) : "memory");
-              }
-            } else {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int c = h ? ca1 : ca0;
-                if (c < p.Cin) {
-                  ok |= 1u << h;
-                  const float4 f0 = fetch4(a.ao, pn, iy, ix, c), f1 = fetch4(a.ao, pn, iy, ix, c + 4);
-                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 2 * h)), "f"(f0.x), "f"(f0.y), "f"(f0.z), "f"(f0.w) : "memory");
-                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 2 * h + 1)), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
-                }
+          for (int h = 0; h < 2; ++h) {
+            const int c = h ? ca1 : ca0;
+            const int iy = poy * p.stride - p.pad + (h ? fr1 : fr0), ix = pox * p.stride - p.pad + (h ? fs1 : fs0);
+            if (c < p.Cin && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+              ok |= 1u << h;
+              if (direct) {
+                const float* xp = p.x.p + pn * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw + c;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 2 * h)), "l"(xp) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 2 * h + 1)), "l"(xp + 4) : "memory");
+              } else {
+                const float4 f0 = fetch4(a.ao, pn, iy, ix, c), f1 = fetch4(a.ao, pn, iy, ix, c + 4);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 2 * h)), "f"(f0.x), "f"(f0.y), "f"(f0.z), "f"(f0.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 2 * h + 1)), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
               }
             }
           }
@@ -335,13 +334,16 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   if (warp < 4 && nchunks > 0) {
     mbar_wait(smem_u32(&bar_acc), 0);
     tc_fence_after();
-    const int ci = cb * WU_K + warp * 32 + lane;
+    const int krow = kb * WU_K + warp * 32 + lane;
+    const bool kvalid = krow < Ktot;
+    const int tap = kvalid ? krow / p.Cin : 0;
+    const int ci = kvalid ? krow - tap * p.Cin : 0;
     const int RS = p.R * p.S;
 #pragma unroll 1
     for (int g = 0; g < NT / 32; ++g) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32), v);
-      if (ci < p.Cin) {
+      if (kvalid) {
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
           const int co = cot * NT + g * 32 + u;
@@ -362,7 +364,11 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   }
 }
 
-static inline int wu_ntile(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256); }
+static inline int wu_ntile(int Cout) {
+  static const int cap = [] { const char* e = getenv("FDG_WGRAD_NT_CAP"); return e ? atoi(e) : 128; }();
+  const int nt = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  return nt > cap ? cap : nt;
+}
 
 int wgrad_umma_supported(const FdgWgrad* p) {
   if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
@@ -389,7 +395,7 @@ static int launch_wu(WUArgs& a, cudaStream_t st) {
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
   a.co_tiles = cdiv(a.c.Cout, NT);
-  a.tiles = a.c.R * a.c.S * a.cblocks * a.co_tiles;
+  a.tiles = a.kblocks * a.co_tiles;
   // split the pixels so that about one wave of CTAs covers the chip; every split is a whole number of chunks
   int64_t splits = a.tiles >= num_sms ? 1 : num_sms / a.tiles;
   const int64_t max_splits = cdiv64(a.M, 4 * WU_P);
@@ -408,7 +414,7 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   a.c = *p;
   a.ao = AOp{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   a.M = (int64_t)p->N * p->OH * p->OW;
-  a.cblocks = cdiv(p->Cin, WU_K);
+  a.kblocks = cdiv(p->R * p->S * p->Cin, WU_K);
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   switch (wu_ntile(p->Cout)) {
     case 64: return launch_wu<64, 2, 2>(a, st);      // ring 2 x 48 KB + staging 2 x 48 KB
