@@ -132,6 +132,13 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     constexpr int RSTEP = ULOAD_WARPS * 4;             // row stride between them
     const int j = t & 7, rbase = t >> 3;
     const bool direct = p.gather == FDG_GATHER_DIRECT;
+    const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);   // 8 bytes per stage
+    const uint32_t aff0 = smem_u32(&aff_s[0][0]);
+    auto lds4u = [](uint32_t addr) -> float4 {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+      return v;
+    };
     // ---- load cursor: (tile, chunk) of the next chunk to fetch, with the tile's pixel coordinates
     int l_tile = blockIdx.x, l_kc = 0, l_r = 0, l_sx = 0, l_cc = 0, l_nt = 0;
     int pn[RPT], piy[RPT], pix[RPT];
@@ -197,8 +204,8 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
           float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
           if (c < p.Cin) {
             if (aff_smem) {
-              sc0 = *reinterpret_cast<const float4*>(&aff_s[0][c]); sc1 = *reinterpret_cast<const float4*>(&aff_s[0][c + 4]);
-              sh0 = *reinterpret_cast<const float4*>(&aff_s[1][c]); sh1 = *reinterpret_cast<const float4*>(&aff_s[1][c + 4]);
+              sc0 = lds4u(aff0 + c * 4); sc1 = lds4u(aff0 + c * 4 + 16);
+              sh0 = lds4u(aff0 + (UMAX_AFF + c) * 4); sh1 = lds4u(aff0 + (UMAX_AFF + c) * 4 + 16);
             } else {
               sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
               sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
@@ -231,10 +238,10 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
             if (!((meta >> i) & 1u)) { v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i]; }
         }
       }
-      mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+      mbar_wait(empty0 + s * 8, ph ^ 1u);
       const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
       if (t == 0) {   // this stage's weight tile (hi + lo) through the bulk-copy engine
-        const uint32_t bar = smem_u32(&bar_full[s]);
+        const uint32_t bar = full0 + s * 8;
         mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
         bulk_g2s(a_lo + A_TILE_BYTES, reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)(meta >> 16) * (2 * B_TILE_BYTES),
                  2 * B_TILE_BYTES, bar);
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       }
       fence_proxy_async();          // make this thread's generic-proxy stores visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));   // one arrival per loader warp
+      if (lane == 0) mbar_arrive(full0 + s * 8);   // one arrival per loader warp
     };
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
@@ -265,8 +272,9 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       if (DEPTH > 0) {
         // ---- cp.async staging: slot d of this thread = RPT rows x 32 bytes, laid out [d][row i][thread]
         constexpr int NLT = ULOAD_WARPS * 32;
-        const uint32_t stg = smem_base + STAGES * STAGE_BYTES + (uint32_t)t * 32u;
+        const uint32_t stg = smem_base + STAGES * STAGE_BYTES + (uint32_t)t * 16u;   // [slot][row][half][thread] x 16 B
         __shared__ uint32_t meta_s[DEPTH > 0 ? DEPTH : 1][ULOAD_WARPS * 32];
+        const uint32_t meta0 = smem_u32(&meta_s[0][0]) + (uint32_t)t * 4u;
         auto issue_async = [&](int d) {
           const int c = l_cc * UKC + j * 8;
           const bool cvalid = c < p.Cin;
@@ -276,22 +284,22 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
           for (int i = 0; i < RPT; ++i) {
             const int iy = piy[i] + l_r, ix = pix[i] + l_sx;
             const bool v = ((pvmask >> i) & 1u) && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-            const uint32_t dst = stg + (uint32_t)((d * RPT + i) * NLT) * 32u;
+            const uint32_t dst = stg + (uint32_t)((d * RPT + i) * 2 * NLT) * 16u;
             if (direct) {
               if (v) {
                 ok |= 1u << i;
                 const float* src = rowp[i] + toff;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 4) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + NLT * 16), "l"(src + 4) : "memory");
               }
             } else {
               float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
               if (v) { ok |= 1u << i; f0 = fetch4(a.ao, pn[i], iy, ix, c); f1 = fetch4(a.ao, pn[i], iy, ix, c + 4); }
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f0.x), "f"(f0.y), "f"(f0.z), "f"(f0.w) : "memory");
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + NLT * 16), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
             }
           }
-          meta_s[d][t] = ok | ((uint32_t)l_cc << 8) | ((uint32_t)(l_nt * a.nchunks + l_kc) << 16);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta0 + d * (NLT * 4)), "r"(ok | ((uint32_t)l_cc << 8) | ((uint32_t)(l_nt * a.nchunks + l_kc) << 16)) : "memory");
           if (++l_cc == a.cchunks) { l_cc = 0; if (++l_sx == p.S) { l_sx = 0; ++l_r; } }
           if (++l_kc == a.nchunks) {
             l_kc = 0; l_r = 0; l_sx = 0; l_cc = 0;
@@ -312,14 +320,15 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
           asm volatile("cp.async.commit_group;" ::: "memory");
           if (++dl == DEPTH) dl = 0;
           asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");
-          const uint32_t meta = meta_s[df][t];
+          uint32_t meta;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(meta) : "r"(meta0 + df * (NLT * 4)) : "memory");
           float4 v0[RPT], v1[RPT];
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
-            const uint32_t src = stg + (uint32_t)((df * RPT + i) * NLT) * 32u;
+            const uint32_t src = stg + (uint32_t)((df * RPT + i) * 2 * NLT) * 16u;
             if ((meta >> i) & 1u) {
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0[i].x), "=f"(v0[i].y), "=f"(v0[i].z), "=f"(v0[i].w) : "r"(src) : "memory");
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1[i].x), "=f"(v1[i].y), "=f"(v1[i].z), "=f"(v1[i].w) : "r"(src + 16) : "memory");
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1[i].x), "=f"(v1[i].y), "=f"(v1[i].z), "=f"(v1[i].w) : "r"(src + NLT * 16) : "memory");
             } else {
               v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               v1[i] = v0[i];
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mt = tile % m_tiles, ntile = tile / m_tiles;
       const int b = it & 1;
-      mbar_wait(smem_u32(&bar_acc_full[b]), ((uint32_t)it >> 1) & 1u);
+      while (!mbar_try_wait(smem_u32(&bar_acc_full[b]), ((uint32_t)it >> 1) & 1u)) __nanosleep(200);   // leave the issue slots to the loaders
       tc_fence_after();
       const int64_t m = (int64_t)mt * UM + quarter * 32 + lane;
       const bool mv = m < a.M;

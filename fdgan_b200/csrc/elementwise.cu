@@ -145,6 +145,91 @@ __global__ void __launch_bounds__(256) ew_bwd_kernel(FdgEwBwd p, int64_t M, int 
   }
 }
 
+// Fast path of ew_bwd: all views are pixel-linear (address = base + pixel * row stride + channel), 4 channels per
+// thread, four pixels per thread in flight per iteration (8 independent 128-bit loads).
+template <bool STATS>
+__global__ void __launch_bounds__(256) ew_bwd_linear_kernel(FdgEwBwd p, int64_t M, int cgroups, int pix_lanes) {
+  extern __shared__ float sm[];
+  const int cg = threadIdx.x % cgroups;
+  const int pl = threadIdx.x / cgroups;
+  const int c = (blockIdx.y * cgroups + cg) * 4;
+  const bool cv = c < p.C && pl < pix_lanes;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ca = sc, cb = sh, cd = sh;
+  if (cv) {
+    if (p.has_affine) { sc = *reinterpret_cast<const float4*>(p.scale + c); sh = *reinterpret_cast<const float4*>(p.shift + c); }
+    if (p.coef) {
+      ca = *reinterpret_cast<const float4*>(p.coef + c);
+      cb = *reinterpret_cast<const float4*>(p.coef + p.C + c);
+      cd = *reinterpret_cast<const float4*>(p.coef + 2 * p.C + c);
+    }
+  }
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const float gs = p.gscale, sl = p.slope;
+  if (cv) {
+    const int64_t step = (int64_t)gridDim.x * pix_lanes;
+    const float* gbase = p.g.p + c;
+    const float* xbase = p.x.p + c;
+    float* obase = p.out.p ? p.out.p + c : nullptr;
+    for (int64_t m0 = (int64_t)blockIdx.x * pix_lanes + pl; m0 < M; m0 += 4 * step) {
+      float4 gv[4], xv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t m = m0 + k * step;
+        if (m < M) {
+          gv[k] = *reinterpret_cast<const float4*>(gbase + m * p.g.sw);
+          xv[k] = __ldg(reinterpret_cast<const float4*>(xbase + m * p.x.sw));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t m = m0 + k * step;
+        if (m < M) {
+          float4 dz;
+          dz.x = gs * gv[k].x * (fmaf(xv[k].x, sc.x, sh.x) > 0.f ? 1.f : sl);
+          dz.y = gs * gv[k].y * (fmaf(xv[k].y, sc.y, sh.y) > 0.f ? 1.f : sl);
+          dz.z = gs * gv[k].z * (fmaf(xv[k].z, sc.z, sh.z) > 0.f ? 1.f : sl);
+          dz.w = gs * gv[k].w * (fmaf(xv[k].w, sc.w, sh.w) > 0.f ? 1.f : sl);
+          if (STATS) {
+            s1.x += dz.x; s1.y += dz.y; s1.z += dz.z; s1.w += dz.w;
+            s2.x = fmaf(dz.x, xv[k].x, s2.x); s2.y = fmaf(dz.y, xv[k].y, s2.y);
+            s2.z = fmaf(dz.z, xv[k].z, s2.z); s2.w = fmaf(dz.w, xv[k].w, s2.w);
+          } else {
+            float4 o;
+            o.x = fmaf(ca.x, dz.x, fmaf(cb.x, xv[k].x, cd.x)); o.y = fmaf(ca.y, dz.y, fmaf(cb.y, xv[k].y, cd.y));
+            o.z = fmaf(ca.z, dz.z, fmaf(cb.z, xv[k].z, cd.z)); o.w = fmaf(ca.w, dz.w, fmaf(cb.w, xv[k].w, cd.w));
+            float* op = obase + m * p.out.sw;
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(op);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(op) = o;
+          }
+        }
+      }
+    }
+  }
+  if (STATS) {
+    const int CW = cgroups * 4;
+    float* r1 = sm;
+    float* r2 = sm + pix_lanes * CW;
+    if (pl < pix_lanes) {
+      *reinterpret_cast<float4*>(&r1[pl * CW + cg * 4]) = s1;
+      *reinterpret_cast<float4*>(&r2[pl * CW + cg * 4]) = s2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CW; i += blockDim.x) {
+      const int cc = blockIdx.y * CW + i;
+      if (cc < p.C) {
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < pix_lanes; ++l) { a += r1[l * CW + i]; b += r2[l * CW + i]; }
+        atomicAdd(p.stats + cc, (double)a);
+        atomicAdd(p.stats + p.C + cc, (double)b);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ max pool 2x2
 __global__ void maxpool2_fwd_kernel(FdgTensor x, FdgTensor y, int64_t total, int OH, int OW, int C) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -370,7 +455,13 @@ int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
   dim3 grid((unsigned)gx, gy);
   ProfScope prof(PF_EW, 4.0 * (double)M * p->C, 4.0 * (double)M * p->C * (p->stats ? 2.0 : (p->accumulate ? 4.0 : 3.0)),
                  (cudaStream_t)stream);
-  if (vec) ew_bwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+  auto linear = [&](const FdgTensor& t) { return t.sh == (int64_t)p->W * t.sw && t.sn == (int64_t)p->H * t.sh; };
+  const bool fast = vec && p->g_gather == FDG_GATHER_DIRECT && linear(p->g) && linear(p->x) && (p->stats || linear(p->out)) &&
+                    (!p->has_affine || (aligned16(p->scale) && aligned16(p->shift))) && (!p->coef || (aligned16(p->coef) && p->C % 4 == 0));
+  if (fast) {
+    if (p->stats) ew_bwd_linear_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+    else ew_bwd_linear_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+  } else if (vec) ew_bwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   else ew_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   return check_launch("fdg_ew_bwd");
 }
