@@ -112,6 +112,7 @@ _SIGS = {
     "fdg_loss_grad": ([C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_profile_enable": ([C.c_int], C.c_int),
     "fdg_profile_collect": ([C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
+    "fdg_set_option": ([C.c_char_p, C.c_int], C.c_int),
     "fdg_last_error": ([], C.c_char_p),
     "fdg_version": ([], C.c_int),
     "fdg_launch_count": ([], C.c_int64),
@@ -147,3 +148,7 @@ def profile_collect() -> dict:
     ms, fl, by, ln = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
     check(lib.fdg_profile_collect(ms, fl, by, ln), "profile_collect")
     return {PROF_FAMILIES[i]: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(ln[i])) for i in range(n)}
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib.fdg_set_option(name.encode(), int(value)), "set_option")

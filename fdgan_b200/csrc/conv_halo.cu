@@ -1,0 +1,391 @@
+// fdg_conv2d, tcgen05 halo-tile path for stride-1 RxS (2..4) convolutions: 3x3 dense-block / VGG / decoder convs,
+// their data gradients, and the 4x4 stride-1 layers of the Fusion-discriminator.
+//
+// conv_umma.cu converts every input pixel from fp32 to bf16 hi/lo once PER FILTER TAP.  Here a CTA owns a 16x8 block
+// of output pixels (UMMA M = 128); for each 64-channel chunk the loaders fetch the (16+R-1) x (8+S-1) input halo
+// ONCE, run the consumer prologue (BatchNorm scale/shift + ReLU/LeakyReLU, zero padding after it), split to bf16
+// hi/lo and store one K-major SWIZZLE_128B tile per halo (row index = hy*HC + hx, swizzle taken from the absolute
+// shared-memory address).  The R*S taps are then pure descriptor arithmetic: tap (ky,kx) reads the same tile through
+// a descriptor whose start address is shifted by (ky*HC + kx) rows and whose stride between 8-row groups (SBO) is the
+// halo pitch HC*128 B, so an 8-pixel output row maps onto 8 consecutive halo rows.  (tests/probes/probe_shift.cu
+// verifies on hardware that row-shifted starts and SBO != 1024 are honoured with base_offset = 0.)
+// Weights: the same pre-swizzled per-(N tile, tap, chunk) images as conv_umma.cu, streamed through a bulk-TMA ring.
+// Persistent, warp-specialised: warps 0-7 halo loaders, 8-11 epilogue (double-buffered TMEM accumulators),
+// warp 12 MMA issue, warp 13 weight-tile producer.
+#include <cstdlib>
+
+#include "aop.cuh"
+#include "umma.cuh"
+#include "umma_epilogue.cuh"
+
+namespace fdg {
+
+constexpr int UKC_H = 64;                          // K elements per chunk
+constexpr int HT_W = 8, HT_H = 16;                 // output tile (8 wide so that one 8-row group = one image row)
+constexpr int H_LOAD_WARPS = 8;
+constexpr int H_THREADS = 14 * 32;
+constexpr int H_MAXROWS = (HT_H + 3) * (HT_W + 3); // 4x4 filter: 19 x 11 halo pixels
+constexpr int H_A_TILE = ((H_MAXROWS * 128 + 1023) / 1024) * 1024;   // 27 KB per hi (or lo) halo tile
+constexpr int H_MAX_AFF = 1024;
+constexpr int H_ITEMS = (H_MAXROWS * 8 + H_LOAD_WARPS * 32 - 1) / (H_LOAD_WARPS * 32);   // 16-byte chunks per loader thread
+
+struct HaloArgs {
+  FdgConv c;
+  int cchunks, tiles_x, tiles_y, n_tiles, total_tiles;
+  int HR, HC;      // halo rows / columns
+  int yvec;
+};
+
+template <int NT, int BSTAGES>
+__global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
+  constexpr int B_TILE_BYTES = NT * 128;
+  constexpr int A_STAGE = 2 * H_A_TILE;
+  constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_a_full[2], bar_a_empty[2], bar_b_full[BSTAGES], bar_b_empty[BSTAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sred[2][4][NT];
+  __shared__ float ep_tile[4][32][33];
+  __shared__ __align__(16) float aff_s[2][H_MAX_AFF];
+
+  const FdgConv& p = a.c;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + 2 * A_STAGE;
+  const int taps = p.R * p.S;
+  const int HP = a.HR * a.HC;
+  const int tiles_img = a.tiles_x * a.tiles_y;
+
+  if (t == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_a_full[s]), H_LOAD_WARPS);
+      mbar_init(smem_u32(&bar_a_empty[s]), 1);
+      mbar_init(smem_u32(&bar_acc_full[s]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[s]), 4);
+    }
+    for (int s = 0; s < BSTAGES; ++s) {
+      mbar_init(smem_u32(&bar_b_full[s]), 1);
+      mbar_init(smem_u32(&bar_b_empty[s]), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const bool aff_smem = p.has_affine && p.Cin <= H_MAX_AFF;
+  if (aff_smem)
+    for (int i = t; i < p.Cin; i += H_THREADS) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // tile id -> (output-channel tile, image, tile row, tile column)
+  auto decode = [&](int tile, int& ntile, int& n, int& oy0, int& ox0) {
+    ntile = tile / (p.N * tiles_img);
+    int r = tile - ntile * (p.N * tiles_img);
+    n = r / tiles_img;
+    r -= n * tiles_img;
+    const int tyi = r / a.tiles_x;
+    oy0 = tyi * HT_H;
+    ox0 = (r - tyi * a.tiles_x) * HT_W;
+  };
+
+  if (warp < H_LOAD_WARPS) {
+    // =============================================================== halo loaders
+    // item i of this thread: halo row (pixel) hrow[i], 16-byte bf16 chunk j (8 channels); fixed for the whole kernel
+    const int j = t & 7;
+    int hy[H_ITEMS], hx[H_ITEMS];
+    bool iv[H_ITEMS];
+#pragma unroll
+    for (int i = 0; i < H_ITEMS; ++i) {
+      const int row = (t >> 3) + i * (H_LOAD_WARPS * 4);
+      iv[i] = row < HP;
+      hy[i] = iv[i] ? row / a.HC : 0;
+      hx[i] = iv[i] ? row - hy[i] * a.HC : 0;
+    }
+    const uint32_t full0 = smem_u32(&bar_a_full[0]), empty0 = smem_u32(&bar_a_empty[0]);
+    const uint32_t aff0 = smem_u32(&aff_s[0][0]);
+    auto lds4u = [](uint32_t addr) -> float4 {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+      return v;
+    };
+    int buf = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      int ntile, n, oy0, ox0;
+      decode(tile, ntile, n, oy0, ox0);
+      const int iy0 = oy0 - p.pad, ix0 = ox0 - p.pad;
+      const float* tbase = p.x.p + n * p.x.sn + (int64_t)iy0 * p.x.sh + (int64_t)ix0 * p.x.sw + j * 8;   // dereferenced only in range
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int i = 0; i < H_ITEMS; ++i) {
+        const int iy = iy0 + hy[i], ix = ix0 + hx[i];
+        if (iv[i] && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) okmask |= 1u << i;
+      }
+      for (int cc = 0; cc < a.cchunks; ++cc) {
+        const int c = cc * UKC_H + j * 8;
+        const bool cvalid = c < p.Cin;
+        // ---- all loads of the chunk first (independent, up to 2*H_ITEMS 128-bit loads in flight per thread)
+        float4 v0[H_ITEMS], v1[H_ITEMS];
+#pragma unroll
+        for (int i = 0; i < H_ITEMS; ++i) {
+          v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          v1[i] = v0[i];
+          if (((okmask >> i) & 1u) && cvalid) {
+            const float* src = tbase + (int64_t)hy[i] * p.x.sh + (int64_t)hx[i] * p.x.sw + cc * UKC_H;
+            v0[i] = ld4(src);
+            v1[i] = ld4(src + 4);
+          }
+        }
+        // ---- consumer prologue
+        const float sl = p.slope;
+        if (p.has_affine) {
+          float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+          if (cvalid) {
+            if (aff_smem) {
+              sc0 = lds4u(aff0 + c * 4); sc1 = lds4u(aff0 + c * 4 + 16);
+              sh0 = lds4u(aff0 + (H_MAX_AFF + c) * 4); sh1 = lds4u(aff0 + (H_MAX_AFF + c) * 4 + 16);
+            } else {
+              sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
+              sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < H_ITEMS; ++i) {
+            v0[i].x = fmaf(v0[i].x, sc0.x, sh0.x); v0[i].y = fmaf(v0[i].y, sc0.y, sh0.y);
+            v0[i].z = fmaf(v0[i].z, sc0.z, sh0.z); v0[i].w = fmaf(v0[i].w, sc0.w, sh0.w);
+            v1[i].x = fmaf(v1[i].x, sc1.x, sh1.x); v1[i].y = fmaf(v1[i].y, sc1.y, sh1.y);
+            v1[i].z = fmaf(v1[i].z, sc1.z, sh1.z); v1[i].w = fmaf(v1[i].w, sc1.w, sh1.w);
+          }
+        }
+        if (sl == 0.f) {
+#pragma unroll
+          for (int i = 0; i < H_ITEMS; ++i) {
+            v0[i].x = fmaxf(v0[i].x, 0.f); v0[i].y = fmaxf(v0[i].y, 0.f); v0[i].z = fmaxf(v0[i].z, 0.f); v0[i].w = fmaxf(v0[i].w, 0.f);
+            v1[i].x = fmaxf(v1[i].x, 0.f); v1[i].y = fmaxf(v1[i].y, 0.f); v1[i].z = fmaxf(v1[i].z, 0.f); v1[i].w = fmaxf(v1[i].w, 0.f);
+          }
+        } else if (sl != 1.f) {
+#pragma unroll
+          for (int i = 0; i < H_ITEMS; ++i) {
+            v0[i].x = prologue_act(v0[i].x, sl); v0[i].y = prologue_act(v0[i].y, sl); v0[i].z = prologue_act(v0[i].z, sl); v0[i].w = prologue_act(v0[i].w, sl);
+            v1[i].x = prologue_act(v1[i].x, sl); v1[i].y = prologue_act(v1[i].y, sl); v1[i].z = prologue_act(v1[i].z, sl); v1[i].w = prologue_act(v1[i].w, sl);
+          }
+        }
+        if (p.has_affine) {   // zero padding is applied AFTER the prologue
+#pragma unroll
+          for (int i = 0; i < H_ITEMS; ++i)
+            if (!(((okmask >> i) & 1u) && cvalid)) { v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i]; }
+        }
+        // ---- split and store into the halo tile of buffer `buf`
+        mbar_wait(empty0 + buf * 8, ph ^ 1u);
+        const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + H_A_TILE;
+#pragma unroll
+        for (int i = 0; i < H_ITEMS; ++i) {
+          if (iv[i]) {
+            const int row = (t >> 3) + i * (H_LOAD_WARPS * 4);
+            const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+            uint32_t h[4], l[4];
+            split2(v0[i].x, v0[i].y, h[0], l[0]);
+            split2(v0[i].z, v0[i].w, h[1], l[1]);
+            split2(v1[i].x, v1[i].y, h[2], l[2]);
+            split2(v1[i].z, v1[i].w, h[3], l[3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + buf * 8);
+        if (++buf == 2) { buf = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // =============================================================== epilogue warps (TMEM lane quarter = warp & 3)
+    const int quarter = warp & 3;
+    const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
+    float acc1[NT / 32], acc2[NT / 32];
+#pragma unroll
+    for (int g = 0; g < NT / 32; ++g) { acc1[g] = 0.f; acc2[g] = 0.f; }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      int ntile, n, oy0, ox0;
+      decode(tile, ntile, n, oy0, ox0);
+      const int b = it & 1;
+      while (!mbar_try_wait(smem_u32(&bar_acc_full[b]), ((uint32_t)it >> 1) & 1u)) __nanosleep(200);
+      tc_fence_after();
+      const int m = quarter * 32 + lane;
+      const int oy = oy0 + (m >> 3), ox = ox0 + (m & 7);
+      const bool mv = oy < p.OH && ox < p.OW;
+      const int cbase = ntile * NT;
+#pragma unroll
+      for (int g = 0; g < NT / 32; ++g) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * NT + g * 32), v);
+        const int c0 = cbase + g * 32;
+        if (c0 < p.Cout) umma_epilogue_group(p, a.yvec, evec, v, mv, n, oy, ox, c0, lane, ep_tile[quarter], acc1[g], acc2[g]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[b]));
+      if (p.stats) {
+        const int next = tile + gridDim.x;
+        if (next >= a.total_tiles || next / (p.N * tiles_img) != ntile) {
+#pragma unroll
+          for (int g = 0; g < NT / 32; ++g) {
+            sred[0][quarter][g * 32 + lane] = acc1[g];
+            sred[1][quarter][g * 32 + lane] = acc2[g];
+            acc1[g] = 0.f; acc2[g] = 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int et = t - 8 * 32;
+          for (int cidx = et; cidx < NT; cidx += 128) {
+            const int c = ntile * NT + cidx;
+            if (c < p.Cout) {
+              atomicAdd(p.stats + c, (double)((sred[0][0][cidx] + sred[0][1][cidx]) + (sred[0][2][cidx] + sred[0][3][cidx])));
+              atomicAdd(p.stats + p.stats_ld + c, (double)((sred[1][0][cidx] + sred[1][1][cidx]) + (sred[1][2][cidx] + sred[1][3][cidx])));
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // =============================================================== MMA issue
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
+      const uint32_t sbo = (uint32_t)a.HC * 128u;
+      int buf = 0, bs = 0, it = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        mbar_wait(smem_u32(&bar_acc_empty[b]), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * NT);
+        for (int cc = 0; cc < a.cchunks; ++cc) {
+          mbar_wait(smem_u32(&bar_a_full[buf]), aph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + H_A_TILE;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int ky = tap / p.S, kx = tap - ky * p.S;
+            const uint32_t shift = (uint32_t)(ky * a.HC + kx) * 128u;
+            mbar_wait(smem_u32(&bar_b_full[bs]), bph);
+            tc_fence_after();
+            const uint32_t b_hi = b_base + bs * (2 * B_TILE_BYTES), b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t aa = (term == 2 ? a_lo : a_hi) + shift;
+              const uint32_t bb = term == 1 ? b_lo : b_hi;
+#pragma unroll
+              for (int k4 = 0; k4 < UKC_H / 16; ++k4) {
+                umma_bf16(d_tmem, umma_desc_k128_sbo(aa + k4 * 32, sbo), umma_desc_k128(bb + k4 * 32), idesc,
+                          (cc > 0 || tap > 0 || term > 0 || k4 > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(smem_u32(&bar_b_empty[bs]));
+            if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
+          }
+          umma_commit(smem_u32(&bar_a_empty[buf]));
+          if (++buf == 2) { buf = 0; aph ^= 1u; }
+        }
+        umma_commit(smem_u32(&bar_acc_full[b]));
+      }
+    }
+  } else if (warp == 13) {
+    // =============================================================== weight-tile producer (bulk TMA ring)
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bph = 0;
+      const int nchunks = taps * a.cchunks;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        int ntile, n, oy0, ox0;
+        decode(tile, ntile, n, oy0, ox0);
+        const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)ntile * nchunks * (2 * B_TILE_BYTES);
+        for (int cc = 0; cc < a.cchunks; ++cc)
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(smem_u32(&bar_b_empty[bs]), bph ^ 1u);
+            const uint32_t bar = smem_u32(&bar_b_full[bs]);
+            mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
+            bulk_g2s(b_base + bs * (2 * B_TILE_BYTES), wimg + (size_t)(tap * a.cchunks + cc) * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+            if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
+          }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+static int g_halo_on = [] { const char* e = getenv("FDG_HALO"); return e ? atoi(e) : 1; }();
+
+int conv2d_halo_supported(const FdgConv* p) {
+  if (!g_halo_on || !p->w_umma) return 0;
+  if (p->gather != FDG_GATHER_DIRECT || p->stride != 1) return 0;
+  if (p->R < 2 || p->R > 4 || p->S < 2 || p->S > 4) return 0;
+  if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
+  AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
+  if (!aop_vec_ok(ao, p->Cin)) return 0;
+  return 1;
+}
+
+template <int NT, int BSTAGES>
+static int launch_halo(const HaloArgs& a, cudaStream_t st) {
+  constexpr int smem = 2 * (2 * H_A_TILE) + BSTAGES * (2 * NT * 128) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(conv_halo_kernel<NT, BSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("fdg_conv2d[tcgen05 halo]: cannot raise dynamic shared memory to %d bytes", smem);
+      return FDG_ECUDA;
+    }
+    attr_done = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  dim3 grid((unsigned)(a.total_tiles < num_sms ? a.total_tiles : num_sms));
+  const double M = (double)a.c.N * a.c.OH * a.c.OW;
+  ProfScope prof(PF_CONV_UMMA, 2.0 * M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
+                 4.0 * (M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
+  conv_halo_kernel<NT, BSTAGES><<<grid, H_THREADS, smem, st>>>(a);
+  return check_launch("fdg_conv2d[tcgen05 halo]");
+}
+
+int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
+  HaloArgs a;
+  a.c = *p;
+  a.cchunks = cdiv(p->Cin, UKC_H);
+  a.tiles_x = cdiv(p->OW, HT_W);
+  a.tiles_y = cdiv(p->OH, HT_H);
+  a.n_tiles = cdiv(p->Cout, nt);
+  a.total_tiles = a.n_tiles * p->N * a.tiles_x * a.tiles_y;
+  a.HR = HT_H + p->R - 1;
+  a.HC = HT_W + p->S - 1;
+  a.yvec = vec4_ok(p->y);
+  switch (nt) {
+    case 32: return launch_halo<32, 4>(a, st);
+    case 64: return launch_halo<64, 4>(a, st);
+    default: return launch_halo<128, 2>(a, st);
+  }
+}
+
+}  // namespace fdg
+
+// Runtime options (tests / benchmarks): "halo" = 0 routes stride-1 RxS convolutions through the generic per-tap
+// tcgen05 kernel instead of the halo-tile kernel.
+extern "C" int fdg_set_option(const char* name, int value) {
+  if (name && name[0] == 'h' && name[1] == 'a' && name[2] == 'l' && name[3] == 'o' && name[4] == 0) { fdg::g_halo_on = value; return FDG_OK; }
+  fdg::set_error("fdg_set_option: unknown option");
+  return FDG_EINVAL;
+}

@@ -21,6 +21,7 @@
 
 #include "aop.cuh"
 #include "umma.cuh"
+#include "umma_epilogue.cuh"
 
 namespace fdg {
 
@@ -416,99 +417,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * NT + g * 32), v);
         const int c0 = cbase + g * 32;
         if (c0 < p.Cout) {
-          const int nvalid = p.Cout - c0 < 32 ? p.Cout - c0 : 32;
-          const bool full = nvalid == 32;
-          // ---- alpha, bias
-          if (p.bias) {
-            if (full) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 bb = ld4(p.bias + c0 + 4 * q);
-                v[4 * q] = fmaf(v[4 * q], p.alpha, bb.x); v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, bb.y);
-                v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, bb.z); v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, bb.w);
-              }
-            } else {
-#pragma unroll
-              for (int u = 0; u < 32; ++u) v[u] = fmaf(v[u], p.alpha, u < nvalid ? __ldg(p.bias + c0 + u) : 0.f);
-            }
-          } else if (p.alpha != 1.f) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u) v[u] *= p.alpha;
-          }
-          // ---- activation (uniform switch hoisted out of the element loop)
-          if (p.act == FDG_ACT_RELU) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u) v[u] = fmaxf(v[u], 0.f);
-          } else if (p.act == FDG_ACT_TANH) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u) v[u] = tanhf(v[u]);
-          } else if (p.act == FDG_ACT_SIGMOID) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u) v[u] = 1.f / (1.f + expf(-v[u]));
-          }
-          // ---- ReLU / LeakyReLU backward mask from a second tensor
-          if (p.e.p && mv) {
-            const float* ep = p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + (int64_t)c0 * p.e.sc;
-            if (evec && full) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 ev = ld4(ep + 4 * q);
-                v[4 * q] *= ev.x > 0.f ? 1.f : p.eslope; v[4 * q + 1] *= ev.y > 0.f ? 1.f : p.eslope;
-                v[4 * q + 2] *= ev.z > 0.f ? 1.f : p.eslope; v[4 * q + 3] *= ev.w > 0.f ? 1.f : p.eslope;
-              }
-            } else {
-#pragma unroll
-              for (int u = 0; u < 32; ++u)
-                if (u < nvalid) v[u] *= __ldg(ep + (int64_t)u * p.e.sc) > 0.f ? 1.f : p.eslope;
-            }
-          }
-          if (!mv || !full) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u) if (!mv || u >= nvalid) v[u] = 0.f;
-          }
-          if (mv) {
-            const int reps = p.store == FDG_STORE_UP2 ? 4 : 1;
-            for (int d = 0; d < reps; ++d) {
-              const int yy = p.store == FDG_STORE_UP2 ? 2 * oy + (d >> 1) : oy, xx = p.store == FDG_STORE_UP2 ? 2 * ox + (d & 1) : ox;
-              float* yp = p.y.p + n * p.y.sn + (int64_t)yy * p.y.sh + (int64_t)xx * p.y.sw + (int64_t)c0 * p.y.sc;
-              if (a.yvec && full) {
-                if (p.store == FDG_STORE_ACCUM) {
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const float4 old = *reinterpret_cast<const float4*>(yp + 4 * q);
-                    *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q] + old.x, v[4 * q + 1] + old.y, v[4 * q + 2] + old.z, v[4 * q + 3] + old.w);
-                  }
-                } else {
-#pragma unroll
-                  for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
-              } else {
-#pragma unroll
-                for (int u = 0; u < 32; ++u)
-                  if (u < nvalid) {
-                    float* q1 = yp + (int64_t)u * p.y.sc;
-                    *q1 = p.store == FDG_STORE_ACCUM ? *q1 + v[u] : v[u];
-                  }
-              }
-            }
-          }
-          if (p.stats) {
-            // column sums through a padded shared-memory transpose: lane l ends up with the sums of column l
-#pragma unroll
-            for (int u = 0; u < 32; ++u) ep_tile[quarter][u][lane] = v[u];
-            __syncwarp();
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-              const float xv = ep_tile[quarter][lane][rr];
-              s1 += xv;
-              s2 = fmaf(xv, xv, s2);
-            }
-            __syncwarp();
-            acc1[g] += s1;
-            acc2[g] += s2;
-          }
+          umma_epilogue_group(p, a.yvec, evec, v, mv, n, oy, ox, c0, lane, ep_tile[quarter], acc1[g], acc2[g]);
         }
       }
       // release the accumulator buffer to the MMA thread
@@ -625,7 +534,11 @@ static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   return check_launch("fdg_conv2d[tcgen05]");
 }
 
+int conv2d_halo_supported(const FdgConv* p);
+int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st);
+
 int conv2d_umma(const FdgConv* p, cudaStream_t st) {
+  if (umma_ntile(p->Cout) <= 128 && conv2d_halo_supported(p)) return conv2d_halo(p, umma_ntile(p->Cout), st);
   UmmaArgs a;
   a.c = *p;
   a.ao = AOp{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};

@@ -100,6 +100,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 __device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 
+// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups (halo tiles: the pitch of one image row)
+__device__ __forceinline__ uint64_t umma_desc_k128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
 // MN-major SWIZZLE_128B descriptor: rows of 64 MN-contiguous bf16 (128 B), 8 K-rows per 1024-byte swizzle atom;
 // LBO = byte stride between 64-element MN blocks, SBO = byte stride between 8-row K groups
 __device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

@@ -268,6 +268,9 @@ int fdg_loss_grad(const float* a, const float* b, float target, int kind, int64_
 int fdg_profile_enable(int on);
 int fdg_profile_collect(double* ms, double* flops, double* bytes, int64_t* launches);
 
+/* Runtime options: "halo" (default 1) = use the halo-tile tcgen05 kernel for stride-1 RxS convolutions. */
+int fdg_set_option(const char* name, int value);
+
 /* diagnostics */
 const char* fdg_last_error(void);
 int fdg_version(void);

@@ -49,20 +49,29 @@ CONV_CASES = [
     (224, 128, 1, 1, 0, 33, 31, 0, True, 0.0, False, 0, 0, True, False),   # ragged M (tail tile), padded K chunk
     (128, 32, 3, 1, 1, 64, 64, 0, True, 0.0, False, 0, 0, True, False),    # many tiles + statistics
     (512, 128, 3, 1, 1, 8, 8, 0, False, 0.0, False, 0, 2, False, True),    # dense_block5.conv2 dgrad-style accumulate
+    (128, 32, 3, 1, 1, 37, 29, 0, True, 0.0, False, 0, 0, True, False),    # halo kernel: ragged 16x8 tiles, statistics
+    (144, 288, 4, 1, 2, 21, 19, 0, True, 0.2, False, 0, 0, False, False),  # D layer 4 data-gradient geometry (4x4, pad 2)
+    (32, 128, 3, 1, 1, 40, 40, 0, False, 1.0, False, 0, 0, False, True),   # dense-layer conv2 data gradient + ReLU mask
+    (64, 64, 3, 1, 1, 5, 3, 0, False, 1.0, True, 1, 0, False, False),      # image smaller than one halo tile
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("variant", ["simt_nhwc", "simt_nchw", "tcgen05"])
+@pytest.mark.parametrize("variant", ["simt_nhwc", "simt_nchw", "tcgen05", "tcgen05_pertap"])
 def test_conv2d(case, variant):
     """fdg_conv2d against fp64 torch on every shape family of the path, through both kernels: the fp32 SIMT path
     (2e-5) and the tcgen05 bf16x3 path (5e-5; ~16 operand mantissa bits, fp32 accumulation in TMEM)."""
     ops = _ops()
     Cin, Cout, R, stride, pad, H, W, gather, affine, slope, bias, act, store, stats, mask = case
     nchw_in = variant == "simt_nchw"
-    impl = ops.IMPL_UMMA if variant == "tcgen05" else ops.IMPL_SIMT
-    if variant == "tcgen05" and not (Cin % 8 == 0 and Cin >= 16):
+    impl = ops.IMPL_UMMA if variant.startswith("tcgen05") else ops.IMPL_SIMT
+    if variant.startswith("tcgen05") and not (Cin % 8 == 0 and Cin >= 16):
         pytest.skip("shape not covered by the tcgen05 path (runs on the SIMT kernel)")
+    halo_shape = gather == 0 and stride == 1 and 2 <= R <= 4
+    if variant == "tcgen05_pertap" and not halo_shape:
+        pytest.skip("same kernel as the tcgen05 variant for this shape")
+    from fdgan_b200 import _lib
+    _lib.set_option("halo", 0 if variant == "tcgen05_pertap" else 1)   # halo-tile kernel vs generic per-tap kernel
     N = 2
     ph, pw = (2 * H, 2 * W) if gather == 1 else ((H + 1) // 2, (W + 1) // 2) if gather == 2 else (H, W)
     if gather == 2:
@@ -100,7 +109,8 @@ def test_conv2d(case, variant):
                bias=b.cuda() if bias else None, act=act, e=ops.View.from_nchw(cl(e)) if mask else None, eslope=0.3,
                store=store, stats=st, stats_ld=Cout + 3, impl=impl)
     torch.cuda.synchronize()
-    assert maxabs(yd, y) <= (5e-5 if variant == "tcgen05" else 2e-5)
+    _lib.set_option("halo", 1)
+    assert maxabs(yd, y) <= (5e-5 if variant.startswith("tcgen05") else 2e-5)
     if stats:
         tol = 2e-6 * float(N * OH * OW) + 1e-3   # fp32 partial sums over the tile, fp64 across tiles
         assert maxabs(st[:Cout], ysum) <= tol and maxabs(st[Cout + 3:2 * Cout + 3], ysq) <= tol
