@@ -33,13 +33,14 @@ struct HaloArgs {
   FdgConv c;
   int cchunks, tiles_x, tiles_y, n_tiles, total_tiles;
   int HR, HC;      // halo rows / columns
+  int a_tile;      // bytes of one bf16 halo tile (hi or lo), multiple of 1024
   int yvec;
 };
 
 template <int NT, int BSTAGES>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
-  constexpr int A_STAGE = 2 * H_A_TILE;
+  const int A_STAGE = 2 * a.a_tile;
   constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full[2], bar_a_empty[2], bar_b_full[BSTAGES], bar_b_empty[BSTAGES];
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         }
         // ---- split and store into the halo tile of buffer `buf`
         mbar_wait(empty0 + buf * 8, ph ^ 1u);
-        const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + H_A_TILE;
+        const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + a.a_tile;
 #pragma unroll
         for (int i = 0; i < H_ITEMS; ++i) {
           if (iv[i]) {
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         for (int cc = 0; cc < a.cchunks; ++cc) {
           mbar_wait(smem_u32(&bar_a_full[buf]), aph);
           tc_fence_after();
-          const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + H_A_TILE;
+          const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + a.a_tile;
           for (int tap = 0; tap < taps; ++tap) {
             const int ky = tap / p.S, kx = tap - ky * p.S;
             const uint32_t shift = (uint32_t)(ky * a.HC + kx) * 128u;
@@ -339,14 +340,14 @@ int conv2d_halo_supported(const FdgConv* p) {
 
 template <int NT, int BSTAGES>
 static int launch_halo(const HaloArgs& a, cudaStream_t st) {
-  constexpr int smem = 2 * (2 * H_A_TILE) + BSTAGES * (2 * NT * 128) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  const int smem = 2 * (2 * a.a_tile) + BSTAGES * (2 * NT * 128) + 1024;
+  static int attr_done = 0;
+  if (attr_done < smem) {
     if (cudaFuncSetAttribute(conv_halo_kernel<NT, BSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05 halo]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
-    attr_done = true;
+    attr_done = smem;
   }
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -372,11 +373,13 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
   a.total_tiles = a.n_tiles * p->N * a.tiles_x * a.tiles_y;
   a.HR = HT_H + p->R - 1;
   a.HC = HT_W + p->S - 1;
+  a.a_tile = ((a.HR * a.HC * 128 + 1023) / 1024) * 1024;
   a.yvec = vec4_ok(p->y);
+  // weight-tile ring depth: as deep as shared memory allows (the ring hides the L2 latency of the bulk copies)
   switch (nt) {
-    case 32: return launch_halo<32, 4>(a, st);
-    case 64: return launch_halo<64, 4>(a, st);
-    default: return launch_halo<128, 2>(a, st);
+    case 32: return launch_halo<32, 10>(a, st);
+    case 64: return launch_halo<64, 5>(a, st);
+    default: return a.a_tile <= 23 * 1024 ? launch_halo<128, 3>(a, st) : launch_halo<128, 2>(a, st);
   }
 }
 
