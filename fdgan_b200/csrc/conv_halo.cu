@@ -260,6 +260,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
       const uint32_t sbo = (uint32_t)a.HC * 128u;
+      const uint32_t b_hw = umma_desc_hi(1024);
+      const uint32_t bfull0 = smem_u32(&bar_b_full[0]), bempty0 = smem_u32(&bar_b_empty[0]);
       int buf = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
@@ -271,24 +273,18 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
           mbar_wait(smem_u32(&bar_a_full[buf]), aph);
           tc_fence_after();
           const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + a.a_tile;
+          const uint32_t ah_lo0 = umma_desc_lo(a_hi, 16), al_lo0 = umma_desc_lo(a_lo, 16), a_hw = umma_desc_hi(sbo);
+          int ky = 0, kx = 0;
           for (int tap = 0; tap < taps; ++tap) {
-            const int ky = tap / p.S, kx = tap - ky * p.S;
-            const uint32_t shift = (uint32_t)(ky * a.HC + kx) * 128u;
-            mbar_wait(smem_u32(&bar_b_full[bs]), bph);
+            const uint32_t shift = (uint32_t)(ky * a.HC + kx) * 8u;            // rows * 128 B, in 16-byte descriptor units
+            mbar_wait(bfull0 + bs * 8, bph);
             tc_fence_after();
-            const uint32_t b_hi = b_base + bs * (2 * B_TILE_BYTES), b_lo = b_hi + B_TILE_BYTES;
-#pragma unroll
-            for (int term = 0; term < 3; ++term) {
-              const uint32_t aa = (term == 2 ? a_lo : a_hi) + shift;
-              const uint32_t bb = term == 1 ? b_lo : b_hi;
-#pragma unroll
-              for (int k4 = 0; k4 < UKC_H / 16; ++k4) {
-                umma_bf16(d_tmem, umma_desc_k128_sbo(aa + k4 * 32, sbo), umma_desc_k128(bb + k4 * 32), idesc,
-                          (cc > 0 || tap > 0 || term > 0 || k4 > 0) ? 1u : 0u);
-              }
-            }
-            umma_commit(smem_u32(&bar_b_empty[bs]));
+            const uint32_t b_hi = b_base + bs * (2 * B_TILE_BYTES);
+            umma_chunk12(d_tmem, ah_lo0 + shift, al_lo0 + shift, a_hw, umma_desc_lo(b_hi, 16), umma_desc_lo(b_hi + B_TILE_BYTES, 16), b_hw,
+                         idesc, (cc > 0 || tap > 0) ? 1u : 0u, 2u);
+            umma_commit(bempty0 + bs * 8);
             if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
+            if (++kx == p.S) { kx = 0; ++ky; }
           }
           umma_commit(smem_u32(&bar_a_empty[buf]));
           if (++buf == 2) { buf = 0; aph ^= 1u; }

@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     // =============================================================== control thread: MMA issue
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(UM, NT);
+      const uint32_t k_hw = umma_desc_hi(1024);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -372,16 +373,8 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
           tc_fence_after();
           const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
           const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
-#pragma unroll
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t aa = term == 2 ? a_lo : a_hi;
-            const uint32_t bb = term == 1 ? b_lo : b_hi;
-#pragma unroll
-            for (int k4 = 0; k4 < UKC / 16; ++k4) {
-              umma_bf16(d_tmem, umma_desc_k128(aa + k4 * 32), umma_desc_k128(bb + k4 * 32), idesc,
-                        (kc > 0 || term > 0 || k4 > 0) ? 1u : 0u);
-            }
-          }
+          umma_chunk12(d_tmem, umma_desc_lo(a_hi, 16), umma_desc_lo(a_lo, 16), k_hw, umma_desc_lo(b_hi, 16), umma_desc_lo(b_lo, 16), k_hw,
+                       idesc, kc > 0 ? 1u : 0u, 2u);
           umma_commit(smem_u32(&bar_empty[s]));                // frees this stage when the MMAs above retire
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }

@@ -118,4 +118,82 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+
+// Low / high 32-bit words of a SWIZZLE_128B descriptor (K-major: LBO field 1, SBO = bytes between 8-row groups;
+// MN-major: LBO = bytes between 64-element blocks).  The 14-bit start-address field lives in the low word, so
+// stepping through K slices or filter taps is a 32-bit add on the low word only.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFF) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+
+// Issues the 12 tcgen05.mma of one 64-deep chunk (bf16x3 split: hi*hi, hi*lo, lo*hi; four K=16 slices each) with the
+// minimum of scalar work per instruction -- a single thread feeds the tensor core, so its instruction latency is the
+// issue-rate ceiling.  kstep = encoded descriptor units between K slices (2 = 32 B for K-major, 128 = 2048 B for MN-major).
+__device__ __forceinline__ void umma_chunk12(uint32_t d_tmem, uint32_t a_hi_lo, uint32_t a_lo_lo, uint32_t a_hw, uint32_t b_hi_lo,
+                                             uint32_t b_lo_lo, uint32_t b_hw, uint32_t idesc, uint32_t accumulate_first, uint32_t kstep) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ta, tb;\n\t"
+      ".reg .pred p, pt;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%4, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, p;\n\t"
+      "mad.lo.u32 ta, %9, 1, %1;\n\t"
+      "mad.lo.u32 tb, %9, 1, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 2, %1;\n\t"
+      "mad.lo.u32 tb, %9, 2, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 3, %1;\n\t"
+      "mad.lo.u32 tb, %9, 3, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%5, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 1, %1;\n\t"
+      "mad.lo.u32 tb, %9, 1, %5;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 2, %1;\n\t"
+      "mad.lo.u32 tb, %9, 2, %5;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 3, %1;\n\t"
+      "mad.lo.u32 tb, %9, 3, %5;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mov.b64 da, {%2, %3};\n\t"
+      "mov.b64 db, {%4, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 1, %2;\n\t"
+      "mad.lo.u32 tb, %9, 1, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 2, %2;\n\t"
+      "mad.lo.u32 tb, %9, 2, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 3, %2;\n\t"
+      "mad.lo.u32 tb, %9, 3, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi_lo), "r"(a_lo_lo), "r"(a_hw), "r"(b_hi_lo), "r"(b_lo_lo), "r"(b_hw), "r"(idesc), "r"(accumulate_first), "r"(kstep)
+      : "memory");
+}
+
 }  // namespace fdg

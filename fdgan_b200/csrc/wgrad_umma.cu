@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   } else if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
     // =============================================================== MMA issue
     constexpr uint32_t idesc = umma_idesc_bf16_mn(WU_K, NT);
+    const uint32_t mn_hw = umma_desc_hi(1024);
     int s = 0;
     uint32_t ph = 0;
     for (int kc = 0; kc < nchunks; ++kc) {
@@ -313,17 +314,10 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       tc_fence_after();
       const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + WU_A_BYTES;
       const uint32_t g_hi = a_lo + WU_A_BYTES, g_lo = g_hi + G_BYTES;
-#pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t aa = term == 2 ? a_lo : a_hi;
-        const uint32_t gg = term == 1 ? g_lo : g_hi;
-#pragma unroll
-        for (int k16 = 0; k16 < WU_P / 16; ++k16) {
-          // 16 pixels = two 8-row swizzle atoms (SBO 1024 B); 64-channel blocks are WU_BLK bytes apart (LBO)
-          umma_bf16(tmem_base, umma_desc_mn128(aa + k16 * 2048, WU_BLK, 1024), umma_desc_mn128(gg + k16 * 2048, WU_BLK, 1024), idesc,
-                    (kc > 0 || term > 0 || k16 > 0) ? 1u : 0u);
-        }
-      }
+      // 16 pixels per slice = two 8-row swizzle atoms (SBO 1024 B); 64-channel blocks are WU_BLK bytes apart (LBO);
+      // consecutive slices are 2048 B = 128 descriptor units apart
+      umma_chunk12(tmem_base, umma_desc_lo(a_hi, WU_BLK), umma_desc_lo(a_lo, WU_BLK), mn_hw, umma_desc_lo(g_hi, WU_BLK),
+                   umma_desc_lo(g_lo, WU_BLK), mn_hw, idesc, kc > 0 ? 1u : 0u, 128u);
       umma_commit(smem_u32(&bar_empty[s]));
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
