@@ -206,13 +206,32 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
 
     int s = 0;
     uint32_t ph = 0;
+    const uint32_t roff_c = (uint32_t)pr * 128u + (uint32_t)((seg ^ (pr & 7)) << 4);
     if (DEPTH > 0) {
+      // ---- in-place staging: the fp32 rows are cp.async'ed straight into the operand ring.  Each thread's 32 bytes of
+      // fp32 per 8-channel chunk land in the two 16-byte slots that will hold that chunk's bf16 hi / lo halves, so the
+      // conversion is read-modify-write of the thread's own slots and every ring stage doubles as prefetch buffer
+      // (STAGES - 1 chunks of loads in flight, no registers tied up).
       constexpr int NLT = WU_LOAD_WARPS * 32;
-      constexpr int PIECES = 4 + 2 * GQ;       // 16-byte pieces per thread per chunk
-      const uint32_t stg = smem_base + STAGES * STAGE_BYTES + (uint32_t)t * 16u;
-      __shared__ uint32_t meta_s[DEPTH > 0 ? DEPTH : 1][WU_LOAD_WARPS * 32];
-      auto slot = [&](int d, int k) -> uint32_t { return stg + (uint32_t)((d * PIECES + k) * NLT) * 16u; };
-      auto issue_async = [&](int d) {
+      __shared__ uint32_t meta_s[STAGES][WU_LOAD_WARPS * 32];
+      const uint32_t meta0 = smem_u32(&meta_s[0][0]) + (uint32_t)t * 4u;
+      const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+      auto slot_a = [&](int st, int h, int lo) -> uint32_t {   // A chunk h (64-channel block h), hi (lo=0) or lo (lo=1) tile
+        return smem_base + st * STAGE_BYTES + (uint32_t)lo * WU_A_BYTES + (uint32_t)h * WU_BLK + roff_c;
+      };
+      auto slot_g = [&](int st, int q, int lo) -> uint32_t {
+        return smem_base + st * STAGE_BYTES + 2 * WU_A_BYTES + (uint32_t)lo * G_BYTES + (uint32_t)q * WU_BLK + roff_c;
+      };
+      auto sts4 = [](uint32_t addr, float4 f) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
+      };
+      auto lds4 = [](uint32_t addr) -> float4 {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+        return v;
+      };
+      auto issue_async = [&](int st, uint32_t eph) {
+        mbar_wait(empty0 + st * 8, eph ^ 1u);          // the MMAs that read this stage have retired
         uint32_t ok = 0;
         if (lm < mend) {
 #pragma unroll
@@ -223,12 +242,11 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
               ok |= 1u << h;
               if (direct) {
                 const float* xp = p.x.p + pn * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw + c;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 2 * h)), "l"(xp) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 2 * h + 1)), "l"(xp + 4) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_a(st, h, 0)), "l"(xp) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_a(st, h, 1)), "l"(xp + 4) : "memory");
               } else {
-                const float4 f0 = fetch4(a.ao, pn, iy, ix, c), f1 = fetch4(a.ao, pn, iy, ix, c + 4);
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 2 * h)), "f"(f0.x), "f"(f0.y), "f"(f0.z), "f"(f0.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 2 * h + 1)), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
+                sts4(slot_a(st, h, 0), fetch4(a.ao, pn, iy, ix, c));
+                sts4(slot_a(st, h, 1), fetch4(a.ao, pn, iy, ix, c + 4));
               }
             }
           }
@@ -239,54 +257,79 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             if (c < p.Cout) {
               ok |= 4u << q;
               if (a.gvec) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 4 + 2 * q)), "l"(gp + c) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot(d, 5 + 2 * q)), "l"(gp + c + 4) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_g(st, q, 0)), "l"(gp + c) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_g(st, q, 1)), "l"(gp + c + 4) : "memory");
               } else {
                 float f[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = c + e < p.Cout ? __ldg(gp + (int64_t)(c + e) * p.g.sc) : 0.f;
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 4 + 2 * q)), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot(d, 5 + 2 * q)), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+                sts4(slot_g(st, q, 0), make_float4(f[0], f[1], f[2], f[3]));
+                sts4(slot_g(st, q, 1), make_float4(f[4], f[5], f[6], f[7]));
               }
             }
           }
         }
-        meta_s[d][t] = ok;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta0 + st * (NLT * 4)), "r"(ok) : "memory");
         lm += WU_P;
         pox += WU_P;
         while (pox >= p.OW) { pox -= p.OW; if (++poy == p.OH) { poy = 0; ++pn; } }
       };
-      auto lds4 = [&](uint32_t addr) -> float4 {
-        float4 v;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-        return v;
+      // convert stage st in place and publish it
+      auto convert = [&](int st) {
+        uint32_t ok;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ok) : "r"(meta0 + st * (NLT * 4)) : "memory");
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float sl = p.slope;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 a0 = z4, a1 = z4;
+          if ((ok >> h) & 1u) {
+            a0 = lds4(slot_a(st, h, 0));
+            a1 = lds4(slot_a(st, h, 1));
+            if (direct) {
+              const float4 sc0 = scv[2 * h], sc1 = scv[2 * h + 1], sh0 = shv[2 * h], sh1 = shv[2 * h + 1];
+              a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
+              a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
+              a1.x = prologue_act(fmaf(a1.x, sc1.x, sh1.x), sl); a1.y = prologue_act(fmaf(a1.y, sc1.y, sh1.y), sl);
+              a1.z = prologue_act(fmaf(a1.z, sc1.z, sh1.z), sl); a1.w = prologue_act(fmaf(a1.w, sc1.w, sh1.w), sl);
+            }
+          }
+          uint32_t hi[4], lo[4];
+          split2(a0.x, a0.y, hi[0], lo[0]); split2(a0.z, a0.w, hi[1], lo[1]);
+          split2(a1.x, a1.y, hi[2], lo[2]); split2(a1.z, a1.w, hi[3], lo[3]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 0)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 1)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+#pragma unroll
+        for (int q = 0; q < GQ; ++q) {
+          float4 g0 = z4, g1 = z4;
+          if (ok & (4u << q)) { g0 = lds4(slot_g(st, q, 0)); g1 = lds4(slot_g(st, q, 1)); }
+          uint32_t hi[4], lo[4];
+          split2(g0.x, g0.y, hi[0], lo[0]); split2(g0.z, g0.w, hi[1], lo[1]);
+          split2(g1.x, g1.y, hi[2], lo[2]); split2(g1.z, g1.w, hi[3], lo[3]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_g(st, q, 0)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_g(st, q, 1)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + st * 8);
       };
-      int dl = 0, df = 0;
+      int sl_ = 0, sf = 0;            // stages of the next chunk to load / to convert
+      uint32_t lph = 0;               // parity of the load side's pass over the ring
 #pragma unroll 1
-      for (int q = 0; q < DEPTH - 1; ++q) {
-        if (q < nchunks) issue_async(dl);
+      for (int q = 0; q < STAGES - 1; ++q) {
+        if (q < nchunks) issue_async(sl_, lph);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (++dl == DEPTH) dl = 0;
+        if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
       }
 #pragma unroll 1
       for (int q = 0; q < nchunks; ++q) {
-        if (q + DEPTH - 1 < nchunks) issue_async(dl);
+        if (q + STAGES - 1 < nchunks) issue_async(sl_, lph);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (++dl == DEPTH) dl = 0;
-        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");
-        const uint32_t ok = meta_s[df][t];
-        float4 av[4], gv[2 * GQ];
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        av[0] = (ok & 1u) ? lds4(slot(df, 0)) : z4; av[1] = (ok & 1u) ? lds4(slot(df, 1)) : z4;
-        av[2] = (ok & 2u) ? lds4(slot(df, 2)) : z4; av[3] = (ok & 2u) ? lds4(slot(df, 3)) : z4;
-#pragma unroll
-        for (int g = 0; g < GQ; ++g) {
-          gv[2 * g] = (ok & (4u << g)) ? lds4(slot(df, 4 + 2 * g)) : z4;
-          gv[2 * g + 1] = (ok & (4u << g)) ? lds4(slot(df, 5 + 2 * g)) : z4;
-        }
-        finish(av, gv, ok & 3u, s, ph);
-        if (++df == DEPTH) df = 0;
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        convert(sf);
+        if (++sf == STAGES) sf = 0;
       }
     } else {
       float4 A0[4], G0[2 * GQ], A1[4], G1[2 * GQ];
@@ -373,7 +416,7 @@ int wgrad_umma_supported(const FdgWgrad* p) {
 
 template <int NT, int STAGES, int DEPTH>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * (NT / 64) * WU_BLK) + DEPTH * (WU_LOAD_WARPS * 32) * (4 + 2 * (NT / 64)) * 16 + 1024;
+  constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * (NT / 64) * WU_BLK) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -411,8 +454,8 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   a.kblocks = cdiv(p->R * p->S * p->Cin, WU_K);
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   switch (wu_ntile(p->Cout)) {
-    case 64: return launch_wu<64, 2, 2>(a, st);      // ring 2 x 48 KB + staging 2 x 48 KB
-    case 128: return launch_wu<128, 1, 2>(a, st);    // ring 64 KB + staging 2 x 64 KB
+    case 64: return launch_wu<64, 4, 1>(a, st);      // 4 x 48 KB in-place staging ring
+    case 128: return launch_wu<128, 3, 1>(a, st);    // 3 x 64 KB in-place staging ring
     default: return launch_wu<256, 2, 0>(a, st);     // ring 2 x 96 KB, register double buffer
   }
 }
