@@ -383,8 +383,14 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
 
 // Runtime options (tests / benchmarks): "halo" = 0 routes stride-1 RxS convolutions through the generic per-tap
 // tcgen05 kernel instead of the halo-tile kernel.
+namespace fdg { void set_wgrad_halo(int on); }
+
 extern "C" int fdg_set_option(const char* name, int value) {
-  if (name && name[0] == 'h' && name[1] == 'a' && name[2] == 'l' && name[3] == 'o' && name[4] == 0) { fdg::g_halo_on = value; return FDG_OK; }
+  if (name && name[0] == 'h' && name[1] == 'a' && name[2] == 'l' && name[3] == 'o' && name[4] == 0) {
+    fdg::g_halo_on = value;
+    fdg::set_wgrad_halo(value);
+    return FDG_OK;
+  }
   fdg::set_error("fdg_set_option: unknown option");
   return FDG_EINVAL;
 }

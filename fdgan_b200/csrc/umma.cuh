@@ -196,4 +196,73 @@ __device__ __forceinline__ void umma_chunk12(uint32_t d_tmem, uint32_t a_hi_lo, 
       : "memory");
 }
 
+// same with different descriptor steps for the A and B operands (halo tiles: A steps by image rows)
+__device__ __forceinline__ void umma_chunk12_ab(uint32_t d_tmem, uint32_t a_hi_lo, uint32_t a_lo_lo, uint32_t a_hw, uint32_t b_hi_lo,
+                                             uint32_t b_lo_lo, uint32_t b_hw, uint32_t idesc, uint32_t accumulate_first, uint32_t kstep, uint32_t kstep_b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ta, tb;\n\t"
+      ".reg .pred p, pt;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%4, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, p;\n\t"
+      "mad.lo.u32 ta, %9, 1, %1;\n\t"
+      "mad.lo.u32 tb, %10, 1, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 2, %1;\n\t"
+      "mad.lo.u32 tb, %10, 2, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 3, %1;\n\t"
+      "mad.lo.u32 tb, %10, 3, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%5, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 1, %1;\n\t"
+      "mad.lo.u32 tb, %10, 1, %5;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 2, %1;\n\t"
+      "mad.lo.u32 tb, %10, 2, %5;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 3, %1;\n\t"
+      "mad.lo.u32 tb, %10, 3, %5;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mov.b64 da, {%2, %3};\n\t"
+      "mov.b64 db, {%4, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 1, %2;\n\t"
+      "mad.lo.u32 tb, %10, 1, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 2, %2;\n\t"
+      "mad.lo.u32 tb, %10, 2, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 3, %2;\n\t"
+      "mad.lo.u32 tb, %10, 3, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi_lo), "r"(a_lo_lo), "r"(a_hw), "r"(b_hi_lo), "r"(b_lo_lo), "r"(b_hw), "r"(idesc), "r"(accumulate_first), "r"(kstep), "r"(kstep_b)
+      : "memory");
+}
+
 }  // namespace fdg

@@ -182,6 +182,8 @@ __global__ void colsum_kernel(FdgTensor x, int64_t M, int HW, int W, int C, floa
 namespace fdg {
 int wgrad_umma_supported(const FdgWgrad* p);
 int wgrad_umma(const FdgWgrad* p, cudaStream_t st);
+int wgrad_halo_supported(const FdgWgrad* p);
+int wgrad_halo(const FdgWgrad* p, cudaStream_t st);
 }  // namespace fdg
 
 using namespace fdg;
@@ -214,7 +216,7 @@ extern "C" int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream) {
     const int ok = wgrad_umma_supported(p);
     if (p->impl == 2 && !ok) { set_error("fdg_conv2d_wgrad: impl=tcgen05 requested but shape/layout unsupported"); return FDG_ENOSUPPORT; }
     if (ok) {
-      const int rc = wgrad_umma(p, st);
+      const int rc = wgrad_halo_supported(p) ? wgrad_halo(p, st) : wgrad_umma(p, st);
       if (rc != FDG_OK) return rc;
       if (p->dbias) return fdg_colsum(&p->g, p->N, p->OH, p->OW, p->Cout, p->dbias, 1, stream);
       return FDG_OK;

@@ -324,12 +324,14 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       }
 #pragma unroll 1
       for (int q = 0; q < nchunks; ++q) {
+        // chunk q's copies have landed when at most STAGES-2 newer groups are pending; convert it first (this overlaps
+        // with the MMAs of chunk q-1), then refill the stage those MMAs are about to release
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES >= 2 ? STAGES - 2 : 0) : "memory");
+        convert(sf);
+        if (++sf == STAGES) sf = 0;
         if (q + STAGES - 1 < nchunks) issue_async(sl_, lph);
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
-        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
-        convert(sf);
-        if (++sf == STAGES) sf = 0;
       }
     } else {
       float4 A0[4], G0[2 * GQ], A1[4], G1[2 * GQ];

@@ -165,17 +165,25 @@ WGRAD_CASES = [
     (128, 32, 3, 1, 1, 33, 29, 0, True, 0.0, False, False),      # K1 with ragged pixel count
     (288, 1, 4, 1, 1, 9, 10, 0, False, 0.2, False, False),       # D layer 5 (single output channel, scalar gradient loads)
     (16, 3, 3, 1, 1, 12, 12, 0, False, 1.0, False, True),        # conv_refin3 (NCHW gradient)
+    (128, 32, 3, 1, 1, 64, 48, 0, True, 0.0, False, False),      # K1, many 8x8 pixel blocks (halo weight-gradient kernel)
+    (160, 40, 3, 1, 1, 19, 21, 0, True, 0.2, False, False),      # two channel blocks, two output-channel tiles, ragged blocks
+    (64, 24, 4, 1, 1, 12, 12, 0, False, 1.0, False, False),      # 4x4 filter: 16 taps = all 512 TMEM columns
 ]
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
-@pytest.mark.parametrize("variant", ["simt", "tcgen05"])
+@pytest.mark.parametrize("variant", ["simt", "tcgen05", "tcgen05_pertap"])
 def test_wgrad(case, variant):
     ops = _ops()
     Cin, Cout, R, stride, pad, H, W, gather, affine, slope, transposed, dbias = case
-    if variant == "tcgen05" and not (Cin % 8 == 0 and Cin >= 16):
+    if variant.startswith("tcgen05") and not (Cin % 8 == 0 and Cin >= 16):
         pytest.skip("shape not covered by the tcgen05 weight-gradient path (runs on the SIMT kernel)")
-    impl = ops.IMPL_UMMA if variant == "tcgen05" else ops.IMPL_SIMT
+    halo_shape = gather == 0 and stride == 1 and 2 <= R <= 4 and Cout <= 64 and not transposed
+    if variant == "tcgen05_pertap" and not halo_shape:
+        pytest.skip("same kernel as the tcgen05 variant for this shape")
+    from fdgan_b200 import _lib
+    _lib.set_option("halo", 0 if variant == "tcgen05_pertap" else 1)
+    impl = ops.IMPL_UMMA if variant.startswith("tcgen05") else ops.IMPL_SIMT
     N = 3
     ph, pw = (2 * H, 2 * W) if gather == 1 else (H, W)
     x = seeded((N, Cin, ph, pw), 1, -1, 1).double()
@@ -198,6 +206,7 @@ def test_wgrad(case, variant):
     ops.wgrad(ops.View.from_nchw(xd), ops.View.from_nchw(cl(g.float())), R, R, stride, pad, dw, gather=gather,
               scale=sc.float().cuda() if affine else None, shift=sh.float().cuda() if affine else None, slope=slope,
               transposed=transposed, dbias=db, impl=impl)
+    _lib.set_option("halo", 1)
     assert maxabs(dw, want) <= 2e-4 * max(1.0, float(want.abs().max()))
     if dbias:
         assert maxabs(db, g.sum((0, 2, 3))) <= 1e-3
