@@ -271,22 +271,12 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       int s = 0;
       uint32_t ph = 0;
       if (DEPTH > 0) {
-        // ---- in-place staging: the fp32 rows are cp.async'ed straight into the operand ring.  A thread's 32 bytes of fp32
-        // per (row, 8-channel chunk) land in the two 16-byte slots that will hold that chunk's bf16 hi / lo halves, so the
-        // conversion is a read-modify-write of the thread's own slots and every ring stage doubles as prefetch buffer
-        // (STAGES - 1 chunks of loads in flight, no registers tied up by loads).
+        // ---- cp.async staging: slot d of this thread = RPT rows x 32 bytes, laid out [d][row i][thread]
         constexpr int NLT = ULOAD_WARPS * 32;
-        __shared__ uint32_t meta_s[STAGES][ULOAD_WARPS * 32];
+        const uint32_t stg = smem_base + STAGES * STAGE_BYTES + (uint32_t)t * 16u;   // [slot][row][half][thread] x 16 B
+        __shared__ uint32_t meta_s[DEPTH > 0 ? DEPTH : 1][ULOAD_WARPS * 32];
         const uint32_t meta0 = smem_u32(&meta_s[0][0]) + (uint32_t)t * 4u;
-        uint32_t roff[RPT];
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const int row = rbase + RSTEP * i;
-          roff[i] = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-        }
-        auto issue_async = [&](int st, uint32_t eph) {
-          mbar_wait(empty0 + st * 8, eph ^ 1u);          // the MMAs that read this stage have retired
-          const uint32_t a_hi = smem_base + st * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+        auto issue_async = [&](int d) {
           const int c = l_cc * UKC + j * 8;
           const bool cvalid = c < p.Cin;
           const int64_t toff = (int64_t)l_r * p.x.sh + (int64_t)l_sx * p.x.sw + l_cc * UKC;
@@ -294,26 +284,23 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             const int iy = piy[i] + l_r, ix = pix[i] + l_sx;
-            if (((pvmask >> i) & 1u) && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-              ok |= 1u << i;
-              if (direct) {
+            const bool v = ((pvmask >> i) & 1u) && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            const uint32_t dst = stg + (uint32_t)((d * RPT + i) * 2 * NLT) * 16u;
+            if (direct) {
+              if (v) {
+                ok |= 1u << i;
                 const float* src = rowp[i] + toff;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(a_hi + roff[i]), "l"(src) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(a_lo + roff[i]), "l"(src + 4) : "memory");
-              } else {
-                const float4 f0 = fetch4(a.ao, pn[i], iy, ix, c), f1 = fetch4(a.ao, pn[i], iy, ix, c + 4);
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + roff[i]), "f"(f0.x), "f"(f0.y), "f"(f0.z), "f"(f0.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + roff[i]), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + NLT * 16), "l"(src + 4) : "memory");
               }
+            } else {
+              float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+              if (v) { ok |= 1u << i; f0 = fetch4(a.ao, pn[i], iy, ix, c); f1 = fetch4(a.ao, pn[i], iy, ix, c + 4); }
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f0.x), "f"(f0.y), "f"(f0.z), "f"(f0.w) : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + NLT * 16), "f"(f1.x), "f"(f1.y), "f"(f1.z), "f"(f1.w) : "memory");
             }
           }
-          if (t == 0) {   // this stage's weight tile (hi + lo) through the bulk-copy engine
-            const uint32_t bar = full0 + st * 8;
-            mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
-            bulk_g2s(a_lo + A_TILE_BYTES, reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)(l_nt * a.nchunks + l_kc) * (2 * B_TILE_BYTES),
-                     2 * B_TILE_BYTES, bar);
-          }
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta0 + st * (NLT * 4)), "r"(ok | ((uint32_t)l_cc << 8)) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta0 + d * (NLT * 4)), "r"(ok | ((uint32_t)l_cc << 8) | ((uint32_t)(l_nt * a.nchunks + l_kc) << 16)) : "memory");
           if (++l_cc == a.cchunks) { l_cc = 0; if (++l_sx == p.S) { l_sx = 0; ++l_r; } }
           if (++l_kc == a.nchunks) {
             l_kc = 0; l_r = 0; l_sx = 0; l_cc = 0;
@@ -321,93 +308,36 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
             if (l_tile < total_tiles) set_tile(l_tile);
           }
         };
-        // convert stage st in place (prologue, bf16 hi/lo split) and publish it
-        auto convert = [&](int st) {
+        int dl = 0, df = 0;     // staging slots of the next chunk to load / to finish
+#pragma unroll 1
+        for (int q = 0; q < DEPTH - 1; ++q) {
+          if (q < total_chunks) issue_async(dl);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (++dl == DEPTH) dl = 0;
+        }
+#pragma unroll 1
+        for (int q = 0; q < total_chunks; ++q) {
+          if (q + DEPTH - 1 < total_chunks) issue_async(dl);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (++dl == DEPTH) dl = 0;
+          asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");
           uint32_t meta;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(meta) : "r"(meta0 + st * (NLT * 4)) : "memory");
-          const uint32_t a_hi = smem_base + st * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(meta) : "r"(meta0 + df * (NLT * 4)) : "memory");
           float4 v0[RPT], v1[RPT];
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
+            const uint32_t src = stg + (uint32_t)((df * RPT + i) * 2 * NLT) * 16u;
             if ((meta >> i) & 1u) {
-              v0[i] = lds4u(a_hi + roff[i]);
-              v1[i] = lds4u(a_lo + roff[i]);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0[i].x), "=f"(v0[i].y), "=f"(v0[i].z), "=f"(v0[i].w) : "r"(src) : "memory");
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1[i].x), "=f"(v1[i].y), "=f"(v1[i].z), "=f"(v1[i].w) : "r"(src + NLT * 16) : "memory");
             } else {
               v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               v1[i] = v0[i];
             }
           }
-          if (direct) {
-            const int c = (int)((meta >> 8) & 0xffu) * UKC + j * 8;
-            const float sl = p.slope;
-            if (p.has_affine) {
-              float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
-              if (c < p.Cin) {
-                if (aff_smem) {
-                  sc0 = lds4u(aff0 + c * 4); sc1 = lds4u(aff0 + c * 4 + 16);
-                  sh0 = lds4u(aff0 + (UMAX_AFF + c) * 4); sh1 = lds4u(aff0 + (UMAX_AFF + c) * 4 + 16);
-                } else {
-                  sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
-                  sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < RPT; ++i) {
-                v0[i].x = fmaf(v0[i].x, sc0.x, sh0.x); v0[i].y = fmaf(v0[i].y, sc0.y, sh0.y);
-                v0[i].z = fmaf(v0[i].z, sc0.z, sh0.z); v0[i].w = fmaf(v0[i].w, sc0.w, sh0.w);
-                v1[i].x = fmaf(v1[i].x, sc1.x, sh1.x); v1[i].y = fmaf(v1[i].y, sc1.y, sh1.y);
-                v1[i].z = fmaf(v1[i].z, sc1.z, sh1.z); v1[i].w = fmaf(v1[i].w, sc1.w, sh1.w);
-              }
-            }
-            if (sl == 0.f) {
-#pragma unroll
-              for (int i = 0; i < RPT; ++i) {
-                v0[i].x = fmaxf(v0[i].x, 0.f); v0[i].y = fmaxf(v0[i].y, 0.f); v0[i].z = fmaxf(v0[i].z, 0.f); v0[i].w = fmaxf(v0[i].w, 0.f);
-                v1[i].x = fmaxf(v1[i].x, 0.f); v1[i].y = fmaxf(v1[i].y, 0.f); v1[i].z = fmaxf(v1[i].z, 0.f); v1[i].w = fmaxf(v1[i].w, 0.f);
-              }
-            } else if (sl != 1.f) {
-#pragma unroll
-              for (int i = 0; i < RPT; ++i) {
-                v0[i].x = prologue_act(v0[i].x, sl); v0[i].y = prologue_act(v0[i].y, sl); v0[i].z = prologue_act(v0[i].z, sl); v0[i].w = prologue_act(v0[i].w, sl);
-                v1[i].x = prologue_act(v1[i].x, sl); v1[i].y = prologue_act(v1[i].y, sl); v1[i].z = prologue_act(v1[i].z, sl); v1[i].w = prologue_act(v1[i].w, sl);
-              }
-            }
-            if (p.has_affine) {         // zero padding is applied AFTER the prologue
-#pragma unroll
-              for (int i = 0; i < RPT; ++i)
-                if (!((meta >> i) & 1u)) { v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i]; }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) {
-            uint32_t h[4], l[4];
-            split2(v0[i].x, v0[i].y, h[0], l[0]);
-            split2(v0[i].z, v0[i].w, h[1], l[1]);
-            split2(v1[i].x, v1[i].y, h[2], l[2]);
-            split2(v1[i].z, v1[i].w, h[3], l[3]);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + roff[i]), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + roff[i]), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full0 + st * 8);
-        };
-        int sl_ = 0, sf = 0;
-        uint32_t lph = 0;
-#pragma unroll 1
-        for (int q = 0; q < STAGES - 1; ++q) {
-          if (q < total_chunks) issue_async(sl_, lph);
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
-        }
-#pragma unroll 1
-        for (int q = 0; q < total_chunks; ++q) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(STAGES >= 2 ? STAGES - 2 : 0) : "memory");
-          convert(sf);
-          if (++sf == STAGES) sf = 0;
-          if (q + STAGES - 1 < total_chunks) issue_async(sl_, lph);
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
+          finish(v0, v1, meta, s, ph);
+          if (++df == DEPTH) df = 0;
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       } else {
         float4 A0[RPT], A1[RPT], B0[RPT], B1[RPT];
@@ -573,7 +503,7 @@ int conv2d_umma_supported(const FdgConv* p) {
 
 template <int NT, int STAGES, int DEPTH>
 static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + 1024;
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + DEPTH * (UM * UKC * 4) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -610,10 +540,10 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
   a.nchunks = p->R * p->S * a.cchunks;
   a.yvec = vec4_ok(p->y);
   switch (umma_ntile(p->Cout)) {
-    case 32: return launch_umma<32, 5, 1>(a, st);     // 5 x 40 KB in-place staging ring
-    case 64: return launch_umma<64, 4, 1>(a, st);     // 4 x 48 KB
-    case 128: return launch_umma<128, 3, 1>(a, st);   // 3 x 64 KB
-    default: return launch_umma<256, 2, 1>(a, st);    // 2 x 96 KB
+    case 32: return launch_umma<32, 2, 3>(a, st);     // ring 2 x 40 KB + staging 3 x 32 KB
+    case 64: return launch_umma<64, 2, 3>(a, st);     // ring 2 x 48 KB + staging 3 x 32 KB
+    case 128: return launch_umma<128, 2, 2>(a, st);   // ring 2 x 64 KB + staging 2 x 32 KB
+    default: return launch_umma<256, 2, 0>(a, st);    // ring 2 x 96 KB, register double buffer
   }
 }
 
