@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfdgan_b200.so")
+LIB_PATH = os.environ.get("FDG_LIB") or os.path.join(_HERE, "libfdgan_b200.so")   # FDG_LIB: A/B builds of the same sources
 
 if not os.path.isfile(LIB_PATH):
     raise ImportError(

@@ -18,6 +18,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_dbg = 0;
+int dbg_flags() { return g_dbg; }
+void set_dbg_flags(int v) { g_dbg = v; }
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int check_launch(const char* what) {

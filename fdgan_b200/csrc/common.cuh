@@ -10,7 +10,9 @@ namespace fdg {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
-int check_launch(const char* what);  // cudaGetLastError -> FDG_ECUDA
+int check_launch(const char* what);
+int dbg_flags();             // ablation switches for the tcgen05 kernels (fdg_set_option("dbg", v)); 0 in production
+void set_dbg_flags(int v);  // cudaGetLastError -> FDG_ECUDA
 
 // optional per-launch CUDA-event timing (bench.py's live roofline measurement); families of kernels
 enum ProfFamily { PF_CONV_SIMT = 0, PF_CONV_UMMA = 1, PF_WGRAD = 2, PF_EW = 3, PF_FREQ = 4, PF_OTHER = 5, PF_COUNT = 6 };

@@ -23,7 +23,8 @@ namespace fdg {
 constexpr int UKC_H = 64;                          // K elements per chunk
 constexpr int HT_W = 8, HT_H = 16;                 // output tile (8 wide so that one 8-row group = one image row)
 constexpr int H_LOAD_WARPS = 8;
-constexpr int H_THREADS = 14 * 32;
+constexpr int H_MMA_WARP = H_LOAD_WARPS, H_W_WARP = H_LOAD_WARPS + 1, H_EPI_WARP0 = H_LOAD_WARPS + 2;
+constexpr int H_THREADS = (H_LOAD_WARPS + 2 + 4) * 32;
 constexpr int H_MAXROWS = (HT_H + 3) * (HT_W + 3); // 4x4 filter: 19 x 11 halo pixels
 constexpr int H_A_TILE = ((H_MAXROWS * 128 + 1023) / 1024) * 1024;   // 27 KB per hi (or lo) halo tile
 constexpr int H_MAX_AFF = 1024;
@@ -35,19 +36,23 @@ struct HaloArgs {
   int HR, HC;      // halo rows / columns
   int a_tile;      // bytes of one bf16 halo tile (hi or lo), multiple of 1024
   int yvec;
+  int dbg;   // ablation: 1 no global loads, 2 no split/stores, 4 no MMA, 8 no epilogue
+  int tma_rank;                 // 4: the epilogue stores through ymap {channel, x, y, image}; 0: coalesced stores
+  alignas(64) CUtensorMap ymap;
 };
 
 template <int NT, int BSTAGES>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   const int A_STAGE = 2 * a.a_tile;
-  constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
+  static_assert(NT <= 128, "two double-width accumulators must fit the 512 TMEM columns");
+  constexpr int TMEM_COLS = 4 * NT;        // two accumulator buffers of [hi*hi | hi*lo + lo*hi] halves
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full[2], bar_a_empty[2], bar_b_full[BSTAGES], bar_b_empty[BSTAGES];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sred[2][4][NT];
-  __shared__ float ep_tile[4][32][33];
+  __shared__ __align__(1024) uint8_t ep_stage[EP_TILE_BYTES];   // epilogue staging tile (SWIZZLE_128B box layout)
   __shared__ __align__(16) float aff_s[2][H_MAX_AFF];
 
   const FdgConv& p = a.c;
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     }
     fence_barrier_init();
   }
-  if (warp == 12) {
+  if (warp == H_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -79,6 +84,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   const bool aff_smem = p.has_affine && p.Cin <= H_MAX_AFF;
   if (aff_smem)
     for (int i = t; i < p.Cin; i += H_THREADS) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
+  for (int i = t; i < 2 * 4 * NT; i += H_THREADS) (&sred[0][0][0])[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         for (int i = 0; i < H_ITEMS; ++i) {
           v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           v1[i] = v0[i];
-          if (((okmask >> i) & 1u) && cvalid) {
+          if (((okmask >> i) & 1u) && cvalid && !(a.dbg & 1)) {
             const float* src = tbase + (int64_t)hy[i] * p.x.sh + (int64_t)hx[i] * p.x.sw + cc * UKC_H;
             v0[i] = ld4(src);
             v1[i] = ld4(src + 4);
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + a.a_tile;
 #pragma unroll
         for (int i = 0; i < H_ITEMS; ++i) {
-          if (iv[i]) {
+          if (iv[i] && !(a.dbg & 2)) {
             const int row = (t >> 3) + i * (H_LOAD_WARPS * 4);
             const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
             uint32_t h[4], l[4];
@@ -205,13 +211,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         if (++buf == 2) { buf = 0; ph ^= 1u; }
       }
     }
-  } else if (warp >= 8 && warp < 12) {
-    // =============================================================== epilogue warps (TMEM lane quarter = warp & 3)
+  } else if (warp >= H_EPI_WARP0) {
+    // =============================================================== epilogue warps (TMEM lane quarter = warp & 3, two per quarter)
     const int quarter = warp & 3;
+    const int et = t - H_EPI_WARP0 * 32;
+    const uint32_t stage = smem_u32(ep_stage);
     const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
-    float acc1[NT / 32], acc2[NT / 32];
-#pragma unroll
-    for (int g = 0; g < NT / 32; ++g) { acc1[g] = 0.f; acc2[g] = 0.f; }
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       int ntile, n, oy0, ox0;
@@ -222,13 +227,32 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       const int m = quarter * 32 + lane;
       const int oy = oy0 + (m >> 3), ox = ox0 + (m & 7);
       const bool mv = oy < p.OH && ox < p.OW;
+      int64_t yoff = 0, eoff = 0;
+      if (mv) {
+        const int us = p.store == FDG_STORE_UP2 ? 2 : 1;
+        yoff = n * p.y.sn + (int64_t)(us * oy) * p.y.sh + (int64_t)(us * ox) * p.y.sw;
+        if (p.e.p) eoff = n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw;
+      }
+      const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, ox0, oy0, n};
       const int cbase = ntile * NT;
-#pragma unroll
+#pragma unroll 1
       for (int g = 0; g < NT / 32; ++g) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * NT + g * 32), v);
         const int c0 = cbase + g * 32;
-        if (c0 < p.Cout) umma_epilogue_group(p, a.yvec, evec, v, mv, n, oy, ox, c0, lane, ep_tile[quarter], acc1[g], acc2[g]);
+        if (c0 < p.Cout && !(a.dbg & 8)) {
+          float v[32];
+          {
+            float v2[32];
+            const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 * NT + g * 32);
+            tmem_ld32_nowait(tcol, v);
+            tmem_ld32_nowait(tcol + NT, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] += v2[u];
+          }
+          float s1 = 0.f, s2 = 0.f;
+          umma_epilogue_group(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, s1, s2);
+          if (p.stats) { sred[0][quarter][g * 32 + lane] += s1; sred[1][quarter][g * 32 + lane] += s2; }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -236,29 +260,25 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       if (p.stats) {
         const int next = tile + gridDim.x;
         if (next >= a.total_tiles || next / (p.N * tiles_img) != ntile) {
-#pragma unroll
-          for (int g = 0; g < NT / 32; ++g) {
-            sred[0][quarter][g * 32 + lane] = acc1[g];
-            sred[1][quarter][g * 32 + lane] = acc2[g];
-            acc1[g] = 0.f; acc2[g] = 0.f;
-          }
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          const int et = t - 8 * 32;
           for (int cidx = et; cidx < NT; cidx += 128) {
             const int c = ntile * NT + cidx;
             if (c < p.Cout) {
               atomicAdd(p.stats + c, (double)((sred[0][0][cidx] + sred[0][1][cidx]) + (sred[0][2][cidx] + sred[0][3][cidx])));
               atomicAdd(p.stats + p.stats_ld + c, (double)((sred[1][0][cidx] + sred[1][1][cidx]) + (sred[1][2][cidx] + sred[1][3][cidx])));
             }
+            sred[0][0][cidx] = 0.f; sred[0][1][cidx] = 0.f; sred[0][2][cidx] = 0.f; sred[0][3][cidx] = 0.f;
+            sred[1][0][cidx] = 0.f; sred[1][1][cidx] = 0.f; sred[1][2][cidx] = 0.f; sred[1][3][cidx] = 0.f;
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
     }
-  } else if (warp == 12) {
+    if (a.tma_rank && et == 0) bulk_wait_read0();
+  } else if (warp == H_MMA_WARP) {
     // =============================================================== MMA issue
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 2 * NT), idesc1 = umma_idesc_bf16(128, NT);
       const uint32_t sbo = (uint32_t)a.HC * 128u;
       const uint32_t b_hw = umma_desc_hi(1024);
       const uint32_t bfull0 = smem_u32(&bar_b_full[0]), bempty0 = smem_u32(&bar_b_empty[0]);
@@ -268,7 +288,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         const int b = it & 1;
         mbar_wait(smem_u32(&bar_acc_empty[b]), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(b * NT);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * 2 * NT);
         for (int cc = 0; cc < a.cchunks; ++cc) {
           mbar_wait(smem_u32(&bar_a_full[buf]), aph);
           tc_fence_after();
@@ -280,8 +300,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             mbar_wait(bfull0 + bs * 8, bph);
             tc_fence_after();
             const uint32_t b_hi = b_base + bs * (2 * B_TILE_BYTES);
-            umma_chunk12(d_tmem, ah_lo0 + shift, al_lo0 + shift, a_hw, umma_desc_lo(b_hi, 16), umma_desc_lo(b_hi + B_TILE_BYTES, 16), b_hw,
-                         idesc, (cc > 0 || tap > 0) ? 1u : 0u, 2u);
+            if (!(a.dbg & 4)) umma_chunk8(d_tmem, ah_lo0 + shift, al_lo0 + shift, a_hw, umma_desc_lo(b_hi, 16), b_hw, idesc2, idesc1,
+                                          (cc > 0 || tap > 0) ? 1u : 0u, 2u, 2u, (uint32_t)NT);
             umma_commit(bempty0 + bs * 8);
             if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
             if (++kx == p.S) { kx = 0; ++ky; }
@@ -292,7 +312,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         umma_commit(smem_u32(&bar_acc_full[b]));
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == H_W_WARP) {
     // =============================================================== weight-tile producer (bulk TMA ring)
     if (lane == 0) {
       int bs = 0;
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == H_MMA_WARP) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -371,6 +391,15 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
   a.HC = HT_W + p->S - 1;
   a.a_tile = ((a.HR * a.HC * 128 + 1023) / 1024) * 1024;
   a.yvec = vec4_ok(p->y);
+  a.dbg = dbg_flags();
+  a.tma_rank = 0;
+  static const int tma_on = [] { const char* e = getenv("FDG_TMA_STORE"); return e ? atoi(e) : 1; }();
+  if (tma_on && a.yvec && p->store == FDG_STORE_NORMAL && !p->e.p) {
+    const uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)p->OW, (uint64_t)p->OH, (uint64_t)p->N};
+    const uint64_t strides[3] = {(uint64_t)p->y.sw * 4, (uint64_t)p->y.sh * 4, (uint64_t)p->y.sn * 4};
+    const uint32_t box[4] = {32, (uint32_t)HT_W, (uint32_t)HT_H, 1};
+    if (make_tmap_f32(&a.ymap, p->y.p, 4, dims, strides, box)) a.tma_rank = 4;
+  }
   // weight-tile ring depth: as deep as shared memory allows (the ring hides the L2 latency of the bulk copies)
   switch (nt) {
     case 32: return launch_halo<32, 10>(a, st);
@@ -389,6 +418,10 @@ extern "C" int fdg_set_option(const char* name, int value) {
   if (name && name[0] == 'h' && name[1] == 'a' && name[2] == 'l' && name[3] == 'o' && name[4] == 0) {
     fdg::g_halo_on = value;
     fdg::set_wgrad_halo(value);
+    return FDG_OK;
+  }
+  if (name && name[0] == 'd' && name[1] == 'b' && name[2] == 'g' && name[3] == 0) {
+    fdg::set_dbg_flags(value);
     return FDG_OK;
   }
   fdg::set_error("fdg_set_option: unknown option");

@@ -39,6 +39,9 @@ struct UmmaArgs {
   int cchunks;   // ceil(Cin / 64)
   int nchunks;   // taps * cchunks
   int yvec;
+  int dbg;   // ablation: 1 no global loads, 2 no split/stores, 4 no MMA, 8 no epilogue
+  int tma_rank;                 // 2: the epilogue stores through ymap {channel, linear pixel}; 0: coalesced stores
+  alignas(64) CUtensorMap ymap;
 };
 
 __device__ __forceinline__ float epi_act_u(float v, int act) {
@@ -82,7 +85,8 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   constexpr int B_TILE_BYTES = NT * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   constexpr int STAGING_BYTES = UM * UKC * 4;          // one raw fp32 chunk
-  constexpr int TMEM_COLS = 2 * NT < 32 ? 32 : 2 * NT;
+  static_assert(NT <= 128, "two double-width accumulators must fit the 512 TMEM columns");
+  constexpr int TMEM_COLS = 4 * NT;        // two accumulator buffers of [hi*hi | hi*lo + lo*hi] halves
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sred[2][4][NT];
-  __shared__ float ep_tile[4][32][33];     // per-epilogue-warp transpose tile for the BatchNorm statistics
+  __shared__ __align__(1024) uint8_t ep_stage[EP_TILE_BYTES];   // epilogue staging tile: 128 pixels x 32 channels, SWIZZLE_128B box layout
   __shared__ __align__(16) float aff_s[2][UMAX_AFF];   // BatchNorm scale / shift of the input channels (when they fit)
 
   const FdgConv& p = a.c;
@@ -121,6 +125,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   if (aff_smem) {
     for (int i = t; i < p.Cin; i += UTHREADS_P) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
   }
+  for (int i = t; i < 2 * 4 * NT; i += UTHREADS_P) (&sred[0][0][0])[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -249,6 +254,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       }
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
+        if (a.dbg & 2) break;
         const int row = rbase + RSTEP * i;
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
         uint32_t h[4], l[4];
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             const int iy = piy[i] + l_r, ix = pix[i] + l_sx;
-            const bool v = ((pvmask >> i) & 1u) && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            const bool v = ((pvmask >> i) & 1u) && cvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && !(a.dbg & 1);
             const uint32_t dst = stg + (uint32_t)((d * RPT + i) * 2 * NLT) * 16u;
             if (direct) {
               if (v) {
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   } else if (warp == ULOAD_WARPS) {
     // =============================================================== control thread: MMA issue
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(UM, NT);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(UM, 2 * NT), idesc1 = umma_idesc_bf16(UM, NT);
       const uint32_t k_hw = umma_desc_hi(1024);
       int s = 0;
       uint32_t ph = 0;
@@ -367,14 +373,14 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
         const int b = it & 1;
         mbar_wait(smem_u32(&bar_acc_empty[b]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(b * NT);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * 2 * NT);
         for (int kc = 0; kc < a.nchunks; ++kc) {
           mbar_wait(smem_u32(&bar_full[s]), ph);
           tc_fence_after();
           const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-          const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
-          umma_chunk12(d_tmem, umma_desc_lo(a_hi, 16), umma_desc_lo(a_lo, 16), k_hw, umma_desc_lo(b_hi, 16), umma_desc_lo(b_lo, 16), k_hw,
-                       idesc, kc > 0 ? 1u : 0u, 2u);
+          const uint32_t b_hi = a_lo + A_TILE_BYTES;     // [B_hi | B_lo] are adjacent: one operand of 2*NT rows
+          if (!(a.dbg & 4)) umma_chunk8(d_tmem, umma_desc_lo(a_hi, 16), umma_desc_lo(a_lo, 16), k_hw, umma_desc_lo(b_hi, 16), k_hw, idesc2, idesc1,
+                                        kc > 0 ? 1u : 0u, 2u, 2u, (uint32_t)NT);
           umma_commit(smem_u32(&bar_empty[s]));                // frees this stage when the MMAs above retire
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -383,11 +389,10 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     }
   } else {
     // =============================================================== epilogue warps (TMEM lane quarter = warp & 3)
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;                      // TMEM lanes this warp may read
+    const int et = t - UEPI_WARP0 * 32;
+    const uint32_t stage = smem_u32(ep_stage);
     const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
-    float acc1[NT / 32], acc2[NT / 32];     // running per-channel sums of this lane's column (BatchNorm statistics)
-#pragma unroll
-    for (int g = 0; g < NT / 32; ++g) { acc1[g] = 0.f; acc2[g] = 0.f; }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mt = tile % m_tiles, ntile = tile / m_tiles;
@@ -396,21 +401,34 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       tc_fence_after();
       const int64_t m = (int64_t)mt * UM + quarter * 32 + lane;
       const bool mv = m < a.M;
-      int n = 0, oy = 0, ox = 0;
+      int64_t yoff = 0, eoff = 0;
       if (mv) {
-        n = (int)(m / OHW);
+        const int n = (int)(m / OHW);
         const int rem = (int)(m - (int64_t)n * OHW);
-        oy = rem / p.OW;
-        ox = rem - oy * p.OW;
+        const int oy = rem / p.OW, ox = rem - oy * p.OW;
+        const int us = p.store == FDG_STORE_UP2 ? 2 : 1;
+        yoff = n * p.y.sn + (int64_t)(us * oy) * p.y.sh + (int64_t)(us * ox) * p.y.sw;
+        if (p.e.p) eoff = n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw;
       }
+      const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, mt * UM, 0, 0};
       const int cbase = ntile * NT;
-#pragma unroll
+#pragma unroll 1
       for (int g = 0; g < NT / 32; ++g) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * NT + g * 32), v);
         const int c0 = cbase + g * 32;
-        if (c0 < p.Cout) {
-          umma_epilogue_group(p, a.yvec, evec, v, mv, n, oy, ox, c0, lane, ep_tile[quarter], acc1[g], acc2[g]);
+        if (c0 < p.Cout && !(a.dbg & 8)) {
+          float v[32];
+          {
+            float v2[32];
+            const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 * NT + g * 32);
+            tmem_ld32_nowait(tcol, v);
+            tmem_ld32_nowait(tcol + NT, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] += v2[u];
+          }
+          float s1 = 0.f, s2 = 0.f;
+          umma_epilogue_group(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, s1, s2);
+          if (p.stats) { sred[0][quarter][g * 32 + lane] += s1; sred[1][quarter][g * 32 + lane] += s2; }
         }
       }
       // release the accumulator buffer to the MMA thread
@@ -421,25 +439,21 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       if (p.stats) {
         const int next = tile + gridDim.x;
         if (next >= total_tiles || next / m_tiles != ntile) {
-#pragma unroll
-          for (int g = 0; g < NT / 32; ++g) {
-            sred[0][quarter][g * 32 + lane] = acc1[g];
-            sred[1][quarter][g * 32 + lane] = acc2[g];
-            acc1[g] = 0.f; acc2[g] = 0.f;
-          }
           asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
-          const int et = t - UEPI_WARP0 * 32;
           for (int cidx = et; cidx < NT; cidx += 128) {
             const int c = ntile * NT + cidx;
             if (c < p.Cout) {
               atomicAdd(p.stats + c, (double)((sred[0][0][cidx] + sred[0][1][cidx]) + (sred[0][2][cidx] + sred[0][3][cidx])));
               atomicAdd(p.stats + p.stats_ld + c, (double)((sred[1][0][cidx] + sred[1][1][cidx]) + (sred[1][2][cidx] + sred[1][3][cidx])));
             }
+            sred[0][0][cidx] = 0.f; sred[0][1][cidx] = 0.f; sred[0][2][cidx] = 0.f; sred[0][3][cidx] = 0.f;
+            sred[1][0][cidx] = 0.f; sred[1][1][cidx] = 0.f; sred[1][2][cidx] = 0.f; sred[1][3][cidx] = 0.f;
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
     }
+    if (a.tma_rank && et == 0) bulk_wait_read0();   // the staging tile must outlive the last bulk store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -489,7 +503,7 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, int ld, int taps, 
 
 static inline int umma_ntile(int Cout) {
   static const int cap = [] { const char* e = getenv("FDG_UMMA_NT_CAP"); return e ? atoi(e) : 128; }();
-  const int nt = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+  const int nt = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
   return nt > cap ? cap : nt;
 }
 
@@ -539,11 +553,23 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
   a.cchunks = cdiv(p->Cin, UKC);
   a.nchunks = p->R * p->S * a.cchunks;
   a.yvec = vec4_ok(p->y);
+  a.dbg = dbg_flags();
+  a.tma_rank = 0;
+  static const int tma_on = [] { const char* e = getenv("FDG_TMA_STORE"); return e ? atoi(e) : 1; }();
+  // bulk tensor stores: plain store into a unit-channel-stride, pixel-linear view (dense NHWC or a channel slice of one)
+  if (tma_on && a.yvec && p->store == FDG_STORE_NORMAL && !p->e.p && p->y.sh == (int64_t)p->OW * p->y.sw &&
+      p->y.sn == (int64_t)p->OH * p->y.sh && a.M < (1ll << 31)) {
+    const uint64_t dims[2] = {(uint64_t)p->Cout, (uint64_t)a.M};
+    const uint64_t strides[1] = {(uint64_t)p->y.sw * 4};
+    const uint32_t box[2] = {32, 128};
+    if (make_tmap_f32(&a.ymap, p->y.p, 2, dims, strides, box)) a.tma_rank = 2;
+  }
+  static const int reg_path = [] { const char* e = getenv("FDG_CONV_REG"); return e ? atoi(e) : 0; }();
+  if (reg_path && umma_ntile(p->Cout) == 128) return launch_umma<128, 3, 0>(a, st);   // register double buffer, no staging ring
   switch (umma_ntile(p->Cout)) {
     case 32: return launch_umma<32, 2, 3>(a, st);     // ring 2 x 40 KB + staging 3 x 32 KB
     case 64: return launch_umma<64, 2, 3>(a, st);     // ring 2 x 48 KB + staging 3 x 32 KB
-    case 128: return launch_umma<128, 2, 2>(a, st);   // ring 2 x 64 KB + staging 2 x 32 KB
-    default: return launch_umma<256, 2, 0>(a, st);    // ring 2 x 96 KB, register double buffer
+    default: return launch_umma<128, 2, 2>(a, st);    // ring 2 x 64 KB + staging 2 x 32 KB
   }
 }
 

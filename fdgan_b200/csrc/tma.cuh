@@ -1,0 +1,28 @@
+// TMA (bulk tensor copy) helpers: host-side tensor-map construction through the driver entry point (no libcuda link
+// dependency) and the device-side store / group instructions used by the tcgen05 epilogues.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fdg {
+
+// fp32 tensor map of rank 2..4 with SWIZZLE_128B boxes whose innermost extent is 32 floats (128 bytes).
+// dims[0] is the contiguous (channel) dimension; strides_bytes[i] is the stride of dims[i + 1].
+// Returns false when the view cannot be described (alignment / stride rules of cuTensorMapEncodeTiled).
+bool make_tmap_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(smem), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+}  // namespace fdg

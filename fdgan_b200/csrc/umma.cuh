@@ -88,6 +88,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// same without the wait: several loads can be in flight before one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+        "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+        "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // fp32 pair -> packed bf16x2 (lo half = first element) and the residual pair
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -262,6 +284,57 @@ __device__ __forceinline__ void umma_chunk12_ab(uint32_t d_tmem, uint32_t a_hi_l
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %7, pt;\n\t"
       "}"
       ::"r"(d_tmem), "r"(a_hi_lo), "r"(a_lo_lo), "r"(a_hw), "r"(b_hi_lo), "r"(b_lo_lo), "r"(b_hw), "r"(idesc), "r"(accumulate_first), "r"(kstep), "r"(kstep_b)
+      : "memory");
+}
+
+// Concatenated-B form of the bf16x3 split: the hi and lo images of the B operand are adjacent in shared memory, so
+// ONE MMA of width 2*NT multiplies A_hi with [B_hi | B_lo] (columns [0, NT) += hi*hi, [NT, 2NT) += hi*lo) and a
+// second one of width NT adds A_lo * B_hi into columns [NT, 2NT): 8 instead of 12 MMAs per 64-deep chunk and one
+// third fewer shared-memory reads of the A operand (the binding resource for small N).  The epilogue adds the two
+// column halves.  idesc2 / idesc1 = instruction descriptors for N = 2NT / NT; kstep_a / kstep_b as in umma_chunk12_ab.
+__device__ __forceinline__ void umma_chunk8(uint32_t d_tmem, uint32_t a_hi_lo, uint32_t a_lo_lo, uint32_t a_hw, uint32_t b_hi_lo,
+                                            uint32_t b_hw, uint32_t idesc2, uint32_t idesc1, uint32_t accumulate_first, uint32_t kstep_a,
+                                            uint32_t kstep_b, uint32_t nt_cols) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ta, tb, d2;\n\t"
+      ".reg .pred p, pt;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.u32 d2, %0, %11;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%4, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t"
+      "mov.b64 da, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 1, %1;\n\t"
+      "mad.lo.u32 tb, %10, 1, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, pt;\n\t"
+      "mad.lo.u32 ta, %9, 1, %2;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 2, %1;\n\t"
+      "mad.lo.u32 tb, %10, 2, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, pt;\n\t"
+      "mad.lo.u32 ta, %9, 2, %2;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %7, pt;\n\t"
+      "mad.lo.u32 ta, %9, 3, %1;\n\t"
+      "mad.lo.u32 tb, %10, 3, %4;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "mov.b64 db, {tb, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, pt;\n\t"
+      "mad.lo.u32 ta, %9, 3, %2;\n\t"
+      "mov.b64 da, {ta, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %7, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi_lo), "r"(a_lo_lo), "r"(a_hw), "r"(b_hi_lo), "r"(b_hw), "r"(idesc2), "r"(idesc1), "r"(accumulate_first),
+        "r"(kstep_a), "r"(kstep_b), "r"(nt_cols)
       : "memory");
 }
 

@@ -1,108 +1,173 @@
-// Epilogue of the tcgen05 convolution kernels: one 32-channel group of one output pixel, held in registers after
-// tcgen05.ld, goes through alpha / bias / activation / backward mask, is stored (normal, 2x2 nearest-upsample or
-// accumulate) and contributes to the per-channel BatchNorm statistics (padded shared-memory transpose: lane l ends up
-// with the column sums of channel c0 + l over the warp's 32 pixels).
+// Epilogue of the tcgen05 convolution kernels.  Four epilogue warps (one per TMEM lane quarter) walk the accumulator
+// in 32-channel groups; after tcgen05.ld a lane holds one output pixel.  alpha / bias / activation happen in
+// registers, then the group goes into a [128 pixels][32 channels] fp32 staging tile in shared memory laid out exactly
+// like a SWIZZLE_128B TMA box (16-byte chunk index XOR row & 7), from where
+//   * the common case (plain store into a unit-channel-stride view) leaves with ONE bulk tensor store per group
+//     (cp.async.bulk.tensor, clipping of partial tiles / channel tails by the tensor map), or
+//   * the other store modes (2x2 nearest-upsample replicas, accumulate, ReLU/LeakyReLU backward mask from a second
+//     tensor, strided channels) leave as coalesced 128-bit rows: one instruction = 4 pixels x 128 bytes.
+// The per-channel BatchNorm statistics are column sums over the same tile (lane = channel).
 #pragma once
 #include "aop.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 
 namespace fdg {
 
-__device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec, bool evec, float (&v)[32], bool mv, int n, int oy,
-                                                    int ox, int c0, int lane, float (*tile)[33], float& acc1, float& acc2) {
-    const int nvalid = p.Cout - c0 < 32 ? p.Cout - c0 : 32;
-    const bool full = nvalid == 32;
-    // ---- alpha, bias
-    if (p.bias) {
-      if (full) {
+constexpr int EP_TILE_BYTES = 128 * 128;   // staging tile: 128 pixels x 32 fp32 channels
+
+struct EpiTma {
+  const void* map;   // tensor map in kernel-parameter space, or nullptr: coalesced path
+  int rank;          // 2: {channel, linear pixel}; 4: {channel, x, y, image}
+  int c1, c2, c3;    // pixel coordinates of the tile (c1 only for rank 2)
+};
+
+// v:      the lane's pixel (tile row quarter*32 + lane), channels c0 .. c0+31 (accumulator values)
+// mv:     the lane's pixel exists
+// yoff:   element offset of the lane's pixel in y (for FDG_STORE_UP2: of its top-left replica), channel 0
+// eoff:   element offset of the lane's pixel in e
+// et:     thread index within the 128 epilogue threads
+// s1, s2: (p.stats only) receive the sum / sum of squares of channel c0 + lane over the warp's 32 pixels
+__device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec, bool evec, float (&v)[32], bool mv, int64_t yoff,
+                                                    int64_t eoff, int c0, int lane, int quarter, int et, uint32_t tile, const EpiTma& tm,
+                                                    float& s1, float& s2) {
+  const int nvalid = p.Cout - c0 < 32 ? p.Cout - c0 : 32;
+  const bool full = nvalid == 32;
+  // ---- alpha, bias
+  if (p.bias) {
+    if (full) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = ld4(p.bias + c0 + 4 * q);
-          v[4 * q] = fmaf(v[4 * q], p.alpha, bb.x); v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, bb.y);
-          v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, bb.z); v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, bb.w);
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] = fmaf(v[u], p.alpha, u < nvalid ? __ldg(p.bias + c0 + u) : 0.f);
+      for (int q = 0; q < 8; ++q) {
+        const float4 bb = ld4(p.bias + c0 + 4 * q);
+        v[4 * q] = fmaf(v[4 * q], p.alpha, bb.x); v[4 * q + 1] = fmaf(v[4 * q + 1], p.alpha, bb.y);
+        v[4 * q + 2] = fmaf(v[4 * q + 2], p.alpha, bb.z); v[4 * q + 3] = fmaf(v[4 * q + 3], p.alpha, bb.w);
       }
-    } else if (p.alpha != 1.f) {
+    } else {
 #pragma unroll
-      for (int u = 0; u < 32; ++u) v[u] *= p.alpha;
+      for (int u = 0; u < 32; ++u) v[u] = fmaf(v[u], p.alpha, u < nvalid ? __ldg(p.bias + c0 + u) : 0.f);
     }
-    // ---- activation (uniform switch hoisted out of the element loop)
-    if (p.act == FDG_ACT_RELU) {
+  } else if (p.alpha != 1.f) {
 #pragma unroll
-      for (int u = 0; u < 32; ++u) v[u] = fmaxf(v[u], 0.f);
-    } else if (p.act == FDG_ACT_TANH) {
+    for (int u = 0; u < 32; ++u) v[u] *= p.alpha;
+  }
+  // ---- activation (uniform switch hoisted out of the element loop)
+  if (p.act == FDG_ACT_RELU) {
 #pragma unroll
-      for (int u = 0; u < 32; ++u) v[u] = tanhf(v[u]);
-    } else if (p.act == FDG_ACT_SIGMOID) {
+    for (int u = 0; u < 32; ++u) v[u] = fmaxf(v[u], 0.f);
+  } else if (p.act == FDG_ACT_TANH) {
 #pragma unroll
-      for (int u = 0; u < 32; ++u) v[u] = 1.f / (1.f + expf(-v[u]));
+    for (int u = 0; u < 32; ++u) v[u] = tanhf(v[u]);
+  } else if (p.act == FDG_ACT_SIGMOID) {
+#pragma unroll
+    for (int u = 0; u < 32; ++u) v[u] = 1.f / (1.f + expf(-v[u]));
+  }
+  if (!mv || !full) {
+#pragma unroll
+    for (int u = 0; u < 32; ++u) if (!mv || u >= nvalid) v[u] = 0.f;
+  }
+  const bool use_tma = tm.map != nullptr;
+  if (use_tma) {
+    // the previous group's bulk store must have finished READING the staging tile before it is overwritten
+    if (et == 0) bulk_wait_read0();
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+  }
+  // ---- staging tile row of this lane's pixel
+  const uint32_t wrow0 = tile + (uint32_t)(quarter * 32) * 128u;      // first row of this warp
+  {
+    const uint32_t trow = wrow0 + (uint32_t)lane * 128u;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (uint32_t)((q ^ sw) << 4)), "f"(v[4 * q]), "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
+  }
+  const bool has_e = p.e.p != nullptr;
+  if (use_tma) {
+    fence_proxy_async();                                   // generic-proxy writes -> visible to the bulk-copy engine
+    asm volatile("bar.sync 3, 128;" ::: "memory");
+    if (et == 0) {
+      if (tm.rank == 2) tma_store_2d(tm.map, tile, c0, tm.c1);
+      else tma_store_4d(tm.map, tile, c0, tm.c1, tm.c2, tm.c3);
+      bulk_commit();
     }
-    // ---- ReLU / LeakyReLU backward mask from a second tensor
-    if (p.e.p && mv) {
-      const float* ep = p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + (int64_t)c0 * p.e.sc;
-      if (evec && full) {
+  } else {
+    __syncwarp();
+    const uint32_t vmask = __ballot_sync(0xffffffffu, mv);
+    const int up2 = p.store == FDG_STORE_UP2;
+    if (yvec && (nvalid & 3) == 0 && (!has_e || evec)) {
+      // ---- coalesced phase: instruction i covers pixels 4i .. 4i+3 of the warp, lane handles channels 4*(lane & 7) .. +3
+      const int q = lane & 7, c4 = q * 4;
+      const bool cv = c4 < nvalid;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 ev = ld4(ep + 4 * q);
-          v[4 * q] *= ev.x > 0.f ? 1.f : p.eslope; v[4 * q + 1] *= ev.y > 0.f ? 1.f : p.eslope;
-          v[4 * q + 2] *= ev.z > 0.f ? 1.f : p.eslope; v[4 * q + 3] *= ev.w > 0.f ? 1.f : p.eslope;
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 32; ++u)
-          if (u < nvalid) v[u] *= __ldg(ep + (int64_t)u * p.e.sc) > 0.f ? 1.f : p.eslope;
-      }
-    }
-    if (!mv || !full) {
-#pragma unroll
-      for (int u = 0; u < 32; ++u) if (!mv || u >= nvalid) v[u] = 0.f;
-    }
-    if (mv) {
-      const int reps = p.store == FDG_STORE_UP2 ? 4 : 1;
-      for (int d = 0; d < reps; ++d) {
-        const int yy = p.store == FDG_STORE_UP2 ? 2 * oy + (d >> 1) : oy, xx = p.store == FDG_STORE_UP2 ? 2 * ox + (d & 1) : ox;
-        float* yp = p.y.p + n * p.y.sn + (int64_t)yy * p.y.sh + (int64_t)xx * p.y.sw + (int64_t)c0 * p.y.sc;
-        if (yvec && full) {
-          if (p.store == FDG_STORE_ACCUM) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 old = *reinterpret_cast<const float4*>(yp + 4 * q);
-              *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q] + old.x, v[4 * q + 1] + old.y, v[4 * q + 2] + old.z, v[4 * q + 3] + old.w);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + (lane >> 3);
+        const int64_t yo = __shfl_sync(0xffffffffu, yoff, row);
+        int64_t eo = 0;
+        if (has_e) eo = __shfl_sync(0xffffffffu, eoff, row);
+        if (((vmask >> row) & 1u) && cv) {
+          float4 val;
+          const uint32_t ta = wrow0 + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(ta) : "memory");
+          if (has_e) {
+            const float4 ev = ld4(p.e.p + eo + c0 + c4);
+            val.x *= ev.x > 0.f ? 1.f : p.eslope; val.y *= ev.y > 0.f ? 1.f : p.eslope;
+            val.z *= ev.z > 0.f ? 1.f : p.eslope; val.w *= ev.w > 0.f ? 1.f : p.eslope;
+            if (p.stats) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
           }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 32; ++u)
-            if (u < nvalid) {
-              float* q1 = yp + (int64_t)u * p.y.sc;
-              *q1 = p.store == FDG_STORE_ACCUM ? *q1 + v[u] : v[u];
-            }
+          float* yp = p.y.p + yo + c0 + c4;
+          if (up2) {
+            *reinterpret_cast<float4*>(yp) = val;
+            *reinterpret_cast<float4*>(yp + p.y.sw) = val;
+            *reinterpret_cast<float4*>(yp + p.y.sh) = val;
+            *reinterpret_cast<float4*>(yp + p.y.sh + p.y.sw) = val;
+          } else if (p.store == FDG_STORE_ACCUM) {
+            const float4 old = *reinterpret_cast<const float4*>(yp);
+            *reinterpret_cast<float4*>(yp) = make_float4(val.x + old.x, val.y + old.y, val.z + old.z, val.w + old.w);
+          } else {
+            *reinterpret_cast<float4*>(yp) = val;
+          }
+        }
+      }
+    } else {
+      // ---- generic phase (odd channel counts, strided channels, unaligned views): the lane walks its own pixel
+      if (mv) {
+        const uint32_t trow = wrow0 + (uint32_t)lane * 128u;
+#pragma unroll 1
+        for (int u = 0; u < nvalid; ++u) {
+          const uint32_t ta = trow + (uint32_t)((((u >> 2) ^ (lane & 7)) << 4) + ((u & 3) << 2));
+          float val;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(ta) : "memory");
+          if (has_e) {
+            val *= __ldg(p.e.p + eoff + (int64_t)(c0 + u) * p.e.sc) > 0.f ? 1.f : p.eslope;
+            if (p.stats) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta), "f"(val) : "memory");
+          }
+          float* yp = p.y.p + yoff + (int64_t)(c0 + u) * p.y.sc;
+          if (up2) {
+            yp[0] = val; yp[p.y.sw] = val; yp[p.y.sh] = val; yp[p.y.sh + p.y.sw] = val;
+          } else if (p.store == FDG_STORE_ACCUM) {
+            *yp += val;
+          } else {
+            *yp = val;
+          }
         }
       }
     }
-    if (p.stats) {
-      // column sums through a padded shared-memory transpose: lane l ends up with the sums of column l
+    __syncwarp();
+  }
+  if (p.stats) {
+    // lane = channel: column sums over the warp's 32 rows (conflict-free: one row per step, 32 distinct words)
+    float a1 = 0.f, a2 = 0.f;
+    const uint32_t cpos = (uint32_t)(lane >> 2), cw = (uint32_t)(lane & 3) << 2;
 #pragma unroll
-      for (int u = 0; u < 32; ++u) tile[u][lane] = v[u];
-      __syncwarp();
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const float xv = tile[lane][rr];
-        s1 += xv;
-        s2 = fmaf(xv, xv, s2);
-      }
-      __syncwarp();
-      acc1 += s1;
-      acc2 += s2;
+    for (int rr = 0; rr < 32; ++rr) {
+      float xv;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv) : "r"(wrow0 + (uint32_t)rr * 128u + (((cpos ^ (uint32_t)(rr & 7)) << 4) + cw)) : "memory");
+      a1 += xv;
+      a2 = fmaf(xv, xv, a2);
     }
+    s1 = a1;
+    s2 = a2;
+  }
+  if (!use_tma) __syncwarp();   // the warp's rows are rewritten by the next group
 }
 
 }  // namespace fdg

@@ -29,6 +29,7 @@ struct WHArgs {
   int cblocks, co_tiles, tiles_x, tiles_y, total_ptiles, ptiles_per_split, splits;
   int HR, HC;
   int gvec;
+  int dbg;
 };
 
 __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_constant__ WHArgs a) {
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
         v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         v1[i] = v0[i];
         const int iy = iy0 + hy[i], ix = ix0 + hx[i];
-        if (iv[i] && cav && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+        if (iv[i] && cav && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && !(a.dbg & 1)) {
           ok |= 1u << i;
           const float* src = tbase + (int64_t)hy[i] * p.x.sh + (int64_t)hx[i] * p.x.sw;
           v0[i] = ld4(src);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
       float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
       {
         const int oy = oy0 + (gpix >> 3), ox = ox0 + (gpix & 7);
-        if (oy < p.OH && ox < p.OW && cg < p.Cout) {
+        if (oy < p.OH && ox < p.OW && cg < p.Cout && !(a.dbg & 1)) {
           const float* gp = p.g.p + n * p.g.sn + (int64_t)oy * p.g.sh + (int64_t)ox * p.g.sw;
           if (a.gvec) { g0 = ld4(gp + cg); g1 = ld4(gp + cg + 4); }
           else {
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
       const uint32_t st = smem_base + buf * WH_STAGE;
 #pragma unroll
       for (int i = 0; i < WH_AITEMS; ++i) {
-        if (iv[i]) {
+        if (iv[i] && !(a.dbg & 2)) {
           const int row = (t >> 4) + i * (WH_LOAD_WARPS * 2);
           const uint32_t off = (uint32_t)ablk * WH_ABLK + (uint32_t)row * 128u + (uint32_t)((acj ^ (row & 7)) << 4);
           uint32_t h[4], l[4];
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
       int ky = 0, kx = 0;
       for (int tap = 0; tap < taps; ++tap) {
         const uint32_t shift = (uint32_t)(ky * a.HC + kx) * 8u;
-        umma_chunk12_ab(tmem_base + (uint32_t)(tap * 32), ah0 + shift, al0 + shift, a_hw, gh0, gl0, g_hw, idesc, it > 0 ? 1u : 0u,
+        if (!(a.dbg & 4)) umma_chunk12_ab(tmem_base + (uint32_t)(tap * 32), ah0 + shift, al0 + shift, a_hw, gh0, gl0, g_hw, idesc, it > 0 ? 1u : 0u,
                         kstep_a, 128u);
         if (++kx == p.S) { kx = 0; ++ky; }
       }
@@ -241,6 +242,7 @@ int wgrad_halo(const FdgWgrad* p, cudaStream_t st) {
   a.HR = WH_T + p->R - 1;
   a.HC = WH_T + p->S - 1;
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
+  a.dbg = dbg_flags();
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;

@@ -32,6 +32,7 @@ struct WUArgs {
   int co_tiles;      // ceil(Cout / NT)
   int tiles;         // kblocks * co_tiles
   int64_t m_per_split;
+  int dbg;           // ablation: 1 no global loads, 2 no split/stores, 4 no MMA
   int gvec;          // gradient rows loadable as float4 (unit channel stride, aligned, Cout % 8 == 0)
 };
 
@@ -41,7 +42,8 @@ template <int NT, int STAGES, int DEPTH>
 __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs a) {
   constexpr int G_BYTES = (NT / 64) * WU_BLK;
   constexpr int STAGE_BYTES = 2 * WU_A_BYTES + 2 * G_BYTES;
-  constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+  constexpr bool CONCAT = NT <= 128;       // [G_hi | G_lo] as one operand of width 2*NT (see umma_chunk8)
+  constexpr int TMEM_COLS = CONCAT ? 2 * NT : NT;
   constexpr int GQ = NT / 64;             // 8-channel gradient chunks per loader thread
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       auto issue_async = [&](int st, uint32_t eph) {
         mbar_wait(empty0 + st * 8, eph ^ 1u);          // the MMAs that read this stage have retired
         uint32_t ok = 0;
-        if (lm < mend) {
+        if (lm < mend && !(a.dbg & 1)) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = h ? ca1 : ca0;
@@ -280,8 +282,10 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ok) : "r"(meta0 + st * (NLT * 4)) : "memory");
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float sl = p.slope;
+        if (a.dbg & 2) ok = 0x80000000u;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          if (ok >> 31) break;
           float4 a0 = z4, a1 = z4;
           if ((ok >> h) & 1u) {
             a0 = lds4(slot_a(st, h, 0));
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
         }
 #pragma unroll
         for (int q = 0; q < GQ; ++q) {
+          if (ok >> 31) break;
           float4 g0 = z4, g1 = z4;
           if (ok & (4u << q)) { g0 = lds4(slot_g(st, q, 0)); g1 = lds4(slot_g(st, q, 1)); }
           uint32_t hi[4], lo[4];
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
     }
   } else if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
     // =============================================================== MMA issue
-    constexpr uint32_t idesc = umma_idesc_bf16_mn(WU_K, NT);
+    constexpr uint32_t idesc = umma_idesc_bf16_mn(WU_K, NT), idesc2 = umma_idesc_bf16_mn(WU_K, CONCAT ? 2 * NT : NT);
     const uint32_t mn_hw = umma_desc_hi(1024);
     int s = 0;
     uint32_t ph = 0;
@@ -361,8 +366,14 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       const uint32_t g_hi = a_lo + WU_A_BYTES, g_lo = g_hi + G_BYTES;
       // 16 pixels per slice = two 8-row swizzle atoms (SBO 1024 B); 64-channel blocks are WU_BLK bytes apart (LBO);
       // consecutive slices are 2048 B = 128 descriptor units apart
-      umma_chunk12(tmem_base, umma_desc_lo(a_hi, WU_BLK), umma_desc_lo(a_lo, WU_BLK), mn_hw, umma_desc_lo(g_hi, WU_BLK),
-                   umma_desc_lo(g_lo, WU_BLK), mn_hw, idesc, kc > 0 ? 1u : 0u, 128u);
+      if (!(a.dbg & 4)) {
+        if (CONCAT)
+          umma_chunk8(tmem_base, umma_desc_lo(a_hi, WU_BLK), umma_desc_lo(a_lo, WU_BLK), mn_hw, umma_desc_lo(g_hi, WU_BLK), mn_hw, idesc2, idesc,
+                      kc > 0 ? 1u : 0u, 128u, 128u, (uint32_t)NT);
+        else
+          umma_chunk12(tmem_base, umma_desc_lo(a_hi, WU_BLK), umma_desc_lo(a_lo, WU_BLK), mn_hw, umma_desc_lo(g_hi, WU_BLK),
+                       umma_desc_lo(g_lo, WU_BLK), mn_hw, idesc, kc > 0 ? 1u : 0u, 128u);
+      }
       umma_commit(smem_u32(&bar_empty[s]));
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
@@ -382,6 +393,12 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
     for (int g = 0; g < NT / 32; ++g) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32), v);
+      if (CONCAT) {
+        float v2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(NT + g * 32), v2);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] += v2[u];
+      }
       if (kvalid) {
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
@@ -455,6 +472,10 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   a.M = (int64_t)p->N * p->OH * p->OW;
   a.kblocks = cdiv(p->R * p->S * p->Cin, WU_K);
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
+  a.dbg = dbg_flags();
+  static const int reg_path = [] { const char* e = getenv("FDG_WGRAD_REG"); return e ? atoi(e) : 0; }();
+  if (reg_path && wu_ntile(p->Cout) == 128) return launch_wu<128, 3, 0>(a, st);
+  if (reg_path && wu_ntile(p->Cout) == 64) return launch_wu<64, 4, 0>(a, st);
   switch (wu_ntile(p->Cout)) {
     case 64: return launch_wu<64, 4, 1>(a, st);      // 4 x 48 KB in-place staging ring
     case 128: return launch_wu<128, 3, 1>(a, st);    // 3 x 64 KB in-place staging ring
