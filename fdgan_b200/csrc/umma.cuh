@@ -338,4 +338,25 @@ __device__ __forceinline__ void umma_chunk8(uint32_t d_tmem, uint32_t a_hi_lo, u
       : "memory");
 }
 
+// one K = 16 slice of the concatenated-B scheme (see umma_chunk8): D[0, 2NT) (+)= A_hi [B_hi | B_lo], D[NT, 2NT) += A_lo B_hi
+__device__ __forceinline__ void umma_concat_slice(uint32_t d_tmem, uint32_t a_hi_lo, uint32_t a_lo_lo, uint32_t a_hw, uint32_t b_lo,
+                                                  uint32_t b_hw, uint32_t idesc2, uint32_t idesc1, uint32_t accumulate, uint32_t nt_cols) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 d2;\n\t"
+      ".reg .pred p, pt;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.u32 d2, %0, %9;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%4, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t"
+      "mov.b64 da, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %7, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi_lo), "r"(a_lo_lo), "r"(a_hw), "r"(b_lo), "r"(b_hw), "r"(idesc2), "r"(idesc1), "r"(accumulate), "r"(nt_cols)
+      : "memory");
+}
+
 }  // namespace fdg

@@ -8,8 +8,8 @@
 //     contiguous, i.e. MN-major for this GEMM, so the loaders store [pixel][64 channels] rows of 128 bytes into the
 //     canonical MN-major SWIZZLE_128B layout and the MMA runs with a_major = b_major = MN.
 //   * bf16 hi/lo split of both operands, three MMAs per 16-pixel slice (hi*hi + hi*lo + lo*hi), fp32 accumulate.
-//   * 16 loader warps with a two-chunk register double buffer keep global loads in flight; one thread issues
-//     tcgen05.mma; mbarrier ring of STAGES chunks of 64 pixels.
+//   * 8 loader warps cp.async the fp32 rows straight into the operand ring and convert them in
+//     place; one thread issues tcgen05.mma; mbarrier ring of STAGES chunks of 32 pixels, STAGES - 2 chunks in flight.
 #include <cstdlib>
 
 #include "aop.cuh"
@@ -18,10 +18,10 @@
 namespace fdg {
 
 constexpr int WU_K = 128;                 // channel rows per tile (MMA M)
-constexpr int WU_P = 64;                  // pixels per chunk
-constexpr int WU_LOAD_WARPS = 16;
+constexpr int WU_P = 32;                  // pixels per chunk (two K = 16 slices)
+constexpr int WU_LOAD_WARPS = 8;          // 256 loader threads: pixel row t >> 3, 8-channel chunk t & 7 of every 64-channel block
 constexpr int WU_THREADS = (WU_LOAD_WARPS + 1) * 32;
-constexpr int WU_BLK = WU_P * 128;        // one [64 pixels x 64 channels] bf16 block = 8 KB
+constexpr int WU_BLK = WU_P * 128;        // one [32 pixels x 64 channels] bf16 block = 4 KB
 constexpr int WU_A_BYTES = 2 * WU_BLK;    // 128 channels = two blocks
 
 struct WUArgs {
@@ -36,20 +36,23 @@ struct WUArgs {
   int gvec;          // gradient rows loadable as float4 (unit channel stride, aligned, Cout % 8 == 0)
 };
 
-// DEPTH > 0: loads go through cp.async into a thread-private staging ring (DEPTH chunks in flight);
-// DEPTH == 0: two-chunk register double buffer.
-template <int NT, int STAGES, int DEPTH>
+// In-place staging: the fp32 rows are cp.async'ed straight into the operand ring.  Each thread's 32 bytes of fp32 per
+// 8-channel chunk land in the two 16-byte slots that will hold that chunk's bf16 hi / lo halves, so the conversion is a
+// read-modify-write of the thread's own slots and every ring stage doubles as prefetch buffer: STAGES - 2 chunks of
+// loads are in flight while one chunk is converted and one is consumed by the tensor core.
+template <int NT, int STAGES>
 __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs a) {
-  constexpr int G_BYTES = (NT / 64) * WU_BLK;
+  static_assert(NT == 64 || NT == 128, "output-channel tile");
+  constexpr int GQ = NT / 64;             // 64-channel gradient blocks
+  constexpr int G_BYTES = GQ * WU_BLK;
   constexpr int STAGE_BYTES = 2 * WU_A_BYTES + 2 * G_BYTES;
-  constexpr bool CONCAT = NT <= 128;       // [G_hi | G_lo] as one operand of width 2*NT (see umma_chunk8)
-  constexpr int TMEM_COLS = CONCAT ? 2 * NT : NT;
-  constexpr int GQ = NT / 64;             // 8-channel gradient chunks per loader thread
+  constexpr int TMEM_COLS = 2 * NT;       // [hi*hi | hi*lo + lo*hi] column halves (see umma_chunk8)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t meta_s[STAGES][WU_LOAD_WARPS * 32];
 
   const FdgWgrad& p = a.c;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -83,11 +86,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
 
   if (warp < WU_LOAD_WARPS && nchunks > 0) {
     // =============================================================== loaders
-    // thread: pixel row pr of the chunk; 8-channel chunks seg and seg+8 of the A block pair; gradient chunks seg + 8q
-    const int pr = t >> 3, seg = t & 7;
+    const int pr = t >> 3, seg = t & 7;         // pixel row of the chunk, 8-channel chunk within a 64-channel block
     const bool direct = p.gather == FDG_GATHER_DIRECT;
-    // running pixel coordinates of (chunk base + pr)
-    int pn, poy, pox;
+    int pn, poy, pox;                           // running pixel coordinates of (chunk base + pr)
     {
       const int64_t m = mbeg + pr;
       const int64_t mm = m < a.M ? m : 0;
@@ -96,16 +97,15 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       poy = rem / p.OW;
       pox = rem - poy * p.OW;
     }
-    int64_t lm = mbeg + pr;        // pixel index of the next chunk to load
-    // this thread's two 8-channel A chunks in the flattened k = tap*Cin + ci index (Cin % 8 == 0: a chunk never
-    // straddles a tap); each has its own filter tap, i.e. its own shifted source pixel
+    int64_t lm = mbeg + pr;                     // pixel index of the next chunk to load
+    // A side: two 8-channel chunks in the flattened k = tap*Cin + ci index (Cin % 8 == 0: a chunk never straddles a tap);
+    // each has its own filter tap, i.e. its own shifted source pixel
     const int k0 = kb * WU_K + seg * 8, k1 = k0 + 64;
     const int tap0 = k0 < Ktot ? k0 / p.Cin : 0, tap1 = k1 < Ktot ? k1 / p.Cin : 0;
     const int ca0 = k0 < Ktot ? k0 - tap0 * p.Cin : p.Cin, ca1 = k1 < Ktot ? k1 - tap1 * p.Cin : p.Cin;   // >= Cin: chunk is padding
     const int fr0 = tap0 / p.S, fs0 = tap0 - fr0 * p.S, fr1 = tap1 / p.S, fs1 = tap1 - fr1 * p.S;
-    const int cg0 = cot * NT + seg * 8;                       // first gradient channel of this thread
-    // BatchNorm scale/shift of this thread's 16 input channels (constant for the whole kernel)
-    float4 scv[4], shv[4];
+    const int cg0 = cot * NT + seg * 8;         // G side: first gradient channel of this thread
+    float4 scv[4], shv[4];                      // BatchNorm scale/shift of the A thread's 16 input channels
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int c = h ? ca1 : ca0;
@@ -115,127 +115,29 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       shv[2 * h] = v ? ld4(p.shift + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       shv[2 * h + 1] = v ? ld4(p.shift + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-
-    auto issue = [&](float4 (&av)[4], float4 (&gv)[2 * GQ]) -> uint32_t {
-      uint32_t ok = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < 2 * GQ; ++i) gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lm < mend) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = h ? ca1 : ca0;
-          const int iy = poy * p.stride - p.pad + (h ? fr1 : fr0), ix = pox * p.stride - p.pad + (h ? fs1 : fs0);
-          if (c < p.Cin && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-            ok |= 1u << h;
-            if (direct) {
-              const float* xp = p.x.p + pn * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw + c;
-              av[2 * h] = ld4(xp); av[2 * h + 1] = ld4(xp + 4);
-            } else {
-              av[2 * h] = fetch4(a.ao, pn, iy, ix, c); av[2 * h + 1] = fetch4(a.ao, pn, iy, ix, c + 4);
-            }
-          }
-        }
-        const float* gp = p.g.p + pn * p.g.sn + (int64_t)poy * p.g.sh + (int64_t)pox * p.g.sw;
-#pragma unroll
-        for (int q = 0; q < GQ; ++q) {
-          const int c = cg0 + 64 * q;
-          if (c < p.Cout) {
-            if (a.gvec) { gv[2 * q] = ld4(gp + c); gv[2 * q + 1] = ld4(gp + c + 4); }
-            else {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = c + e < p.Cout ? __ldg(gp + (int64_t)(c + e) * p.g.sc) : 0.f;
-              gv[2 * q] = make_float4(f[0], f[1], f[2], f[3]);
-              gv[2 * q + 1] = make_float4(f[4], f[5], f[6], f[7]);
-            }
-          }
-        }
-      }
-      // advance the pixel cursor by one chunk
-      lm += WU_P;
-      pox += WU_P;
-      while (pox >= p.OW) { pox -= p.OW; if (++poy == p.OH) { poy = 0; ++pn; } }
-      return ok;
-    };
-    auto finish = [&](float4 (&av)[4], float4 (&gv)[2 * GQ], uint32_t ok, int s, uint32_t ph) {
-      if (direct) {
-        const float sl = p.slope;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if ((ok >> h) & 1u) {
-            const float4 sc0 = scv[2 * h], sc1 = scv[2 * h + 1], sh0 = shv[2 * h], sh1 = shv[2 * h + 1];
-            float4& a0 = av[2 * h];
-            float4& a1 = av[2 * h + 1];
-            a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
-            a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
-            a1.x = prologue_act(fmaf(a1.x, sc1.x, sh1.x), sl); a1.y = prologue_act(fmaf(a1.y, sc1.y, sh1.y), sl);
-            a1.z = prologue_act(fmaf(a1.z, sc1.z, sh1.z), sl); a1.w = prologue_act(fmaf(a1.w, sc1.w, sh1.w), sl);
-          }
-        }
-      }
-      mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-      const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + WU_A_BYTES;
-      const uint32_t g_hi = a_lo + WU_A_BYTES, g_lo = g_hi + G_BYTES;
-      const uint32_t roff = (uint32_t)pr * 128u + (uint32_t)((seg ^ (pr & 7)) << 4);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t hi[4], lo[4];
-        split2(av[2 * h].x, av[2 * h].y, hi[0], lo[0]);
-        split2(av[2 * h].z, av[2 * h].w, hi[1], lo[1]);
-        split2(av[2 * h + 1].x, av[2 * h + 1].y, hi[2], lo[2]);
-        split2(av[2 * h + 1].z, av[2 * h + 1].w, hi[3], lo[3]);
-        const uint32_t off = (uint32_t)h * WU_BLK + roff;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-      }
-#pragma unroll
-      for (int q = 0; q < GQ; ++q) {
-        uint32_t hi[4], lo[4];
-        split2(gv[2 * q].x, gv[2 * q].y, hi[0], lo[0]);
-        split2(gv[2 * q].z, gv[2 * q].w, hi[1], lo[1]);
-        split2(gv[2 * q + 1].x, gv[2 * q + 1].y, hi[2], lo[2]);
-        split2(gv[2 * q + 1].z, gv[2 * q + 1].w, hi[3], lo[3]);
-        const uint32_t off = (uint32_t)q * WU_BLK + roff;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(g_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
-    };
-
-    int s = 0;
-    uint32_t ph = 0;
     const uint32_t roff_c = (uint32_t)pr * 128u + (uint32_t)((seg ^ (pr & 7)) << 4);
-    if (DEPTH > 0) {
-      // ---- in-place staging: the fp32 rows are cp.async'ed straight into the operand ring.  Each thread's 32 bytes of
-      // fp32 per 8-channel chunk land in the two 16-byte slots that will hold that chunk's bf16 hi / lo halves, so the
-      // conversion is read-modify-write of the thread's own slots and every ring stage doubles as prefetch buffer
-      // (STAGES - 1 chunks of loads in flight, no registers tied up).
-      constexpr int NLT = WU_LOAD_WARPS * 32;
-      __shared__ uint32_t meta_s[STAGES][WU_LOAD_WARPS * 32];
-      const uint32_t meta0 = smem_u32(&meta_s[0][0]) + (uint32_t)t * 4u;
-      const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
-      auto slot_a = [&](int st, int h, int lo) -> uint32_t {   // A chunk h (64-channel block h), hi (lo=0) or lo (lo=1) tile
-        return smem_base + st * STAGE_BYTES + (uint32_t)lo * WU_A_BYTES + (uint32_t)h * WU_BLK + roff_c;
-      };
-      auto slot_g = [&](int st, int q, int lo) -> uint32_t {
-        return smem_base + st * STAGE_BYTES + 2 * WU_A_BYTES + (uint32_t)lo * G_BYTES + (uint32_t)q * WU_BLK + roff_c;
-      };
-      auto sts4 = [](uint32_t addr, float4 f) {
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
-      };
-      auto lds4 = [](uint32_t addr) -> float4 {
-        float4 v;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-        return v;
-      };
-      auto issue_async = [&](int st, uint32_t eph) {
-        mbar_wait(empty0 + st * 8, eph ^ 1u);          // the MMAs that read this stage have retired
-        uint32_t ok = 0;
-        if (lm < mend && !(a.dbg & 1)) {
+    const uint32_t meta0 = smem_u32(&meta_s[0][0]) + (uint32_t)t * 4u;
+    const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+    constexpr int NLT = WU_LOAD_WARPS * 32;
+    auto slot_a = [&](int st, int h, int lo) -> uint32_t {   // A chunk h (64-channel block h), hi (lo=0) or lo (lo=1) tile
+      return smem_base + st * STAGE_BYTES + (uint32_t)lo * WU_A_BYTES + (uint32_t)h * WU_BLK + roff_c;
+    };
+    auto slot_g = [&](int st, int q, int lo) -> uint32_t {
+      return smem_base + st * STAGE_BYTES + 2 * WU_A_BYTES + (uint32_t)lo * G_BYTES + (uint32_t)q * WU_BLK + roff_c;
+    };
+    auto sts4 = [](uint32_t addr, float4 f) {
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
+    };
+    auto lds4 = [](uint32_t addr) -> float4 {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+      return v;
+    };
+    auto issue_async = [&](int st, uint32_t eph) {
+      mbar_wait(empty0 + st * 8, eph ^ 1u);          // the MMAs that read this stage have retired
+      uint32_t ok = 0;
+      if (lm < mend && !(a.dbg & 1)) {
+        {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = h ? ca1 : ca0;
@@ -252,6 +154,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
               }
             }
           }
+        }
+        {
           const float* gp = p.g.p + pn * p.g.sn + (int64_t)poy * p.g.sh + (int64_t)pox * p.g.sw;
 #pragma unroll
           for (int q = 0; q < GQ; ++q) {
@@ -271,91 +175,80 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             }
           }
         }
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta0 + st * (NLT * 4)), "r"(ok) : "memory");
-        lm += WU_P;
-        pox += WU_P;
-        while (pox >= p.OW) { pox -= p.OW; if (++poy == p.OH) { poy = 0; ++pn; } }
-      };
-      // convert stage st in place and publish it
-      auto convert = [&](int st) {
-        uint32_t ok;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ok) : "r"(meta0 + st * (NLT * 4)) : "memory");
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float sl = p.slope;
-        if (a.dbg & 2) ok = 0x80000000u;
+      }
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta0 + st * (NLT * 4)), "r"(ok) : "memory");
+      lm += WU_P;
+      pox += WU_P;
+      while (pox >= p.OW) { pox -= p.OW; if (++poy == p.OH) { poy = 0; ++pn; } }
+    };
+    // convert stage st in place and publish it
+    auto convert = [&](int st) {
+      uint32_t ok;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ok) : "r"(meta0 + st * (NLT * 4)) : "memory");
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!(a.dbg & 2)) {
+        {
+          const float sl = p.slope;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (ok >> 31) break;
-          float4 a0 = z4, a1 = z4;
-          if ((ok >> h) & 1u) {
-            a0 = lds4(slot_a(st, h, 0));
-            a1 = lds4(slot_a(st, h, 1));
-            if (direct) {
-              const float4 sc0 = scv[2 * h], sc1 = scv[2 * h + 1], sh0 = shv[2 * h], sh1 = shv[2 * h + 1];
-              a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
-              a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
-              a1.x = prologue_act(fmaf(a1.x, sc1.x, sh1.x), sl); a1.y = prologue_act(fmaf(a1.y, sc1.y, sh1.y), sl);
-              a1.z = prologue_act(fmaf(a1.z, sc1.z, sh1.z), sl); a1.w = prologue_act(fmaf(a1.w, sc1.w, sh1.w), sl);
+          for (int h = 0; h < 2; ++h) {
+            float4 a0 = z4, a1 = z4;
+            if ((ok >> h) & 1u) {
+              a0 = lds4(slot_a(st, h, 0));
+              a1 = lds4(slot_a(st, h, 1));
+              if (direct) {
+                const float4 sc0 = scv[2 * h], sc1 = scv[2 * h + 1], sh0 = shv[2 * h], sh1 = shv[2 * h + 1];
+                a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
+                a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
+                a1.x = prologue_act(fmaf(a1.x, sc1.x, sh1.x), sl); a1.y = prologue_act(fmaf(a1.y, sc1.y, sh1.y), sl);
+                a1.z = prologue_act(fmaf(a1.z, sc1.z, sh1.z), sl); a1.w = prologue_act(fmaf(a1.w, sc1.w, sh1.w), sl);
+              }
             }
+            uint32_t hi[4], lo[4];
+            split2(a0.x, a0.y, hi[0], lo[0]); split2(a0.z, a0.w, hi[1], lo[1]);
+            split2(a1.x, a1.y, hi[2], lo[2]); split2(a1.z, a1.w, hi[3], lo[3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 0)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 1)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
           }
-          uint32_t hi[4], lo[4];
-          split2(a0.x, a0.y, hi[0], lo[0]); split2(a0.z, a0.w, hi[1], lo[1]);
-          split2(a1.x, a1.y, hi[2], lo[2]); split2(a1.z, a1.w, hi[3], lo[3]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 0)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 1)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
+        {
 #pragma unroll
-        for (int q = 0; q < GQ; ++q) {
-          if (ok >> 31) break;
-          float4 g0 = z4, g1 = z4;
-          if (ok & (4u << q)) { g0 = lds4(slot_g(st, q, 0)); g1 = lds4(slot_g(st, q, 1)); }
-          uint32_t hi[4], lo[4];
-          split2(g0.x, g0.y, hi[0], lo[0]); split2(g0.z, g0.w, hi[1], lo[1]);
-          split2(g1.x, g1.y, hi[2], lo[2]); split2(g1.z, g1.w, hi[3], lo[3]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_g(st, q, 0)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_g(st, q, 1)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + st * 8);
-      };
-      int sl_ = 0, sf = 0;            // stages of the next chunk to load / to convert
-      uint32_t lph = 0;               // parity of the load side's pass over the ring
-#pragma unroll 1
-      for (int q = 0; q < STAGES - 1; ++q) {
-        if (q < nchunks) issue_async(sl_, lph);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
-      }
-#pragma unroll 1
-      for (int q = 0; q < nchunks; ++q) {
-        // chunk q's copies have landed when at most STAGES-2 newer groups are pending; convert it first (this overlaps
-        // with the MMAs of chunk q-1), then refill the stage those MMAs are about to release
-        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES >= 2 ? STAGES - 2 : 0) : "memory");
-        convert(sf);
-        if (++sf == STAGES) sf = 0;
-        if (q + STAGES - 1 < nchunks) issue_async(sl_, lph);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
-      }
-    } else {
-      float4 A0[4], G0[2 * GQ], A1[4], G1[2 * GQ];
-      uint32_t ok0, ok1 = 0;
-      ok0 = issue(A0, G0);
-      for (int q = 0; q < nchunks; q += 2) {
-        if (q + 1 < nchunks) ok1 = issue(A1, G1);
-        finish(A0, G0, ok0, s, ph);
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
-        if (q + 1 < nchunks) {
-          if (q + 2 < nchunks) ok0 = issue(A0, G0);
-          finish(A1, G1, ok1, s, ph);
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          for (int q = 0; q < GQ; ++q) {
+            float4 g0 = z4, g1 = z4;
+            if (ok & (4u << q)) { g0 = lds4(slot_g(st, q, 0)); g1 = lds4(slot_g(st, q, 1)); }
+            uint32_t hi[4], lo[4];
+            split2(g0.x, g0.y, hi[0], lo[0]); split2(g0.z, g0.w, hi[1], lo[1]);
+            split2(g1.x, g1.y, hi[2], lo[2]); split2(g1.z, g1.w, hi[3], lo[3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_g(st, q, 0)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_g(st, q, 1)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+          }
         }
       }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + st * 8);
+    };
+    int sl_ = 0, sf = 0;            // stages of the next chunk to load / to convert
+    uint32_t lph = 0;               // parity of the load side's pass over the ring
+#pragma unroll 1
+    for (int q = 0; q < STAGES - 2; ++q) {
+      if (q < nchunks) issue_async(sl_, lph);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
+    }
+#pragma unroll 1
+    for (int q = 0; q < nchunks; ++q) {
+      // refill first (the stage released two chunks ago), then convert chunk q, whose copies have landed when at most
+      // STAGES-2 newer groups are pending
+      if (q + STAGES - 2 < nchunks) issue_async(sl_, lph);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+      convert(sf);
+      if (++sf == STAGES) sf = 0;
     }
   } else if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
     // =============================================================== MMA issue
-    constexpr uint32_t idesc = umma_idesc_bf16_mn(WU_K, NT), idesc2 = umma_idesc_bf16_mn(WU_K, CONCAT ? 2 * NT : NT);
+    constexpr uint32_t idesc1 = umma_idesc_bf16_mn(WU_K, NT), idesc2 = umma_idesc_bf16_mn(WU_K, 2 * NT);
     const uint32_t mn_hw = umma_desc_hi(1024);
     int s = 0;
     uint32_t ph = 0;
@@ -363,16 +256,13 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       mbar_wait(smem_u32(&bar_full[s]), ph);
       tc_fence_after();
       const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + WU_A_BYTES;
-      const uint32_t g_hi = a_lo + WU_A_BYTES, g_lo = g_hi + G_BYTES;
+      const uint32_t g_hi = a_lo + WU_A_BYTES;      // [G_hi | G_lo] blocks are adjacent: one operand of width 2*NT
       // 16 pixels per slice = two 8-row swizzle atoms (SBO 1024 B); 64-channel blocks are WU_BLK bytes apart (LBO);
       // consecutive slices are 2048 B = 128 descriptor units apart
       if (!(a.dbg & 4)) {
-        if (CONCAT)
-          umma_chunk8(tmem_base, umma_desc_lo(a_hi, WU_BLK), umma_desc_lo(a_lo, WU_BLK), mn_hw, umma_desc_lo(g_hi, WU_BLK), mn_hw, idesc2, idesc,
-                      kc > 0 ? 1u : 0u, 128u, 128u, (uint32_t)NT);
-        else
-          umma_chunk12(tmem_base, umma_desc_lo(a_hi, WU_BLK), umma_desc_lo(a_lo, WU_BLK), mn_hw, umma_desc_lo(g_hi, WU_BLK),
-                       umma_desc_lo(g_lo, WU_BLK), mn_hw, idesc, kc > 0 ? 1u : 0u, 128u);
+        const uint32_t ah = umma_desc_lo(a_hi, WU_BLK), al = umma_desc_lo(a_lo, WU_BLK), gh = umma_desc_lo(g_hi, WU_BLK);
+        umma_concat_slice(tmem_base, ah, al, mn_hw, gh, mn_hw, idesc2, idesc1, kc > 0 ? 1u : 0u, (uint32_t)NT);
+        umma_concat_slice(tmem_base, ah + 128u, al + 128u, mn_hw, gh + 128u, mn_hw, idesc2, idesc1, 1u, (uint32_t)NT);
       }
       umma_commit(smem_u32(&bar_empty[s]));
       if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -391,21 +281,18 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
     const int RS = p.R * p.S;
 #pragma unroll 1
     for (int g = 0; g < NT / 32; ++g) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32), v);
-      if (CONCAT) {
-        float v2[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(NT + g * 32), v2);
-#pragma unroll
-        for (int u = 0; u < 32; ++u) v[u] += v2[u];
-      }
+      float v[32], v2[32];
+      const uint32_t tcol = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32);
+      tmem_ld32_nowait(tcol, v);
+      tmem_ld32_nowait(tcol + NT, v2);
+      tmem_ld_wait();
       if (kvalid) {
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
           const int co = cot * NT + g * 32 + u;
           if (co < p.Cout) {
             const int64_t idx = p.transposed ? (int64_t)ci * p.Cout + co : ((int64_t)co * p.Cin + ci) * RS + tap;
-            atomicAdd(p.dw + idx, v[u]);
+            atomicAdd(p.dw + idx, v[u] + v2[u]);
           }
         }
       }
@@ -420,11 +307,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   }
 }
 
-static inline int wu_ntile(int Cout) {
-  static const int cap = [] { const char* e = getenv("FDG_WGRAD_NT_CAP"); return e ? atoi(e) : 128; }();
-  const int nt = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
-  return nt > cap ? cap : nt;
-}
+static inline int wu_ntile(int Cout) { return Cout <= 64 ? 64 : 128; }
 
 int wgrad_umma_supported(const FdgWgrad* p) {
   if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
@@ -433,12 +316,12 @@ int wgrad_umma_supported(const FdgWgrad* p) {
   return 1;
 }
 
-template <int NT, int STAGES, int DEPTH>
+template <int NT, int STAGES>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * (NT / 64) * WU_BLK) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d_wgrad[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -454,14 +337,14 @@ static int launch_wu(WUArgs& a, cudaStream_t st) {
   a.tiles = a.kblocks * a.co_tiles;
   // split the pixels so that about one wave of CTAs covers the chip; every split is a whole number of chunks
   int64_t splits = a.tiles >= num_sms ? 1 : num_sms / a.tiles;
-  const int64_t max_splits = cdiv64(a.M, 4 * WU_P);
+  const int64_t max_splits = cdiv64(a.M, 8 * WU_P);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   a.m_per_split = cdiv64(cdiv64(a.M, splits), WU_P) * WU_P;
   splits = cdiv64(a.M, a.m_per_split);
   ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  wgrad_umma_kernel<NT, STAGES, DEPTH><<<(unsigned)(a.tiles * splits), WU_THREADS, smem, st>>>(a);
+  wgrad_umma_kernel<NT, STAGES><<<(unsigned)(a.tiles * splits), WU_THREADS, smem, st>>>(a);
   return check_launch("fdg_conv2d_wgrad[tcgen05]");
 }
 
@@ -473,14 +356,8 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   a.kblocks = cdiv(p->R * p->S * p->Cin, WU_K);
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   a.dbg = dbg_flags();
-  static const int reg_path = [] { const char* e = getenv("FDG_WGRAD_REG"); return e ? atoi(e) : 0; }();
-  if (reg_path && wu_ntile(p->Cout) == 128) return launch_wu<128, 3, 0>(a, st);
-  if (reg_path && wu_ntile(p->Cout) == 64) return launch_wu<64, 4, 0>(a, st);
-  switch (wu_ntile(p->Cout)) {
-    case 64: return launch_wu<64, 4, 1>(a, st);      // 4 x 48 KB in-place staging ring
-    case 128: return launch_wu<128, 3, 1>(a, st);    // 3 x 64 KB in-place staging ring
-    default: return launch_wu<256, 2, 0>(a, st);     // ring 2 x 96 KB, register double buffer
-  }
+  if (wu_ntile(p->Cout) == 64) return launch_wu<64, 8>(a, st);     // 8 x 24 KB in-place staging ring
+  return launch_wu<128, 6>(a, st);                                  // 6 x 32 KB in-place staging ring
 }
 
 }  // namespace fdg
