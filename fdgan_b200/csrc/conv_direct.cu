@@ -1,0 +1,236 @@
+// fdg_conv2d, direct fp32 paths for the thin layers that are pure HBM traffic: there is no GEMM worth
+// tiling when K = R*S*Cin is a few dozen or the input has one channel.
+//
+//  * conv_thin_kernel: K <= 160, Cout in {16, 36, 64} (stem conv_refin1 3->64, Vgg16 conv1_1 3->64, Fusion-D layer 1
+//    9->36 4x4 stride 2).  One thread owns one output pixel and all its channels: the K input values are read once
+//    (lanes = consecutive pixels), the weights come from shared memory as warp-wide broadcasts, the result goes through
+//    a per-warp shared-memory tile so that the stores are coalesced rows and the BatchNorm statistics are column sums.
+//  * conv_cin1_kernel: Cin == 1 (data gradient of Fusion-D layer 5, 1 -> 288 channels, with the LeakyReLU mask of the
+//    layer input): one thread per (pixel, 4 channels), R*S taps, 128-bit stores.
+#include <cstdlib>
+
+#include "aop.cuh"
+
+namespace fdg {
+
+constexpr int TH_THREADS = 256;
+constexpr int TH_MAXK = 160;
+
+struct ThinArgs {
+  FdgConv c;
+  int64_t M;
+  int K;
+};
+
+template <int NC4>   // Cout = 4 * NC4
+__global__ void __launch_bounds__(TH_THREADS) conv_thin_kernel(const __grid_constant__ ThinArgs a) {
+  constexpr int CO = 4 * NC4;
+  constexpr int PITCH = CO + 4;                       // floats per tile row (16-byte aligned rows, conflict-free 128-bit access)
+  extern __shared__ __align__(16) float smem[];
+  float* ws = smem;                                   // [K][CO]
+  float* tiles = smem + TH_MAXK * CO;                 // [8 warps][32][PITCH]
+  __shared__ float red[2][8][CO];
+  const FdgConv& p = a.c;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int i = t; i < a.K * CO; i += TH_THREADS) ws[i] = __ldg(p.w + (int64_t)(i / CO) * p.w_ld + (i % CO));
+  __syncthreads();
+  float* tile = tiles + warp * 32 * PITCH;
+  const int OHW = p.OH * p.OW;
+  float st1[(CO + 31) / 32], st2[(CO + 31) / 32];     // running statistics of channels lane, lane + 32
+#pragma unroll
+  for (int g = 0; g < (CO + 31) / 32; ++g) { st1[g] = 0.f; st2[g] = 0.f; }
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t m0 = ((int64_t)blockIdx.x * 8 + warp) * 32; m0 < a.M; m0 += nwarps * 32) {
+    const int64_t m = m0 + lane;
+    const bool mv = m < a.M;
+    float v[CO];
+#pragma unroll
+    for (int u = 0; u < CO; ++u) v[u] = 0.f;
+    int64_t yoff = 0;
+    if (mv) {
+      const int n = (int)(m / OHW);
+      const int rem = (int)(m - (int64_t)n * OHW);
+      const int oy = rem / p.OW, ox = rem - oy * p.OW;
+      yoff = n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox * p.y.sw;
+      const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+      const float* xb = p.x.p + n * p.x.sn;
+      int k = 0;
+      for (int r = 0; r < p.R; ++r) {
+        const int iy = iy0 + r;
+        for (int s = 0; s < p.S; ++s) {
+          const int ix = ix0 + s;
+          const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          const float* xp = xb + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw;
+          for (int ci = 0; ci < p.Cin; ++ci, ++k) {
+            float xv = in ? __ldg(xp + (int64_t)ci * p.x.sc) : 0.f;
+            if (in) xv = prologue_act(xv, p.slope);
+            const float4* wr = reinterpret_cast<const float4*>(ws + k * CO);
+#pragma unroll
+            for (int q = 0; q < NC4; ++q) {
+              const float4 wv = wr[q];                 // same address in every lane: broadcast
+              v[4 * q] = fmaf(xv, wv.x, v[4 * q]); v[4 * q + 1] = fmaf(xv, wv.y, v[4 * q + 1]);
+              v[4 * q + 2] = fmaf(xv, wv.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(xv, wv.w, v[4 * q + 3]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CO; ++u) {
+        float r = v[u] * p.alpha + (p.bias ? __ldg(p.bias + u) : 0.f);
+        if (p.act == FDG_ACT_RELU) r = fmaxf(r, 0.f);
+        else if (p.act == FDG_ACT_TANH) r = tanhf(r);
+        else if (p.act == FDG_ACT_SIGMOID) r = 1.f / (1.f + expf(-r));
+        v[u] = r;
+      }
+    }
+    // ---- tile row of this pixel
+#pragma unroll
+    for (int q = 0; q < NC4; ++q)
+      *reinterpret_cast<float4*>(tile + lane * PITCH + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+    // ---- coalesced rows: flat float4 index f = row * NC4 + c4
+    for (int f = lane; f < 32 * NC4; f += 32) {
+      const int row = f / NC4, c4 = f - row * NC4;
+      const int64_t yo = __shfl_sync(0xffffffffu, yoff, row);
+      if (m0 + row < a.M) *reinterpret_cast<float4*>(p.y.p + yo + 4 * c4) = *reinterpret_cast<const float4*>(tile + row * PITCH + 4 * c4);
+    }
+    if (p.stats) {
+#pragma unroll
+      for (int g = 0; g < (CO + 31) / 32; ++g) {
+        const int c = g * 32 + lane;
+        if (c < CO) {
+          float s1 = 0.f, s2 = 0.f;
+          for (int rr = 0; rr < 32; ++rr) {
+            const float xv = tile[rr * PITCH + c];     // rows past the end hold zeros
+            s1 += xv;
+            s2 = fmaf(xv, xv, s2);
+          }
+          st1[g] += s1;
+          st2[g] += s2;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (p.stats) {
+#pragma unroll
+    for (int g = 0; g < (CO + 31) / 32; ++g) {
+      const int c = g * 32 + lane;
+      if (c < CO) { red[0][warp][c] = st1[g]; red[1][warp][c] = st2[g]; }
+    }
+    __syncthreads();
+    for (int c = t; c < CO; c += TH_THREADS) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int w = 0; w < 8; ++w) { s1 += (double)red[0][w][c]; s2 += (double)red[1][w][c]; }
+      atomicAdd(p.stats + c, s1);
+      atomicAdd(p.stats + p.stats_ld + c, s2);
+    }
+  }
+}
+
+int conv2d_thin_supported(const FdgConv* p) {
+  static const int on = [] { const char* e = getenv("FDG_THIN"); return e ? atoi(e) : 1; }();
+  if (!on || p->impl != 0) return 0;                  // impl = 1 keeps the generic SIMT kernel (the tests' fp32 arbiter)
+  const int K = p->R * p->S * p->Cin;
+  if (K > TH_MAXK || p->Cin > 16 || !(p->Cout == 16 || p->Cout == 36 || p->Cout == 64)) return 0;
+  if (p->gather != FDG_GATHER_DIRECT || p->has_affine || p->e.p || p->store != FDG_STORE_NORMAL) return 0;
+  if (!vec4_ok(p->y)) return 0;
+  return 1;
+}
+
+template <int NC4>
+static int launch_thin(const ThinArgs& a, cudaStream_t st) {
+  constexpr int CO = 4 * NC4;
+  constexpr int smem = (TH_MAXK * CO + 8 * 32 * (CO + 4)) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(conv_thin_kernel<NC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("fdg_conv2d[thin]: cannot raise dynamic shared memory to %d bytes", smem);
+      return FDG_ECUDA;
+    }
+    attr_done = true;
+  }
+  int64_t blocks = cdiv64(a.M, 8 * 32);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope prof(PF_CONV_SIMT, 2.0 * (double)a.M * a.K * CO, 4.0 * ((double)a.M * CO + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
+  conv_thin_kernel<NC4><<<(unsigned)blocks, TH_THREADS, smem, st>>>(a);
+  return check_launch("fdg_conv2d[thin]");
+}
+
+int conv2d_thin(const FdgConv* p, cudaStream_t st) {
+  ThinArgs a;
+  a.c = *p;
+  a.M = (int64_t)p->N * p->OH * p->OW;
+  a.K = p->R * p->S * p->Cin;
+  switch (p->Cout) {
+    case 16: return launch_thin<4>(a, st);
+    case 36: return launch_thin<9>(a, st);
+    default: return launch_thin<16>(a, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Cin == 1
+struct Cin1Args {
+  FdgConv c;
+  int64_t total;   // pixels * Cout / 4
+  int c4n;         // Cout / 4
+  int evec;
+};
+
+__global__ void __launch_bounds__(256) conv_cin1_kernel(const __grid_constant__ Cin1Args a) {
+  const FdgConv& p = a.c;
+  const int OHW = p.OH * p.OW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / a.c4n;
+    const int c = (int)(i - m * a.c4n) * 4;
+    const int n = (int)(m / OHW);
+    const int rem = (int)(m - (int64_t)n * OHW);
+    const int oy = rem / p.OW, ox = rem - oy * p.OW;
+    const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+    const float* xb = p.x.p + n * p.x.sn;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < p.R; ++r) {
+      const int iy = iy0 + r;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int s = 0; s < p.S; ++s) {
+        const int ix = ix0 + s;
+        if (ix < 0 || ix >= p.W) continue;
+        const float xv = prologue_act(__ldg(xb + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw), p.slope);
+        const float4 wv = ld4(p.w + (int64_t)(r * p.S + s) * p.w_ld + c);
+        acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+      }
+    }
+    acc.x *= p.alpha; acc.y *= p.alpha; acc.z *= p.alpha; acc.w *= p.alpha;
+    if (p.e.p) {
+      const float4 ev = ld4(p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + c);
+      acc.x *= ev.x > 0.f ? 1.f : p.eslope; acc.y *= ev.y > 0.f ? 1.f : p.eslope;
+      acc.z *= ev.z > 0.f ? 1.f : p.eslope; acc.w *= ev.w > 0.f ? 1.f : p.eslope;
+    }
+    *reinterpret_cast<float4*>(p.y.p + n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox * p.y.sw + c) = acc;
+  }
+}
+
+int conv2d_cin1_supported(const FdgConv* p) {
+  static const int on = [] { const char* e = getenv("FDG_THIN"); return e ? atoi(e) : 1; }();
+  if (!on || p->impl != 0) return 0;
+  if (p->Cin != 1 || p->Cout % 4 != 0 || p->gather != FDG_GATHER_DIRECT || p->has_affine) return 0;
+  if (p->bias || p->act != FDG_ACT_NONE || p->stats || p->store != FDG_STORE_NORMAL) return 0;
+  if (!vec4_ok(p->y) || !aligned16(p->w) || p->w_ld % 4 != 0) return 0;
+  if (p->e.p && !vec4_ok(p->e)) return 0;
+  return 1;
+}
+
+int conv2d_cin1(const FdgConv* p, cudaStream_t st) {
+  Cin1Args a;
+  a.c = *p;
+  a.c4n = p->Cout / 4;
+  a.total = (int64_t)p->N * p->OH * p->OW * a.c4n;
+  a.evec = 1;
+  int64_t blocks = cdiv64(a.total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope prof(PF_CONV_SIMT, 2.0 * (double)a.total * 4 * p->R * p->S, 4.0 * (double)a.total * 4 * (p->e.p ? 2 : 1), st);
+  conv_cin1_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  return check_launch("fdg_conv2d[cin1]");
+}
+
+}  // namespace fdg

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       }
       for (int cc = 0; cc < a.cchunks; ++cc) {
         const int c = cc * UKC_H + j * 8;
-        const bool cvalid = c < p.Cin;
+        const bool cvalid = c < p.Cin, cvalid2 = c + 4 < p.Cin;     // Cin % 4 == 0: the second half of a chunk may be padding
         // ---- all loads of the chunk first (independent, up to 2*H_ITEMS 128-bit loads in flight per thread)
         float4 v0[H_ITEMS], v1[H_ITEMS];
 #pragma unroll
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
           if (((okmask >> i) & 1u) && cvalid && !(a.dbg & 1)) {
             const float* src = tbase + (int64_t)hy[i] * p.x.sh + (int64_t)hx[i] * p.x.sw + cc * UKC_H;
             v0[i] = ld4(src);
-            v1[i] = ld4(src + 4);
+            if (cvalid2) v1[i] = ld4(src + 4);
           }
         }
         // ---- consumer prologue
@@ -155,11 +155,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
           float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
           if (cvalid) {
             if (aff_smem) {
-              sc0 = lds4u(aff0 + c * 4); sc1 = lds4u(aff0 + c * 4 + 16);
-              sh0 = lds4u(aff0 + (H_MAX_AFF + c) * 4); sh1 = lds4u(aff0 + (H_MAX_AFF + c) * 4 + 16);
+              sc0 = lds4u(aff0 + c * 4); sh0 = lds4u(aff0 + (H_MAX_AFF + c) * 4);
+              if (cvalid2) { sc1 = lds4u(aff0 + c * 4 + 16); sh1 = lds4u(aff0 + (H_MAX_AFF + c) * 4 + 16); }
             } else {
-              sc0 = ld4(p.scale + c); sc1 = ld4(p.scale + c + 4);
-              sh0 = ld4(p.shift + c); sh1 = ld4(p.shift + c + 4);
+              sc0 = ld4(p.scale + c); sh0 = ld4(p.shift + c);
+              if (cvalid2) { sc1 = ld4(p.scale + c + 4); sh1 = ld4(p.shift + c + 4); }
             }
           }
 #pragma unroll
@@ -348,7 +348,7 @@ int conv2d_halo_supported(const FdgConv* p) {
   if (!g_halo_on || !p->w_umma) return 0;
   if (p->gather != FDG_GATHER_DIRECT || p->stride != 1) return 0;
   if (p->R < 2 || p->R > 4 || p->S < 2 || p->S > 4) return 0;
-  if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
+  if (p->Cin % 4 != 0 || p->Cin < 16 || p->Cout < 1) return 0;      // 8-channel loader chunks, second half optional
   AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   if (!aop_vec_ok(ao, p->Cin)) return 0;
   return 1;

@@ -507,9 +507,12 @@ static inline int umma_ntile(int Cout) {
   return nt > cap ? cap : nt;
 }
 
+int conv2d_halo_supported(const FdgConv* p);
+
 int conv2d_umma_supported(const FdgConv* p) {
   if (!p->w_umma) return 0;
-  if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
+  if (p->Cin % 8 != 0) return p->Cin % 4 == 0 && conv2d_halo_supported(p);   // only the halo kernel takes half chunks
+  if (p->Cin < 16 || p->Cout < 1) return 0;
   AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   if (!aop_vec_ok(ao, p->Cin)) return 0;
   return 1;

@@ -70,10 +70,11 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
     // A item i: halo pixel row (t >> 4) + 16 i, 8-channel chunk cj = t & 15 of the 128-channel block
     const int cj = t & 15;
     const int ca = cb * 128 + cj * 8;                 // first channel of this thread's chunk
-    const bool cav = ca < p.Cin;
+    const bool cav = ca < p.Cin, cav2 = ca + 4 < p.Cin;     // Cin % 4 == 0: the second half of a chunk may be padding
     const int ablk = cj >> 3, acj = cj & 7;
     float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
-    if (p.has_affine && cav) { sc0 = ld4(p.scale + ca); sc1 = ld4(p.scale + ca + 4); sh0 = ld4(p.shift + ca); sh1 = ld4(p.shift + ca + 4); }
+    if (p.has_affine && cav) { sc0 = ld4(p.scale + ca); sh0 = ld4(p.shift + ca); }
+    if (p.has_affine && cav2) { sc1 = ld4(p.scale + ca + 4); sh1 = ld4(p.shift + ca + 4); }
     int hy[WH_AITEMS], hx[WH_AITEMS];
     bool iv[WH_AITEMS];
 #pragma unroll
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
           ok |= 1u << i;
           const float* src = tbase + (int64_t)hy[i] * p.x.sh + (int64_t)hx[i] * p.x.sw;
           v0[i] = ld4(src);
-          v1[i] = ld4(src + 4);
+          if (cav2) v1[i] = ld4(src + 4);
         }
       }
       float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
@@ -225,7 +226,9 @@ int wgrad_halo_supported(const FdgWgrad* p) {
   if (!g_wgrad_halo_on) return 0;
   if (p->gather != FDG_GATHER_DIRECT || p->stride != 1 || p->transposed) return 0;
   if (p->R < 2 || p->R > 4 || p->S < 2 || p->S > 4) return 0;
-  if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1 || p->Cout > 64) return 0;
+  if (p->Cin % 4 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
+  // every 32-channel output tile re-reads the input halo: wide layers go to wgrad_umma when it can take them
+  if (p->Cout > 64 && !(p->Cin % 8 != 0 && p->Cout <= 96)) return 0;
   AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   if (!aop_vec_ok(ao, p->Cin)) return 0;
   return 1;

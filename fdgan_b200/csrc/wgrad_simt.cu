@@ -213,7 +213,7 @@ extern "C" int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream) {
   FDG_REQUIRE(!p->has_affine || (p->scale && p->shift), "fdg_conv2d_wgrad: affine prologue without scale/shift");
   cudaStream_t st = (cudaStream_t)stream;
   if (p->impl != 1) {
-    const int ok = wgrad_umma_supported(p);
+    const int ok = wgrad_umma_supported(p) || wgrad_halo_supported(p);
     if (p->impl == 2 && !ok) { set_error("fdg_conv2d_wgrad: impl=tcgen05 requested but shape/layout unsupported"); return FDG_ENOSUPPORT; }
     if (ok) {
       const int rc = wgrad_halo_supported(p) ? wgrad_halo(p, st) : wgrad_umma(p, st);

@@ -79,9 +79,10 @@ _NULLT = L.FdgTensor(None, 0, 0, 0, 0)
 USE_UMMA = True
 
 
-def umma_eligible(x: View, Cout: int) -> bool:
-    return (x.C % 8 == 0 and x.C >= 16 and Cout >= 1 and x.sc == 1 and x.ptr % 16 == 0 and x.sn % 4 == 0 and
-            x.sh % 4 == 0 and x.sw % 4 == 0)
+def umma_eligible(x: View, Cout: int, R: int = 1, S: int = 1, stride: int = 1, gather: int = GATHER_DIRECT) -> bool:
+    halo = stride == 1 and 2 <= R <= 4 and 2 <= S <= 4 and gather == GATHER_DIRECT   # conv_halo.cu takes Cin % 4 == 0
+    return ((x.C % 8 == 0 or (halo and x.C % 4 == 0)) and x.C >= 16 and Cout >= 1 and x.sc == 1 and x.ptr % 16 == 0 and
+            x.sn % 4 == 0 and x.sh % 4 == 0 and x.sw % 4 == 0)
 
 
 def pack_weight_umma(w, w_ld: int, taps: int, Cin: int, Cout: int, device) -> torch.Tensor:
@@ -109,7 +110,7 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
         raise ValueError("conv2d: output view %s does not match %s" % ((y.N, y.H, y.W, y.C), (x.N, mul * OH, mul * OW, Cout)))
     if e is not None and (e.N, e.H, e.W, e.C) != (x.N, OH, OW, Cout):
         raise ValueError("conv2d: mask view shape mismatch")
-    if w_umma is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and umma_eligible(x, Cout):
+    if w_umma is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and umma_eligible(x, Cout, R, S, stride, gather):
         w_umma = pack_weight_umma(w, w_ld, R * S, x.C, Cout, x.base.device)
     d = L.FdgConv(
         x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
