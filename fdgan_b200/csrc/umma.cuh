@@ -359,4 +359,20 @@ __device__ __forceinline__ void umma_concat_slice(uint32_t d_tmem, uint32_t a_hi
       : "memory");
 }
 
+// one tcgen05.mma from 32-bit descriptor halves
+__device__ __forceinline__ void umma_single(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hw, uint32_t b_lo, uint32_t b_hw, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hw), "r"(b_lo), "r"(b_hw), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 }  // namespace fdg

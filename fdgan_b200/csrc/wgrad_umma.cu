@@ -42,11 +42,14 @@ struct WUArgs {
 // loads are in flight while one chunk is converted and one is consumed by the tensor core.
 template <int NT, int STAGES>
 __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs a) {
-  static_assert(NT == 64 || NT == 128, "output-channel tile");
-  constexpr int GQ = NT / 64;             // 64-channel gradient blocks
+  static_assert(NT == 64 || NT == 128 || NT == 256 || NT == 320, "output-channel tile");
+  constexpr bool CONCAT = NT <= 128;      // [G_hi | G_lo] as one operand of width 2*NT (see umma_chunk8); wide tiles run
+                                          // the three passes as N = N1 + N2 MMAs into one [128 x NT] accumulator
+  constexpr int GQ = (NT + 63) / 64;      // 64-channel gradient blocks
   constexpr int G_BYTES = GQ * WU_BLK;
   constexpr int STAGE_BYTES = 2 * WU_A_BYTES + 2 * G_BYTES;
-  constexpr int TMEM_COLS = 2 * NT;       // [hi*hi | hi*lo + lo*hi] column halves (see umma_chunk8)
+  constexpr int TMEM_COLS = CONCAT ? 2 * NT : (NT <= 256 ? 256 : 512);
+  constexpr int N1 = NT == 320 ? 192 : NT / 2, N2 = NT - N1;   // block-aligned column split of the wide tiles
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[STAGES];
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
     }
   } else if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
     // =============================================================== MMA issue
-    constexpr uint32_t idesc1 = umma_idesc_bf16_mn(WU_K, NT), idesc2 = umma_idesc_bf16_mn(WU_K, 2 * NT);
+    constexpr uint32_t idesc1 = umma_idesc_bf16_mn(WU_K, CONCAT ? NT : N1), idesc2 = umma_idesc_bf16_mn(WU_K, CONCAT ? 2 * NT : N2);
     const uint32_t mn_hw = umma_desc_hi(1024);
     int s = 0;
     uint32_t ph = 0;
@@ -261,8 +264,24 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       // consecutive slices are 2048 B = 128 descriptor units apart
       if (!(a.dbg & 4)) {
         const uint32_t ah = umma_desc_lo(a_hi, WU_BLK), al = umma_desc_lo(a_lo, WU_BLK), gh = umma_desc_lo(g_hi, WU_BLK);
-        umma_concat_slice(tmem_base, ah, al, mn_hw, gh, mn_hw, idesc2, idesc1, kc > 0 ? 1u : 0u, (uint32_t)NT);
-        umma_concat_slice(tmem_base, ah + 128u, al + 128u, mn_hw, gh + 128u, mn_hw, idesc2, idesc1, 1u, (uint32_t)NT);
+        if (CONCAT) {
+          umma_concat_slice(tmem_base, ah, al, mn_hw, gh, mn_hw, idesc2, idesc1, kc > 0 ? 1u : 0u, (uint32_t)NT);
+          umma_concat_slice(tmem_base, ah + 128u, al + 128u, mn_hw, gh + 128u, mn_hw, idesc2, idesc1, 1u, (uint32_t)NT);
+        } else {
+          const uint32_t gl = umma_desc_lo(g_hi + G_BYTES, WU_BLK);
+          constexpr uint32_t b2 = (uint32_t)(N1 / 64) * (WU_BLK >> 4);      // descriptor units to the first block of the N2 columns
+#pragma unroll
+          for (uint32_t sl = 0; sl < 2; ++sl) {
+            const uint32_t o = sl * 128u;
+            const uint32_t acc = (kc > 0 || sl > 0) ? 1u : 0u;
+            umma_single(tmem_base, ah + o, mn_hw, gh + o, mn_hw, idesc1, acc);
+            umma_single(tmem_base + N1, ah + o, mn_hw, gh + o + b2, mn_hw, idesc2, acc);
+            umma_single(tmem_base, ah + o, mn_hw, gl + o, mn_hw, idesc1, 1u);
+            umma_single(tmem_base + N1, ah + o, mn_hw, gl + o + b2, mn_hw, idesc2, 1u);
+            umma_single(tmem_base, al + o, mn_hw, gh + o, mn_hw, idesc1, 1u);
+            umma_single(tmem_base + N1, al + o, mn_hw, gh + o + b2, mn_hw, idesc2, 1u);
+          }
+        }
       }
       umma_commit(smem_u32(&bar_empty[s]));
       if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -281,18 +300,25 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
     const int RS = p.R * p.S;
 #pragma unroll 1
     for (int g = 0; g < NT / 32; ++g) {
-      float v[32], v2[32];
+      float v[32];
       const uint32_t tcol = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 32);
       tmem_ld32_nowait(tcol, v);
-      tmem_ld32_nowait(tcol + NT, v2);
-      tmem_ld_wait();
-      if (kvalid) {
+      if (CONCAT) {
+        float v2[32];
+        tmem_ld32_nowait(tcol + NT, v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] += v2[u];
+      } else {
+        tmem_ld_wait();
+      }
+      if (kvalid && cot * NT + g * 32 < p.Cout) {
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
           const int co = cot * NT + g * 32 + u;
           if (co < p.Cout) {
             const int64_t idx = p.transposed ? (int64_t)ci * p.Cout + co : ((int64_t)co * p.Cin + ci) * RS + tap;
-            atomicAdd(p.dw + idx, v[u] + v2[u]);
+            atomicAdd(p.dw + idx, v[u]);
           }
         }
       }
@@ -307,7 +333,16 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   }
 }
 
-static inline int wu_ntile(int Cout) { return Cout <= 64 ? 64 : 128; }
+// Output-channel tile: one CTA covers as many output channels as TMEM and shared memory allow, because every extra
+// channel tile re-reads and re-converts the A operand (and every extra k block the gradient operand).
+static inline int wu_ntile(int Cout) {
+  static const int wide = [] { const char* e = getenv("FDG_WGRAD_WIDE"); return e ? atoi(e) : 1; }();
+  if (Cout <= 64) return 64;
+  if (Cout <= 128 || !wide) return 128;
+  if (Cout <= 256) return 256;
+  if (Cout <= 320) return 320;
+  return Cout % 256 == 0 ? 256 : 128;
+}
 
 int wgrad_umma_supported(const FdgWgrad* p) {
   if (p->Cin % 8 != 0 || p->Cin < 16 || p->Cout < 1) return 0;
@@ -318,7 +353,7 @@ int wgrad_umma_supported(const FdgWgrad* p) {
 
 template <int NT, int STAGES>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * (NT / 64) * WU_BLK) + 1024;
+  constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * ((NT + 63) / 64) * WU_BLK) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -356,8 +391,12 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   a.kblocks = cdiv(p->R * p->S * p->Cin, WU_K);
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   a.dbg = dbg_flags();
-  if (wu_ntile(p->Cout) == 64) return launch_wu<64, 8>(a, st);     // 8 x 24 KB in-place staging ring
-  return launch_wu<128, 6>(a, st);                                  // 6 x 32 KB in-place staging ring
+  switch (wu_ntile(p->Cout)) {
+    case 64: return launch_wu<64, 8>(a, st);      // 8 x 24 KB in-place staging ring
+    case 128: return launch_wu<128, 6>(a, st);    // 6 x 32 KB
+    case 256: return launch_wu<256, 4>(a, st);    // 4 x 48 KB
+    default: return launch_wu<320, 3>(a, st);     // 3 x 56 KB
+  }
 }
 
 }  // namespace fdg
