@@ -234,3 +234,200 @@ int conv2d_cin1(const FdgConv* p, cudaStream_t st) {
 }
 
 }  // namespace fdg
+
+// ------------------------------------------------------------------------------------------------ thin-layer gradients
+// Data gradient of a strided convolution with few input channels (Fusion-D layer 1: 4x4 stride 2, 36 -> 9): one thread
+// per input pixel and all its channels; the gradient rows are read as float4, the weights sit in shared memory as
+// [tap][co][12] so that the 9 products of one (tap, co) are three 128-bit broadcasts.
+namespace fdg {
+
+constexpr int DS_CI = 12;
+
+__global__ void __launch_bounds__(128) dgrad_strided_small_kernel(const __grid_constant__ FdgDgradStrided p, int64_t total) {
+  extern __shared__ __align__(16) float ws[];      // [R*S][Cout][DS_CI]
+  const int taps = p.R * p.S;
+  for (int i = threadIdx.x; i < taps * p.Cout * DS_CI; i += blockDim.x) {
+    const int ci = i % DS_CI;
+    const int co = (i / DS_CI) % p.Cout;
+    const int tap = i / (DS_CI * p.Cout);
+    ws[i] = ci < p.Cin ? __ldg(p.w + ((int64_t)co * p.Cin + ci) * taps + tap) : 0.f;
+  }
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p.W);
+    int64_t r = i / p.W;
+    const int y = (int)(r % p.H);
+    const int n = (int)(r / p.H);
+    float acc[DS_CI];
+#pragma unroll
+    for (int c = 0; c < DS_CI; ++c) acc[c] = 0.f;
+    for (int kr = 0; kr < p.R; ++kr) {
+      const int ty = y + p.pad - kr;
+      if (ty < 0 || ty % p.stride != 0) continue;
+      const int oy = ty / p.stride;
+      if (oy >= p.OH) continue;
+      for (int ks = 0; ks < p.S; ++ks) {
+        const int tx = x + p.pad - ks;
+        if (tx < 0 || tx % p.stride != 0) continue;
+        const int ox = tx / p.stride;
+        if (ox >= p.OW) continue;
+        const float* gp = p.g.p + n * p.g.sn + (int64_t)oy * p.g.sh + (int64_t)ox * p.g.sw;
+        const float4* wt = reinterpret_cast<const float4*>(ws + (size_t)(kr * p.S + ks) * p.Cout * DS_CI);
+        for (int co = 0; co < p.Cout; co += 4) {
+          const float4 g4 = ld4(gp + co);
+          const float gq[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 w0 = wt[(co + u) * 3], w1 = wt[(co + u) * 3 + 1], w2 = wt[(co + u) * 3 + 2];
+            acc[0] = fmaf(gq[u], w0.x, acc[0]); acc[1] = fmaf(gq[u], w0.y, acc[1]); acc[2] = fmaf(gq[u], w0.z, acc[2]); acc[3] = fmaf(gq[u], w0.w, acc[3]);
+            acc[4] = fmaf(gq[u], w1.x, acc[4]); acc[5] = fmaf(gq[u], w1.y, acc[5]); acc[6] = fmaf(gq[u], w1.z, acc[6]); acc[7] = fmaf(gq[u], w1.w, acc[7]);
+            acc[8] = fmaf(gq[u], w2.x, acc[8]); acc[9] = fmaf(gq[u], w2.y, acc[9]); acc[10] = fmaf(gq[u], w2.z, acc[10]); acc[11] = fmaf(gq[u], w2.w, acc[11]);
+          }
+        }
+      }
+    }
+    float* o = p.dx.p + n * p.dx.sn + (int64_t)y * p.dx.sh + (int64_t)x * p.dx.sw;
+#pragma unroll
+    for (int c = 0; c < DS_CI; ++c)
+      if (c < p.Cin) {
+        float* oc = o + (int64_t)c * p.dx.sc;
+        *oc = p.accumulate ? *oc + acc[c] : acc[c];
+      }
+  }
+}
+
+int dgrad_strided_small(const FdgDgradStrided* p, cudaStream_t st) {
+  static const int on = [] { const char* e = getenv("FDG_THIN"); return e ? atoi(e) : 1; }();
+  const int smem = p->R * p->S * p->Cout * DS_CI * 4;
+  if (!on || p->Cin > DS_CI || p->Cout % 4 != 0 || smem > 48 * 1024 || !vec4_ok(p->g)) return 1;   // 1 = not taken
+  const int64_t total = (int64_t)p->N * p->H * p->W;
+  int64_t blocks = cdiv64(total, 128);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dgrad_strided_small_kernel<<<(unsigned)blocks, 128, smem, st>>>(*p, total);
+  return check_launch("fdg_conv2d_dgrad_strided[small]");
+}
+
+// Weight gradient of a thin layer (K = R*S*Cin <= 160, Cout <= 64: stem conv_refin1, Fusion-D layer 1).  A CTA walks
+// a range of output pixels in batches of 32: the im2col rows [32][K] and the gradient rows [32][Cout] are staged in
+// shared memory with coalesced loads, every thread owns a KB x 4 block of dW in registers, and the CTA adds its partial
+// sums atomically into the OIHW parameter layout at the end.
+constexpr int WT_P = 32;
+constexpr int WT_THREADS = 256;
+
+struct WThinArgs {
+  FdgWgrad c;
+  int64_t M, m_per_cta;
+  int K, kb, kgroups, cgroups;
+};
+
+template <int KB>
+__global__ void __launch_bounds__(WT_THREADS) wgrad_thin_kernel(const __grid_constant__ WThinArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const FdgWgrad& p = a.c;
+  const int K = a.K, Cout = p.Cout;
+  const int KP = a.kgroups * KB;                 // padded K (rows of the x tile)
+  const int CP = a.cgroups * 4;                  // padded Cout
+  float* xs = sm;                                // [WT_P][KP]
+  float* gs = sm + WT_P * KP;                    // [WT_P][CP]
+  const int t = threadIdx.x;
+  const bool worker = t < a.kgroups * a.cgroups;
+  const int kg = worker ? t / a.cgroups : 0, cg = worker ? t % a.cgroups : 0;
+  float acc[KB][4];
+#pragma unroll
+  for (int i = 0; i < KB; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+  const int OHW = p.OH * p.OW;
+  const int64_t mbeg = (int64_t)blockIdx.x * a.m_per_cta;
+  const int64_t mend = mbeg + a.m_per_cta < a.M ? mbeg + a.m_per_cta : a.M;
+  const bool kfast = p.x.sc == 1;                // NHWC: consecutive k of one filter row are contiguous
+  for (int64_t m0 = mbeg; m0 < mend; m0 += WT_P) {
+    // ---- stage the im2col rows and the gradient rows of 32 pixels
+    for (int i = t; i < WT_P * KP; i += WT_THREADS) {
+      const int pi = kfast ? i / KP : i % WT_P;
+      const int k = kfast ? i % KP : i / WT_P;
+      const int64_t m = m0 + pi;
+      float v = 0.f;
+      if (m < mend && k < K) {
+        const int n = (int)(m / OHW);
+        const int rem = (int)(m - (int64_t)n * OHW);
+        const int oy = rem / p.OW, ox = rem - oy * p.OW;
+        const int tap = k / p.Cin, ci = k - tap * p.Cin;
+        const int r = tap / p.S, s = tap - r * p.S;
+        const int iy = oy * p.stride - p.pad + r, ix = ox * p.stride - p.pad + s;
+        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          v = __ldg(p.x.p + n * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw + (int64_t)ci * p.x.sc);
+          if (p.has_affine) v = fmaf(v, __ldg(p.scale + ci), __ldg(p.shift + ci));
+          v = prologue_act(v, p.slope);
+        }
+      }
+      xs[pi * KP + k] = v;
+    }
+    for (int i = t; i < WT_P * CP; i += WT_THREADS) {
+      const int pi = i / CP, c = i - pi * CP;
+      const int64_t m = m0 + pi;
+      float v = 0.f;
+      if (m < mend && c < Cout) {
+        const int n = (int)(m / OHW);
+        const int rem = (int)(m - (int64_t)n * OHW);
+        const int oy = rem / p.OW, ox = rem - oy * p.OW;
+        v = __ldg(p.g.p + n * p.g.sn + (int64_t)oy * p.g.sh + (int64_t)ox * p.g.sw + (int64_t)c * p.g.sc);
+      }
+      gs[pi * CP + c] = v;
+    }
+    __syncthreads();
+    if (worker) {
+#pragma unroll 4
+      for (int pi = 0; pi < WT_P; ++pi) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gs + pi * CP + cg * 4);
+        const float* xr = xs + pi * KP + kg * KB;
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+          const float xv = xr[i];
+          acc[i][0] = fmaf(xv, g4.x, acc[i][0]); acc[i][1] = fmaf(xv, g4.y, acc[i][1]);
+          acc[i][2] = fmaf(xv, g4.z, acc[i][2]); acc[i][3] = fmaf(xv, g4.w, acc[i][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (worker) {
+    const int RS = p.R * p.S;
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+      const int k = kg * KB + i;
+      if (k < K) {
+        const int tap = k / p.Cin, ci = k - tap * p.Cin;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int co = cg * 4 + u;
+          if (co < Cout) atomicAdd(p.dw + ((int64_t)co * p.Cin + ci) * RS + tap, acc[i][u]);
+        }
+      }
+    }
+  }
+}
+
+// returns 1 when the shape is not taken by this path
+int wgrad_thin(const FdgWgrad* p, cudaStream_t st) {
+  static const int on = [] { const char* e = getenv("FDG_THIN"); return e ? atoi(e) : 1; }();
+  const int K = p->R * p->S * p->Cin;
+  if (!on || p->impl != 0 || K > TH_MAXK || p->Cin > 16 || p->Cout > 64 || p->gather != FDG_GATHER_DIRECT || p->transposed) return 1;
+  WThinArgs a;
+  a.c = *p;
+  a.M = (int64_t)p->N * p->OH * p->OW;
+  a.K = K;
+  a.cgroups = cdiv(p->Cout, 4);
+  const int kb = cdiv(K * a.cgroups, WT_THREADS) <= 3 ? 3 : 6;    // k rows per thread so that kgroups * cgroups <= 256
+  a.kb = kb;
+  a.kgroups = cdiv(K, kb);
+  if (a.kgroups * a.cgroups > WT_THREADS) return 1;
+  int64_t ctas = 148 * 4;
+  a.m_per_cta = cdiv64(cdiv64(a.M, ctas), WT_P) * WT_P;
+  ctas = cdiv64(a.M, a.m_per_cta);
+  const int smem = WT_P * (a.kgroups * kb + a.cgroups * 4) * 4;
+  ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * K * p->Cout, 4.0 * ((double)a.M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);
+  if (kb == 3) wgrad_thin_kernel<3><<<(unsigned)ctas, WT_THREADS, smem, st>>>(a);
+  else wgrad_thin_kernel<6><<<(unsigned)ctas, WT_THREADS, smem, st>>>(a);
+  return check_launch("fdg_conv2d_wgrad[thin]");
+}
+
+}  // namespace fdg

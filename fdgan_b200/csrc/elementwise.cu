@@ -418,6 +418,8 @@ static inline unsigned grid_for(int64_t total, int block) {
 
 using namespace fdg;
 
+namespace fdg { int dgrad_strided_small(const FdgDgradStrided* p, cudaStream_t st); }
+
 extern "C" {
 
 int fdg_bn_finalize(const FdgBnFinalize* p, fdg_stream_t stream) {
@@ -503,6 +505,10 @@ int fdg_conv2d_dgrad_strided(const FdgDgradStrided* p, fdg_stream_t stream) {
                   p->H > 0 && p->W > 0, "fdg_conv2d_dgrad_strided: bad extents");
   FDG_REQUIRE(p->OH == (p->H + 2 * p->pad - p->R) / p->stride + 1 && p->OW == (p->W + 2 * p->pad - p->S) / p->stride + 1,
               "fdg_conv2d_dgrad_strided: OH/OW inconsistent");
+  {
+    const int rc = fdg::dgrad_strided_small(p, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   const int64_t total = (int64_t)p->N * p->H * p->W * p->Cin;
   dgrad_strided_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(*p, total);
   return check_launch("fdg_conv2d_dgrad_strided");

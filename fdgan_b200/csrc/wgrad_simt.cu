@@ -183,6 +183,7 @@ namespace fdg {
 int wgrad_umma_supported(const FdgWgrad* p);
 int wgrad_umma(const FdgWgrad* p, cudaStream_t st);
 int wgrad_halo_supported(const FdgWgrad* p);
+int wgrad_thin(const FdgWgrad* p, cudaStream_t st);
 int wgrad_halo(const FdgWgrad* p, cudaStream_t st);
 }  // namespace fdg
 
@@ -212,6 +213,11 @@ extern "C" int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream) {
   FDG_REQUIRE(!p->transposed || (p->R == 1 && p->S == 1), "fdg_conv2d_wgrad: transposed layout is 1x1 only");
   FDG_REQUIRE(!p->has_affine || (p->scale && p->shift), "fdg_conv2d_wgrad: affine prologue without scale/shift");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int rc = wgrad_thin(p, st);        // thin layers (stem, Fusion-D layer 1): direct kernel
+    if (rc < 0) return rc;
+    if (rc == 0) return p->dbias ? fdg_colsum(&p->g, p->N, p->OH, p->OW, p->Cout, p->dbias, 1, stream) : FDG_OK;
+  }
   if (p->impl != 1) {
     const int ok = wgrad_umma_supported(p) || wgrad_halo_supported(p);
     if (p->impl == 2 && !ok) { set_error("fdg_conv2d_wgrad: impl=tcgen05 requested but shape/layout unsupported"); return FDG_ENOSUPPORT; }
