@@ -41,7 +41,7 @@ class FdgConv(C.Structure):
         ("Cout", C.c_int), ("OH", C.c_int), ("OW", C.c_int), ("bias", C.c_void_p), ("act", C.c_int),
         ("e", FdgTensor), ("eslope", C.c_float), ("y", FdgTensor), ("store", C.c_int),
         ("stats", C.c_void_p), ("stats_ld", C.c_int), ("alpha", C.c_float), ("impl", C.c_int),
-        ("w_umma", C.c_void_p),
+        ("w_umma", C.c_void_p), ("e_scale", C.c_void_p), ("e_shift", C.c_void_p),
     ]
 
 
@@ -105,6 +105,7 @@ _SIGS = {
     "fdg_copy4d": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p], C.c_int),
     "fdg_act_bwd": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p], C.c_int),
     "fdg_conv2d_dgrad_strided": ([_P(FdgDgradStrided), C.c_void_p], C.c_int),
+    "fdg_affine_accum": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_colsum": ([_P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_fwd": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_bwd": ([_P(FdgTensor), _P(FdgTensor), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),

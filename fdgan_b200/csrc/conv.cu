@@ -22,6 +22,7 @@ extern "C" int fdg_conv2d(const FdgConv* p, fdg_stream_t stream) {
     if (fdg::conv2d_thin_supported(p)) return fdg::conv2d_thin(p, st);
   }
   const int ok = fdg::conv2d_umma_supported(p);
+  if (p->e_scale && !ok) { fdg::set_error("fdg_conv2d: BatchNorm-backward epilogue requested but the shape is not tcgen05-eligible"); return FDG_ENOSUPPORT; }
   if (p->impl == 2) {
     if (!ok) { fdg::set_error("fdg_conv2d: impl=tcgen05 requested but shape/layout unsupported"); return FDG_ENOSUPPORT; }
     return fdg::conv2d_umma(p, st);

@@ -133,7 +133,7 @@ int conv2d_thin_supported(const FdgConv* p) {
   if (!on || p->impl != 0) return 0;                  // impl = 1 keeps the generic SIMT kernel (the tests' fp32 arbiter)
   const int K = p->R * p->S * p->Cin;
   if (K > TH_MAXK || p->Cin > 16 || !(p->Cout == 16 || p->Cout == 36 || p->Cout == 64)) return 0;
-  if (p->gather != FDG_GATHER_DIRECT || p->has_affine || p->e.p || p->store != FDG_STORE_NORMAL) return 0;
+  if (p->gather != FDG_GATHER_DIRECT || p->has_affine || p->e.p || p->e_scale || p->store != FDG_STORE_NORMAL) return 0;
   if (!vec4_ok(p->y)) return 0;
   return 1;
 }
@@ -214,7 +214,7 @@ int conv2d_cin1_supported(const FdgConv* p) {
   static const int on = [] { const char* e = getenv("FDG_THIN"); return e ? atoi(e) : 1; }();
   if (!on || p->impl != 0) return 0;
   if (p->Cin != 1 || p->Cout % 4 != 0 || p->gather != FDG_GATHER_DIRECT || p->has_affine) return 0;
-  if (p->bias || p->act != FDG_ACT_NONE || p->stats || p->store != FDG_STORE_NORMAL) return 0;
+  if (p->bias || p->act != FDG_ACT_NONE || p->stats || p->e_scale || p->store != FDG_STORE_NORMAL) return 0;
   if (!vec4_ok(p->y) || !aligned16(p->w) || p->w_ld % 4 != 0) return 0;
   if (p->e.p && !vec4_ok(p->e)) return 0;
   return 1;

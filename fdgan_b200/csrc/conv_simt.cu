@@ -308,9 +308,15 @@ int conv2d_validate(const FdgConv* p) {
   FDG_REQUIRE(!p->has_affine || (p->scale && p->shift), "fdg_conv2d: affine prologue without scale/shift");
   FDG_REQUIRE(p->w_ld >= p->Cout, "fdg_conv2d: w_ld < Cout");
   FDG_REQUIRE(p->store >= 0 && p->store <= 2, "fdg_conv2d: bad store mode %d", p->store);
-  FDG_REQUIRE(!(p->stats && p->store != FDG_STORE_NORMAL), "fdg_conv2d: stats need the normal store mode");
+  FDG_REQUIRE(!(p->stats && p->store != FDG_STORE_NORMAL && !p->e_scale), "fdg_conv2d: stats need the normal store mode");
   FDG_REQUIRE(!p->stats || p->stats_ld >= p->Cout, "fdg_conv2d: stats_ld < Cout");
   FDG_REQUIRE((int64_t)p->R * p->S * p->Cin < (1ll << 31), "fdg_conv2d: K too large");
+  if (p->e_scale) {
+    FDG_REQUIRE(p->e_shift && p->e.p && p->store != FDG_STORE_UP2 && p->Cout % 4 == 0 && vec4_ok(p->y) && vec4_ok(p->e) &&
+                    aligned16(p->e_scale) && aligned16(p->e_shift) && !p->bias && p->act == FDG_ACT_NONE,
+                "fdg_conv2d: the BatchNorm-backward epilogue needs e, e_shift, 128-bit y/e views, Cout %% 4 == 0, no bias/activation");
+    FDG_REQUIRE(p->impl != 1, "fdg_conv2d: the BatchNorm-backward epilogue exists on the tcgen05 path only");
+  }
   return FDG_OK;
 }
 

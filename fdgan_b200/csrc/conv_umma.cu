@@ -426,9 +426,8 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
 #pragma unroll
             for (int u = 0; u < 32; ++u) v[u] += v2[u];
           }
-          float s1 = 0.f, s2 = 0.f;
-          umma_epilogue_group(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, s1, s2);
-          if (p.stats) { sred[0][quarter][g * 32 + lane] += s1; sred[1][quarter][g * 32 + lane] += s2; }
+          umma_epilogue_group(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, &sred[0][quarter][g * 32],
+                              &sred[1][quarter][g * 32]);
         }
       }
       // release the accumulator buffer to the MMA thread

@@ -230,6 +230,24 @@ __global__ void __launch_bounds__(256) ew_bwd_linear_kernel(FdgEwBwd p, int64_t 
   }
 }
 
+// ------------------------------------------------------------------ deferred affine part of the BatchNorm backward
+__global__ void __launch_bounds__(256) affine_accum_kernel(FdgTensor x, FdgTensor out, int64_t total4, int H, int W, int C4, const float* cb,
+                                                           const float* cd) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    int64_t r = i / C4;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x.p + n * x.sn + (int64_t)h * x.sh + (int64_t)w * x.sw + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(cb + c)), d = __ldg(reinterpret_cast<const float4*>(cd + c));
+    float4* op = reinterpret_cast<float4*>(out.p + n * out.sn + (int64_t)h * out.sh + (int64_t)w * out.sw + c);
+    float4 o = *op;
+    o.x += fmaf(b.x, xv.x, d.x); o.y += fmaf(b.y, xv.y, d.y); o.z += fmaf(b.z, xv.z, d.z); o.w += fmaf(b.w, xv.w, d.w);
+    *op = o;
+  }
+}
+
 // ------------------------------------------------------------------ max pool 2x2
 __global__ void maxpool2_fwd_kernel(FdgTensor x, FdgTensor y, int64_t total, int OH, int OW, int C) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -466,6 +484,17 @@ int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
   } else if (vec) ew_bwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   else ew_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   return check_launch("fdg_ew_bwd");
+}
+
+int fdg_affine_accum(const FdgTensor* x, const FdgTensor* out, int N, int H, int W, int C, const float* cb, const float* cd,
+                     fdg_stream_t stream) {
+  FDG_REQUIRE(x && out && x->p && out->p && cb && cd && N > 0 && H > 0 && W > 0 && C > 0, "fdg_affine_accum: bad arguments");
+  FDG_REQUIRE(C % 4 == 0 && vec4_ok(*x) && vec4_ok(*out) && aligned16(cb) && aligned16(cd),
+              "fdg_affine_accum: needs unit-stride channels, C % 4 == 0 and 16-byte aligned views / vectors");
+  const int64_t total4 = (int64_t)N * H * W * (C / 4);
+  ProfScope prof(PF_EW, 2.0 * (double)total4 * 4, 4.0 * (double)total4 * 4 * 3.0, (cudaStream_t)stream);
+  affine_accum_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(*x, *out, total4, H, W, C / 4, cb, cd);
+  return check_launch("fdg_affine_accum");
 }
 
 int fdg_maxpool2_fwd(const FdgTensor* x, const FdgTensor* y, int N, int OH, int OW, int C, fdg_stream_t stream) {

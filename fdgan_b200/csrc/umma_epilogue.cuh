@@ -27,10 +27,11 @@ struct EpiTma {
 // yoff:   element offset of the lane's pixel in y (for FDG_STORE_UP2: of its top-left replica), channel 0
 // eoff:   element offset of the lane's pixel in e
 // et:     thread index within the 128 epilogue threads
-// s1, s2: (p.stats only) receive the sum / sum of squares of channel c0 + lane over the warp's 32 pixels
+// st1, st2: (p.stats only) this warp's running per-channel sums for channels c0 .. c0+31 in shared memory; they receive
+//         sum v, sum v^2 over the warp's 32 pixels -- or, in the BatchNorm-backward mode (p.e_scale), sum dz, sum dz*e
 __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec, bool evec, float (&v)[32], bool mv, int64_t yoff,
                                                     int64_t eoff, int c0, int lane, int quarter, int et, uint32_t tile, const EpiTma& tm,
-                                                    float& s1, float& s2) {
+                                                    float* st1, float* st2) {
   const int nvalid = p.Cout - c0 < 32 ? p.Cout - c0 : 32;
   const bool full = nvalid == 32;
   // ---- alpha, bias
@@ -81,6 +82,7 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (uint32_t)((q ^ sw) << 4)), "f"(v[4 * q]), "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
   }
   const bool has_e = p.e.p != nullptr;
+  const bool bnbwd = p.e_scale != nullptr;
   if (use_tma) {
     fence_proxy_async();                                   // generic-proxy writes -> visible to the bulk-copy engine
     asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -97,18 +99,36 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
       // ---- coalesced phase: instruction i covers pixels 4i .. 4i+3 of the warp, lane handles channels 4*(lane & 7) .. +3
       const int q = lane & 7, c4 = q * 4;
       const bool cv = c4 < nvalid;
+      float4 bsc = make_float4(0.f, 0.f, 0.f, 0.f), bsh = bsc, ps1 = bsc, ps2 = bsc;
+      if (bnbwd && cv) { bsc = ld4(p.e_scale + c0 + c4); bsh = ld4(p.e_shift + c0 + c4); }
+      // all mask-tensor loads of the group first: eight independent 128-bit loads in flight per lane
+      float4 evs[8];
+      if (has_e) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + (lane >> 3);
+          const int64_t eo = __shfl_sync(0xffffffffu, eoff, row);
+          evs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (((vmask >> row) & 1u) && cv) evs[i] = ld4(p.e.p + eo + c0 + c4);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = 4 * i + (lane >> 3);
         const int64_t yo = __shfl_sync(0xffffffffu, yoff, row);
-        int64_t eo = 0;
-        if (has_e) eo = __shfl_sync(0xffffffffu, eoff, row);
         if (((vmask >> row) & 1u) && cv) {
           float4 val;
           const uint32_t ta = wrow0 + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(ta) : "memory");
-          if (has_e) {
-            const float4 ev = ld4(p.e.p + eo + c0 + c4);
+          if (bnbwd) {
+            const float4 ev = evs[i];
+            val.x *= fmaf(ev.x, bsc.x, bsh.x) > 0.f ? 1.f : p.eslope; val.y *= fmaf(ev.y, bsc.y, bsh.y) > 0.f ? 1.f : p.eslope;
+            val.z *= fmaf(ev.z, bsc.z, bsh.z) > 0.f ? 1.f : p.eslope; val.w *= fmaf(ev.w, bsc.w, bsh.w) > 0.f ? 1.f : p.eslope;
+            ps1.x += val.x; ps1.y += val.y; ps1.z += val.z; ps1.w += val.w;
+            ps2.x = fmaf(val.x, ev.x, ps2.x); ps2.y = fmaf(val.y, ev.y, ps2.y); ps2.z = fmaf(val.z, ev.z, ps2.z); ps2.w = fmaf(val.w, ev.w, ps2.w);
+            val.x *= bsc.x; val.y *= bsc.y; val.z *= bsc.z; val.w *= bsc.w;
+          } else if (has_e) {
+            const float4 ev = evs[i];
             val.x *= ev.x > 0.f ? 1.f : p.eslope; val.y *= ev.y > 0.f ? 1.f : p.eslope;
             val.z *= ev.z > 0.f ? 1.f : p.eslope; val.w *= ev.w > 0.f ? 1.f : p.eslope;
             if (p.stats) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
@@ -120,11 +140,26 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
             *reinterpret_cast<float4*>(yp + p.y.sh) = val;
             *reinterpret_cast<float4*>(yp + p.y.sh + p.y.sw) = val;
           } else if (p.store == FDG_STORE_ACCUM) {
-            const float4 old = *reinterpret_cast<const float4*>(yp);
-            *reinterpret_cast<float4*>(yp) = make_float4(val.x + old.x, val.y + old.y, val.z + old.z, val.w + old.w);
+            // fire-and-forget 128-bit reduction at L2: no round trip for the old value (every address is touched by
+            // exactly one lane per launch, so the result is deterministic)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yp), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
           } else {
             *reinterpret_cast<float4*>(yp) = val;
           }
+        }
+      }
+      if (bnbwd && p.stats) {
+        // lanes l, l+8, l+16, l+24 hold partial sums of the same four channels: fold them, lanes 0..7 publish
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+          ps1.x += __shfl_xor_sync(0xffffffffu, ps1.x, off); ps1.y += __shfl_xor_sync(0xffffffffu, ps1.y, off);
+          ps1.z += __shfl_xor_sync(0xffffffffu, ps1.z, off); ps1.w += __shfl_xor_sync(0xffffffffu, ps1.w, off);
+          ps2.x += __shfl_xor_sync(0xffffffffu, ps2.x, off); ps2.y += __shfl_xor_sync(0xffffffffu, ps2.y, off);
+          ps2.z += __shfl_xor_sync(0xffffffffu, ps2.z, off); ps2.w += __shfl_xor_sync(0xffffffffu, ps2.w, off);
+        }
+        if (lane < 8 && cv) {
+          st1[c4] += ps1.x; st1[c4 + 1] += ps1.y; st1[c4 + 2] += ps1.z; st1[c4 + 3] += ps1.w;
+          st2[c4] += ps2.x; st2[c4 + 1] += ps2.y; st2[c4 + 2] += ps2.z; st2[c4 + 3] += ps2.w;
         }
       }
     } else {
@@ -153,7 +188,7 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
     }
     __syncwarp();
   }
-  if (p.stats) {
+  if (p.stats && !bnbwd) {
     // lane = channel: column sums over the warp's 32 rows (conflict-free: one row per step, 32 distinct words)
     float a1 = 0.f, a2 = 0.f;
     const uint32_t cpos = (uint32_t)(lane >> 2), cw = (uint32_t)(lane & 3) << 2;
@@ -164,8 +199,8 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
       a1 += xv;
       a2 = fmaf(xv, xv, a2);
     }
-    s1 = a1;
-    s2 = a2;
+    st1[lane] += a1;
+    st2[lane] += a2;
   }
   if (!use_tma) __syncwarp();   // the warp's rows are rewritten by the next group
 }

@@ -225,26 +225,51 @@ def _conv_dgrad_w(weight):
     return ops.pack_weight(weight, 1)
 
 
+FUSED_BN1_BWD = True   # norm1 backward inside the conv1 data-gradient epilogue + deferred per-channel affine term
+
+
 def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, grads, dpool):
+    """Backward of one torchvision dense block.  norm1 of layer j reads concat channels [0, cin_j) with the SAME batch
+    statistics as every other consumer of those channels, so its backward dx = alpha dz + (beta x + delta) splits into
+    a part the conv1 data-gradient epilogue adds straight into dX (alpha dz, FdgConv.e_scale) and a per-channel affine
+    part whose coefficients simply add up over the consumers; that sum is applied ONCE per channel, right before the
+    channel's gradient is consumed (ops.affine_accum) -- instead of a reduce pass and a 4-stream apply pass over
+    cin_j channels for every layer."""
     N, H, W = X.N, X.H, X.W
     dev = X.base.device
+    Ctot = X.C
     dA2 = View.alloc(N, H, W, BOTTLENECK, dev)
     cmax = c_in + GROWTH * (n_layers - 1)
-    dA1buf = torch.empty(N * H * W * cmax, dtype=torch.float32, device=dev)
+    fused = FUSED_BN1_BWD and ops.USE_UMMA
+    dA1buf = None if fused else torch.empty(N * H * W * cmax, dtype=torch.float32, device=dev)
+    cbd = torch.zeros(2, Ctot, dtype=torch.float32, device=dev) if fused else None   # deferred beta / delta sums
     for i in reversed(range(n_layers)):
         lyr = getattr(block, "denselayer%d" % (i + 1))
         p = "%s.denselayer%d" % (prefix, i + 1)
         cin = c_in + GROWTH * i
         T, bn1, bn2 = layers[i]
+        if fused and i < n_layers - 1:   # the later layers' affine terms for this layer's 32 new channels
+            ops.affine_accum(X.ch(cin, cin + GROWTH), dX.ch(cin, cin + GROWTH), cbd[0, cin:cin + GROWTH], cbd[1, cin:cin + GROWTH])
         g2 = dX.ch(cin, cin + GROWTH)
         ops.wgrad(T, g2, 3, 3, 1, 1, grads[p + ".conv2.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.0)
         wd, ldd = _conv_dgrad_w(lyr.conv2.weight)
         ops.conv2d(g2, wd, ldd, 3, 3, 1, 1, BOTTLENECK, dA2)
         _bn_bwd(dA2, T, bn2, dA2, dpool, grads, p + ".norm2")                      # dA2 <- dL/d(conv1 output), in place
         ops.wgrad(X.ch(0, cin), dA2, 1, 1, 1, 0, grads[p + ".conv1.weight"], scale=bn1.scale, shift=bn1.shift, slope=0.0)
-        dA1 = View.nhwc(dA1buf, N, H, W, cin)
-        ops.conv2d(dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dA1)
-        _bn_bwd(dA1, X.ch(0, cin), bn1, dX.ch(0, cin), dpool, grads, p + ".norm1", accumulate=True)
+        if fused:
+            st = dpool.take(2 * cin)
+            ops.conv2d(dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dX.ch(0, cin), store=STORE_ACCUM, e=X.ch(0, cin), eslope=0.0,
+                       e_scale=bn1.scale, e_shift=bn1.shift, stats=st, stats_ld=cin)
+            coef = torch.empty(3, cin, dtype=torch.float32, device=dev)
+            ops.bn_bwd_finalize(st, cin, bn1.count, bn1.mod.weight, bn1.mean, bn1.invstd, coef,
+                                grads.get(p + ".norm1.weight"), grads.get(p + ".norm1.bias"), accumulate=True)
+            cbd[:, :cin] += coef[1:]
+        else:
+            dA1 = View.nhwc(dA1buf, N, H, W, cin)
+            ops.conv2d(dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dA1)
+            _bn_bwd(dA1, X.ch(0, cin), bn1, dX.ch(0, cin), dpool, grads, p + ".norm1", accumulate=True)
+    if fused:
+        ops.affine_accum(X.ch(0, c_in), dX.ch(0, c_in), cbd[0, :c_in], cbd[1, :c_in])
 
 
 def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dpool):

@@ -95,7 +95,7 @@ def pack_weight_umma(w, w_ld: int, taps: int, Cin: int, Cout: int, device) -> to
 
 def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_DIRECT, scale=None, shift=None,
            slope=1.0, bias=None, act=ACT_NONE, e: View | None = None, eslope=0.0, store=STORE_NORMAL, stats=None,
-           stats_ld=0, alpha=1.0, impl=IMPL_AUTO, w_umma=None):
+           stats_ld=0, alpha=1.0, impl=IMPL_AUTO, w_umma=None, e_scale=None, e_shift=None):
     """fdg_conv2d.  ``w`` is the packed [K][w_ld] operand (tensor or pointer)."""
     if gather == GATHER_AVGPOOL2:
         H, W = x.H // 2, x.W // 2
@@ -115,7 +115,8 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
     d = L.FdgConv(
         x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
         _ptr(w), w_ld, R, S, stride, pad, Cout, OH, OW, _ptr(bias), act,
-        e.ft() if e is not None else _NULLT, eslope, y.ft(), store, _ptr(stats), stats_ld, alpha, impl, _ptr(w_umma))
+        e.ft() if e is not None else _NULLT, eslope, y.ft(), store, _ptr(stats), stats_ld, alpha, impl, _ptr(w_umma),
+        _ptr(e_scale), _ptr(e_shift))
     L.check(L.lib.fdg_conv2d(_byref(d), _stream()), "conv2d")
 
 
@@ -176,6 +177,13 @@ def ew_bwd(g: View, x: View, *, out: View | None = None, stats=None, g_gather=GA
                    _ptr(scale), _ptr(shift), slope, _ptr(coef), out.ft() if out is not None else _NULLT,
                    1 if accumulate else 0, _ptr(stats))
     L.check(L.lib.fdg_ew_bwd(_byref(d), _stream()), "ew_bwd")
+
+
+def affine_accum(x: View, out: View, cb, cd):
+    """fdg_affine_accum: out += cb[c] * x + cd[c] (deferred affine part of the BatchNorm backward)."""
+    assert (x.N, x.H, x.W, x.C) == (out.N, out.H, out.W, out.C)
+    xt, ot = x.ft(), out.ft()
+    L.check(L.lib.fdg_affine_accum(_byref(xt), _byref(ot), x.N, x.H, x.W, x.C, _ptr(cb), _ptr(cd), _stream()), "affine_accum")
 
 
 def bn_bwd_finalize(stats, Cc, count, gamma, mean, invstd, coef, dgamma=None, dbeta=None, accumulate=True):

@@ -91,6 +91,14 @@ typedef struct FdgConv {
   float alpha;          /* result scale applied before the bias (4 = adjoint of nearest x2 through FDG_GATHER_AVGPOOL2) */
   int impl;             /* 0 auto, 1 force SIMT fp32, 2 force tcgen05 (error if unsupported) */
   const void* w_umma;   /* tcgen05 operand image of the weights (fdg_pack_weight_umma) or NULL */
+  /* BatchNorm-backward epilogue (tcgen05 path, 128-bit views only), enabled by e_scale != NULL: with z = e_scale*e + e_shift
+   * (the BatchNorm output whose (Leaky)ReLU mask applies) and dz = acc * (z > 0 ? 1 : eslope), the kernel stores
+   * y (=|+=) e_scale * dz and reduces stats[c] += sum dz, stats[stats_ld + c] += sum dz * e.  Together with
+   * fdg_bn_bwd_finalize (dx = alpha dz + beta x + delta) this leaves only the per-channel affine term beta x + delta,
+   * which fdg_affine_accum applies later, once per channel, for ALL consumers of that channel (the dense-block layers
+   * share the batch statistics of a concat channel, so their beta / delta simply add up). */
+  const float* e_scale; /* [Cout] or NULL */
+  const float* e_shift; /* [Cout] */
 } FdgConv;
 
 int fdg_conv2d(const FdgConv* p, fdg_stream_t stream);
@@ -230,6 +238,10 @@ typedef struct FdgDgradStrided {
 } FdgDgradStrided;
 
 int fdg_conv2d_dgrad_strided(const FdgDgradStrided* p, fdg_stream_t stream);
+
+/* out[n,h,w,c] += cb[c] * x[n,h,w,c] + cd[c]: the deferred affine part of the BatchNorm backward (see FdgConv.e_scale). */
+int fdg_affine_accum(const FdgTensor* x, const FdgTensor* out, int N, int H, int W, int C, const float* cb, const float* cd,
+                     fdg_stream_t stream);
 
 /* per-channel column sum: out[c] (+)= sum over (n,h,w) of x (bias gradients). */
 int fdg_colsum(const FdgTensor* x, int N, int H, int W, int C, float* out, int accumulate, fdg_stream_t stream);

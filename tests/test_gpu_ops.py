@@ -249,6 +249,45 @@ def test_bn_finalize_and_backward_pieces():
     assert maxabs(buf[:C], want) <= 1e-5
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 96, 9, 7, 0.0), (1, 128, 224, 33, 31, 0.0), (2, 64, 160, 12, 10, 0.2)])
+def test_conv2d_bn_backward_epilogue(shape):
+    """1x1 data-gradient conv with the BatchNorm-backward epilogue (FdgConv.e_scale) + fdg_bn_bwd_finalize + fdg_affine_accum
+    == autograd through conv1x1(leaky_relu(batch_norm(x))) w.r.t. x (dense-layer norm1/conv1 backward, torchvision
+    densenet.py:_DenseLayer), accumulated into an existing gradient buffer."""
+    ops = _ops()
+    N, Cmid, Cx, H, W, slope = shape
+    x = seeded((N, Cx, H, W), 1, -2, 3).double().requires_grad_(True)
+    gamma = seeded((Cx,), 2, 0.5, 1.5).double().requires_grad_(True)
+    beta = seeded((Cx,), 3, -0.5, 0.5).double().requires_grad_(True)
+    w = (seeded((Cmid, Cx, 1, 1), 4, -1, 1) / math.sqrt(Cx)).double()
+    gout = seeded((N, Cmid, H, W), 5, -1, 1).double()            # dL/d(conv output)
+    y = F.conv2d(F.leaky_relu(F.batch_norm(x, None, None, gamma, beta, True, 0.1, 1e-5), slope), w)
+    (y * gout).sum().backward()
+    base = seeded((N, Cx, H, W), 9, -1, 1)
+    # ---- device: forward statistics -> scale/shift, then the fused backward
+    cnt = N * H * W
+    xd = cl(x.detach().float())
+    st = torch.stack([x.detach().sum((0, 2, 3)), (x.detach() ** 2).sum((0, 2, 3))]).reshape(-1).cuda()
+    buf = torch.zeros(4 * Cx, device="cuda")
+    ops.bn_finalize(st, Cx, Cx, cnt, gamma.detach().float().cuda(), beta.detach().float().cuda(), 1e-5, 0.1, None, None, True,
+                    buf[:Cx], buf[Cx:2 * Cx], buf[2 * Cx:3 * Cx], buf[3 * Cx:])
+    dxd = cl(base.clone())
+    st2 = torch.zeros(2 * Cx, dtype=torch.float64, device="cuda")
+    wd = w.float().cuda().reshape(Cmid, Cx).contiguous()          # [K = Cmid][Cx]: the 1x1 data-gradient operand
+    xv = ops.View.from_nchw(xd)
+    ops.conv2d(ops.View.from_nchw(cl(gout.float())), wd, Cx, 1, 1, 1, 0, Cx, ops.View.from_nchw(dxd), store=ops.STORE_ACCUM,
+               e=xv, eslope=slope, e_scale=buf[:Cx], e_shift=buf[Cx:2 * Cx], stats=st2, stats_ld=Cx)
+    coef = torch.empty(3 * Cx, device="cuda")
+    dgm, dbt = torch.zeros(Cx, device="cuda"), torch.zeros(Cx, device="cuda")
+    ops.bn_bwd_finalize(st2, Cx, cnt, gamma.detach().float().cuda(), buf[2 * Cx:3 * Cx], buf[3 * Cx:], coef, dgm, dbt)
+    assert maxabs(coef[:Cx], buf[:Cx]) <= 1e-6                     # alpha == the forward scale (what the epilogue multiplied by)
+    ops.affine_accum(xv, ops.View.from_nchw(dxd), coef[Cx:2 * Cx], coef[2 * Cx:])
+    torch.cuda.synchronize()
+    assert maxabs(dxd, x.grad + base.double()) <= 1e-4
+    scale_g = float(gamma.grad.abs().max())
+    assert maxabs(dgm, gamma.grad) <= 2e-4 * max(1.0, scale_g) and maxabs(dbt, beta.grad) <= 2e-4 * max(1.0, float(beta.grad.abs().max()))
+
+
 def test_ew_bwd_pooled_gradient_scalar_path():
     ops = _ops()
     N, C, H, W = 2, 9, 6, 8   # C=9: scalar path
