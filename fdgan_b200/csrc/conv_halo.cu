@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
 #pragma unroll
             for (int u = 0; u < 32; ++u) v[u] += v2[u];
           }
-          umma_epilogue_group(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, &sred[0][quarter][g * 32],
+          umma_epilogue_group<true>(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, &sred[0][quarter][g * 32],
                               &sred[1][quarter][g * 32]);
         }
       }

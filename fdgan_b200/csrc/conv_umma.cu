@@ -41,6 +41,7 @@ struct UmmaArgs {
   int yvec;
   int dbg;   // ablation: 1 no global loads, 2 no split/stores, 4 no MMA, 8 no epilogue
   int tma_rank;                 // 2: the epilogue stores through ymap {channel, linear pixel}; 0: coalesced stores
+  int bn_linear;                // BatchNorm-backward epilogue: y and e are pixel-linear views (pipelined variant)
   alignas(64) CUtensorMap ymap;
 };
 
@@ -80,7 +81,7 @@ constexpr int UTHREADS_P = (ULOAD_WARPS + 1 + 4) * 32;
 
 // DEPTH > 0: the loaders fetch through cp.async into a thread-private shared-memory staging ring (DEPTH chunks in
 // flight, no registers tied up by loads in flight); DEPTH == 0: two-chunk register double buffer.
-template <int NT, int STAGES, int DEPTH>
+template <int NT, int STAGES, int DEPTH, bool BNBWD>
 __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
@@ -393,6 +394,22 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     const int et = t - UEPI_WARP0 * 32;
     const uint32_t stage = smem_u32(ep_stage);
     const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
+    // BatchNorm-backward epilogue on pixel-linear views (dense-block conv1 data gradient): the mask-tensor rows of the
+    // NEXT 32-channel group (or of the next tile's first group) are fetched while the current group is processed, so
+    // their HBM latency never sits between tcgen05.ld and the stores.
+    const bool bn_lin = BNBWD;      // separate instantiation: its register needs must not spill the common kernel
+    float4 evn[8];
+    const int bq = lane & 7, bc4 = bq * 4, brs = lane >> 3;
+    auto bn_prefetch = [&](int tile_, int g_) {
+      const int mt_ = tile_ % m_tiles, c0_ = (tile_ / m_tiles) * NT + g_ * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m_ = (int64_t)mt_ * UM + quarter * 32 + 4 * i + brs;
+        evn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m_ < a.M && c0_ + bc4 < p.Cout) evn[i] = ld4(p.e.p + m_ * p.e.sw + c0_ + bc4);
+      }
+    };
+    if (BNBWD && (int)blockIdx.x < total_tiles) bn_prefetch(blockIdx.x, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mt = tile % m_tiles, ntile = tile / m_tiles;
@@ -412,6 +429,73 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       }
       const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, mt * UM, 0, 0};
       const int cbase = ntile * NT;
+      if constexpr (BNBWD) {
+        const int ngroups = (p.Cout - cbase + 31) / 32 < NT / 32 ? (p.Cout - cbase + 31) / 32 : NT / 32;
+        const uint32_t wrow0 = stage + (uint32_t)(quarter * 32) * 128u;
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+          const int c0 = cbase + g * 32;
+          {
+            float v[32], v2[32];
+            const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 * NT + g * 32);
+            tmem_ld32_nowait(tcol, v);
+            tmem_ld32_nowait(tcol + NT, v2);
+            tmem_ld_wait();
+            const uint32_t trow = wrow0 + (uint32_t)lane * 128u;
+            const int sw = lane & 7;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (uint32_t)((qq ^ sw) << 4)), "f"(v[4 * qq] + v2[4 * qq]),
+                           "f"(v[4 * qq + 1] + v2[4 * qq + 1]), "f"(v[4 * qq + 2] + v2[4 * qq + 2]), "f"(v[4 * qq + 3] + v2[4 * qq + 3]) : "memory");
+          }
+          __syncwarp();
+          const bool cv = c0 + bc4 < p.Cout;
+          float4 bsc = make_float4(0.f, 0.f, 0.f, 0.f), bsh = bsc, ps1 = bsc, ps2 = bsc;
+          if (cv) { bsc = ld4(p.e_scale + c0 + bc4); bsh = ld4(p.e_shift + c0 + bc4); }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + brs;
+            const int64_t mr = (int64_t)mt * UM + quarter * 32 + row;
+            if (mr < a.M && cv) {
+              float4 val;
+              const uint32_t ta = wrow0 + (uint32_t)row * 128u + (uint32_t)((bq ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(ta) : "memory");
+              const float4 ev = evn[i];
+              const float al = p.alpha;
+              val.x *= fmaf(ev.x, bsc.x, bsh.x) > 0.f ? al : al * p.eslope; val.y *= fmaf(ev.y, bsc.y, bsh.y) > 0.f ? al : al * p.eslope;
+              val.z *= fmaf(ev.z, bsc.z, bsh.z) > 0.f ? al : al * p.eslope; val.w *= fmaf(ev.w, bsc.w, bsh.w) > 0.f ? al : al * p.eslope;
+              ps1.x += val.x; ps1.y += val.y; ps1.z += val.z; ps1.w += val.w;
+              ps2.x = fmaf(val.x, ev.x, ps2.x); ps2.y = fmaf(val.y, ev.y, ps2.y); ps2.z = fmaf(val.z, ev.z, ps2.z); ps2.w = fmaf(val.w, ev.w, ps2.w);
+              val.x *= bsc.x; val.y *= bsc.y; val.z *= bsc.z; val.w *= bsc.w;
+              float* yp = p.y.p + mr * p.y.sw + c0 + bc4;
+              if (p.store == FDG_STORE_ACCUM)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yp), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+              else
+                *reinterpret_cast<float4*>(yp) = val;
+            }
+          }
+          // mask rows of the next group (or of the next tile's first group): in flight during the statistics fold, the
+          // next tcgen05.ld / staging stores and, across tiles, the wait for the accumulator
+          if (g + 1 < ngroups) bn_prefetch(tile, g + 1);
+          else if (tile + (int)gridDim.x < total_tiles) bn_prefetch(tile + gridDim.x, 0);
+          if (p.stats) {
+#pragma unroll
+            for (int off = 8; off <= 16; off <<= 1) {
+              ps1.x += __shfl_xor_sync(0xffffffffu, ps1.x, off); ps1.y += __shfl_xor_sync(0xffffffffu, ps1.y, off);
+              ps1.z += __shfl_xor_sync(0xffffffffu, ps1.z, off); ps1.w += __shfl_xor_sync(0xffffffffu, ps1.w, off);
+              ps2.x += __shfl_xor_sync(0xffffffffu, ps2.x, off); ps2.y += __shfl_xor_sync(0xffffffffu, ps2.y, off);
+              ps2.z += __shfl_xor_sync(0xffffffffu, ps2.z, off); ps2.w += __shfl_xor_sync(0xffffffffu, ps2.w, off);
+            }
+            if (lane < 8 && cv) {
+              float* st1 = &sred[0][quarter][g * 32 + bc4];
+              float* st2 = &sred[1][quarter][g * 32 + bc4];
+              st1[0] += ps1.x; st1[1] += ps1.y; st1[2] += ps1.z; st1[3] += ps1.w;
+              st2[0] += ps2.x; st2[1] += ps2.y; st2[2] += ps2.z; st2[3] += ps2.w;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
 #pragma unroll 1
       for (int g = 0; g < NT / 32; ++g) {
         const int c0 = cbase + g * 32;
@@ -426,9 +510,10 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
 #pragma unroll
             for (int u = 0; u < 32; ++u) v[u] += v2[u];
           }
-          umma_epilogue_group(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, &sred[0][quarter][g * 32],
+          umma_epilogue_group<false>(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, &sred[0][quarter][g * 32],
                               &sred[1][quarter][g * 32]);
         }
+      }
       }
       // release the accumulator buffer to the MMA thread
       tc_fence_before();
@@ -517,12 +602,12 @@ int conv2d_umma_supported(const FdgConv* p) {
   return 1;
 }
 
-template <int NT, int STAGES, int DEPTH>
+template <int NT, int STAGES, int DEPTH, bool BNBWD = false>
 static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + DEPTH * (UM * UKC * 4) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES, DEPTH, BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -539,7 +624,7 @@ static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
   ProfScope prof(PF_CONV_UMMA, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  conv_umma_kernel<NT, STAGES, DEPTH><<<grid, UTHREADS_P, smem, st>>>(a);
+  conv_umma_kernel<NT, STAGES, DEPTH, BNBWD><<<grid, UTHREADS_P, smem, st>>>(a);
   return check_launch("fdg_conv2d[tcgen05]");
 }
 
@@ -557,6 +642,10 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
   a.yvec = vec4_ok(p->y);
   a.dbg = dbg_flags();
   a.tma_rank = 0;
+  {
+    auto lin = [&](const FdgTensor& t) { return t.sh == (int64_t)p->OW * t.sw && t.sn == (int64_t)p->OH * t.sh; };
+    a.bn_linear = p->e_scale && p->e.p && lin(p->y) && lin(p->e) && vec4_ok(p->y) && vec4_ok(p->e) && p->store != FDG_STORE_UP2;
+  }
   static const int tma_on = [] { const char* e = getenv("FDG_TMA_STORE"); return e ? atoi(e) : 1; }();
   // bulk tensor stores: plain store into a unit-channel-stride, pixel-linear view (dense NHWC or a channel slice of one)
   if (tma_on && a.yvec && p->store == FDG_STORE_NORMAL && !p->e.p && p->y.sh == (int64_t)p->OW * p->y.sw &&
@@ -568,6 +657,13 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
   }
   static const int reg_path = [] { const char* e = getenv("FDG_CONV_REG"); return e ? atoi(e) : 0; }();
   if (reg_path && umma_ntile(p->Cout) == 128) return launch_umma<128, 3, 0>(a, st);   // register double buffer, no staging ring
+  if (p->e_scale) {   // BatchNorm-backward epilogue: own instantiation (pixel-linear 128-bit views, wide outputs)
+    if (!a.bn_linear || umma_ntile(p->Cout) < 64) {
+      set_error("fdg_conv2d[tcgen05]: the BatchNorm-backward epilogue of the per-tap kernel needs pixel-linear y / e views and Cout > 32");
+      return FDG_ENOSUPPORT;
+    }
+    return umma_ntile(p->Cout) == 64 ? launch_umma<64, 2, 3, true>(a, st) : launch_umma<128, 2, 2, true>(a, st);
+  }
   switch (umma_ntile(p->Cout)) {
     case 32: return launch_umma<32, 2, 3>(a, st);     // ring 2 x 40 KB + staging 3 x 32 KB
     case 64: return launch_umma<64, 2, 3>(a, st);     // ring 2 x 48 KB + staging 3 x 32 KB

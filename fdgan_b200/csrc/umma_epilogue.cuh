@@ -29,6 +29,7 @@ struct EpiTma {
 // et:     thread index within the 128 epilogue threads
 // st1, st2: (p.stats only) this warp's running per-channel sums for channels c0 .. c0+31 in shared memory; they receive
 //         sum v, sum v^2 over the warp's 32 pixels -- or, in the BatchNorm-backward mode (p.e_scale), sum dz, sum dz*e
+template <bool BN>   // BN: the BatchNorm-backward mode (p.e_scale) is compiled in
 __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec, bool evec, float (&v)[32], bool mv, int64_t yoff,
                                                     int64_t eoff, int c0, int lane, int quarter, int et, uint32_t tile, const EpiTma& tm,
                                                     float* st1, float* st2) {
@@ -82,7 +83,7 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (uint32_t)((q ^ sw) << 4)), "f"(v[4 * q]), "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
   }
   const bool has_e = p.e.p != nullptr;
-  const bool bnbwd = p.e_scale != nullptr;
+  const bool bnbwd = BN && p.e_scale != nullptr;
   if (use_tma) {
     fence_proxy_async();                                   // generic-proxy writes -> visible to the bulk-copy engine
     asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -101,50 +102,53 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
       const bool cv = c4 < nvalid;
       float4 bsc = make_float4(0.f, 0.f, 0.f, 0.f), bsh = bsc, ps1 = bsc, ps2 = bsc;
       if (bnbwd && cv) { bsc = ld4(p.e_scale + c0 + c4); bsh = ld4(p.e_shift + c0 + c4); }
-      // all mask-tensor loads of the group first: eight independent 128-bit loads in flight per lane
-      float4 evs[8];
-      if (has_e) {
+      // mask-tensor loads four rows at a time: four independent 128-bit loads in flight per lane, then their stores
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = 4 * i + (lane >> 3);
-          const int64_t eo = __shfl_sync(0xffffffffu, eoff, row);
-          evs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (((vmask >> row) & 1u) && cv) evs[i] = ld4(p.e.p + eo + c0 + c4);
-        }
-      }
+      for (int hb = 0; hb < 2; ++hb) {
+        float4 evs[4];
+        if (has_e) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = 4 * i + (lane >> 3);
-        const int64_t yo = __shfl_sync(0xffffffffu, yoff, row);
-        if (((vmask >> row) & 1u) && cv) {
-          float4 val;
-          const uint32_t ta = wrow0 + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(ta) : "memory");
-          if (bnbwd) {
-            const float4 ev = evs[i];
-            val.x *= fmaf(ev.x, bsc.x, bsh.x) > 0.f ? 1.f : p.eslope; val.y *= fmaf(ev.y, bsc.y, bsh.y) > 0.f ? 1.f : p.eslope;
-            val.z *= fmaf(ev.z, bsc.z, bsh.z) > 0.f ? 1.f : p.eslope; val.w *= fmaf(ev.w, bsc.w, bsh.w) > 0.f ? 1.f : p.eslope;
-            ps1.x += val.x; ps1.y += val.y; ps1.z += val.z; ps1.w += val.w;
-            ps2.x = fmaf(val.x, ev.x, ps2.x); ps2.y = fmaf(val.y, ev.y, ps2.y); ps2.z = fmaf(val.z, ev.z, ps2.z); ps2.w = fmaf(val.w, ev.w, ps2.w);
-            val.x *= bsc.x; val.y *= bsc.y; val.z *= bsc.z; val.w *= bsc.w;
-          } else if (has_e) {
-            const float4 ev = evs[i];
-            val.x *= ev.x > 0.f ? 1.f : p.eslope; val.y *= ev.y > 0.f ? 1.f : p.eslope;
-            val.z *= ev.z > 0.f ? 1.f : p.eslope; val.w *= ev.w > 0.f ? 1.f : p.eslope;
-            if (p.stats) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+          for (int i = 0; i < 4; ++i) {
+            const int row = 4 * (4 * hb + i) + (lane >> 3);
+            const int64_t eo = __shfl_sync(0xffffffffu, eoff, row);
+            evs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (((vmask >> row) & 1u) && cv) evs[i] = ld4(p.e.p + eo + c0 + c4);
           }
-          float* yp = p.y.p + yo + c0 + c4;
-          if (up2) {
-            *reinterpret_cast<float4*>(yp) = val;
-            *reinterpret_cast<float4*>(yp + p.y.sw) = val;
-            *reinterpret_cast<float4*>(yp + p.y.sh) = val;
-            *reinterpret_cast<float4*>(yp + p.y.sh + p.y.sw) = val;
-          } else if (p.store == FDG_STORE_ACCUM) {
-            // fire-and-forget 128-bit reduction at L2: no round trip for the old value (every address is touched by
-            // exactly one lane per launch, so the result is deterministic)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yp), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
-          } else {
-            *reinterpret_cast<float4*>(yp) = val;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = 4 * (4 * hb + i) + (lane >> 3);
+          const int64_t yo = __shfl_sync(0xffffffffu, yoff, row);
+          if (((vmask >> row) & 1u) && cv) {
+            float4 val;
+            const uint32_t ta = wrow0 + (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(ta) : "memory");
+            if (bnbwd) {
+              const float4 ev = evs[i];
+              val.x *= fmaf(ev.x, bsc.x, bsh.x) > 0.f ? 1.f : p.eslope; val.y *= fmaf(ev.y, bsc.y, bsh.y) > 0.f ? 1.f : p.eslope;
+              val.z *= fmaf(ev.z, bsc.z, bsh.z) > 0.f ? 1.f : p.eslope; val.w *= fmaf(ev.w, bsc.w, bsh.w) > 0.f ? 1.f : p.eslope;
+              ps1.x += val.x; ps1.y += val.y; ps1.z += val.z; ps1.w += val.w;
+              ps2.x = fmaf(val.x, ev.x, ps2.x); ps2.y = fmaf(val.y, ev.y, ps2.y); ps2.z = fmaf(val.z, ev.z, ps2.z); ps2.w = fmaf(val.w, ev.w, ps2.w);
+              val.x *= bsc.x; val.y *= bsc.y; val.z *= bsc.z; val.w *= bsc.w;
+            } else if (has_e) {
+              const float4 ev = evs[i];
+              val.x *= ev.x > 0.f ? 1.f : p.eslope; val.y *= ev.y > 0.f ? 1.f : p.eslope;
+              val.z *= ev.z > 0.f ? 1.f : p.eslope; val.w *= ev.w > 0.f ? 1.f : p.eslope;
+              if (p.stats) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+            }
+            float* yp = p.y.p + yo + c0 + c4;
+            if (up2) {
+              *reinterpret_cast<float4*>(yp) = val;
+              *reinterpret_cast<float4*>(yp + p.y.sw) = val;
+              *reinterpret_cast<float4*>(yp + p.y.sh) = val;
+              *reinterpret_cast<float4*>(yp + p.y.sh + p.y.sw) = val;
+            } else if (p.store == FDG_STORE_ACCUM) {
+              // fire-and-forget 128-bit reduction at L2: no round trip for the old value (every address is touched by
+              // exactly one lane per launch, so the result is deterministic)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yp), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+            } else {
+              *reinterpret_cast<float4*>(yp) = val;
+            }
           }
         }
       }

@@ -249,7 +249,7 @@ def test_bn_finalize_and_backward_pieces():
     assert maxabs(buf[:C], want) <= 1e-5
 
 
-@pytest.mark.parametrize("shape", [(2, 128, 96, 9, 7, 0.0), (1, 128, 224, 33, 31, 0.0), (2, 64, 160, 12, 10, 0.2)])
+@pytest.mark.parametrize("shape", [(2, 128, 96, 9, 7, 0.0), (1, 128, 224, 33, 31, 0.0), (2, 64, 160, 12, 10, 0.2), (2, 128, 64, 10, 6, 0.0)])
 def test_conv2d_bn_backward_epilogue(shape):
     """1x1 data-gradient conv with the BatchNorm-backward epilogue (FdgConv.e_scale) + fdg_bn_bwd_finalize + fdg_affine_accum
     == autograd through conv1x1(leaky_relu(batch_norm(x))) w.r.t. x (dense-layer norm1/conv1 backward, torchvision
