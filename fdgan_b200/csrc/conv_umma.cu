@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       return meta;
     };
     // prologue (direct gather), bf16 hi/lo split and swizzled store of one K chunk into stage s
+    uint32_t held[STAGES];            // thread 0: which weight tile each stage holds
+#pragma unroll
+    for (int j = 0; j < STAGES; ++j) held[j] = 0xffffffffu;
     auto finish = [&](float4 (&v0)[RPT], float4 (&v1)[RPT], uint32_t meta, int s, uint32_t ph) {
       if (direct) {
         const int c = (int)((meta >> 8) & 0xffu) * UKC + j * 8;
@@ -248,10 +251,22 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       mbar_wait(empty0 + s * 8, ph ^ 1u);
       const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
       if (t == 0) {   // this stage's weight tile (hi + lo) through the bulk-copy engine
+        // A stage keeps its weight tile until a different one is needed: with one or two K chunks per tile (1x1 convs of
+        // up to 128 input channels, every dense-layer conv1 data gradient) the tiles stay resident across M tiles and
+        // their L2 latency disappears from the ring.
         const uint32_t bar = full0 + s * 8;
-        mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
-        bulk_g2s(a_lo + A_TILE_BYTES, reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)(meta >> 16) * (2 * B_TILE_BYTES),
-                 2 * B_TILE_BYTES, bar);
+        const uint32_t want = meta >> 16;
+        uint32_t have = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < STAGES; ++j) if (j == s) have = held[j];
+        if (have != want) {
+          mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
+          bulk_g2s(a_lo + A_TILE_BYTES, reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)want * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+#pragma unroll
+          for (int j = 0; j < STAGES; ++j) if (j == s) held[j] = want;
+        } else {
+          mbar_arrive(bar);
+        }
       }
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
