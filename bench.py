@@ -40,6 +40,16 @@ def peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def ncu_family_profile(family):
+    """Per-launch DRAM traffic / tensor-pipe activity of a kernel family from the committed ncu launch list of this same
+    command (profiles/r01d_traffic.json; numbers taken under ncu are never bench values, they only annotate the roofline)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01d_traffic.json")) as f:
+            return json.load(f)["families"].get(family)
+    except Exception:
+        return None
+
+
 def synth_pair(index: int, size: int):
     """J ~ U[0,1), t ~ U[0.3,0.9], A ~ U[0.7,1.0] scalars, I = J t + A (1 - t); seed 1234 + index."""
     g = torch.Generator().manual_seed(1234 + index)
@@ -264,16 +274,22 @@ def run_ours(args):
     if d["ms"] > 0:
         if dom in ("conv_simt_f32", "conv_tcgen05", "wgrad"):
             achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
+            prof = ncu_family_profile(dom)
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["tf_sustained"], "traffic": None, "kernel": dom,
+                    "frac": achieved / pk["tf_sustained"], "traffic": prof["dram_bytes_per_launch"] if prof else None, "kernel": dom,
+                    "traffic_source": "profiles/r01d_traffic.json: mean dram__bytes_read+write per launch of this family (ncu, same command)" if prof else None,
+                    "tensor_pipe_active_pct_ncu": prof["tensor_pipe_active_pct"] if prof else None,
+                    "note": "fp32 operands run as bf16 hi/lo splits: 3 algorithmic bf16 passes per MAC (issued as 2 MMAs of width 2N and N), "
+                            "so the algorithmic ceiling is 1/3 of the bf16 peak; achieved counts each MAC once",
                     "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                     "share_of_profiled_kernel_time": d["ms"] / tot_ms, "launches_per_step": d["launches"] / prof_steps,
                     "avg_launch_ms": d["ms"] / max(1, d["launches"]),
                     "flops_per_launch": d["flops"] / max(1, d["launches"])}
         else:
             achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9
+            prof = ncu_family_profile(dom)
             roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
-                    "traffic": None, "kernel": dom, "peak_source": pk["src"],
+                    "traffic": prof["dram_bytes_per_launch"] if prof else None, "kernel": dom, "peak_source": pk["src"],
                     "share_of_profiled_kernel_time": d["ms"] / tot_ms}
     families = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
                     "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else 0.0,
