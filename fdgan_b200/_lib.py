@@ -41,7 +41,7 @@ class FdgConv(C.Structure):
         ("Cout", C.c_int), ("OH", C.c_int), ("OW", C.c_int), ("bias", C.c_void_p), ("act", C.c_int),
         ("e", FdgTensor), ("eslope", C.c_float), ("y", FdgTensor), ("store", C.c_int),
         ("stats", C.c_void_p), ("stats_ld", C.c_int), ("alpha", C.c_float), ("impl", C.c_int),
-        ("w_umma", C.c_void_p), ("e_scale", C.c_void_p), ("e_shift", C.c_void_p),
+        ("w_umma", C.c_void_p), ("e_scale", C.c_void_p), ("e_shift", C.c_void_p), ("w_k1", C.c_void_p),
     ]
 
 
@@ -96,6 +96,8 @@ _SIGS = {
     "fdg_conv2d_wgrad": ([_P(FdgWgrad), C.c_void_p], C.c_int),
     "fdg_pack_weight": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "fdg_umma_weight_bytes": ([C.c_int, C.c_int, C.c_int], C.c_int64),
+    "fdg_k1_weight_bytes": ([C.c_int], C.c_int64),
+    "fdg_pack_weight_k1": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_pack_weight_umma": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_bn_finalize": ([_P(FdgBnFinalize), C.c_void_p], C.c_int),
     "fdg_ew_bwd": ([_P(FdgEwBwd), C.c_void_p], C.c_int),

@@ -10,6 +10,8 @@ int conv2d_thin_supported(const FdgConv* p);
 int conv2d_thin(const FdgConv* p, cudaStream_t st);
 int conv2d_cin1_supported(const FdgConv* p);
 int conv2d_cin1(const FdgConv* p, cudaStream_t st);
+int conv2d_k1_supported(const FdgConv* p);
+int conv2d_k1(const FdgConv* p, cudaStream_t st);
 }  // namespace fdg
 
 extern "C" int fdg_conv2d(const FdgConv* p, fdg_stream_t stream) {
@@ -21,6 +23,7 @@ extern "C" int fdg_conv2d(const FdgConv* p, fdg_stream_t stream) {
     if (fdg::conv2d_cin1_supported(p)) return fdg::conv2d_cin1(p, st);
     if (fdg::conv2d_thin_supported(p)) return fdg::conv2d_thin(p, st);
   }
+  if (!p->e_scale && fdg::conv2d_k1_supported(p)) return fdg::conv2d_k1(p, st);
   const int ok = fdg::conv2d_umma_supported(p);
   if (p->e_scale && !ok) { fdg::set_error("fdg_conv2d: BatchNorm-backward epilogue requested but the shape is not tcgen05-eligible"); return FDG_ENOSUPPORT; }
   if (p->impl == 2) {

@@ -77,12 +77,25 @@ _NULLT = L.FdgTensor(None, 0, 0, 0, 0)
 # tcgen05 path switch: True = every eligible convolution runs on the tensor cores (bf16x3 split, fp32 accumulate);
 # False = fp32 SIMT everywhere (used by tests to compare the two paths).
 USE_UMMA = True
+USE_K1 = True      # 3x3 / stride 1 / pad 1 / Cout <= 32 convolutions on the filter-row-concatenated kernel (conv_k1.cu)
 
 
 def umma_eligible(x: View, Cout: int, R: int = 1, S: int = 1, stride: int = 1, gather: int = GATHER_DIRECT) -> bool:
     halo = stride == 1 and 2 <= R <= 4 and 2 <= S <= 4 and gather == GATHER_DIRECT   # conv_halo.cu takes Cin % 4 == 0
     return ((x.C % 8 == 0 or (halo and x.C % 4 == 0)) and x.C >= 16 and Cout >= 1 and x.sc == 1 and x.ptr % 16 == 0 and
             x.sn % 4 == 0 and x.sh % 4 == 0 and x.sw % 4 == 0)
+
+
+def k1_eligible(x: View, Cout: int, R: int, S: int, stride: int, pad: int, gather: int) -> bool:
+    return (USE_K1 and R == 3 and S == 3 and stride == 1 and pad == 1 and gather == GATHER_DIRECT and 1 <= Cout <= 32 and
+            x.C % 4 == 0 and x.C >= 16 and x.sc == 1 and x.ptr % 16 == 0 and x.sn % 4 == 0 and x.sh % 4 == 0 and x.sw % 4 == 0)
+
+
+def pack_weight_k1(w, w_ld: int, Cin: int, Cout: int, device) -> torch.Tensor:
+    """fdg_pack_weight_k1: [W(ky=0) | W(ky=1) | W(ky=2)] bf16 hi/lo tiles per (64-channel chunk, filter column)."""
+    out = torch.empty(int(L.lib.fdg_k1_weight_bytes(Cin)) // 4, dtype=torch.int32, device=device)
+    L.check(L.lib.fdg_pack_weight_k1(_ptr(w), w_ld, Cin, Cout, out.data_ptr(), _stream()), "pack_weight_k1")
+    return out
 
 
 def pack_weight_umma(w, w_ld: int, taps: int, Cin: int, Cout: int, device) -> torch.Tensor:
@@ -95,7 +108,7 @@ def pack_weight_umma(w, w_ld: int, taps: int, Cin: int, Cout: int, device) -> to
 
 def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_DIRECT, scale=None, shift=None,
            slope=1.0, bias=None, act=ACT_NONE, e: View | None = None, eslope=0.0, store=STORE_NORMAL, stats=None,
-           stats_ld=0, alpha=1.0, impl=IMPL_AUTO, w_umma=None, e_scale=None, e_shift=None):
+           stats_ld=0, alpha=1.0, impl=IMPL_AUTO, w_umma=None, e_scale=None, e_shift=None, w_k1=None):
     """fdg_conv2d.  ``w`` is the packed [K][w_ld] operand (tensor or pointer)."""
     if gather == GATHER_AVGPOOL2:
         H, W = x.H // 2, x.W // 2
@@ -110,13 +123,15 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
         raise ValueError("conv2d: output view %s does not match %s" % ((y.N, y.H, y.W, y.C), (x.N, mul * OH, mul * OW, Cout)))
     if e is not None and (e.N, e.H, e.W, e.C) != (x.N, OH, OW, Cout):
         raise ValueError("conv2d: mask view shape mismatch")
-    if w_umma is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and umma_eligible(x, Cout, R, S, stride, gather):
+    if w_umma is None and w_k1 is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and k1_eligible(x, Cout, R, S, stride, pad, gather):
+        w_k1 = pack_weight_k1(w, w_ld, x.C, Cout, x.base.device)
+    elif w_umma is None and w_k1 is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and umma_eligible(x, Cout, R, S, stride, gather):
         w_umma = pack_weight_umma(w, w_ld, R * S, x.C, Cout, x.base.device)
     d = L.FdgConv(
         x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
         _ptr(w), w_ld, R, S, stride, pad, Cout, OH, OW, _ptr(bias), act,
         e.ft() if e is not None else _NULLT, eslope, y.ft(), store, _ptr(stats), stats_ld, alpha, impl, _ptr(w_umma),
-        _ptr(e_scale), _ptr(e_shift))
+        _ptr(e_scale), _ptr(e_shift), _ptr(w_k1))
     L.check(L.lib.fdg_conv2d(_byref(d), _stream()), "conv2d")
 
 

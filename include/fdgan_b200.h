@@ -99,6 +99,7 @@ typedef struct FdgConv {
    * share the batch statistics of a concat channel, so their beta / delta simply add up). */
   const float* e_scale; /* [Cout] or NULL */
   const float* e_shift; /* [Cout] */
+  const void* w_k1;     /* operand image for the 3x3 / stride 1 / pad 1 / Cout <= 32 kernel (fdg_pack_weight_k1) or NULL */
 } FdgConv;
 
 int fdg_conv2d(const FdgConv* p, fdg_stream_t stream);
@@ -142,6 +143,11 @@ int fdg_pack_weight(const float* w, int Cout, int Cin, int R, int S, int mode, f
  * kernel fetches each stage with one bulk TMA copy.  fdg_umma_weight_bytes gives the size of `out` (16-byte aligned). */
 int64_t fdg_umma_weight_bytes(int taps, int Cin, int Cout);
 int fdg_pack_weight_umma(const float* w, int w_ld, int taps, int Cin, int Cout, void* out, fdg_stream_t stream);
+
+/* Operand image for the growth-convolution kernel (3x3, stride 1, pad 1, Cout <= 32; conv_k1.cu): per (64-channel chunk,
+ * filter column kx) one [192 x 64] bf16 tile whose rows are the three filter rows' output channels, hi then lo. */
+int64_t fdg_k1_weight_bytes(int Cin);
+int fdg_pack_weight_k1(const float* w, int w_ld, int Cin, int Cout, void* out, fdg_stream_t stream);
 
 /*
  * BatchNorm2d training-mode bookkeeping (nn.BatchNorm2d as used at README.md:38: always batch statistics).

@@ -63,9 +63,11 @@ def main():
         for m in MODES:
             _lib.set_option("dbg", m)
             if kind == "conv":
-                wu = ops.pack_weight_umma(wp, ld, R * R, Cin, Cout, dev)
+                wu = wk = None
+                if ops.k1_eligible(x, Cout, R, R, 1, pad, 0): wk = ops.pack_weight_k1(wp, ld, Cin, Cout, dev)
+                else: wu = ops.pack_weight_umma(wp, ld, R * R, Cin, Cout, dev)
                 ms = timeit(lambda: ops.conv2d(x, wp, ld, R, R, 1, pad, Cout, y, scale=sc, shift=sh, slope=0.0 if affine else 1.0,
-                                               stats=st, stats_ld=Cout, impl=ops.IMPL_UMMA, w_umma=wu))
+                                               stats=st, stats_ld=Cout, impl=ops.IMPL_UMMA, w_umma=wu, w_k1=wk))
             else:
                 y.base.normal_()
                 dw = torch.zeros_like(w)

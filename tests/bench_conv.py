@@ -56,9 +56,12 @@ def main():
         for impl, tag in ((ops.IMPL_SIMT, "simt"), (ops.IMPL_UMMA, "umma")):
             if which not in (tag, "both"):
                 continue
-            wu = ops.pack_weight_umma(wp, ld, R * R, Cin, Cout, dev) if impl == ops.IMPL_UMMA else None
+            wu = wk = None
+            if impl == ops.IMPL_UMMA:
+                if ops.k1_eligible(x, Cout, R, R, 1, pad, 0): wk = ops.pack_weight_k1(wp, ld, Cin, Cout, dev)
+                else: wu = ops.pack_weight_umma(wp, ld, R * R, Cin, Cout, dev)
             ms = timeit(lambda: ops.conv2d(x, wp, ld, R, R, 1, pad, Cout, y, scale=sc, shift=sh, slope=0.0 if affine else 1.0,
-                                           stats=st, stats_ld=Cout, impl=impl, w_umma=wu))
+                                           stats=st, stats_ld=Cout, impl=impl, w_umma=wu, w_k1=wk))
             out += "  %s %8.3f ms %7.1f TF/s" % (tag, ms, flops / ms / 1e9)
         # weight gradient (SIMT today)
         if which in ("both", "wgrad") or os.environ.get("BENCH_WGRAD"):

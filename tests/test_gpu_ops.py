@@ -57,7 +57,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("variant", ["simt_nhwc", "simt_nchw", "tcgen05", "tcgen05_pertap"])
+@pytest.mark.parametrize("variant", ["simt_nhwc", "simt_nchw", "tcgen05", "tcgen05_halo", "tcgen05_pertap"])
 def test_conv2d(case, variant):
     """fdg_conv2d against fp64 torch on every shape family of the path, through both kernels: the fp32 SIMT path
     (2e-5) and the tcgen05 bf16x3 path (5e-5; ~16 operand mantissa bits, fp32 accumulation in TMEM)."""
@@ -70,6 +70,10 @@ def test_conv2d(case, variant):
     halo_shape = gather == 0 and stride == 1 and 2 <= R <= 4
     if variant == "tcgen05_pertap" and not halo_shape:
         pytest.skip("same kernel as the tcgen05 variant for this shape")
+    k1_shape = halo_shape and R == 3 and pad == 1 and Cout <= 32
+    if variant == "tcgen05_halo" and not k1_shape:
+        pytest.skip("same kernel as the tcgen05 variant for this shape")
+    ops.USE_K1 = variant == "tcgen05"        # filter-row-concatenated kernel vs the halo-tile kernel for the growth convolutions
     from fdgan_b200 import _lib
     _lib.set_option("halo", 0 if variant == "tcgen05_pertap" else 1)   # halo-tile kernel vs generic per-tap kernel
     N = 2
@@ -110,6 +114,7 @@ def test_conv2d(case, variant):
                store=store, stats=st, stats_ld=Cout + 3, impl=impl)
     torch.cuda.synchronize()
     _lib.set_option("halo", 1)
+    ops.USE_K1 = True
     assert maxabs(yd, y) <= (5e-5 if variant.startswith("tcgen05") else 2e-5)
     if stats:
         tol = 2e-6 * float(N * OH * OW) + 1e-3   # fp32 partial sums over the tile, fp64 across tiles
