@@ -318,6 +318,7 @@ struct WThinArgs {
   FdgWgrad c;
   int64_t M, m_per_cta;
   int K, kb, kgroups, cgroups;
+  int gvec;      // gradient rows loadable as float4
 };
 
 template <int KB>
@@ -339,20 +340,38 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_thin_kernel(const __grid_con
   const int64_t mbeg = (int64_t)blockIdx.x * a.m_per_cta;
   const int64_t mend = mbeg + a.m_per_cta < a.M ? mbeg + a.m_per_cta : a.M;
   const bool kfast = p.x.sc == 1;                // NHWC: consecutive k of one filter row are contiguous
+  // index tables: the filter-tap decomposition of k once per CTA, the pixel coordinates once per batch -- the staging
+  // loops below do no division by runtime values other than KP / CP
+  __shared__ int k_r[TH_MAXK + 8], k_s[TH_MAXK + 8], k_c[TH_MAXK + 8];
+  __shared__ int p_n[WT_P], p_y[WT_P], p_x[WT_P];
+  for (int k = t; k < KP; k += WT_THREADS) {
+    const int kk = k < K ? k : 0;
+    const int tap = kk / p.Cin;
+    k_c[k] = k < K ? kk - tap * p.Cin : -1;
+    k_r[k] = tap / p.S;
+    k_s[k] = tap - (tap / p.S) * p.S;
+  }
+  const bool gvec4 = a.gvec != 0;
   for (int64_t m0 = mbeg; m0 < mend; m0 += WT_P) {
-    // ---- stage the im2col rows and the gradient rows of 32 pixels
-    for (int i = t; i < WT_P * KP; i += WT_THREADS) {
-      const int pi = kfast ? i / KP : i % WT_P;
-      const int k = kfast ? i % KP : i / WT_P;
-      const int64_t m = m0 + pi;
-      float v = 0.f;
-      if (m < mend && k < K) {
+    if (t < WT_P) {
+      const int64_t m = m0 + t;
+      if (m < mend) {
         const int n = (int)(m / OHW);
         const int rem = (int)(m - (int64_t)n * OHW);
-        const int oy = rem / p.OW, ox = rem - oy * p.OW;
-        const int tap = k / p.Cin, ci = k - tap * p.Cin;
-        const int r = tap / p.S, s = tap - r * p.S;
-        const int iy = oy * p.stride - p.pad + r, ix = ox * p.stride - p.pad + s;
+        p_n[t] = n; p_y[t] = rem / p.OW; p_x[t] = rem - (rem / p.OW) * p.OW;
+      } else {
+        p_n[t] = -1;
+      }
+    }
+    __syncthreads();
+    // ---- stage the im2col rows and the gradient rows of 32 pixels
+    for (int i = t; i < WT_P * KP; i += WT_THREADS) {
+      const int pi = kfast ? i / KP : i & (WT_P - 1);
+      const int k = kfast ? i - pi * KP : i >> 5;
+      float v = 0.f;
+      const int n = p_n[pi], ci = k_c[k];
+      if (n >= 0 && ci >= 0) {
+        const int iy = p_y[pi] * p.stride - p.pad + k_r[k], ix = p_x[pi] * p.stride - p.pad + k_s[k];
         if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
           v = __ldg(p.x.p + n * p.x.sn + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw + (int64_t)ci * p.x.sc);
           if (p.has_affine) v = fmaf(v, __ldg(p.scale + ci), __ldg(p.shift + ci));
@@ -361,17 +380,23 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_thin_kernel(const __grid_con
       }
       xs[pi * KP + k] = v;
     }
-    for (int i = t; i < WT_P * CP; i += WT_THREADS) {
-      const int pi = i / CP, c = i - pi * CP;
-      const int64_t m = m0 + pi;
-      float v = 0.f;
-      if (m < mend && c < Cout) {
-        const int n = (int)(m / OHW);
-        const int rem = (int)(m - (int64_t)n * OHW);
-        const int oy = rem / p.OW, ox = rem - oy * p.OW;
-        v = __ldg(p.g.p + n * p.g.sn + (int64_t)oy * p.g.sh + (int64_t)ox * p.g.sw + (int64_t)c * p.g.sc);
+    if (gvec4) {
+      const int c4n = CP >> 2;
+      for (int i = t; i < WT_P * c4n; i += WT_THREADS) {
+        const int pi = i / c4n, c = (i - pi * c4n) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n = p_n[pi];
+        if (n >= 0 && c < Cout) v = ld4(p.g.p + n * p.g.sn + (int64_t)p_y[pi] * p.g.sh + (int64_t)p_x[pi] * p.g.sw + c);
+        *reinterpret_cast<float4*>(gs + pi * CP + c) = v;
       }
-      gs[pi * CP + c] = v;
+    } else {
+      for (int i = t; i < WT_P * CP; i += WT_THREADS) {
+        const int pi = i / CP, c = i - pi * CP;
+        float v = 0.f;
+        const int n = p_n[pi];
+        if (n >= 0 && c < Cout) v = __ldg(p.g.p + n * p.g.sn + (int64_t)p_y[pi] * p.g.sh + (int64_t)p_x[pi] * p.g.sw + (int64_t)c * p.g.sc);
+        gs[pi * CP + c] = v;
+      }
     }
     __syncthreads();
     if (worker) {
@@ -416,11 +441,13 @@ int wgrad_thin(const FdgWgrad* p, cudaStream_t st) {
   a.M = (int64_t)p->N * p->OH * p->OW;
   a.K = K;
   a.cgroups = cdiv(p->Cout, 4);
+  a.gvec = vec4_ok(p->g) && p->Cout % 4 == 0;
   const int kb = cdiv(K * a.cgroups, WT_THREADS) <= 3 ? 3 : 6;    // k rows per thread so that kgroups * cgroups <= 256
   a.kb = kb;
   a.kgroups = cdiv(K, kb);
   if (a.kgroups * a.cgroups > WT_THREADS) return 1;
-  int64_t ctas = 148 * 4;
+  static const int cta_mul = [] { const char* e = getenv("FDG_WTHIN_CTAS"); return e ? atoi(e) : 4; }();
+  int64_t ctas = 148 * cta_mul;
   a.m_per_cta = cdiv64(cdiv64(a.M, ctas), WT_P) * WT_P;
   ctas = cdiv64(a.M, a.m_per_cta);
   const int smem = WT_P * (a.kgroups * kb + a.cgroups * 4) * 4;
