@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -123,10 +125,19 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
         raise ValueError("conv2d: output view %s does not match %s" % ((y.N, y.H, y.W, y.C), (x.N, mul * OH, mul * OW, Cout)))
     if e is not None and (e.N, e.H, e.W, e.C) != (x.N, OH, OW, Cout):
         raise ValueError("conv2d: mask view shape mismatch")
+    images = getattr(w, "_fdg_images", None)      # packed operand of a frozen parameter: its tcgen05 images are cached
     if w_umma is None and w_k1 is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and k1_eligible(x, Cout, R, S, stride, pad, gather):
-        w_k1 = pack_weight_k1(w, w_ld, x.C, Cout, x.base.device)
+        w_k1 = images.get(("k1", x.C, Cout)) if images is not None else None
+        if w_k1 is None:
+            w_k1 = pack_weight_k1(w, w_ld, x.C, Cout, x.base.device)
+            if images is not None:
+                images[("k1", x.C, Cout)] = w_k1
     elif w_umma is None and w_k1 is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and umma_eligible(x, Cout, R, S, stride, gather):
-        w_umma = pack_weight_umma(w, w_ld, R * S, x.C, Cout, x.base.device)
+        w_umma = images.get(("umma", R * S, x.C, Cout)) if images is not None else None
+        if w_umma is None:
+            w_umma = pack_weight_umma(w, w_ld, R * S, x.C, Cout, x.base.device)
+            if images is not None:
+                images[("umma", R * S, x.C, Cout)] = w_umma
     d = L.FdgConv(
         x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
         _ptr(w), w_ld, R, S, stride, pad, Cout, OH, OW, _ptr(bias), act,
@@ -157,9 +168,38 @@ def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scal
     L.check(L.lib.fdg_conv2d_wgrad(_byref(d), _stream()), "conv2d_wgrad")
 
 
+# Operand images of FROZEN parameters (requires_grad == False: the Vgg16 feature extractor, D during the generator update
+# of an autograd user) are packed once and reused until the parameter changes (torch bumps ``_version`` on in-place
+# writes; the training step's own optimiser never touches frozen parameters).
+_FROZEN = {}
+
+
+def _frozen_lookup(w: torch.Tensor, mode: int):
+    if w.requires_grad or not isinstance(w, torch.nn.Parameter):
+        return None, None
+    key = (w.data_ptr(), tuple(w.shape), mode)
+    hit = _FROZEN.get(key)
+    if hit is not None and hit[0] == w._version and hit[3]() is w:      # same live parameter object, unchanged
+        return key, hit
+    return key, None
+
+
 def pack_weight(w: torch.Tensor, mode: int) -> tuple[torch.Tensor, int]:
     """fdg_pack_weight.  mode 0: OIHW -> [(r,s,ci)][co]; 1: OIHW -> flipped [(r,s,co)][ci]; 2: [Cin][Cout] -> [co][ci]."""
     assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    key, hit = _frozen_lookup(w, mode)
+    if hit is not None:
+        return hit[1], hit[2]
+    out, ld = _pack_weight(w, mode)
+    if key is not None:
+        if len(_FROZEN) > 4096:
+            _FROZEN.clear()
+        out._fdg_images = {}          # tcgen05 images of this packed operand, filled by conv2d
+        _FROZEN[key] = (w._version, out, ld, weakref.ref(w))
+    return out, ld
+
+
+def _pack_weight(w: torch.Tensor, mode: int) -> tuple[torch.Tensor, int]:
     if mode == 2:
         cin, cout, R, S = w.shape
     else:
