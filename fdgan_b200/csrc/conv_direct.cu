@@ -177,28 +177,18 @@ struct Cin1Args {
   int evec;
 };
 
-// one thread per (pixel, 16 output channels): the R*S input values are read once per 16 outputs, the weights come from
-// shared memory ([tap][Cout], 128-bit reads), mask loads and stores are 64 contiguous bytes per thread
 __global__ void __launch_bounds__(256) conv_cin1_kernel(const __grid_constant__ Cin1Args a) {
-  extern __shared__ __align__(16) float wsm[];      // [R*S][Cout]
   const FdgConv& p = a.c;
-  const int taps = p.R * p.S;
-  for (int i = threadIdx.x; i < taps * p.Cout; i += blockDim.x) wsm[i] = __ldg(p.w + (int64_t)(i / p.Cout) * p.w_ld + (i % p.Cout));
-  __syncthreads();
   const int OHW = p.OH * p.OW;
-  const int g16 = (p.Cout + 15) / 16;               // 16-channel groups per pixel
-  const int64_t total = (int64_t)p.N * OHW * g16;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / g16;
-    const int c = (int)(i - m * g16) * 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / a.c4n;
+    const int c = (int)(i - m * a.c4n) * 4;
     const int n = (int)(m / OHW);
     const int rem = (int)(m - (int64_t)n * OHW);
     const int oy = rem / p.OW, ox = rem - oy * p.OW;
     const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
     const float* xb = p.x.p + n * p.x.sn;
-    float4 acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < p.R; ++r) {
       const int iy = iy0 + r;
       if (iy < 0 || iy >= p.H) continue;
@@ -206,31 +196,17 @@ __global__ void __launch_bounds__(256) conv_cin1_kernel(const __grid_constant__ 
         const int ix = ix0 + s;
         if (ix < 0 || ix >= p.W) continue;
         const float xv = prologue_act(__ldg(xb + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw), p.slope);
-        const float* wr = wsm + (r * p.S + s) * p.Cout + c;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (c + 4 * q < p.Cout) {
-            const float4 wv = *reinterpret_cast<const float4*>(wr + 4 * q);
-            acc[q].x = fmaf(xv, wv.x, acc[q].x); acc[q].y = fmaf(xv, wv.y, acc[q].y);
-            acc[q].z = fmaf(xv, wv.z, acc[q].z); acc[q].w = fmaf(xv, wv.w, acc[q].w);
-          }
-        }
+        const float4 wv = ld4(p.w + (int64_t)(r * p.S + s) * p.w_ld + c);
+        acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
       }
     }
-    const float* ep = p.e.p ? p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + c : nullptr;
-    float* yp = p.y.p + n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox * p.y.sw + c;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (c + 4 * q < p.Cout) {
-        float4 o = make_float4(acc[q].x * p.alpha, acc[q].y * p.alpha, acc[q].z * p.alpha, acc[q].w * p.alpha);
-        if (ep) {
-          const float4 ev = ld4(ep + 4 * q);
-          o.x *= ev.x > 0.f ? 1.f : p.eslope; o.y *= ev.y > 0.f ? 1.f : p.eslope;
-          o.z *= ev.z > 0.f ? 1.f : p.eslope; o.w *= ev.w > 0.f ? 1.f : p.eslope;
-        }
-        *reinterpret_cast<float4*>(yp + 4 * q) = o;
-      }
+    acc.x *= p.alpha; acc.y *= p.alpha; acc.z *= p.alpha; acc.w *= p.alpha;
+    if (p.e.p) {
+      const float4 ev = ld4(p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + c);
+      acc.x *= ev.x > 0.f ? 1.f : p.eslope; acc.y *= ev.y > 0.f ? 1.f : p.eslope;
+      acc.z *= ev.z > 0.f ? 1.f : p.eslope; acc.w *= ev.w > 0.f ? 1.f : p.eslope;
     }
+    *reinterpret_cast<float4*>(p.y.p + n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox * p.y.sw + c) = acc;
   }
 }
 
@@ -241,7 +217,6 @@ int conv2d_cin1_supported(const FdgConv* p) {
   if (p->bias || p->act != FDG_ACT_NONE || p->stats || p->e_scale || p->store != FDG_STORE_NORMAL) return 0;
   if (!vec4_ok(p->y) || !aligned16(p->w) || p->w_ld % 4 != 0) return 0;
   if (p->e.p && !vec4_ok(p->e)) return 0;
-  if (p->R * p->S * p->Cout * 4 > 48 * 1024) return 0;     // weights in shared memory
   return 1;
 }
 
@@ -251,10 +226,10 @@ int conv2d_cin1(const FdgConv* p, cudaStream_t st) {
   a.c4n = p->Cout / 4;
   a.total = (int64_t)p->N * p->OH * p->OW * a.c4n;
   a.evec = 1;
-  int64_t blocks = cdiv64((int64_t)p->N * p->OH * p->OW * cdiv(p->Cout, 16), 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  int64_t blocks = cdiv64(a.total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope prof(PF_CONV_SIMT, 2.0 * (double)a.total * 4 * p->R * p->S, 4.0 * (double)a.total * 4 * (p->e.p ? 2 : 1), st);
-  conv_cin1_kernel<<<(unsigned)blocks, 256, p->R * p->S * p->Cout * 4, st>>>(a);
+  conv_cin1_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
   return check_launch("fdg_conv2d[cin1]");
 }
 
