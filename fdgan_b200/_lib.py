@@ -41,7 +41,7 @@ class FdgConv(C.Structure):
         ("Cout", C.c_int), ("OH", C.c_int), ("OW", C.c_int), ("bias", C.c_void_p), ("act", C.c_int),
         ("e", FdgTensor), ("eslope", C.c_float), ("y", FdgTensor), ("store", C.c_int),
         ("stats", C.c_void_p), ("stats_ld", C.c_int), ("alpha", C.c_float), ("impl", C.c_int),
-        ("w_umma", C.c_void_p), ("e_scale", C.c_void_p), ("e_shift", C.c_void_p), ("w_k1", C.c_void_p),
+        ("w_umma", C.c_void_p), ("e_scale", C.c_void_p), ("e_shift", C.c_void_p), ("w_k1", C.c_void_p), ("x_split", C.c_void_p),
     ]
 
 
@@ -52,7 +52,7 @@ class FdgWgrad(C.Structure):
         ("slope", C.c_float), ("g", FdgTensor),
         ("R", C.c_int), ("S", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
         ("Cout", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
-        ("dw", C.c_void_p), ("transposed", C.c_int), ("dbias", C.c_void_p), ("impl", C.c_int),
+        ("dw", C.c_void_p), ("transposed", C.c_int), ("dbias", C.c_void_p), ("impl", C.c_int), ("g_split", C.c_void_p),
     ]
 
 
@@ -70,7 +70,7 @@ class FdgEwBwd(C.Structure):
         ("g", FdgTensor), ("g_gather", C.c_int), ("gscale", C.c_float), ("x", FdgTensor),
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
         ("has_affine", C.c_int), ("scale", C.c_void_p), ("shift", C.c_void_p), ("slope", C.c_float),
-        ("coef", C.c_void_p), ("out", FdgTensor), ("accumulate", C.c_int), ("stats", C.c_void_p),
+        ("coef", C.c_void_p), ("out", FdgTensor), ("accumulate", C.c_int), ("stats", C.c_void_p), ("out_split", C.c_void_p),
     ]
 
 

@@ -42,6 +42,9 @@ struct UmmaArgs {
   int dbg;   // ablation: 1 no global loads, 2 no split/stores, 4 no MMA, 8 no epilogue
   int tma_rank;                 // 2: the epilogue stores through ymap {channel, linear pixel}; 0: coalesced stores
   int bn_linear;                // BatchNorm-backward epilogue: y and e are pixel-linear views (pipelined variant)
+  int a_split;                  // the A operand arrives as split-bf16 planes through xmap_hi / xmap_lo (no loader work)
+  alignas(64) CUtensorMap xmap_hi;
+  alignas(64) CUtensorMap xmap_lo;
   alignas(64) CUtensorMap ymap;
 };
 
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
 
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), ULOAD_WARPS + 1);
+      mbar_init(smem_u32(&bar_full[s]), (BNBWD && a.a_split) ? 1 : ULOAD_WARPS + 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -132,7 +135,41 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < ULOAD_WARPS) {
+  if (BNBWD && a.a_split && warp < ULOAD_WARPS) {
+    // =============================================================== split-bf16 input: both operands by the bulk-copy engine
+    // The producer of the input (fdg_ew_bwd, out_split) already wrote it as bf16 hi / lo planes, i.e. in the operand
+    // format; one thread streams [128 pixels x 64 channels] boxes of both planes (SWIZZLE_128B tensor maps place them
+    // exactly like the loaders would) and the weight tile of the stage when it changed.  No loading, converting and
+    // re-storing through the LSU pipe.
+    if (t == 0) {
+      uint32_t held[STAGES];
+#pragma unroll
+      for (int j = 0; j < STAGES; ++j) held[j] = 0xffffffffu;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles, nt = tile / m_tiles;
+        for (int kc = 0; kc < a.nchunks; ++kc) {
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES, b_hi = a_lo + A_TILE_BYTES;
+          const uint32_t bar = smem_u32(&bar_full[s]);
+          const uint32_t want = (uint32_t)(nt * a.nchunks + kc);
+          uint32_t have = 0xffffffffu;
+#pragma unroll
+          for (int j = 0; j < STAGES; ++j) if (j == s) have = held[j];
+          mbar_arrive_expect_tx(bar, 2 * A_TILE_BYTES + (have != want ? 2 * B_TILE_BYTES : 0));
+          tma_load_2d(a_hi, &a.xmap_hi, kc * UKC, mt * UM, bar);
+          tma_load_2d(a_lo, &a.xmap_lo, kc * UKC, mt * UM, bar);
+          if (have != want) {
+            bulk_g2s(b_hi, reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)want * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+#pragma unroll
+            for (int j = 0; j < STAGES; ++j) if (j == s) held[j] = want;
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp < ULOAD_WARPS) {
     // =============================================================== A loaders
     // thread handles the 16-byte bf16 chunk j (8 channels) of rows rbase + 64*i, i = 0..1
     constexpr int RPT = UM * 8 / (ULOAD_WARPS * 32);   // rows per thread
@@ -660,6 +697,23 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
   {
     auto lin = [&](const FdgTensor& t) { return t.sh == (int64_t)p->OW * t.sw && t.sn == (int64_t)p->OH * t.sh; };
     a.bn_linear = p->e_scale && p->e.p && lin(p->y) && lin(p->e) && vec4_ok(p->y) && vec4_ok(p->e) && p->store != FDG_STORE_UP2;
+  }
+  a.a_split = 0;
+  if (p->x_split) {
+    if (!(a.bn_linear && p->R == 1 && p->S == 1 && p->stride == 1 && p->pad == 0 && p->gather == FDG_GATHER_DIRECT && !p->has_affine &&
+          p->slope == 1.f && p->Cin % 64 == 0 && a.M < (1ll << 31))) {
+      set_error("fdg_conv2d[tcgen05]: x_split needs a 1x1 / stride 1 / direct / prologue-free conv with Cin %% 64 == 0 and the BatchNorm-backward epilogue");
+      return FDG_ENOSUPPORT;
+    }
+    const uint64_t dims[2] = {(uint64_t)p->Cin, (uint64_t)a.M};
+    const uint64_t strides[1] = {(uint64_t)p->Cin * 2};
+    const uint32_t box[2] = {64, 128};
+    const uint8_t* hi = reinterpret_cast<const uint8_t*>(p->x_split);
+    if (!make_tmap_bf16(&a.xmap_hi, hi, 2, dims, strides, box) || !make_tmap_bf16(&a.xmap_lo, hi + (size_t)a.M * p->Cin * 2, 2, dims, strides, box)) {
+      set_error("fdg_conv2d[tcgen05]: cannot build the tensor maps of the split-bf16 input");
+      return FDG_ECUDA;
+    }
+    a.a_split = 1;
   }
   static const int tma_on = [] { const char* e = getenv("FDG_TMA_STORE"); return e ? atoi(e) : 1; }();
   // bulk tensor stores: plain store into a unit-channel-stride, pixel-linear view (dense NHWC or a channel slice of one)

@@ -2,6 +2,8 @@
 // BatchNorm/ReLU/LeakyReLU backward, max pooling, strided copies, weight repacking and fused Adam.
 // All of them stream NHWC rows with 128-bit accesses when the views allow it and reduce per-channel
 // partial sums with warp shuffles before touching global memory.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace fdg {
@@ -198,6 +200,18 @@ __global__ void __launch_bounds__(256) ew_bwd_linear_kernel(FdgEwBwd p, int64_t 
             float4 o;
             o.x = fmaf(ca.x, dz.x, fmaf(cb.x, xv[k].x, cd.x)); o.y = fmaf(ca.y, dz.y, fmaf(cb.y, xv[k].y, cd.y));
             o.z = fmaf(ca.z, dz.z, fmaf(cb.z, xv[k].z, cd.z)); o.w = fmaf(ca.w, dz.w, fmaf(cb.w, xv[k].w, cd.w));
+            if (p.out_split) {      // split-bf16 planes [M][C]: hi, then lo (the tensor-core kernels' operand format)
+              __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.out_split) + m * p.C + c;
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+              const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+              const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+              uint2 hv, lv;
+              hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+              lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+              *reinterpret_cast<uint2*>(hp) = hv;
+              *reinterpret_cast<uint2*>(hp + M * p.C) = lv;
+              continue;
+            }
             float* op = obase + m * p.out.sw;
             if (p.accumulate) {
               const float4 old = *reinterpret_cast<const float4*>(op);
@@ -457,10 +471,10 @@ int fdg_bn_bwd_finalize(const FdgBnBwdFinalize* p, fdg_stream_t stream) {
 
 int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
   FDG_REQUIRE(p && p->g.p && p->x.p && p->N > 0 && p->H > 0 && p->W > 0 && p->C > 0, "fdg_ew_bwd: bad arguments");
-  FDG_REQUIRE(p->stats || p->out.p, "fdg_ew_bwd: neither stats nor out given");
+  FDG_REQUIRE(p->stats || p->out.p || p->out_split, "fdg_ew_bwd: neither stats nor out given");
   FDG_REQUIRE(!p->has_affine || (p->scale && p->shift), "fdg_ew_bwd: affine without scale/shift");
   FDG_REQUIRE(p->g_gather == FDG_GATHER_DIRECT || p->g_gather == FDG_GATHER_UP2, "fdg_ew_bwd: bad gather");
-  const bool vec = vec4_ok(p->g) && vec4_ok(p->x) && (p->stats || vec4_ok(p->out)) && (p->C % 4 == 0);
+  const bool vec = vec4_ok(p->g) && vec4_ok(p->x) && (p->stats || p->out_split || vec4_ok(p->out)) && (p->C % 4 == 0);
   const int VW = vec ? 4 : 1;
   const int groups_total = cdiv(p->C, VW);
   const int cgroups = groups_total < 64 ? groups_total : 64;   // channel groups per CTA
@@ -476,8 +490,12 @@ int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
   ProfScope prof(PF_EW, 4.0 * (double)M * p->C, 4.0 * (double)M * p->C * (p->stats ? 2.0 : (p->accumulate ? 4.0 : 3.0)),
                  (cudaStream_t)stream);
   auto linear = [&](const FdgTensor& t) { return t.sh == (int64_t)p->W * t.sw && t.sn == (int64_t)p->H * t.sh; };
-  const bool fast = vec && p->g_gather == FDG_GATHER_DIRECT && linear(p->g) && linear(p->x) && (p->stats || linear(p->out)) &&
+  const bool fast = vec && p->g_gather == FDG_GATHER_DIRECT && linear(p->g) && linear(p->x) && (p->stats || p->out_split || linear(p->out)) &&
                     (!p->has_affine || (aligned16(p->scale) && aligned16(p->shift))) && (!p->coef || (aligned16(p->coef) && p->C % 4 == 0));
+  if (p->out_split && !p->stats) {
+    FDG_REQUIRE(fast && !p->accumulate && aligned16(p->out_split),
+                "fdg_ew_bwd: out_split needs the pixel-linear 128-bit path (unit channel stride, C %% 4 == 0, direct gather) and no accumulate");
+  }
   if (fast) {
     if (p->stats) ew_bwd_linear_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
     else ew_bwd_linear_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);

@@ -11,6 +11,15 @@ namespace fdg {
 // dims[0] is the contiguous (channel) dimension; strides_bytes[i] is the stride of dims[i + 1].
 // Returns false when the view cannot be described (alignment / stride rules of cuTensorMapEncodeTiled).
 bool make_tmap_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+// same for a bf16 tensor (boxes whose innermost extent is 64 elements = 128 bytes)
+bool make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
+// bulk tensor load global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t smem, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem),
+               "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
 
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem), "r"(c0), "r"(c1)

@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "aop.cuh"
+#include "tma.cuh"
 #include "umma.cuh"
 
 namespace fdg {
@@ -34,6 +35,9 @@ struct WUArgs {
   int64_t m_per_split;
   int dbg;           // ablation: 1 no global loads, 2 no split/stores, 4 no MMA
   int gvec;          // gradient rows loadable as float4 (unit channel stride, aligned, Cout % 8 == 0)
+  int g_split;       // the gradient operand arrives as split-bf16 planes through gmap_hi / gmap_lo (bulk tensor loads)
+  alignas(64) CUtensorMap gmap_hi;
+  alignas(64) CUtensorMap gmap_lo;
 };
 
 // In-place staging: the fp32 rows are cp.async'ed straight into the operand ring.  Each thread's 32 bytes of fp32 per
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
 
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), WU_LOAD_WARPS);
+      mbar_init(smem_u32(&bar_full[s]), WU_LOAD_WARPS + (a.g_split ? 1 : 0));
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             }
           }
         }
-        {
+        if (!a.g_split) {
           const float* gp = p.g.p + pn * p.g.sn + (int64_t)poy * p.g.sh + (int64_t)pox * p.g.sw;
 #pragma unroll
           for (int q = 0; q < GQ; ++q) {
@@ -177,6 +181,17 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
               }
             }
           }
+        }
+      }
+      if (a.g_split && t == 0) {
+        // split-bf16 gradient: [32 pixels x 64 channels] boxes of the hi and lo planes straight into the operand slots
+        const uint32_t bar = full0 + st * 8;
+        const uint32_t gbase = smem_base + st * STAGE_BYTES + 2 * WU_A_BYTES;
+        mbar_arrive_expect_tx(bar, 2 * G_BYTES);
+#pragma unroll
+        for (int q = 0; q < GQ; ++q) {
+          tma_load_2d(gbase + q * WU_BLK, &a.gmap_hi, cot * NT + 64 * q, (int)lm, bar);
+          tma_load_2d(gbase + G_BYTES + q * WU_BLK, &a.gmap_lo, cot * NT + 64 * q, (int)lm, bar);
         }
       }
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta0 + st * (NLT * 4)), "r"(ok) : "memory");
@@ -213,7 +228,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 1)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
           }
         }
-        {
+        if (!a.g_split) {
 #pragma unroll
           for (int q = 0; q < GQ; ++q) {
             float4 g0 = z4, g1 = z4;
@@ -391,6 +406,22 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   a.kblocks = cdiv(p->R * p->S * p->Cin, WU_K);
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   a.dbg = dbg_flags();
+  a.g_split = 0;
+  if (p->g_split) {
+    if (p->Cout % 64 != 0 || a.M >= (1ll << 31)) {
+      set_error("fdg_conv2d_wgrad[tcgen05]: g_split needs Cout %% 64 == 0");
+      return FDG_ENOSUPPORT;
+    }
+    const uint64_t dims[2] = {(uint64_t)p->Cout, (uint64_t)a.M};
+    const uint64_t strides[1] = {(uint64_t)p->Cout * 2};
+    const uint32_t box[2] = {64, (uint32_t)WU_P};
+    const uint8_t* hi = reinterpret_cast<const uint8_t*>(p->g_split);
+    if (!make_tmap_bf16(&a.gmap_hi, hi, 2, dims, strides, box) || !make_tmap_bf16(&a.gmap_lo, hi + (size_t)a.M * p->Cout * 2, 2, dims, strides, box)) {
+      set_error("fdg_conv2d_wgrad[tcgen05]: cannot build the tensor maps of the split-bf16 gradient");
+      return FDG_ECUDA;
+    }
+    a.g_split = 1;
+  }
   switch (wu_ntile(p->Cout)) {
     case 64: return launch_wu<64, 8>(a, st);      // 8 x 24 KB in-place staging ring
     case 128: return launch_wu<128, 6>(a, st);    // 6 x 32 KB

@@ -66,8 +66,9 @@ def _bn_run(mod, stats, stats_ld, C, count, training, fpool, nbt_list):
 
 
 def _bn_bwd(g: View, x: View, run: BNRun, out: View, dpool, grads, prefix, *, slope=0.0, accumulate=False,
-            g_gather=GATHER_DIRECT, gscale=1.0):
-    """BatchNorm + (Leaky)ReLU backward: out (=|+=) dL/dx given g = dL/d(act(bn(x)))."""
+            g_gather=GATHER_DIRECT, gscale=1.0, out_split=None):
+    """BatchNorm + (Leaky)ReLU backward: out (=|+=) dL/dx given g = dL/d(act(bn(x))).  With ``out_split`` the result is
+    written as split-bf16 planes (the tensor-core operand format) instead of ``out``."""
     C = run.C
     st = dpool.take(2 * C)
     ops.ew_bwd(g, x, stats=st, scale=run.scale, shift=run.shift, slope=slope, g_gather=g_gather, gscale=gscale)
@@ -75,8 +76,8 @@ def _bn_bwd(g: View, x: View, run: BNRun, out: View, dpool, grads, prefix, *, sl
     dgamma = grads.get(prefix + ".weight") if grads is not None else None
     dbeta = grads.get(prefix + ".bias") if grads is not None else None
     ops.bn_bwd_finalize(st, C, run.count, run.mod.weight, run.mean, run.invstd, coef, dgamma, dbeta, accumulate=True)
-    ops.ew_bwd(g, x, out=out, scale=run.scale, shift=run.shift, slope=slope, coef=coef, accumulate=accumulate,
-               g_gather=g_gather, gscale=gscale)
+    ops.ew_bwd(g, x, out=None if out_split is not None else out, scale=run.scale, shift=run.shift, slope=slope, coef=coef,
+               accumulate=accumulate, g_gather=g_gather, gscale=gscale, out_split=out_split)
 
 
 # ======================================================================================================
@@ -226,6 +227,7 @@ def _conv_dgrad_w(weight):
 
 
 FUSED_BN1_BWD = True   # norm1 backward inside the conv1 data-gradient epilogue + deferred per-channel affine term
+SPLIT_GRADS = True     # the bottleneck gradient travels as split-bf16 planes: its two consumers are fed by bulk tensor loads
 
 
 def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, grads, dpool):
@@ -241,6 +243,10 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
     dA2 = View.alloc(N, H, W, BOTTLENECK, dev)
     cmax = c_in + GROWTH * (n_layers - 1)
     fused = FUSED_BN1_BWD and ops.USE_UMMA
+    split = fused and SPLIT_GRADS
+    # dL/d(conv1 output) after the norm2 backward, as bf16 hi / lo planes [pixels][128] (same bytes as fp32)
+    dA2s = torch.empty(N * H * W * BOTTLENECK, dtype=torch.float32, device=dev) if split else None
+    dA2sv = View.nhwc(dA2s, N, H, W, BOTTLENECK) if split else None
     dA1buf = None if fused else torch.empty(N * H * W * cmax, dtype=torch.float32, device=dev)
     cbd = torch.zeros(2, Ctot, dtype=torch.float32, device=dev) if fused else None   # deferred beta / delta sums
     for i in reversed(range(n_layers)):
@@ -254,12 +260,13 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
         ops.wgrad(T, g2, 3, 3, 1, 1, grads[p + ".conv2.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.0)
         wd, ldd = _conv_dgrad_w(lyr.conv2.weight)
         ops.conv2d(g2, wd, ldd, 3, 3, 1, 1, BOTTLENECK, dA2)
-        _bn_bwd(dA2, T, bn2, dA2, dpool, grads, p + ".norm2")                      # dA2 <- dL/d(conv1 output), in place
-        ops.wgrad(X.ch(0, cin), dA2, 1, 1, 1, 0, grads[p + ".conv1.weight"], scale=bn1.scale, shift=bn1.shift, slope=0.0)
+        _bn_bwd(dA2, T, bn2, dA2, dpool, grads, p + ".norm2", out_split=dA2s)      # dA2 <- dL/d(conv1 output) (in place / planes)
+        ops.wgrad(X.ch(0, cin), dA2sv if split else dA2, 1, 1, 1, 0, grads[p + ".conv1.weight"], scale=bn1.scale, shift=bn1.shift,
+                  slope=0.0, g_split=dA2s)
         if fused:
             st = dpool.take(2 * cin)
-            ops.conv2d(dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dX.ch(0, cin), store=STORE_ACCUM, e=X.ch(0, cin), eslope=0.0,
-                       e_scale=bn1.scale, e_shift=bn1.shift, stats=st, stats_ld=cin)
+            ops.conv2d(dA2sv if split else dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dX.ch(0, cin), store=STORE_ACCUM, e=X.ch(0, cin),
+                       eslope=0.0, e_scale=bn1.scale, e_shift=bn1.shift, stats=st, stats_ld=cin, x_split=dA2s)
             coef = torch.empty(3, cin, dtype=torch.float32, device=dev)
             ops.bn_bwd_finalize(st, cin, bn1.count, bn1.mod.weight, bn1.mean, bn1.invstd, coef,
                                 grads.get(p + ".norm1.weight"), grads.get(p + ".norm1.bias"), accumulate=True)

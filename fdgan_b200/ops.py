@@ -110,7 +110,7 @@ def pack_weight_umma(w, w_ld: int, taps: int, Cin: int, Cout: int, device) -> to
 
 def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_DIRECT, scale=None, shift=None,
            slope=1.0, bias=None, act=ACT_NONE, e: View | None = None, eslope=0.0, store=STORE_NORMAL, stats=None,
-           stats_ld=0, alpha=1.0, impl=IMPL_AUTO, w_umma=None, e_scale=None, e_shift=None, w_k1=None):
+           stats_ld=0, alpha=1.0, impl=IMPL_AUTO, w_umma=None, e_scale=None, e_shift=None, w_k1=None, x_split=None):
     """fdg_conv2d.  ``w`` is the packed [K][w_ld] operand (tensor or pointer)."""
     if gather == GATHER_AVGPOOL2:
         H, W = x.H // 2, x.W // 2
@@ -142,12 +142,12 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
         x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
         _ptr(w), w_ld, R, S, stride, pad, Cout, OH, OW, _ptr(bias), act,
         e.ft() if e is not None else _NULLT, eslope, y.ft(), store, _ptr(stats), stats_ld, alpha, impl, _ptr(w_umma),
-        _ptr(e_scale), _ptr(e_shift), _ptr(w_k1))
+        _ptr(e_scale), _ptr(e_shift), _ptr(w_k1), _ptr(x_split))
     L.check(L.lib.fdg_conv2d(_byref(d), _stream()), "conv2d")
 
 
 def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scale=None, shift=None, slope=1.0,
-          transposed=False, dbias=None, impl=None):
+          transposed=False, dbias=None, impl=None, g_split=None):
     """fdg_conv2d_wgrad: dw (+)= A^T g in the parameter's own layout (dw must be pre-zeroed or accumulating).
     ``dw is None`` (frozen parameter) skips the launch."""
     if dw is None:
@@ -164,7 +164,7 @@ def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scal
         raise ValueError("wgrad: gradient view %s does not match output extent %s" % ((g.N, g.H, g.W), (x.N, OH, OW)))
     d = L.FdgWgrad(x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
                    g.ft(), R, S, stride, pad, g.C, OH, OW, _ptr(dw), 1 if transposed else 0, _ptr(dbias),
-                   (IMPL_AUTO if USE_UMMA else IMPL_SIMT) if impl is None else impl)
+                   (IMPL_AUTO if USE_UMMA else IMPL_SIMT) if impl is None else impl, _ptr(g_split))
     L.check(L.lib.fdg_conv2d_wgrad(_byref(d), _stream()), "conv2d_wgrad")
 
 
@@ -221,7 +221,7 @@ def bn_finalize(stats, stats_ld, Cc, count, gamma, beta, eps, momentum, running_
 
 
 def ew_bwd(g: View, x: View, *, out: View | None = None, stats=None, g_gather=GATHER_DIRECT, gscale=1.0, scale=None,
-           shift=None, slope=0.0, coef=None, accumulate=False):
+           shift=None, slope=0.0, coef=None, accumulate=False, out_split=None):
     if g_gather == GATHER_UP2:
         assert (g.N, g.H, g.W, g.C) == (x.N, x.H // 2, x.W // 2, x.C), "ew_bwd: pooled gradient extent mismatch"
     else:
@@ -230,7 +230,7 @@ def ew_bwd(g: View, x: View, *, out: View | None = None, stats=None, g_gather=GA
         assert (out.N, out.H, out.W, out.C) == (x.N, x.H, x.W, x.C)
     d = L.FdgEwBwd(g.ft(), g_gather, gscale, x.ft(), x.N, x.H, x.W, x.C, 1 if scale is not None else 0,
                    _ptr(scale), _ptr(shift), slope, _ptr(coef), out.ft() if out is not None else _NULLT,
-                   1 if accumulate else 0, _ptr(stats))
+                   1 if accumulate else 0, _ptr(stats), _ptr(out_split))
     L.check(L.lib.fdg_ew_bwd(_byref(d), _stream()), "ew_bwd")
 
 

@@ -100,6 +100,11 @@ typedef struct FdgConv {
   const float* e_scale; /* [Cout] or NULL */
   const float* e_shift; /* [Cout] */
   const void* w_k1;     /* operand image for the 3x3 / stride 1 / pad 1 / Cout <= 32 kernel (fdg_pack_weight_k1) or NULL */
+  /* Split-bf16 input (or NULL): the input as two dense bf16 planes [N*H*W][Cin], hi at x_split and lo right behind it
+   * (value = hi + lo, exactly the operand split the tensor-core kernels apply to fp32 inputs).  Produced by
+   * fdg_ew_bwd(out_split); lets the kernel feed its A operand with bulk tensor loads instead of loading, converting and
+   * re-storing it.  1x1 / stride 1 / direct gather / no prologue / Cin % 64 == 0 / BatchNorm-backward epilogue only. */
+  const void* x_split;
 } FdgConv;
 
 int fdg_conv2d(const FdgConv* p, fdg_stream_t stream);
@@ -126,6 +131,7 @@ typedef struct FdgWgrad {
   int transposed;
   float* dbias;         /* [Cout] (+)= sum_pixels g, or NULL */
   int impl;             /* 0 auto, 1 force SIMT fp32, 2 force tcgen05 (error if unsupported) */
+  const void* g_split;  /* the gradient as split-bf16 planes [N*OH*OW][Cout] (see FdgConv.x_split) or NULL; Cout % 64 == 0 */
 } FdgWgrad;
 
 int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream);
@@ -196,6 +202,7 @@ typedef struct FdgEwBwd {
   FdgTensor out;
   int accumulate;
   double* stats;       /* [2*C] or NULL */
+  void* out_split;     /* apply pass: write the result as split-bf16 planes [N*H*W][C] (hi, then lo) instead of `out`; or NULL */
 } FdgEwBwd;
 
 int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream);

@@ -293,6 +293,49 @@ def test_conv2d_bn_backward_epilogue(shape):
     assert maxabs(dgm, gamma.grad) <= 2e-4 * max(1.0, scale_g) and maxabs(dbt, beta.grad) <= 2e-4 * max(1.0, float(beta.grad.abs().max()))
 
 
+def test_split_bf16_operands():
+    """Split-bf16 planes (fdg_ew_bwd out_split) feeding fdg_conv2d (x_split, BatchNorm-backward epilogue) and
+    fdg_conv2d_wgrad (g_split) give the same results as the fp32 tensors they replace: the kernels apply exactly this
+    split to fp32 operands themselves."""
+    ops = _ops()
+    N, H, W, Cm, Cx = 2, 20, 13, 128, 160
+    P = N * H * W
+    g = seeded((N, Cm, H, W), 1, -1, 1)
+    t = seeded((N, Cm, H, W), 2, -1, 1)
+    coef = torch.cat([seeded((Cm,), 3, 0.5, 1.5), seeded((Cm,), 4, -0.2, 0.2), seeded((Cm,), 5, -0.1, 0.1)]).cuda()
+    gv, tv = ops.View.from_nchw(cl(g)), ops.View.from_nchw(cl(t))
+    # fp32 apply pass vs split apply pass
+    d32 = ops.View.alloc(N, H, W, Cm, "cuda")
+    ops.ew_bwd(gv, tv, out=d32, slope=0.0, coef=coef)
+    planes = torch.empty(P * Cm, dtype=torch.float32, device="cuda")
+    ops.ew_bwd(gv, tv, slope=0.0, coef=coef, out_split=planes)
+    bf = planes.view(torch.bfloat16)
+    rec = (bf[:P * Cm].float() + bf[P * Cm:].float()).view(N, H, W, Cm)
+    assert maxabs(rec, d32.base.view(N, H, W, Cm)) <= 1e-5
+    # conv (BatchNorm-backward epilogue) from the planes vs from the fp32 tensor
+    x = seeded((N, Cx, H, W), 6, -2, 2)
+    xv = ops.View.from_nchw(cl(x))
+    sc, sh = seeded((Cx,), 7, 0.5, 1.5).cuda(), seeded((Cx,), 8, -0.3, 0.3).cuda()
+    wd = (seeded((Cm, Cx), 9, -1, 1) / math.sqrt(Cm)).cuda().contiguous()
+    outs = []
+    for use_split in (False, True):
+        y = cl(seeded((N, Cx, H, W), 10, -1, 1))
+        st = torch.zeros(2 * Cx, dtype=torch.float64, device="cuda")
+        src = ops.View.nhwc(planes, N, H, W, Cm) if use_split else d32
+        ops.conv2d(src, wd, Cx, 1, 1, 1, 0, Cx, ops.View.from_nchw(y), store=ops.STORE_ACCUM, e=xv, eslope=0.0, e_scale=sc, e_shift=sh,
+                   stats=st, stats_ld=Cx, x_split=planes if use_split else None)
+        outs.append((y, st))
+    torch.cuda.synchronize()
+    assert maxabs(outs[1][0], outs[0][0]) <= 2e-5 and maxabs(outs[1][1], outs[0][1]) <= 1e-2
+    # weight gradient with the gradient operand from the planes
+    w1 = torch.zeros(Cm, Cx, 1, 1, device="cuda")
+    w2 = torch.zeros_like(w1)
+    ops.wgrad(xv, d32, 1, 1, 1, 0, w1, scale=sc, shift=sh, slope=0.0)
+    ops.wgrad(xv, ops.View.nhwc(planes, N, H, W, Cm), 1, 1, 1, 0, w2, scale=sc, shift=sh, slope=0.0, g_split=planes)
+    torch.cuda.synchronize()
+    assert maxabs(w2, w1) <= 1e-4 * max(1.0, float(w1.abs().max()))
+
+
 def test_ew_bwd_pooled_gradient_scalar_path():
     ops = _ops()
     N, C, H, W = 2, 9, 6, 8   # C=9: scalar path
