@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[b]), 4);
+      mbar_init(smem_u32(&bar_acc_empty[b]), (BNBWD && a.a_split) ? 8 : 4);   // split input: a second epilogue set (warps 4-7)
     }
     fence_barrier_init();
   }
@@ -135,7 +135,10 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (BNBWD && a.a_split && warp < ULOAD_WARPS) {
+  // With a split-bf16 input the loader warps have nothing to load: warp 0 drives the bulk copies and warps 4-7 become a
+  // second set of epilogue warps (the kernel is then bound by its epilogue: mask reads, L2 reductions, statistics).
+  const bool epi2 = BNBWD && a.a_split && warp >= 4 && warp < ULOAD_WARPS;
+  if (BNBWD && a.a_split && warp < 4) {
     // =============================================================== split-bf16 input: both operands by the bulk-copy engine
     // The producer of the input (fdg_ew_bwd, out_split) already wrote it as bf16 hi / lo planes, i.e. in the operand
     // format; one thread streams [128 pixels x 64 channels] boxes of both planes (SWIZZLE_128B tensor maps place them
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
         }
       }
     }
-  } else if (warp < ULOAD_WARPS) {
+  } else if (warp < ULOAD_WARPS && !epi2) {
     // =============================================================== A loaders
     // thread handles the 16-byte bf16 chunk j (8 channels) of rows rbase + 64*i, i = 0..1
     constexpr int RPT = UM * 8 / (ULOAD_WARPS * 32);   // rows per thread
@@ -443,8 +446,9 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   } else {
     // =============================================================== epilogue warps (TMEM lane quarter = warp & 3)
     const int quarter = warp & 3;                      // TMEM lanes this warp may read
-    const int et = t - UEPI_WARP0 * 32;
-    const uint32_t stage = smem_u32(ep_stage);
+    const int wset = epi2 ? 1 : 0, nsets = (BNBWD && a.a_split) ? 2 : 1;   // epilogue set: 32-channel groups g = wset (mod nsets)
+    const int et = epi2 ? t : t - UEPI_WARP0 * 32;     // set 1 (threads 128..255) keeps its thread index
+    const uint32_t stage = epi2 ? smem_base + STAGES * STAGE_BYTES : smem_u32(ep_stage);   // set 1 stages in the idle cp.async ring
     const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
     // BatchNorm-backward epilogue on pixel-linear views (dense-block conv1 data gradient): the mask-tensor rows of the
     // NEXT 32-channel group (or of the next tile's first group) are fetched while the current group is processed, so
@@ -461,7 +465,16 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
         if (m_ < a.M && c0_ + bc4 < p.Cout) evn[i] = ld4(p.e.p + m_ * p.e.sw + c0_ + bc4);
       }
     };
-    if (BNBWD && (int)blockIdx.x < total_tiles) bn_prefetch(blockIdx.x, 0);
+    auto bn_ngroups = [&](int tile_) {
+      const int left = (p.Cout - (tile_ / m_tiles) * NT + 31) / 32;
+      return left < NT / 32 ? left : NT / 32;
+    };
+    // first (tile, group) of this set at or after tile_: tiles whose channel tail has no group for the set are skipped
+    auto bn_first = [&](int tile_) {
+      while (tile_ < total_tiles && wset >= bn_ngroups(tile_)) tile_ += gridDim.x;
+      return tile_;
+    };
+    if (BNBWD) { const int t0_ = bn_first(blockIdx.x); if (t0_ < total_tiles) bn_prefetch(t0_, wset); }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mt = tile % m_tiles, ntile = tile / m_tiles;
@@ -485,7 +498,7 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
         const int ngroups = (p.Cout - cbase + 31) / 32 < NT / 32 ? (p.Cout - cbase + 31) / 32 : NT / 32;
         const uint32_t wrow0 = stage + (uint32_t)(quarter * 32) * 128u;
 #pragma unroll 1
-        for (int g = 0; g < ngroups; ++g) {
+        for (int g = wset; g < ngroups; g += nsets) {
           const int c0 = cbase + g * 32;
           {
             float v[32], v2[32];
@@ -528,8 +541,8 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
           }
           // mask rows of the next group (or of the next tile's first group): in flight during the statistics fold, the
           // next tcgen05.ld / staging stores and, across tiles, the wait for the accumulator
-          if (g + 1 < ngroups) bn_prefetch(tile, g + 1);
-          else if (tile + (int)gridDim.x < total_tiles) bn_prefetch(tile + gridDim.x, 0);
+          if (g + nsets < ngroups) bn_prefetch(tile, g + nsets);
+          else { const int tn_ = bn_first(tile + gridDim.x); if (tn_ < total_tiles) bn_prefetch(tn_, wset); }
           if (p.stats) {
 #pragma unroll
             for (int off = 8; off <= 16; off <<= 1) {
@@ -575,7 +588,9 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       if (p.stats) {
         const int next = tile + gridDim.x;
         if (next >= total_tiles || next / m_tiles != ntile) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
+          if (nsets == 2) asm volatile("bar.sync 1, 256;" ::: "memory"); else
+          asm volatile("bar.sync 1, 128;" ::: "memory");      // the epilogue warps
+          if (!epi2)
           for (int cidx = et; cidx < NT; cidx += 128) {
             const int c = ntile * NT + cidx;
             if (c < p.Cout) {
@@ -585,11 +600,12 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
             sred[0][0][cidx] = 0.f; sred[0][1][cidx] = 0.f; sred[0][2][cidx] = 0.f; sred[0][3][cidx] = 0.f;
             sred[1][0][cidx] = 0.f; sred[1][1][cidx] = 0.f; sred[1][2][cidx] = 0.f; sred[1][3][cidx] = 0.f;
           }
+          if (nsets == 2) asm volatile("bar.sync 1, 256;" ::: "memory"); else
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
     }
-    if (a.tma_rank && et == 0) bulk_wait_read0();   // the staging tile must outlive the last bulk store's read
+    if (a.tma_rank && et == 0 && !epi2) bulk_wait_read0();   // the staging tile must outlive the last bulk store's read
   }
   tc_fence_before();
   __syncthreads();
