@@ -293,14 +293,25 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
           tc_fence_after();
           const uint32_t a_hi = smem_base + buf * A_STAGE, a_lo = a_hi + a.a_tile;
           const uint32_t ah_lo0 = umma_desc_lo(a_hi, 16), al_lo0 = umma_desc_lo(a_lo, 16), a_hw = umma_desc_hi(sbo);
+          const int cleft = p.Cin - cc * UKC_H;
+          const int kslices = cleft >= UKC_H ? 4 : (cleft + 15) / 16;     // K = 16 slices of this chunk that hold channels
           int ky = 0, kx = 0;
           for (int tap = 0; tap < taps; ++tap) {
             const uint32_t shift = (uint32_t)(ky * a.HC + kx) * 8u;            // rows * 128 B, in 16-byte descriptor units
             mbar_wait(bfull0 + bs * 8, bph);
             tc_fence_after();
             const uint32_t b_hi = b_base + bs * (2 * B_TILE_BYTES);
-            if (!(a.dbg & 4)) umma_chunk8(d_tmem, ah_lo0 + shift, al_lo0 + shift, a_hw, umma_desc_lo(b_hi, 16), b_hw, idesc2, idesc1,
-                                          (cc > 0 || tap > 0) ? 1u : 0u, 2u, 2u, (uint32_t)NT);
+            if (!(a.dbg & 4)) {
+              if (kslices == 4) {
+                umma_chunk8(d_tmem, ah_lo0 + shift, al_lo0 + shift, a_hw, umma_desc_lo(b_hi, 16), b_hw, idesc2, idesc1,
+                            (cc > 0 || tap > 0) ? 1u : 0u, 2u, 2u, (uint32_t)NT);
+              } else {   // channel tail of the last chunk (e.g. the 32-channel data gradients): only the K slices that hold data
+                const uint32_t bl = umma_desc_lo(b_hi, 16);
+                for (int sl = 0; sl < kslices; ++sl)
+                  umma_concat_slice(d_tmem, ah_lo0 + shift + 2u * sl, al_lo0 + shift + 2u * sl, a_hw, bl + 2u * sl, b_hw, idesc2, idesc1,
+                                    (cc > 0 || tap > 0 || sl > 0) ? 1u : 0u, (uint32_t)NT);
+              }
+            }
             umma_commit(bempty0 + bs * 8);
             if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
             if (++kx == p.S) { kx = 0; ++ky; }

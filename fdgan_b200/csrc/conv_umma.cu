@@ -435,8 +435,18 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
           tc_fence_after();
           const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
           const uint32_t b_hi = a_lo + A_TILE_BYTES;     // [B_hi | B_lo] are adjacent: one operand of 2*NT rows
-          if (!(a.dbg & 4)) umma_chunk8(d_tmem, umma_desc_lo(a_hi, 16), umma_desc_lo(a_lo, 16), k_hw, umma_desc_lo(b_hi, 16), k_hw, idesc2, idesc1,
-                                        kc > 0 ? 1u : 0u, 2u, 2u, (uint32_t)NT);
+          const int cleft = p.Cin - (kc % a.cchunks) * UKC;
+          const int kslices = cleft >= UKC ? 4 : (cleft + 15) / 16;      // K = 16 slices of this chunk that hold channels
+          if (!(a.dbg & 4)) {
+            if (kslices == 4) {
+              umma_chunk8(d_tmem, umma_desc_lo(a_hi, 16), umma_desc_lo(a_lo, 16), k_hw, umma_desc_lo(b_hi, 16), k_hw, idesc2, idesc1,
+                          kc > 0 ? 1u : 0u, 2u, 2u, (uint32_t)NT);
+            } else {
+              const uint32_t ah = umma_desc_lo(a_hi, 16), al = umma_desc_lo(a_lo, 16), bl = umma_desc_lo(b_hi, 16);
+              for (int sl = 0; sl < kslices; ++sl)
+                umma_concat_slice(d_tmem, ah + 2u * sl, al + 2u * sl, k_hw, bl + 2u * sl, k_hw, idesc2, idesc1, (kc > 0 || sl > 0) ? 1u : 0u, (uint32_t)NT);
+            }
+          }
           umma_commit(smem_u32(&bar_empty[s]));                // frees this stage when the MMAs above retire
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
