@@ -2,6 +2,7 @@
 
     python profiles/make_summary.py launches gpurun_out/launches_X.csv profiles/rNN_launches.md "title"
     python profiles/make_summary.py kernel   gpurun_out/Y.ncu-rep      profiles/rNN_kernel_Y.md "title"
+    python profiles/make_summary.py traffic  gpurun_out/launches_X.csv profiles/rNN_traffic.md "title" [profiles/rNN_traffic.json]
 """
 import collections
 import csv
@@ -76,5 +77,85 @@ def kernel(src, dst, title):
     open(dst, "w").write("\n".join(md) + "\n")
 
 
+
+def traffic(src, dst_md, title, dst_json=None):
+    """Launch list with per-launch DRAM bytes and tensor-pipe activity (ncu --metrics gpu__time_duration.sum,
+    dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed)."""
+    import json
+    with open(src) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    r = csv.reader(lines)
+    hdr = next(r)
+    ik, im, iv, iu, iid = (hdr.index(x) for x in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
+    rows = collections.OrderedDict()
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for row in r:
+        k = row[ik].split("(")[0].replace("void fdg::", "").replace("void ", "").replace("fdg::", "")
+        d = rows.setdefault(row[iid], {"k": k})
+        v = float(row[iv].replace(",", ""))
+        u = row[iu]
+        if row[im] == "gpu__time_duration.sum":
+            d["us"] = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+        elif row[im].startswith("dram__bytes_read"):
+            d["rd"] = v * scale[u]
+        elif row[im].startswith("dram__bytes_write"):
+            d["wr"] = v * scale[u]
+        else:
+            d["tc"] = v
+    rows = list(rows.values())
+
+    def famof(k):
+        if "conv_umma" in k or "conv_halo" in k or "conv_k1" in k:
+            return "conv_tcgen05"
+        if "wgrad" in k:
+            return "wgrad"
+        if "ew_bwd" in k or "affine_accum" in k:
+            return "ew_bwd"
+        if "conv_simt" in k or "conv_thin" in k or "conv_cin1" in k:
+            return "conv_simt_f32"
+        if "freq" in k:
+            return "freq"
+        return "other"
+
+    fam = collections.OrderedDict()
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
+    for d in rows:
+        a = fam.setdefault(famof(d["k"]), dict(launches=0, ms=0.0, dram=0.0, tc_ms=0.0))
+        a["launches"] += 1
+        a["ms"] += d["us"] / 1e3
+        a["dram"] += d.get("rd", 0) + d.get("wr", 0)
+        a["tc_ms"] += d.get("tc", 0) / 100 * d["us"] / 1e3
+        b = agg[d["k"]]
+        b[0] += 1; b[1] += d["us"]; b[2] += d.get("rd", 0); b[3] += d.get("wr", 0); b[4] += d.get("tc", 0) * d["us"]
+    tot = sum(b[1] for b in agg.values())
+    rd, wr = sum(d.get("rd", 0) for d in rows), sum(d.get("wr", 0) for d in rows)
+    out = ["# %s" % title, "",
+           "Source: `ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none` around ONE timed step of",
+           "`bench.py --steps 1 --warmup 3 --quick` (batch 16, 256x256, 1 GPU).  Per-launch times under ncu are cold-cache and "
+           "serialised: compare SHARES, not absolutes.", "",
+           "Total: %.1f ms over %d launches; DRAM read %.1f GB + write %.1f GB per step (= %.1f ms at the measured 6547.5 GB/s)."
+           % (tot / 1e3, len(rows), rd / 1e9, wr / 1e9, (rd + wr) / 6547.5e9 * 1e3), "",
+           "| kernel | launches | total ms | share | DRAM read GB | DRAM write GB | DRAM TB/s | tensor pipe active % |",
+           "|---|---:|---:|---:|---:|---:|---:|---:|"]
+    for k, b in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+        out.append("| `%s` | %d | %.2f | %.1f %% | %.2f | %.2f | %.2f | %.1f |"
+                   % (k[:70], b[0], b[1] / 1e3, 100 * b[1] / tot, b[2] / 1e9, b[3] / 1e9, (b[2] + b[3]) / b[1] / 1e6, b[4] / b[1]))
+    out += ["", "| family | launches | ms | DRAM GB | mean DRAM MB / launch | tensor pipe active % |", "|---|---:|---:|---:|---:|---:|"]
+    for k, v in fam.items():
+        out.append("| %s | %d | %.2f | %.1f | %.1f | %.1f |" % (k, v["launches"], v["ms"], v["dram"] / 1e9, v["dram"] / v["launches"] / 1e6,
+                                                               100 * v["tc_ms"] / v["ms"]))
+    with open(dst_md, "w") as f:
+        f.write("\n".join(out) + "\n")
+    if dst_json:
+        js = {"source": "ncu launch list of one step of bench.py --steps 1 --warmup 3 --quick (batch 16, 256x256, 1 B200): " + src,
+              "families": {k: dict(launches=v["launches"], ms_under_ncu=round(v["ms"], 3), dram_bytes_per_launch=round(v["dram"] / v["launches"]),
+                                   dram_gbs_under_ncu=round(v["dram"] / v["ms"] / 1e6, 1), tensor_pipe_active_pct=round(100 * v["tc_ms"] / v["ms"], 1))
+                           for k, v in fam.items()}}
+        with open(dst_json, "w") as f:
+            json.dump(js, f, indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else sys.argv[3])
+    (traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else None) if sys.argv[1] == "traffic" else
+     {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else sys.argv[3]))
