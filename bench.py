@@ -42,9 +42,9 @@ def peaks():
 
 def ncu_family_profile(family):
     """Per-launch DRAM traffic / tensor-pipe activity of a kernel family from the committed ncu launch list of this same
-    command (profiles/r01d_traffic.json; numbers taken under ncu are never bench values, they only annotate the roofline)."""
+    command (profiles/r01g_traffic.json; numbers taken under ncu are never bench values, they only annotate the roofline)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01d_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01g_traffic.json")) as f:
             return json.load(f)["families"].get(family)
     except Exception:
         return None
@@ -277,7 +277,7 @@ def run_ours(args):
             prof = ncu_family_profile(dom)
             roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tf_sustained"], "traffic": prof["dram_bytes_per_launch"] if prof else None, "kernel": dom,
-                    "traffic_source": "profiles/r01d_traffic.json: mean dram__bytes_read+write per launch of this family (ncu, same command)" if prof else None,
+                    "traffic_source": "profiles/r01g_traffic.json: mean dram__bytes_read+write per launch of this family (ncu, same command)" if prof else None,
                     "tensor_pipe_active_pct_ncu": prof["tensor_pipe_active_pct"] if prof else None,
                     "note": "fp32 operands run as bf16 hi/lo splits: 3 algorithmic bf16 passes per MAC (issued as 2 MMAs of width 2N and N), "
                             "so the algorithmic ceiling is 1/3 of the bf16 peak; achieved counts each MAC once",
