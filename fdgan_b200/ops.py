@@ -313,6 +313,17 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, gra
 LOSS_L1, LOSS_MSE, LOSS_BCE = L.LOSS_L1, L.LOSS_MSE, L.LOSS_BCE
 
 
+def ssim_loss_grad(x: View, y: View, lscale: float, gscale: float, loss: torch.Tensor, grad: View | None = None, accumulate=False):
+    """fdg_ssim_loss_grad: loss += lscale * sum(ssim_map(x, y)); grad (=|+=) gscale * d(sum ssim_map)/dx."""
+    assert loss.dtype == torch.float64 and loss.numel() == 1
+    assert (x.N, x.H, x.W, x.C) == (y.N, y.H, y.W, y.C)
+    scratch = torch.empty(3 * x.N * x.C * x.H * x.W, dtype=torch.float32, device=x.base.device)
+    xt, yt = x.ft(), y.ft()
+    gt = grad.ft() if grad is not None else None
+    L.check(L.lib.fdg_ssim_loss_grad(_byref(xt), _byref(yt), x.N, x.H, x.W, x.C, lscale, gscale, _byref(gt) if gt is not None else None,
+                                     1 if accumulate else 0, loss.data_ptr(), scratch.data_ptr(), _stream()), "ssim_loss_grad")
+
+
 def loss_grad(kind, a: torch.Tensor, b, n, scale, loss: torch.Tensor, grad=None, accumulate=False, target=0.0):
     """fdg_loss_grad over the first ``n`` floats of the (identically laid out) buffers a and b."""
     assert loss.dtype == torch.float64 and loss.numel() == 1

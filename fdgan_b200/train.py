@@ -68,7 +68,7 @@ class GANTrainer:
         fdist.broadcast_flat_(self.sG.flat, 0, process_group)
         fdist.broadcast_flat_(self.sD.flat, 0, process_group)
         dev = self.sG.flat.device
-        self.loss_buf = torch.zeros(4, dtype=torch.float64, device=dev)   # lossD, weighted l1 / perceptual / adversarial terms of lossG
+        self.loss_buf = torch.zeros(5, dtype=torch.float64, device=dev)   # lossD, weighted l1 / perceptual / adversarial / -w*mean(ssim) terms of lossG
         self.last = {}
 
     # ------------------------------------------------------------------
@@ -117,6 +117,10 @@ class GANTrainer:
         ops.freq_concat_bwd(View.from_nchw(dz), View.from_nchw(dfake), scratch)
         n_img = fake.numel()
         ops.loss_grad(ops.LOSS_L1, fake, clean, n_img, self.w["l1"] / n_img, lb[1:2], dfake, accumulate=True)
+        w_ssim = float(self.w.get("ssim", 0.0))
+        if w_ssim != 0.0:      # w * (1 - mean ssim_map(fake, clean)), models/pytorch_ssim/__init__.py:17-37
+            ops.ssim_loss_grad(View.from_nchw(fake), View.from_nchw(clean), -w_ssim / n_img, -w_ssim / n_img, lb[4:5],
+                               View.from_nchw(dfake), accumulate=True)
         if self.w["perc"] != 0.0 and self.perc_layers:
             _fo, vctx = engine.vgg_forward(V, fake, True)
             _co, cctx = engine.vgg_forward(V, clean, False)
@@ -137,5 +141,7 @@ class GANTrainer:
 
         if sync_losses:
             v = lb.tolist()    # the step's device->host read; slots 1..3 hold the WEIGHTED generator terms
-            self.last = dict(loss_d=v[0], l1_weighted=v[1], perc_weighted=v[2], adv_weighted=v[3], loss_g=v[1] + v[2] + v[3])
+            ssim_w = (w_ssim + v[4]) if w_ssim != 0.0 else 0.0
+            self.last = dict(loss_d=v[0], l1_weighted=v[1], perc_weighted=v[2], adv_weighted=v[3], ssim_weighted=ssim_w,
+                             loss_g=v[1] + v[2] + v[3] + ssim_w)
         return fake

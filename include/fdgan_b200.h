@@ -269,6 +269,14 @@ int fdg_freq_concat_fwd(const FdgTensor* x, const FdgTensor* z, int N, int H, in
 int fdg_freq_concat_bwd(const FdgTensor* dz, const FdgTensor* dx, float* scratch /* N*3*H*W floats */, int N, int H,
                         int W, fdg_stream_t stream);
 
+/* SSIM term of the generator loss and its gradient (reference arithmetic pytorch_ssim._ssim,
+ * models/pytorch_ssim/__init__.py:17-37: window 11, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2):
+ *   loss[0] += lscale * sum over (n,c,h,w) of ssim_map(x, y);   grad (=|+=) gscale * d(sum ssim_map)/dx   (grad may be NULL)
+ * x, y, grad: strided [N,H,W,C] views of any strides; scratch: 3*N*C*H*W floats.  For the loss w*(1 - mean(ssim_map)) pass
+ * lscale = gscale = -w / (N*C*H*W) and add the constant w. */
+int fdg_ssim_loss_grad(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int C, float lscale, float gscale,
+                       const FdgTensor* grad, int accumulate, double* loss, float* scratch, fdg_stream_t stream);
+
 /* Fused Adam over a flat fp32 buffer (torch.optim.Adam arithmetic; --lrG/--lrD 2e-4, --beta1 0.5: demo.py:43-46).
  * grad_scale multiplies the gradient first (1/world_size after the NCCL sum). */
 int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

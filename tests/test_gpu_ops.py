@@ -408,6 +408,28 @@ def test_freq_concat_fwd_bwd(shape):
     assert maxabs(xd.grad, x.grad) <= 1e-4
 
 
+@pytest.mark.parametrize("shape,layout", [((2, 3, 40, 56), "nchw"), ((1, 3, 33, 65), "cl"), ((1, 1, 7, 9), "nchw")])
+def test_ssim_loss_grad(shape, layout):
+    """fdg_ssim_loss_grad against autograd through the oracle's restatement of pytorch_ssim._ssim (which
+    tests/test_oracle_golden.py pins to the reference module's own output): value of sum(ssim_map) and d/dx."""
+    from oracle import fdgan_oracle as O
+    ops = _ops()
+    x = seeded(shape, 1, 0.0, 1.0).double().requires_grad_(True)
+    y = seeded(shape, 2, 0.0, 1.0).double()
+    n = x.numel()
+    val = O.ssim(x, y)
+    (0.7 * (1 - val)).backward()
+    mk = (lambda t: cl(t)) if layout == "cl" else (lambda t: t.cuda().contiguous())
+    xd, yd = mk(x.detach().float()), mk(y.float())
+    base = seeded(shape, 3, -1, 1)
+    gd = mk(base.clone())
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ops.ssim_loss_grad(ops.View.from_nchw(xd), ops.View.from_nchw(yd), -0.7 / n, -0.7 / n, loss, ops.View.from_nchw(gd), accumulate=True)
+    torch.cuda.synchronize()
+    assert abs((0.7 + float(loss)) - float(0.7 * (1 - val))) <= 2e-6
+    assert maxabs(gd, x.grad + base.double()) <= 1e-6 + 2e-3 * float(x.grad.abs().max())
+
+
 def test_adam_flat():
     ops = _ops()
     p = seeded((1000,), 1, -1, 1)

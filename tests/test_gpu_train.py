@@ -46,6 +46,24 @@ def test_train_step_matches_oracle(batch, hw):
     assert moved <= 1e-3
 
 
+def test_train_step_with_ssim_term_matches_oracle():
+    """The generator loss with the SSIM term: w_ssim * (1 - ssim(fake, clean)), pytorch_ssim semantics."""
+    from fdgan_b200.train import GANTrainer
+    G, D, V = _nets()
+    wts = dict(ssim=0.4)
+    tr = GANTrainer(G, D, V, weights=wts)
+    g_sd, d_sd, v_sd = O.make_fdgan_state(0), O.make_d_state(9, 36, 1), O.make_vgg_state(2)
+    hazy, clean = seeded((2, 3, 48, 48), 5), seeded((2, 3, 48, 48), 6)
+    parts, gd, gg, fake_o = O.train_step(g_sd, d_sd, v_sd, hazy, clean, {}, {}, weights=wts)
+    fake = tr.step(hazy.cuda(), clean.cuda())
+    assert maxabs(fake, fake_o) <= 2e-4
+    assert abs(tr.last["loss_g"] - parts["loss_g"]) <= 2e-3 * max(1.0, abs(parts["loss_g"])), (tr.last, parts)
+    want_ssim = 0.4 * (1 - float(O.ssim(fake_o, clean)))
+    assert abs(tr.last["ssim_weighted"] - want_ssim) <= 1e-4
+    for k, g in gg.items():
+        grad_close(tr.sG.grad_views[k], g, "G " + k, rel_l2=6e-2, rel_max=0.5)
+
+
 def test_trainer_uses_flat_buffers():
     from fdgan_b200.train import GANTrainer
     G, D, V = _nets()
