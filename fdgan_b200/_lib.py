@@ -113,6 +113,9 @@ _SIGS = {
     "fdg_freq_concat_bwd": ([_P(FdgTensor), _P(FdgTensor), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_ssim_loss_grad": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P(FdgTensor), C.c_int,
                            C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "fdg_image_minmax": ([_P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
+    "fdg_image_pack_u8": ([_P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "fdg_psnr_ssim_u8": ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_adam_flat": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p], C.c_int),
     "fdg_loss_grad": ([C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_profile_enable": ([C.c_int], C.c_int),

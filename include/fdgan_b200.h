@@ -277,6 +277,16 @@ int fdg_freq_concat_bwd(const FdgTensor* dz, const FdgTensor* dx, float* scratch
 int fdg_ssim_loss_grad(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int C, float lscale, float gscale,
                        const FdgTensor* grad, int accumulate, double* loss, float* scratch, fdg_stream_t stream);
 
+/* Output path and quality metrics.
+ * fdg_image_minmax: out2 = {min, max} over the whole [N,H,W,C] view; fdg_image_pack_u8: the bytes
+ * torchvision.utils.save_image(normalize=True, scale_each=False) would write (demo.py:151), dense uint8 [N][H][W][C].
+ * fdg_psnr_ssim_u8: PSNRSSIM.py:201-240 on two uint8 [H][W][3] images: sums4[0] = sum of squared /255 differences over the
+ * 1-pixel-cropped images, sums4[1..3] = sum of the 5-pixel-cropped Gaussian-weighted SSIM map of each channel;
+ * PSNR = 10 log10(3 (H-2)(W-2) / sums4[0]), SSIM = mean_c sums4[1+c] / ((H-12)(W-12)). */
+int fdg_image_minmax(const FdgTensor* x, int N, int H, int W, int C, float* out2, fdg_stream_t stream);
+int fdg_image_pack_u8(const FdgTensor* x, int N, int H, int W, int C, const float* minmax, uint8_t* out, fdg_stream_t stream);
+int fdg_psnr_ssim_u8(const uint8_t* ref, const uint8_t* res, int H, int W, double* sums4, fdg_stream_t stream);
+
 /* Fused Adam over a flat fp32 buffer (torch.optim.Adam arithmetic; --lrG/--lrD 2e-4, --beta1 0.5: demo.py:43-46).
  * grad_scale multiplies the gradient first (1/world_size after the NCCL sum). */
 int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

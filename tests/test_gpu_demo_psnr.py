@@ -41,5 +41,11 @@ def test_demo_forward_psnr_ssim_match_to_2dp(path):
         assert round(p_ref, 2) == round(p_out, 2) or abs(p_ref - p_out) < 5e-3
         assert round(s_ref, 2) == round(s_out, 2) or abs(s_ref - s_out) < 5e-3
         assert M.psnr(ref_u8, out_u8) > 55.0 or np.array_equal(ref_u8, out_u8)
+        # the same pipeline entirely on the GPU (fdgan_b200.metrics: save_image bytes + PSNRSSIM.py arithmetic)
+        from fdgan_b200 import metrics
+        out_u8_gpu = metrics.save_image_u8(y[0])
+        assert np.array_equal(out_u8_gpu.cpu().numpy(), out_u8)
+        p_gpu, s_gpu = metrics.psnr_ssim(torch.from_numpy(gt_u8).cuda(), out_u8_gpu)
+        assert abs(p_gpu - p_out) <= 1e-9 and abs(s_gpu - s_out) <= 1e-9
     finally:
         ops.USE_UMMA = old
