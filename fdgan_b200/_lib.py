@@ -117,6 +117,7 @@ _SIGS = {
     "fdg_image_pack_u8": ([_P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_psnr_ssim_u8": ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_adam_flat": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p], C.c_int),
+    "fdg_adam_flat_dev": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float, C.c_void_p], C.c_int),
     "fdg_loss_grad": ([C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_profile_enable": ([C.c_int], C.c_int),
     "fdg_profile_collect": ([C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),

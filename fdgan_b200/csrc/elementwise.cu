@@ -404,6 +404,28 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Device-side step counter (CUDA-graph replay: no host value may change between replays).  state = {step, bc1, sqrt(bc2)}
+__global__ void adam_prepare_kernel(float* state, float b1, float b2) {
+  const float step = state[0] + 1.f;
+  state[0] = step;
+  state[1] = 1.f - powf(b1, step);
+  state[2] = sqrtf(1.f - powf(b2, step));
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                float lr, float b1, float b2, float eps, const float* __restrict__ state, float gscale) {
+  const float bc1 = state[1], bc2_sqrt = state[2];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gr = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gr;
+    const float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
 // ------------------------------------------------------------------ fused loss value + gradient
 __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, float target,
                                                         int kind, int64_t n, float scale, float* __restrict__ grad,
@@ -589,6 +611,19 @@ int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_av
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                   bc1, sqrtf(bc2), grad_scale);
   return check_launch("fdg_adam_flat");
+}
+
+// Same update with the step counter and the bias corrections kept on the device (state: 3 floats, zero-initialised), so that
+// a captured CUDA graph of the training step can be replayed without any host-side value changing between replays.
+int fdg_adam_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float* state, float grad_scale, fdg_stream_t stream) {
+  FDG_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n > 0, "fdg_adam_flat_dev: bad arguments");
+  adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+  int rc = check_launch("fdg_adam_flat_dev[prepare]");
+  if (rc != FDG_OK) return rc;
+  adam_dev_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state,
+                                                                      grad_scale);
+  return check_launch("fdg_adam_flat_dev");
 }
 
 }  // extern "C"

@@ -310,6 +310,14 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, gra
                                 lr, beta1, beta2, eps, step, grad_scale, _stream()), "adam_flat")
 
 
+def adam_flat_dev(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, state, grad_scale=1.0):
+    """fdg_adam_flat_dev: step counter / bias corrections live in ``state`` (3 floats on the device)."""
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n and state.numel() >= 3
+    L.check(L.lib.fdg_adam_flat_dev(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
+                                    lr, beta1, beta2, eps, state.data_ptr(), grad_scale, _stream()), "adam_flat_dev")
+
+
 LOSS_L1, LOSS_MSE, LOSS_BCE = L.LOSS_L1, L.LOSS_MSE, L.LOSS_BCE
 
 

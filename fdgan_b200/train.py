@@ -43,6 +43,7 @@ class FlatState:
             p.data = v
             self.grad_views[n] = self.grad[o:o + p.numel()].view(p.shape)
         self.step = 0
+        self.dev_state = None
         self.module = module
 
     def zero_grad(self):
@@ -50,7 +51,16 @@ class FlatState:
 
     def adam(self, lr, beta1, beta2, eps, grad_scale):
         self.step += 1
-        ops.adam_flat(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, self.step, grad_scale)
+        if self.dev_state is not None:      # CUDA-graph mode: the step counter lives on the device
+            ops.adam_flat_dev(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, self.dev_state, grad_scale)
+        else:
+            ops.adam_flat(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, self.step, grad_scale)
+
+    def use_device_step(self):
+        """Move the step counter / bias corrections to the device (idempotent); continues from the current step."""
+        if self.dev_state is None:
+            self.dev_state = torch.zeros(3, dtype=torch.float32, device=self.flat.device)
+            self.dev_state[0] = float(self.step)
 
 
 class GANTrainer:
@@ -72,6 +82,51 @@ class GANTrainer:
         self.last = {}
 
     # ------------------------------------------------------------------
+    def step_graphed(self, hazy: torch.Tensor, clean: torch.Tensor, sync_losses: bool = True):
+        """``step`` replayed from a captured CUDA graph (single-GPU; fixed input shape).  At small batch the step is
+        launch-bound (~1150 kernel launches); the graph removes the Python / launch overhead.  The first call warms up
+        eagerly and captures; the step counter of Adam lives on the device so that replays stay correct."""
+        if self.world != 1:
+            raise RuntimeError("step_graphed: single-process only (the NCCL all-reduce is not captured)")
+        key = (tuple(hazy.shape), tuple(clean.shape))
+        if getattr(self, "_graph_key", None) != key:
+            self.sG.use_device_step()
+            self.sD.use_device_step()
+            self._static_hazy, self._static_clean = hazy.clone(), clean.clone()
+            # the warm-up below is a real step: snapshot everything it changes and put it back afterwards
+            state = [self.sG.flat, self.sG.exp_avg, self.sG.exp_avg_sq, self.sG.dev_state, self.sD.flat, self.sD.exp_avg,
+                     self.sD.exp_avg_sq, self.sD.dev_state] + list(self.G.buffers()) + list(self.D.buffers())
+            snap = [t.clone() for t in state]
+            step0 = (self.sG.step, self.sD.step)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.step(self._static_hazy, self._static_clean, sync_losses=False)      # warm-up: attributes, caches, pools
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_fake = self.step(self._static_hazy, self._static_clean, sync_losses=False)
+            self._graph_key = key
+            for t_, s_ in zip(state, snap):
+                t_.copy_(s_)
+            self.sG.step, self.sD.step = step0
+        self._static_hazy.copy_(hazy)
+        self._static_clean.copy_(clean)
+        self._graph.replay()
+        self.sG.step += 1
+        self.sD.step += 1
+        if sync_losses:
+            self._read_losses()
+        return self._static_fake
+
+    def _read_losses(self):
+        v = self.loss_buf.tolist()    # the step's device->host read; slots 1..3 hold the WEIGHTED generator terms
+        w_ssim = float(self.w.get("ssim", 0.0))
+        ssim_w = (w_ssim + v[4]) if w_ssim != 0.0 else 0.0
+        self.last = dict(loss_d=v[0], l1_weighted=v[1], perc_weighted=v[2], adv_weighted=v[3], ssim_weighted=ssim_w,
+                         loss_g=v[1] + v[2] + v[3] + ssim_w)
+
     def step(self, hazy: torch.Tensor, clean: torch.Tensor, sync_losses: bool = True):
         """One D update and one G update on this rank's shard.  hazy, clean: [b,3,H,W] fp32 CUDA."""
         G, D, V = self.G, self.D, self.V
@@ -140,8 +195,5 @@ class GANTrainer:
         self.sG.adam(self.lr, b1, b2, self.eps, gscale)
 
         if sync_losses:
-            v = lb.tolist()    # the step's device->host read; slots 1..3 hold the WEIGHTED generator terms
-            ssim_w = (w_ssim + v[4]) if w_ssim != 0.0 else 0.0
-            self.last = dict(loss_d=v[0], l1_weighted=v[1], perc_weighted=v[2], adv_weighted=v[3], ssim_weighted=ssim_w,
-                             loss_g=v[1] + v[2] + v[3] + ssim_w)
+            self._read_losses()
         return fake

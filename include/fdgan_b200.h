@@ -292,6 +292,11 @@ int fdg_psnr_ssim_u8(const uint8_t* ref, const uint8_t* res, int H, int W, doubl
 int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int step, float grad_scale, fdg_stream_t stream);
 
+/* fdg_adam_flat with the step counter and bias corrections on the device (state: 3 floats {step, 1-b1^t, sqrt(1-b2^t)},
+ * zero-initialised by the caller): lets a captured CUDA graph of the training step be replayed unchanged. */
+int fdg_adam_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float* state, float grad_scale, fdg_stream_t stream);
+
 /* Fused scalar loss + its gradient over flat arrays (the training step never builds an autograd graph for these):
  *   kind FDG_LOSS_L1:  loss += scale * sum |a-b|        grad (=|+=) scale * sign(a-b)       (F.l1_loss, mean folded into scale)
  *   kind FDG_LOSS_MSE: loss += scale * sum (a-b)^2      grad (=|+=) 2 scale (a-b)           (F.mse_loss on VGG features)

@@ -27,6 +27,8 @@ tr = GANTrainer(G, D, V, weights=dict(perc=0.0))
 hz, cl = torch.rand(1, 3, 256, 256, device="cuda"), torch.rand(1, 3, 256, 256, device="cuda")
 ms = ev_time(lambda: tr.step(hz, cl, sync_losses=False), 10)
 print("config[1] G+D adversarial step, B=1 256x256: %.2f ms/step -> %.1f images/s" % (ms, 1e3 / ms), flush=True)
+ms = ev_time(lambda: tr.step_graphed(hz, cl, sync_losses=False), 10)
+print("           replayed from a CUDA graph (GANTrainer.step_graphed): %.2f ms/step -> %.1f images/s" % (ms, 1e3 / ms), flush=True)
 tr2 = GANTrainer(G, D, V)
 ms = ev_time(lambda: tr2.step(hz, cl, sync_losses=False), 10)
 print("           with the VGG16 perceptual term, B=1: %.2f ms/step -> %.1f images/s" % (ms, 1e3 / ms), flush=True)

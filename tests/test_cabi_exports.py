@@ -64,6 +64,11 @@ def test_no_cpu_fallback(lib):
         net(torch.zeros(1, 3, 32, 32))
     with pytest.raises(RuntimeError):
         fdgan_b200.freq_concat(torch.zeros(1, 3, 32, 32))
+    from fdgan_b200 import metrics
+    with pytest.raises(RuntimeError):
+        metrics.save_image_u8(torch.zeros(3, 32, 32))
+    with pytest.raises(RuntimeError):
+        metrics.psnr_ssim(torch.zeros(32, 32, 3, dtype=torch.uint8), torch.zeros(32, 32, 3, dtype=torch.uint8))
 
 
 def test_product_does_not_import_oracle():
