@@ -37,3 +37,28 @@ def test_psnr_ssim_matches_metric_script(hw):
         assert abs(s - M.mssim(a, b)) <= 1e-9
     p, s = metrics.psnr_ssim(torch.from_numpy(ref).cuda(), torch.from_numpy(ref).cuda())
     assert p == float("inf") and abs(s - 1.0) <= 1e-12
+
+
+def test_run_demo_loop(tmp_path, monkeypatch):
+    """fdgan_b200.io.run_demo (demo.py:118-151) on the committed 256x256 crop of testsample1/3.h5 (the HDF5 reader itself is
+    a CPU test against the reference's files): generator forward, GPU byte conversion, PNG on disk == oracle pipeline."""
+    import os
+    import fdgan_b200
+    from fdgan_b200 import io as fio
+    from oracle import fdgan_oracle as O
+    from tests.util import GOLDEN
+    Image = pytest.importorskip("PIL.Image")
+    haze = torch.from_numpy(np.load(os.path.join(GOLDEN, "testsample1_3_crop256.npz"))["haze"])          # [3,256,256]
+    monkeypatch.setattr(fio, "read_h5_pair", lambda path: (haze.clone(), haze.clone()))
+    net = fdgan_b200.FDGAN()
+    net.load_state_dict(O.make_fdgan_state(0))
+    net = net.cuda().train()
+    pairs = fio.run_demo(net, str(tmp_path), str(tmp_path / "out"), 1)
+    out_u8, gt_u8 = pairs[0]
+    png = np.asarray(Image.open(str(tmp_path / "out" / "0.png")).convert("RGB"))
+    assert np.array_equal(png, out_u8.cpu().numpy())
+    with torch.no_grad():
+        y_ref = O.fdgan_forward(O.make_fdgan_state(0), haze.unsqueeze(0), True, False)
+    ref_u8 = M.save_image_u8(y_ref[0])
+    assert M.psnr(ref_u8, png) > 55.0 or np.array_equal(ref_u8, png)
+    assert np.array_equal(gt_u8.cpu().numpy(), M.save_image_u8(haze))
