@@ -18,6 +18,25 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// One process may drive several GPUs from several threads (nn.DataParallel, demo.py:89): function attributes, __constant__
+// uploads and the SM count are per device, so the kernels' one-time launch state is indexed by the current device.
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < 64 ? dev : 63;
+}
+
+int device_sm_count() {
+  static std::atomic<int> sms[64];
+  const int dev = current_device();
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 static int g_dbg = 0;
 int dbg_flags() { return g_dbg; }
 void set_dbg_flags(int v) { g_dbg = v; }

@@ -142,13 +142,14 @@ template <int NC4>
 static int launch_thin(const ThinArgs& a, cudaStream_t st) {
   constexpr int CO = 4 * NC4;
   constexpr int smem = (TH_MAXK * CO + 8 * 32 * (CO + 4)) * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_done[64] = {0};           // per device
+  const int adev = current_device();
+  if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(conv_thin_kernel<NC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[thin]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
-    attr_done = true;
+    attr_done[adev] = 1;
   }
   int64_t blocks = cdiv64(a.M, 8 * 32);
   if (blocks > 148 * 8) blocks = 148 * 8;

@@ -367,20 +367,16 @@ int conv2d_halo_supported(const FdgConv* p) {
 template <int NT, int BSTAGES>
 static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   const int smem = 2 * (2 * a.a_tile) + BSTAGES * (2 * NT * 128) + 1024;
-  static int attr_done = 0;
-  if (attr_done < smem) {
+  static int attr_done[64] = {0};           // per device: largest size configured so far
+  const int adev = current_device();
+  if (attr_done[adev] < smem) {
     if (cudaFuncSetAttribute(conv_halo_kernel<NT, BSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05 halo]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
-    attr_done = smem;
+    attr_done[adev] = smem;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = device_sm_count();
   dim3 grid((unsigned)(a.total_tiles < num_sms ? a.total_tiles : num_sms));
   const double M = (double)a.c.N * a.c.OH * a.c.OW;
   ProfScope prof(PF_CONV_UMMA, 2.0 * M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,

@@ -416,20 +416,16 @@ int conv2d_k1(const FdgConv* p, cudaStream_t st) {
     const uint32_t box[4] = {32, (uint32_t)K1_TW, (uint32_t)K1_OH, 1};
     if (make_tmap_f32(&a.ymap, p->y.p, 4, dims, strides, box)) a.tma_rank = 4;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_done[64] = {0};           // per device
+  const int adev = current_device();
+  if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(conv_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05 k1]: cannot raise dynamic shared memory to %d bytes", K1_SMEM);
       return FDG_ECUDA;
     }
-    attr_done = true;
+    attr_done[adev] = 1;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = device_sm_count();
   dim3 grid((unsigned)(a.total_tiles < num_sms ? a.total_tiles : num_sms));
   const double M = (double)p->N * p->OH * p->OW;
   ProfScope prof(PF_CONV_UMMA, 2.0 * M * 9 * p->Cin * p->Cout, 4.0 * (M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);

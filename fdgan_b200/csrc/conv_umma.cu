@@ -683,21 +683,17 @@ int conv2d_umma_supported(const FdgConv* p) {
 template <int NT, int STAGES, int DEPTH, bool BNBWD = false>
 static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + DEPTH * (UM * UKC * 4) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_done[64] = {0};           // per device
+  const int adev = current_device();
+  if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES, DEPTH, BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
-    attr_done = true;
+    attr_done[adev] = 1;
   }
   const int64_t tiles = cdiv64(a.M, UM) * cdiv(a.c.Cout, NT);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = device_sm_count();
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));
   const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
   ProfScope prof(PF_CONV_UMMA, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,

@@ -153,13 +153,14 @@ extern "C" int fdg_image_pack_u8(const FdgTensor* x, int N, int H, int W, int C,
 
 extern "C" int fdg_psnr_ssim_u8(const uint8_t* ref, const uint8_t* res, int H, int W, double* sums4, fdg_stream_t stream) {
   FDG_REQUIRE(ref && res && sums4 && H >= 13 && W >= 13, "fdg_psnr_ssim_u8: bad arguments (images of at least 13x13 after the crops)");
-  static bool window_done = false;
-  if (!window_done) {   // scipy.ndimage.gaussian_filter(sigma=1.5): radius int(4.0 * 1.5 + 0.5) = 6, normalised exp(-x^2 / (2 sigma^2))
+  static int window_done[64] = {0};         // __constant__ memory is per device
+  const int wdev = current_device();
+  if (!window_done[wdev]) {   // scipy.ndimage.gaussian_filter(sigma=1.5): radius int(4.0 * 1.5 + 0.5) = 6, normalised exp(-x^2 / (2 sigma^2))
     double w[13], s = 0;
     for (int i = 0; i < 13; ++i) { w[i] = exp(-0.5 * (double)((i - 6) * (i - 6)) / (1.5 * 1.5)); s += w[i]; }
     for (int i = 0; i < 13; ++i) w[i] /= s;
     if (cudaMemcpyToSymbol(c_ps_w, w, sizeof(w)) != cudaSuccess) { set_error("fdg_psnr_ssim_u8: cannot upload the window"); return FDG_ECUDA; }
-    window_done = true;
+    window_done[wdev] = 1;
   }
   if (cudaMemsetAsync(sums4, 0, 4 * sizeof(double), (cudaStream_t)stream) != cudaSuccess) { set_error("fdg_psnr_ssim_u8: memset failed"); return FDG_ECUDA; }
   dim3 grid((unsigned)cdiv(W - 2, PS_T), (unsigned)cdiv(H - 2, PS_T), 3);

@@ -152,13 +152,14 @@ extern "C" int fdg_ssim_loss_grad(const FdgTensor* x, const FdgTensor* y, int N,
                                   const FdgTensor* grad, int accumulate, double* loss, float* scratch, fdg_stream_t stream) {
   FDG_REQUIRE(x && y && x->p && y->p && loss && scratch && N > 0 && H > 0 && W > 0 && C > 0, "fdg_ssim_loss_grad: bad arguments");
   FDG_REQUIRE((int64_t)N * C <= 65535, "fdg_ssim_loss_grad: too many image planes");
-  static bool window_done = false;
-  if (!window_done) {   // gaussian(11, 1.5) in fp32 like the reference (models/pytorch_ssim/__init__.py:7-9)
+  static int window_done[64] = {0};         // __constant__ memory is per device
+  const int wdev = current_device();
+  if (!window_done[wdev]) {   // gaussian(11, 1.5) in fp32 like the reference (models/pytorch_ssim/__init__.py:7-9)
     float w[11], s = 0.f;
     for (int i = 0; i < 11; ++i) { w[i] = expf(-(float)((i - 5) * (i - 5)) / (2.f * 1.5f * 1.5f)); s += w[i]; }
     for (int i = 0; i < 11; ++i) w[i] /= s;
     if (cudaMemcpyToSymbol(c_ssim_w, w, sizeof(w)) != cudaSuccess) { set_error("fdg_ssim_loss_grad: cannot upload the window"); return FDG_ECUDA; }
-    window_done = true;
+    window_done[wdev] = 1;
   }
   SsimArgs a;
   a.x = *x; a.y = *y;

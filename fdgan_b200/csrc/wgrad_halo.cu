@@ -246,12 +246,7 @@ int wgrad_halo(const FdgWgrad* p, cudaStream_t st) {
   a.HC = WH_T + p->S - 1;
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   a.dbg = dbg_flags();
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = device_sm_count();
   const int groups = a.cblocks * a.co_tiles;
   int splits = groups >= num_sms ? 1 : num_sms / groups;
   if (splits > a.total_ptiles) splits = a.total_ptiles;
@@ -259,13 +254,14 @@ int wgrad_halo(const FdgWgrad* p, cudaStream_t st) {
   a.ptiles_per_split = cdiv(a.total_ptiles, splits);
   a.splits = cdiv(a.total_ptiles, a.ptiles_per_split);
   constexpr int smem = 2 * WH_STAGE + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_done[64] = {0};           // per device
+  const int adev = current_device();
+  if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d_wgrad[tcgen05 halo]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
-    attr_done = true;
+    attr_done[adev] = 1;
   }
   const double M = (double)p->N * p->OH * p->OW;
   ProfScope prof(PF_WGRAD, 2.0 * M * p->R * p->S * p->Cin * p->Cout, 4.0 * (M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);

@@ -369,20 +369,16 @@ int wgrad_umma_supported(const FdgWgrad* p) {
 template <int NT, int STAGES>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * ((NT + 63) / 64) * WU_BLK) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_done[64] = {0};           // per device
+  const int adev = current_device();
+  if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d_wgrad[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
-    attr_done = true;
+    attr_done[adev] = 1;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = device_sm_count();
   a.co_tiles = cdiv(a.c.Cout, NT);
   a.tiles = a.kblocks * a.co_tiles;
   // split the pixels so that about one wave of CTAs covers the chip; every split is a whole number of chunks
