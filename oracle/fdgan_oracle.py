@@ -340,11 +340,11 @@ def blur(x, l=15, sigma=3.0, use_input_norm=True):
     one l x l Gaussian applied to every (batch, channel) plane."""
     b, c, h, w = x.shape
     if use_input_norm:
-        mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype).view(1, 3, 1, 1)
-        std = torch.tensor(IMAGENET_STD, dtype=x.dtype).view(1, 3, 1, 1)
+        mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+        std = torch.tensor(IMAGENET_STD, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
         x = (x - mean) / std
     pad = F.pad(x, (l // 2,) * 4, mode="reflect")
-    k = isotropic_gaussian_kernel(l, sigma, x.dtype).view(1, 1, l, l)
+    k = isotropic_gaussian_kernel(l, sigma, x.dtype).view(1, 1, l, l).to(x.device)
     hp, wp = pad.shape[-2:]
     return F.conv2d(pad.reshape(c * b, 1, hp, wp), k).view(b, c, h, w)
 
@@ -354,7 +354,7 @@ def laplacian(x, kernel_size=3):
     if x.dim() != 4:
         raise ValueError("Invalid input shape, we expect BxCxHxW. Got: {}".format(tuple(x.shape)))
     c = x.shape[1]
-    k = torch.ones(kernel_size, kernel_size, dtype=x.dtype)
+    k = torch.ones(kernel_size, kernel_size, dtype=x.dtype, device=x.device)
     k[kernel_size // 2, kernel_size // 2] = 1 - kernel_size ** 2
     return F.conv2d(x, k.view(1, 1, kernel_size, kernel_size).repeat(c, 1, 1, 1), padding=(kernel_size - 1) // 2, groups=c)
 
@@ -378,7 +378,7 @@ def ssim_window(window_size=11, sigma=1.5, dtype=torch.float32):
 def ssim(img1, img2, window_size=11):
     """pytorch_ssim._ssim (models/pytorch_ssim/__init__.py:17-37), size_average=True."""
     c = img1.shape[1]
-    w = ssim_window(window_size, 1.5, img1.dtype).expand(c, 1, window_size, window_size).contiguous()
+    w = ssim_window(window_size, 1.5, img1.dtype).to(img1.device).expand(c, 1, window_size, window_size).contiguous()
     p = window_size // 2
     mu1 = F.conv2d(img1, w, padding=p, groups=c)
     mu2 = F.conv2d(img2, w, padding=p, groups=c)
