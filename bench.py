@@ -314,7 +314,7 @@ def run_ours(args):
                        "parallelism": "dp%d (batch shard, one NCCL all-reduce per network per step)" % world,
                        "l2": "inputs larger than L2: each step streams several GB of activations (>> 126 MB L2); no explicit flush"},
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 3 * size * size * 4, "d2h_bytes_per_step": 32,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 3 * size * size * 4, "d2h_bytes_per_step": 40,      # GANTrainer.loss_buf: five fp64 loss terms
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof,

@@ -325,6 +325,40 @@ __global__ void copy4d_kernel(FdgTensor x, FdgTensor y, int64_t total, int H, in
   }
 }
 
+// same arithmetic, four channels per thread: both views have unit channel stride, 16-byte aligned rows and C % 4 == 0
+// (channel slices of the NHWC concat buffers: every copy of the generator's forward / backward walk)
+__global__ void __launch_bounds__(256) copy4d_vec4_kernel(FdgTensor x, FdgTensor y, int64_t total4, int H, int W, int C4, int gather,
+                                                          float slope, float scale, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    int64_t r = i / C4;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    float4 v;
+    if (gather == FDG_GATHER_AVGPOOL2) {
+      const float* b = x.p + n * x.sn + (int64_t)(2 * h) * x.sh + (int64_t)(2 * w) * x.sw + c;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(b)), v1 = __ldg(reinterpret_cast<const float4*>(b + x.sw));
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(b + x.sh)), v3 = __ldg(reinterpret_cast<const float4*>(b + x.sh + x.sw));
+      v.x = 0.25f * ((prologue_act(v0.x, slope) + prologue_act(v1.x, slope)) + (prologue_act(v2.x, slope) + prologue_act(v3.x, slope)));
+      v.y = 0.25f * ((prologue_act(v0.y, slope) + prologue_act(v1.y, slope)) + (prologue_act(v2.y, slope) + prologue_act(v3.y, slope)));
+      v.z = 0.25f * ((prologue_act(v0.z, slope) + prologue_act(v1.z, slope)) + (prologue_act(v2.z, slope) + prologue_act(v3.z, slope)));
+      v.w = 0.25f * ((prologue_act(v0.w, slope) + prologue_act(v1.w, slope)) + (prologue_act(v2.w, slope) + prologue_act(v3.w, slope)));
+    } else {
+      const int hh = gather == FDG_GATHER_UP2 ? h >> 1 : h, ww = gather == FDG_GATHER_UP2 ? w >> 1 : w;
+      v = __ldg(reinterpret_cast<const float4*>(x.p + n * x.sn + (int64_t)hh * x.sh + (int64_t)ww * x.sw + c));
+      v.x = prologue_act(v.x, slope); v.y = prologue_act(v.y, slope); v.z = prologue_act(v.z, slope); v.w = prologue_act(v.w, slope);
+    }
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    float4* o = reinterpret_cast<float4*>(y.p + n * y.sn + (int64_t)h * y.sh + (int64_t)w * y.sw + c);
+    if (accumulate) {
+      const float4 q = *o;
+      v.x = q.x + v.x; v.y = q.y + v.y; v.z = q.z + v.z; v.w = q.w + v.w;
+    }
+    *o = v;
+  }
+}
+
 __global__ void act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ out, int64_t n,
                                int act) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -558,6 +592,11 @@ int fdg_copy4d(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int 
   FDG_REQUIRE(x && y && x->p && y->p && N > 0 && H > 0 && W > 0 && C > 0, "fdg_copy4d: bad arguments");
   FDG_REQUIRE(gather >= 0 && gather <= 2, "fdg_copy4d: bad gather mode");
   const int64_t total = (int64_t)N * H * W * C;
+  if (C % 4 == 0 && fdg::vec4_ok(*x) && fdg::vec4_ok(*y)) {
+    copy4d_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y, total / 4, H, W, C / 4, gather, slope, scale,
+                                                                                   accumulate);
+    return check_launch("fdg_copy4d");
+  }
   copy4d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y, total, H, W, C, gather, slope, scale, accumulate);
   return check_launch("fdg_copy4d");
 }

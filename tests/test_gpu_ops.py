@@ -121,6 +121,26 @@ def test_conv2d(case, variant):
         assert maxabs(st[:Cout], ysum) <= tol and maxabs(st[Cout + 3:2 * Cout + 3], ysq) <= tol
 
 
+@pytest.mark.parametrize("Cout,R,pad,mask", [(288, 4, 2, True), (288, 4, 2, False), (8, 4, 1, True), (288, 3, 1, True)])
+def test_conv2d_single_input_channel(Cout, R, pad, mask):
+    """Cin == 1 direct kernels (data gradient of Fusion-D layer 5: 1 -> 288 channels, 4x4, LeakyReLU mask of the layer
+    input): the register-weight 4x4 kernel and the generic one (3x3), automatic dispatch, fp32 arithmetic."""
+    ops = _ops()
+    N, H, W = 2, 9, 10
+    x = seeded((N, 1, H, W), 1, -1.0, 1.0)
+    w = seeded((Cout, 1, R, R), 2, -1.0, 1.0) / R
+    y = F.conv2d(x.double(), w.double(), padding=pad)
+    OH, OW = y.shape[-2:]
+    e = seeded((N, Cout, OH, OW), 6, -1.0, 1.0) if mask else None
+    if mask:
+        y = y * torch.where(e.double() > 0, 1.0, 0.2)
+    wp, ld = ops.pack_weight(w.cuda(), 0)
+    yd = cl(torch.full((N, Cout, OH, OW), 7.0))
+    ops.conv2d(ops.View.from_nchw(cl(x)), wp, ld, R, R, 1, pad, Cout, ops.View.from_nchw(yd), alpha=0.5,
+               e=ops.View.from_nchw(cl(e)) if mask else None, eslope=0.2)
+    assert maxabs(yd, 0.5 * y) <= 2e-6
+
+
 def test_conv2d_nchw_output_and_errors():
     ops = _ops()
     x = seeded((1, 16, 9, 9), 1, -1, 1)
@@ -369,6 +389,19 @@ def test_maxpool_copy_colsum_actbwd():
     o2 = cl(torch.ones(2, 8, 12, 12))
     ops.copy4d(ops.View.from_nchw(cl(a)), ops.View.from_nchw(o2), gather=ops.GATHER_UP2, scale=0.25, slope=0.0, accumulate=True)
     assert maxabs(o2, 1 + 0.25 * F.interpolate(torch.relu(a), scale_factor=2, mode="nearest")) <= 1e-6
+    # direct copy between channel slices of NHWC buffers (four channels per thread) and between NCHW views (scalar path)
+    src = seeded((2, 16, 5, 7), 6, -1, 1)
+    dst = cl(torch.zeros(2, 24, 5, 7))
+    ops.copy4d(ops.View.from_nchw(cl(src)).ch(4, 12), ops.View.from_nchw(dst).ch(8, 16), slope=0.0)
+    exp = torch.zeros(2, 24, 5, 7)
+    exp[:, 8:16] = torch.relu(src[:, 4:12])
+    assert maxabs(dst, exp) == 0.0
+    ops.copy4d(ops.View.from_nchw(cl(src)).ch(2, 8), ops.View.from_nchw(dst).ch(16, 22), scale=0.5, accumulate=True)   # slices off 16 bytes
+    exp[:, 16:22] += 0.5 * src[:, 2:8]
+    assert maxabs(dst, exp) == 0.0
+    d2 = torch.ones(2, 3, 5, 7, device="cuda")
+    ops.copy4d(ops.View.from_nchw(src[:, :3].contiguous().cuda()), ops.View.from_nchw(d2), accumulate=True)
+    assert maxabs(d2, 1 + src[:, :3]) == 0.0
     cs = torch.zeros(8, device="cuda")
     ops.colsum(ops.View.from_nchw(cl(a)), cs)
     assert maxabs(cs, a.sum((0, 2, 3))) <= 1e-4
