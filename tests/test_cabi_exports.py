@@ -30,6 +30,33 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.lib.fdg_version() >= 100
 
 
+def test_ctypes_structs_match_the_header_layout(lib, tmp_path):
+    """The header compiles as plain C (no CUDA / torch types) and every descriptor struct has the size and field offsets
+    the ctypes binding assumes -- the check a maintainer of another host binding (cgo, JNI ...) would run."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    names = ["FdgTensor", "FdgConv", "FdgWgrad", "FdgBnFinalize", "FdgEwBwd", "FdgBnBwdFinalize", "FdgDgradStrided"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fdgan_b200.h"', "int main(void) {"]
+    for n in names:
+        cls = getattr(lib, n)
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (n, n))
+        for f in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (n, f[0], n, f[0]))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.rsplit(" ", 1) for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for n in names:
+        cls = getattr(lib, n)
+        assert int(got["%s size" % n]) == ctypes.sizeof(cls), n
+        for f in cls._fields_:
+            assert int(got["%s.%s" % (n, f[0])]) == getattr(cls, f[0]).offset, (n, f[0])
+
+
 def test_descriptor_validation_needs_no_gpu(lib):
     d = lib.FdgConv()
     rc = lib.lib.fdg_conv2d(ctypes.byref(d), None)
