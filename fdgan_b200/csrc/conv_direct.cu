@@ -211,65 +211,70 @@ __global__ void __launch_bounds__(256) conv_cin1_kernel(const __grid_constant__ 
   }
 }
 
-// Same arithmetic (taps accumulated in the same order) with the R*S weights of the thread's four channels held in
-// registers: a thread keeps its channel group and walks over pixels, PPB pixels per block and round.  Per pixel and
-// thread: R*S warp-broadcast loads of the single input channel, 4*R*S FMAs, one 128-bit mask load (issued one round
-// ahead) and one 128-bit store -- no weight traffic in the loop (the kernel above re-reads 16 B of weights per 4 FMAs).
-constexpr int C1_MAXT = 320;
+// Same arithmetic (taps accumulated in the same order), four horizontally adjacent pixels x four channels per thread
+// (stride 1): a weight vector is loaded once per tap and used for four pixels, the (S + 3) input values of a filter row
+// are shared by the four pixels, and four 128-bit mask loads are in flight per thread.  L1 wavefronts per output
+// vector drop from ~22 to ~8.  (Tried and measured slower, 0.70 vs 0.55 ms: all R*S weights in registers with one pixel
+// per thread -- 122 registers leave 16 warps per SM and one mask load in flight per thread.)
 template <int R, int S>
-__global__ void __launch_bounds__(C1_MAXT) conv_cin1_regw_kernel(const __grid_constant__ Cin1Args a, int ppb) {
+__global__ void __launch_bounds__(256) conv_cin1_px4_kernel(const __grid_constant__ Cin1Args a, int owg, int64_t total) {
   const FdgConv& p = a.c;
-  const int slot = threadIdx.x / a.c4n;
-  const int c = (threadIdx.x - slot * a.c4n) * 4;
-  if (slot >= ppb) return;
-  float4 wv[R * S];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c, og, oy, n;
+    if (total <= 0x7fffffffLL) {      // 32-bit index arithmetic (a 64-bit division costs ~100 instructions)
+      const int i32 = (int)i, r0 = i32 / a.c4n, r1 = r0 / owg;
+      c = (i32 - r0 * a.c4n) * 4; og = r0 - r1 * owg; n = r1 / p.OH; oy = r1 - n * p.OH;
+    } else {
+      int64_t r_ = i / a.c4n;
+      c = (int)(i - r_ * a.c4n) * 4;
+      og = (int)(r_ % owg); r_ /= owg;
+      oy = (int)(r_ % p.OH);
+      n = (int)(r_ / p.OH);
+    }
+    const int ox0 = og * 4;
+    const int npx = p.OW - ox0 < 4 ? p.OW - ox0 : 4;
+    float4 ev[4];
+    const float* ep = p.e.p ? p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox0 * p.e.sw + c : nullptr;
 #pragma unroll
-  for (int k = 0; k < R * S; ++k) wv[k] = ld4(p.w + (int64_t)k * p.w_ld + c);
-  const int OHW = p.OH * p.OW;
-  const int64_t M = (int64_t)p.N * OHW;
-  const int64_t step = (int64_t)gridDim.x * ppb;
-  const bool has_e = p.e.p != nullptr;
-  auto e_at = [&](int64_t m) -> float4 {
-    const int n = (int)(m / OHW);
-    const int rem = (int)(m - (int64_t)n * OHW);
-    const int oy = rem / p.OW, ox = rem - oy * p.OW;
-    return ld4(p.e.p + n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + c);
-  };
-  int64_t m = (int64_t)blockIdx.x * ppb + slot;
-  float4 ev = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (has_e && m < M) ev = e_at(m);
-  for (; m < M; m += step) {
-    float4 ev_next = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (has_e && m + step < M) ev_next = e_at(m + step);
-    const int n = (int)(m / OHW);
-    const int rem = (int)(m - (int64_t)n * OHW);
-    const int oy = rem / p.OW, ox = rem - oy * p.OW;
-    const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+    for (int k = 0; k < 4; ++k) ev[k] = (ep && k < npx) ? ld4(ep + (int64_t)k * p.e.sw) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const int iy0 = oy - p.pad, ix0 = ox0 - p.pad;
     const float* xb = p.x.p + n * p.x.sn;
-    float xs[R * S];
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int iy = iy0 + r;
+      const bool rin = iy >= 0 && iy < p.H;
+      float xs[S + 3];
+#pragma unroll
+      for (int q = 0; q < S + 3; ++q) {
+        const int ix = ix0 + q;
+        xs[q] = (rin && ix >= 0 && ix < p.W) ? prologue_act(__ldg(xb + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw), p.slope) : 0.f;
+      }
 #pragma unroll
       for (int q = 0; q < S; ++q) {
-        const int ix = ix0 + q;
-        const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        xs[r * S + q] = in ? prologue_act(__ldg(xb + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw), p.slope) : 0.f;
+        const float4 wv = ld4(p.w + (int64_t)(r * S + q) * p.w_ld + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[k].x = fmaf(xs[q + k], wv.x, acc[k].x); acc[k].y = fmaf(xs[q + k], wv.y, acc[k].y);
+          acc[k].z = fmaf(xs[q + k], wv.z, acc[k].z); acc[k].w = fmaf(xs[q + k], wv.w, acc[k].w);
+        }
       }
     }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* yp = p.y.p + n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox0 * p.y.sw + c;
 #pragma unroll
-    for (int k = 0; k < R * S; ++k) {
-      acc.x = fmaf(xs[k], wv[k].x, acc.x); acc.y = fmaf(xs[k], wv[k].y, acc.y);
-      acc.z = fmaf(xs[k], wv[k].z, acc.z); acc.w = fmaf(xs[k], wv[k].w, acc.w);
+    for (int k = 0; k < 4; ++k) {
+      if (k < npx) {
+        float4 o = acc[k];
+        o.x *= p.alpha; o.y *= p.alpha; o.z *= p.alpha; o.w *= p.alpha;
+        if (ep) {
+          o.x *= ev[k].x > 0.f ? 1.f : p.eslope; o.y *= ev[k].y > 0.f ? 1.f : p.eslope;
+          o.z *= ev[k].z > 0.f ? 1.f : p.eslope; o.w *= ev[k].w > 0.f ? 1.f : p.eslope;
+        }
+        *reinterpret_cast<float4*>(yp + (int64_t)k * p.y.sw) = o;
+      }
     }
-    acc.x *= p.alpha; acc.y *= p.alpha; acc.z *= p.alpha; acc.w *= p.alpha;
-    if (has_e) {
-      acc.x *= ev.x > 0.f ? 1.f : p.eslope; acc.y *= ev.y > 0.f ? 1.f : p.eslope;
-      acc.z *= ev.z > 0.f ? 1.f : p.eslope; acc.w *= ev.w > 0.f ? 1.f : p.eslope;
-    }
-    *reinterpret_cast<float4*>(p.y.p + n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox * p.y.sw + c) = acc;
-    ev = ev_next;
   }
 }
 
@@ -292,15 +297,14 @@ int conv2d_cin1(const FdgConv* p, cudaStream_t st) {
   int64_t blocks = cdiv64(a.total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope prof(PF_CONV_SIMT, 2.0 * (double)a.total * 4 * p->R * p->S, 4.0 * (double)a.total * 4 * (p->e.p ? 2 : 1), st);
-  static const int regw = [] { const char* e = getenv("FDG_CIN1_REGW"); return e ? atoi(e) : 1; }();
-  if (regw && p->R == 4 && p->S == 4 && a.c4n <= C1_MAXT) {   // Fusion-D layer 5 data gradient: weights in registers
-    // ~122 registers per thread: about 16 resident warps per SM whatever the block shape; small blocks pack them best
-    const int ppb = a.c4n >= 160 ? 1 : 160 / a.c4n;
-    const int64_t pixels = (int64_t)p->N * p->OH * p->OW;
-    int64_t nb = cdiv64(pixels, ppb);
-    const int64_t cap = (int64_t)device_sm_count() * 6;
+  static const int px4 = [] { const char* e = getenv("FDG_CIN1_PX4"); return e ? atoi(e) : 1; }();
+  if (px4 && p->R == 4 && p->S == 4 && p->stride == 1) {   // Fusion-D layer 5 data gradient
+    const int owg = cdiv(p->OW, 4);
+    const int64_t total = (int64_t)p->N * p->OH * owg * a.c4n;
+    int64_t nb = cdiv64(total, 256);
+    const int64_t cap = (int64_t)device_sm_count() * 16;
     if (nb > cap) nb = cap;
-    conv_cin1_regw_kernel<4, 4><<<(unsigned)nb, a.c4n * ppb, 0, st>>>(a, ppb);
+    conv_cin1_px4_kernel<4, 4><<<(unsigned)nb, 256, 0, st>>>(a, owg, total);
     return check_launch("fdg_conv2d[cin1]");
   }
   conv_cin1_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);

@@ -85,40 +85,59 @@ __global__ void __launch_bounds__(256) ew_bwd_kernel(FdgEwBwd p, int64_t M, int 
   for (int u = 0; u < VW; ++u) { s1[u] = 0.f; s2[u] = 0.f; }
 
   if (cv) {
-    for (int64_t m = (int64_t)blockIdx.x * pix_lanes + pl; m < M; m += (int64_t)gridDim.x * pix_lanes) {
-      const int n = (int)(m / HW);
-      const int rem = (int)(m - (int64_t)n * HW);
-      const int h = rem / p.W, w = rem - h * p.W;
-      const int gh = p.g_gather == FDG_GATHER_UP2 ? h >> 1 : h, gw = p.g_gather == FDG_GATHER_UP2 ? w >> 1 : w;
-      const float* gp = p.g.p + n * p.g.sn + (int64_t)gh * p.g.sh + (int64_t)gw * p.g.sw + (int64_t)c * p.g.sc;
-      const float* xp = p.x.p + n * p.x.sn + (int64_t)h * p.x.sh + (int64_t)w * p.x.sw + (int64_t)c * p.x.sc;
-      float gv[VW], xv[VW];
-      if (VW == 4) {
-        const float4 a = *reinterpret_cast<const float4*>(gp);  // plain load: out may alias g (in-place)
-        const float4 b = __ldg(reinterpret_cast<const float4*>(xp));
-        gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w;
-        xv[0] = b.x; xv[1] = b.y; xv[2] = b.z; xv[3] = b.w;
-      } else {
-        gv[0] = *gp;
-        xv[0] = __ldg(xp);
-      }
-      float o[VW];
+    // four pixels per thread in flight per iteration (loads first, then arithmetic in the same pixel order as a plain loop)
+    constexpr int UNR = 4;
+    const bool small = M <= 0x7fffffffLL;
+    const int64_t step = (int64_t)gridDim.x * pix_lanes;
+    for (int64_t m0 = (int64_t)blockIdx.x * pix_lanes + pl; m0 < M; m0 += UNR * step) {
+      float gv[UNR][VW], xv[UNR][VW];
+      int64_t oo[UNR];
 #pragma unroll
-      for (int u = 0; u < VW; ++u) {
-        const float v = fmaf(xv[u], sc[u], sh[u]);
-        const float dz = p.gscale * gv[u] * (v > 0.f ? 1.f : p.slope);
-        s1[u] += dz;
-        s2[u] += dz * xv[u];
-        o[u] = fmaf(ca[u], dz, fmaf(cb[u], xv[u], cd[u]));
+      for (int k = 0; k < UNR; ++k) {
+        const int64_t m = m0 + k * step;
+        if (m < M) {
+          // 64-bit division costs ~100 instructions; M < 2^31 for every tensor of the path
+          const int n = small ? (int)m / HW : (int)(m / HW);
+          const int rem = small ? (int)m - n * HW : (int)(m - (int64_t)n * HW);
+          const int h = rem / p.W, w = rem - h * p.W;
+          const int gh = p.g_gather == FDG_GATHER_UP2 ? h >> 1 : h, gw = p.g_gather == FDG_GATHER_UP2 ? w >> 1 : w;
+          const float* gp = p.g.p + n * p.g.sn + (int64_t)gh * p.g.sh + (int64_t)gw * p.g.sw + (int64_t)c * p.g.sc;
+          const float* xp = p.x.p + n * p.x.sn + (int64_t)h * p.x.sh + (int64_t)w * p.x.sw + (int64_t)c * p.x.sc;
+          oo[k] = n * p.out.sn + (int64_t)h * p.out.sh + (int64_t)w * p.out.sw + (int64_t)c * p.out.sc;
+          if (VW == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(gp);  // plain load: out may alias g (in-place)
+            const float4 b = __ldg(reinterpret_cast<const float4*>(xp));
+            gv[k][0] = a.x; gv[k][1] = a.y; gv[k][2] = a.z; gv[k][3] = a.w;
+            xv[k][0] = b.x; xv[k][1] = b.y; xv[k][2] = b.z; xv[k][3] = b.w;
+          } else {
+            gv[k][0] = *gp;
+            xv[k][0] = __ldg(xp);
+          }
+        }
       }
-      if (!p.stats) {
-        float* op = p.out.p + n * p.out.sn + (int64_t)h * p.out.sh + (int64_t)w * p.out.sw + (int64_t)c * p.out.sc;
-        if (VW == 4) {
-          float4 r = make_float4(o[0], o[1], o[2], o[3]);
-          if (p.accumulate) { const float4 old = *reinterpret_cast<const float4*>(op); r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
-          *reinterpret_cast<float4*>(op) = r;
-        } else {
-          *op = p.accumulate ? *op + o[0] : o[0];
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) {
+        const int64_t m = m0 + k * step;
+        if (m < M) {
+          float o[VW];
+#pragma unroll
+          for (int u = 0; u < VW; ++u) {
+            const float v = fmaf(xv[k][u], sc[u], sh[u]);
+            const float dz = p.gscale * gv[k][u] * (v > 0.f ? 1.f : p.slope);
+            s1[u] += dz;
+            s2[u] += dz * xv[k][u];
+            o[u] = fmaf(ca[u], dz, fmaf(cb[u], xv[k][u], cd[u]));
+          }
+          if (!p.stats) {
+            float* op = p.out.p + oo[k];
+            if (VW == 4) {
+              float4 r = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.accumulate) { const float4 old = *reinterpret_cast<const float4*>(op); r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+              *reinterpret_cast<float4*>(op) = r;
+            } else {
+              *op = p.accumulate ? *op + o[0] : o[0];
+            }
+          }
         }
       }
     }
@@ -330,11 +349,17 @@ __global__ void copy4d_kernel(FdgTensor x, FdgTensor y, int64_t total, int H, in
 __global__ void __launch_bounds__(256) copy4d_vec4_kernel(FdgTensor x, FdgTensor y, int64_t total4, int H, int W, int C4, int gather,
                                                           float slope, float scale, int accumulate) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    int64_t r = i / C4;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H);
-    const int n = (int)(r / H);
+    int c, w, h, n;
+    if (total4 <= 0x7fffffffLL) {     // 32-bit index arithmetic (a 64-bit division costs ~100 instructions)
+      const int i32 = (int)i, r0 = i32 / C4, r1 = r0 / W;
+      c = (i32 - r0 * C4) * 4; w = r0 - r1 * W; n = r1 / H; h = r1 - n * H;
+    } else {
+      c = (int)(i % C4) * 4;
+      int64_t r = i / C4;
+      w = (int)(r % W); r /= W;
+      h = (int)(r % H);
+      n = (int)(r / H);
+    }
     float4 v;
     if (gather == FDG_GATHER_AVGPOOL2) {
       const float* b = x.p + n * x.sn + (int64_t)(2 * h) * x.sh + (int64_t)(2 * w) * x.sw + c;

@@ -177,6 +177,45 @@ __global__ void colsum_kernel(FdgTensor x, int64_t M, int HW, int W, int C, floa
   }
 }
 
+// 128-bit variant (unit channel stride, C % 4 == 0): thread = (4-channel group, pixel lane), four pixels in flight per
+// iteration, partial sums reduced across the pixel lanes of the CTA in shared memory, one float atomic per channel
+__global__ void __launch_bounds__(256) colsum_vec4_kernel(FdgTensor x, int64_t M, int HW, int W, int C, int cgroups, int pix_lanes,
+                                                          float* out) {
+  __shared__ float4 red[256];
+  const int cg = threadIdx.x % cgroups, pl = threadIdx.x / cgroups;
+  const int c = (blockIdx.y * cgroups + cg) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C && pl < pix_lanes) {
+    const bool small = M <= 0x7fffffffLL;
+    const int64_t step = (int64_t)gridDim.x * pix_lanes;
+    for (int64_t m0 = (int64_t)blockIdx.x * pix_lanes + pl; m0 < M; m0 += 4 * step) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t m = m0 + k * step;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M) {
+          const int n = small ? (int)m / HW : (int)(m / HW);
+          const int rem = small ? (int)m - n * HW : (int)(m - (int64_t)n * HW);
+          const int h = rem / W, w = rem - h * W;
+          v[k] = __ldg(reinterpret_cast<const float4*>(x.p + n * x.sn + (int64_t)h * x.sh + (int64_t)w * x.sw + c));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    for (int l = 1; l < pix_lanes; ++l) {
+      const float4 q = red[l * cgroups + cg];
+      s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    }
+    atomicAdd(out + c, s.x); atomicAdd(out + c + 1, s.y); atomicAdd(out + c + 2, s.z); atomicAdd(out + c + 3, s.w);
+  }
+}
+
 }  // namespace fdg
 
 namespace fdg {
@@ -197,6 +236,17 @@ extern "C" int fdg_colsum(const FdgTensor* x, int N, int H, int W, int C, float*
     if (cudaMemsetAsync(out, 0, sizeof(float) * C, st) != cudaSuccess) { set_error("fdg_colsum: memset failed"); return FDG_ECUDA; }
   }
   const int64_t M = (int64_t)N * H * W;
+  if (C % 4 == 0 && vec4_ok(*x)) {
+    const int groups_total = C / 4;
+    const int cgroups = groups_total < 64 ? groups_total : 64;
+    const int pix_lanes = 256 / cgroups;
+    const int gyc = cdiv(groups_total, cgroups);
+    int64_t gx = cdiv64(M, (int64_t)pix_lanes * 16);
+    const int64_t cap = (int64_t)device_sm_count() * 8 / gyc + 1;
+    if (gx > cap) gx = cap;
+    colsum_vec4_kernel<<<dim3((unsigned)gx, gyc), 256, 0, st>>>(*x, M, H * W, W, C, cgroups, pix_lanes, out);
+    return check_launch("fdg_colsum");
+  }
   int64_t gy = cdiv64(M, 8 * 64);
   if (gy > 1024) gy = 1024;
   dim3 grid(cdiv(C, 32), (unsigned)gy);

@@ -368,6 +368,29 @@ def test_ew_bwd_pooled_gradient_scalar_path():
     assert maxabs(out, want) <= 1e-6
 
 
+def test_ew_bwd_pooled_gradient_vector_path():
+    """Transition backward: gradient at half resolution (adjoint of the 2x2 average pool folded into the gather), BatchNorm
+    scale/shift + ReLU mask, statistics pass and apply pass with (alpha, beta, delta); 128-bit generic kernel."""
+    ops = _ops()
+    N, C, H, W = 3, 24, 10, 14
+    x = seeded((N, C, H, W), 1, -1, 1)
+    g = seeded((N, C, H // 2, W // 2), 2, -1, 1)
+    sc, sh = seeded((C,), 3, 0.5, 1.5), seeded((C,), 4, -0.3, 0.3)
+    coef = torch.cat([seeded((C,), 5, 0.5, 1.5), seeded((C,), 6, -0.2, 0.2), seeded((C,), 7, -0.1, 0.1)])
+    gv, xv = ops.View.from_nchw(cl(g)), ops.View.from_nchw(cl(x))
+    v = x.double() * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1)
+    dz = 0.25 * F.interpolate(g.double(), scale_factor=2, mode="nearest") * (v > 0)
+    st = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    ops.ew_bwd(gv, xv, stats=st, scale=sc.cuda(), shift=sh.cuda(), slope=0.0, g_gather=ops.GATHER_UP2, gscale=0.25)
+    assert maxabs(st[:C], dz.sum((0, 2, 3))) <= 1e-4 and maxabs(st[C:], (dz * x.double()).sum((0, 2, 3))) <= 1e-4
+    out0 = seeded((N, C, H, W), 8, -1, 1)
+    out = cl(out0.clone())
+    ops.ew_bwd(gv, xv, out=ops.View.from_nchw(out), scale=sc.cuda(), shift=sh.cuda(), slope=0.0, g_gather=ops.GATHER_UP2, gscale=0.25,
+               coef=coef.cuda(), accumulate=True)
+    a_, b_, d_ = (coef[i * C:(i + 1) * C].double().view(1, -1, 1, 1) for i in range(3))
+    assert maxabs(out, out0.double() + a_ * dz + b_ * x.double() + d_) <= 1e-5
+
+
 def test_maxpool_copy_colsum_actbwd():
     ops = _ops()
     x = seeded((2, 12, 9, 10), 1, -1, 1).requires_grad_(True)
@@ -405,6 +428,13 @@ def test_maxpool_copy_colsum_actbwd():
     cs = torch.zeros(8, device="cuda")
     ops.colsum(ops.View.from_nchw(cl(a)), cs)
     assert maxabs(cs, a.sum((0, 2, 3))) <= 1e-4
+    # 128-bit column sums: channel-group counts that do not divide the CTA, several channel tiles, accumulate, a channel slice;
+    # scalar kernel for C = 3
+    for C_, c0, c1 in ((144, 0, 144), (520, 0, 520), (64, 16, 48), (3, 0, 3)):
+        b_ = seeded((2, C_, 9, 11), 7, -1, 1)
+        cs = torch.ones(c1 - c0, device="cuda")
+        ops.colsum(ops.View.from_nchw(cl(b_)).ch(c0, c1), cs, accumulate=True)
+        assert maxabs(cs, 1 + b_[:, c0:c1].double().sum((0, 2, 3))) <= 2e-4
     yv, gv = torch.tanh(seeded((1000,), 4, -2, 2)), seeded((1000,), 5, -1, 1)
     od = torch.empty(1000, device="cuda")
     ops.act_bwd(gv.cuda(), yv.cuda(), od, ops.ACT_TANH)
