@@ -62,7 +62,7 @@ __global__ void bn_bwd_finalize_kernel(FdgBnBwdFinalize p) {
 // One warp-wide row of channels per pixel group: thread handles channel group cg (VW channels) for
 // pixels strided by the number of pixel lanes.  Stats mode keeps per-thread partial sums over its pixels
 // and reduces across the pixel lanes of the CTA in shared memory before the fp64 atomics.
-template <int VW>
+template <int VW, int UNR>
 __global__ void __launch_bounds__(256) ew_bwd_kernel(FdgEwBwd p, int64_t M, int cgroups, int pix_lanes) {
   extern __shared__ float sm[];  // stats: [2][pix_lanes][cgroups*VW] partials
   const int cg = threadIdx.x % cgroups;
@@ -85,8 +85,7 @@ __global__ void __launch_bounds__(256) ew_bwd_kernel(FdgEwBwd p, int64_t M, int 
   for (int u = 0; u < VW; ++u) { s1[u] = 0.f; s2[u] = 0.f; }
 
   if (cv) {
-    // four pixels per thread in flight per iteration (loads first, then arithmetic in the same pixel order as a plain loop)
-    constexpr int UNR = 4;
+    // UNR pixels per thread in flight per iteration (loads first, then arithmetic in the same pixel order as a plain loop)
     const bool small = M <= 0x7fffffffLL;
     const int64_t step = (int64_t)gridDim.x * pix_lanes;
     for (int64_t m0 = (int64_t)blockIdx.x * pix_lanes + pl; m0 < M; m0 += UNR * step) {
@@ -580,8 +579,11 @@ int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
   if (fast) {
     if (p->stats) ew_bwd_linear_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
     else ew_bwd_linear_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
-  } else if (vec) ew_bwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
-  else ew_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+  } else if (vec) {
+    static const int unr = [] { const char* e = getenv("FDG_EW_UNR"); return e ? atoi(e) : 4; }();
+    if (unr == 4) ew_bwd_kernel<4, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+    else ew_bwd_kernel<4, 1><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+  } else ew_bwd_kernel<1, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   return check_launch("fdg_ew_bwd");
 }
 
