@@ -4,6 +4,8 @@
 // partial sums with warp shuffles before touching global memory.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fdg {
@@ -580,7 +582,9 @@ int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
     if (p->stats) ew_bwd_linear_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
     else ew_bwd_linear_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   } else if (vec) {
-    static const int unr = [] { const char* e = getenv("FDG_EW_UNR"); return e ? atoi(e) : 4; }();
+    // measured on the three transition backward passes (gradient gathered at half resolution): four pixels in flight cost
+    // 104 registers and occupancy, 3.16 ms / step against 2.79 ms for the plain loop (profiles/r01h_launches_final.md)
+    static const int unr = [] { const char* e = getenv("FDG_EW_UNR"); return e ? atoi(e) : 1; }();
     if (unr == 4) ew_bwd_kernel<4, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
     else ew_bwd_kernel<4, 1><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
   } else ew_bwd_kernel<1, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
