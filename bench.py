@@ -128,6 +128,16 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(B, world, size):
+    """`config` of the JSON line: BASELINE.json configs[2]; shared by both arms so that the driver compares like with like."""
+    return {"workload": "G+D+VGG16 perceptual train step (SURVEY 3.3 reconstruction): FDGAN fwd+bwd, D(9,36) x3 fwd / x2 wgrad / x1 dgrad, "
+                        "freq decomposition fwd+bwd, Vgg16 fwd x2 + dgrad, Adam x2",
+            "per_gpu_batch": B, "global_batch": B * world, "image": "%dx%d" % (size, size),
+            "loss": "L1 + 0.5*MSE(vgg relu2_2, relu4_3) + 0.01*BCE adversarial; D: BCE real/fake",
+            "parallelism": "dp%d (batch shard, one NCCL all-reduce per network per step)" % world,
+            "l2": "inputs larger than L2: each step streams several GB of activations (>> 126 MB L2); no explicit flush"}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port of the reference arithmetic)
 # ------------------------------------------------------------------------------------------------------------------
@@ -154,14 +164,13 @@ def run_reference(args):
     if rank != 0:
         return 0
     sample = 2
-    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)      # exactly K timed steps of the bounded sample (~2 s each on 16 cores)
     ips, s_per_step, cores = cpu_step_images_per_s(sample, args.size, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "G+D+VGG16 perceptual train step, 256x256 (reference arithmetic on host CPU, torch eager fp32)",
-                   "per_gpu_batch": args.batch, "image": "%dx%d" % (args.size, args.size)},
+        "config": workload_config(args.batch, args.gpus, args.size),      # the fdgan_b200 arm's config, key for key
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d-image batches, %d timed steps of the full step (oracle/fdgan_oracle.py:train_step)" % (sample, steps)},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -307,12 +316,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "G+D+VGG16 perceptual train step (SURVEY 3.3 reconstruction): FDGAN fwd+bwd, D(9,36) x3 fwd / x2 wgrad / x1 dgrad, "
-                                   "freq decomposition fwd+bwd, Vgg16 fwd x2 + dgrad, Adam x2",
-                       "per_gpu_batch": B, "global_batch": B * world, "image": "%dx%d" % (size, size),
-                       "loss": "L1 + 0.5*MSE(vgg relu2_2, relu4_3) + 0.01*BCE adversarial; D: BCE real/fake",
-                       "parallelism": "dp%d (batch shard, one NCCL all-reduce per network per step)" % world,
-                       "l2": "inputs larger than L2: each step streams several GB of activations (>> 126 MB L2); no explicit flush"},
+            "config": workload_config(B, world, size),
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 3 * size * size * 4, "d2h_bytes_per_step": 40,      # GANTrainer.loss_buf: five fp64 loss terms
                     "ms_per_step": ms_e2e / args.steps},

@@ -1,0 +1,46 @@
+"""CPU checks of bench.py's contract: the reference arm (the oracle port on the host cores) prints one JSON line with the
+agreed keys on the fdgan_b200 arm's metric / unit / config, only rank 0 works under torchrun, and the fdgan_b200 arm
+refuses to run without a GPU instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env_extra=None):
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, env=env, cwd=ROOT,
+                          timeout=600)
+
+
+def test_reference_arm_line():
+    r = _run(["--impl", "reference", "--size", "64", "--steps", "2", "--warmup", "1", "--gpus", "2"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 2
+    assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["metric"] == bench.METRIC
+    assert d["config"] == bench.workload_config(16, 2, 64)      # the fdgan_b200 arm's config, key for key
+
+
+def test_reference_arm_other_ranks_do_no_work():
+    r = _run(["--impl", "reference", "--gpus", "2"], {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_product_arm_needs_a_gpu():
+    if torch.cuda.is_available():
+        return
+    r = _run(["--steps", "1", "--warmup", "1"])
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
