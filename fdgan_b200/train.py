@@ -37,11 +37,13 @@ class FlatState:
         self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad_views = {}
+        self.slices = {}                    # name -> (offset, numel, shape) in the flat buffers
         for (n, p), o in zip(named, offs):
             v = self.flat[o:o + p.numel()].view(p.shape)
             v.copy_(p.data)
             p.data = v
             self.grad_views[n] = self.grad[o:o + p.numel()].view(p.shape)
+            self.slices[n] = (o, p.numel(), tuple(p.shape))
         self.step = 0
         self.dev_state = None
         self.module = module
@@ -55,6 +57,29 @@ class FlatState:
             ops.adam_flat_dev(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, self.dev_state, grad_scale)
         else:
             ops.adam_flat(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, self.step, grad_scale)
+
+    def state_dict(self):
+        """Adam state by parameter name (the layout of the flat buffers is an implementation detail): the moments and the
+        step count, as torch.optim.Adam keeps them per parameter."""
+        def by_name(buf):
+            return {n: buf[o:o + k].view(shape).clone() for n, (o, k, shape) in self.slices.items()}
+        return {"step": int(self.step), "exp_avg": by_name(self.exp_avg), "exp_avg_sq": by_name(self.exp_avg_sq)}
+
+    def load_state_dict(self, sd):
+        for key in ("exp_avg", "exp_avg_sq"):
+            if set(sd[key]) != set(self.slices):
+                missing, extra = set(self.slices) - set(sd[key]), set(sd[key]) - set(self.slices)
+                raise KeyError("optimizer state %s: missing %s, unexpected %s" % (key, sorted(missing)[:3], sorted(extra)[:3]))
+        with torch.no_grad():
+            for key, buf in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+                for n, (o, k, shape) in self.slices.items():
+                    t = sd[key][n]
+                    if tuple(t.shape) != shape:
+                        raise ValueError("optimizer state %s[%s]: shape %s, expected %s" % (key, n, tuple(t.shape), shape))
+                    buf[o:o + k].view(shape).copy_(t)      # in place: a captured CUDA graph keeps pointing at these buffers
+            self.step = int(sd["step"])
+            if self.dev_state is not None:
+                self.dev_state[0] = float(self.step)
 
     def use_device_step(self):
         """Move the step counter / bias corrections to the device (idempotent); continues from the current step."""
@@ -119,6 +144,33 @@ class GANTrainer:
         if sync_losses:
             self._read_losses()
         return self._static_fake
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything a resumed run needs: both networks (reference-keyed state dicts, loadable by the reference's modules and
+        by demo.py:78-86), both Adam states by parameter name, and the hyper-parameters for a consistency check."""
+        return {"version": 1, "netG": {k: v.detach().clone() for k, v in self.G.state_dict().items()},
+                "netD": {k: v.detach().clone() for k, v in self.D.state_dict().items()},
+                "optG": self.sG.state_dict(), "optD": self.sD.state_dict(),
+                "hyper": {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weights": dict(self.w),
+                          "perc_layers": tuple(self.perc_layers)}}
+
+    def load_state_dict(self, sd, strict_hyper: bool = False):
+        """In place: parameters stay views of the flat buffers (module.load_state_dict copies), so flat gradients, the fused
+        Adam and a captured CUDA graph remain valid."""
+        if sd.get("version") != 1:
+            raise ValueError("unknown trainer checkpoint version %r" % (sd.get("version"),))
+        if strict_hyper:
+            mine = self.state_dict_hyper()
+            if sd["hyper"] != mine:
+                raise ValueError("hyper-parameters differ: checkpoint %s, trainer %s" % (sd["hyper"], mine))
+        self.G.load_state_dict(sd["netG"])
+        self.D.load_state_dict(sd["netD"])
+        self.sG.load_state_dict(sd["optG"])
+        self.sD.load_state_dict(sd["optD"])
+
+    def state_dict_hyper(self):
+        return {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weights": dict(self.w), "perc_layers": tuple(self.perc_layers)}
 
     def _read_losses(self):
         v = self.loss_buf.tolist()    # the step's device->host read; slots 1..3 hold the WEIGHTED generator terms
