@@ -184,6 +184,17 @@ def _frozen_lookup(w: torch.Tensor, mode: int):
     return key, None
 
 
+def drop_frozen_in_range(lo: int, hi: int) -> int:
+    """Forget cached operand images of parameters stored in [lo, hi) (device addresses).  The fused flat Adam writes
+    parameters through raw pointers, which does not bump ``_version``: a parameter that is frozen for one phase and updated
+    by ``FlatState.adam`` in another (an autograd user's D during the generator update) must not keep a stale image.
+    Writes through ``param.data`` bypass the version counter too: call this (or re-create the parameter) after such writes."""
+    stale = [k for k in _FROZEN if lo <= k[0] < hi]
+    for k in stale:
+        del _FROZEN[k]
+    return len(stale)
+
+
 def pack_weight(w: torch.Tensor, mode: int) -> tuple[torch.Tensor, int]:
     """fdg_pack_weight.  mode 0: OIHW -> [(r,s,ci)][co]; 1: OIHW -> flipped [(r,s,co)][ci]; 2: [Cin][Cout] -> [co][ci]."""
     assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()

@@ -57,6 +57,8 @@ class FlatState:
             ops.adam_flat_dev(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, self.dev_state, grad_scale)
         else:
             ops.adam_flat(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, self.step, grad_scale)
+        if ops._FROZEN:     # the kernel writes through raw pointers (no _version bump): drop cached images of these parameters
+            ops.drop_frozen_in_range(self.flat.data_ptr(), self.flat.data_ptr() + 4 * self.n)
 
     def state_dict(self):
         """Adam state by parameter name (the layout of the flat buffers is an implementation detail): the moments and the

@@ -74,3 +74,16 @@ def test_trainer_state_rejects_mismatch(nets):
     bad["optD"]["exp_avg_sq"][name] = t.reshape(-1)[:-1]
     with pytest.raises(ValueError):
         b.load_state_dict(bad)
+
+
+def test_fused_adam_drops_cached_images_of_its_parameters(nets):
+    """The flat Adam kernel writes parameters through raw pointers (no ``_version`` bump): operand images cached for a phase in
+    which such a parameter was frozen must not survive the update.  Host bookkeeping only."""
+    from fdgan_b200 import ops
+    ops._FROZEN.clear()
+    ops._FROZEN[(1000, (4,), 0)] = ("inside",)
+    ops._FROZEN[(1012, (4,), 1)] = ("inside",)
+    ops._FROZEN[(2000, (4,), 0)] = ("other network",)
+    assert ops.drop_frozen_in_range(1000, 1016) == 2
+    assert list(ops._FROZEN) == [(2000, (4,), 0)]
+    ops._FROZEN.clear()
