@@ -177,14 +177,15 @@ class _NetFn(torch.autograd.Function):
         need_w = any(ctx.needs_input_grad[2:])
         named = mod._used_named_parameters()
         grads = None
+        sink = None if getattr(mod, "_is_replica", False) else mod._grad_sink   # a replica's gradients go back through autograd
         if need_w:
-            if mod._grad_sink is not None:
-                grads = mod._grad_sink           # caller-owned flat gradient buffer (training step fast path)
+            if sink is not None:
+                grads = sink                     # caller-owned flat gradient buffer (training step fast path)
             else:
                 _flat, grads = _alloc_grads(named)
         dx = mod._run_backward(ctx.ectx, dout, grads, need_dx)
         ctx.ectx = None
-        if not need_w or mod._grad_sink is not None:
+        if not need_w or sink is not None:
             return (None, dx) + (None,) * len(named)
         return (None, dx) + tuple(grads[n] if ctx.needs_input_grad[2 + i] else None for i, (n, _p) in enumerate(named))
 
@@ -195,6 +196,17 @@ class _KernelNet(nn.Module):
     _grad_sink = None
 
     def _used_named_parameters(self):
+        if getattr(self, "_is_replica", False):
+            # nn.DataParallel replica (demo.py:89 with several GPUs): torch.nn.parallel.replicate copies __dict__ (the cache
+            # below would still name the ORIGINAL module's parameters), empties _parameters and stores this device's copies as
+            # plain attributes, listed in _former_parameters.  Same names, same order as named_parameters() of the original.
+            out = []
+            for mname, m in self.named_modules():
+                for k, v in getattr(m, "_former_parameters", {}).items():
+                    n = mname + "." + k if mname else k
+                    if self._is_used(n):
+                        out.append((n, v))
+            return out
         cache = getattr(self, "_used_cache", None)
         if cache is None:
             cache = [(n, p) for n, p in self.named_parameters() if self._is_used(n)]
