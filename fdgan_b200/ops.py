@@ -189,9 +189,9 @@ def drop_frozen_in_range(lo: int, hi: int) -> int:
     parameters through raw pointers, which does not bump ``_version``: a parameter that is frozen for one phase and updated
     by ``FlatState.adam`` in another (an autograd user's D during the generator update) must not keep a stale image.
     Writes through ``param.data`` bypass the version counter too: call this (or re-create the parameter) after such writes."""
-    stale = [k for k in _FROZEN if lo <= k[0] < hi]
+    stale = [k for k in list(_FROZEN) if lo <= k[0] < hi]      # snapshot: DataParallel worker threads may insert concurrently
     for k in stale:
-        del _FROZEN[k]
+        _FROZEN.pop(k, None)
     return len(stale)
 
 
