@@ -115,6 +115,73 @@ def gen_ssim():
     print("ssim", float(v))
 
 
+TRAIN_G_KEYS = ["conv_refin1.weight", "dense_block1.denselayer1.norm1.weight", "dense_block2.denselayer12.conv2.weight",
+                "trans_block3.conv.weight", "dense_block4.conv2.weight", "trans_block6.conv1.weight", "conv_refin3.bias"]
+TRAIN_D_KEYS = ["main.layer1.conv.weight", "main.layer2.layer2.bn.weight", "main.layer3.layer3.conv.weight", "main.layer5.conv.weight"]
+
+
+def train_inputs(batch=2, hw=32):
+    return seeded((batch, 3, hw, hw), 30), seeded((batch, 3, hw, hw), 31)
+
+
+def gen_train_step():
+    """The reconstructed FD-GAN iteration composed from the REFERENCE's own modules (FDGAN, D, Vgg16, pytorch_ssim),
+    torch.optim.Adam (demo.py:43-46 flags) and torch's loss functions; only the frequency decomposition comes from the oracle
+    (loss.py survives as bytecode).  Two consecutive steps, with and without the SSIM term: pins oracle.train_step's composition
+    (D update first, detach, updated-D-as-constant in the G update, three BatchNorm running-stat updates of D per step) and its
+    Adam arithmetic."""
+    import torch.nn.functional as F
+    for tag, w_ssim in (("plain", 0.0), ("ssim", 0.1)):
+        netG = R.load_state(R.ref_fdgan(), O.make_fdgan_state(0)).train()
+        netD = R.load_state(R.ref_d(9, 36), O.make_d_state(9, 36, 1)).train()
+        vgg = R.load_state(R.ref_vgg16(), O.make_vgg_state(2))
+        ssim = R.ref_ssim()
+        for p in vgg.parameters():
+            p.requires_grad_(False)
+        optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        optD = torch.optim.Adam(netD.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        hazy, clean = train_inputs()
+        out = {}
+        for it in range(2):
+            fake = netG(hazy)
+            optD.zero_grad()
+            pr, pf = netD(O.freq_concat(clean)), netD(O.freq_concat(fake.detach()))
+            loss_d = F.binary_cross_entropy(pr, torch.ones_like(pr)) + F.binary_cross_entropy(pf, torch.zeros_like(pf))
+            loss_d.backward()
+            gd = {k: p.grad.clone() for k, p in netD.named_parameters()}
+            optD.step()
+            optG.zero_grad()
+            for p in netD.parameters():
+                p.requires_grad_(False)
+            l1 = F.l1_loss(fake, clean)
+            fv, cv = vgg(fake), vgg(clean)
+            perc = sum(F.mse_loss(fv[k], cv[k].detach()) for k in (1, 3))
+            pg = netD(O.freq_concat(fake))
+            adv = F.binary_cross_entropy(pg, torch.ones_like(pg))
+            loss_g = 1.0 * l1 + 0.5 * perc + 0.01 * adv
+            if w_ssim:
+                loss_g = loss_g + w_ssim * (1 - ssim(fake, clean))
+            loss_g.backward()
+            for p in netD.parameters():
+                p.requires_grad_(True)
+            gg = {k: p.grad.clone() for k, p in netG.named_parameters() if p.grad is not None}
+            optG.step()
+            out["it%d:losses" % it] = np.array([float(loss_d), float(l1), float(0.5 * perc), float(0.01 * adv), float(loss_g)])
+            for k in TRAIN_G_KEYS:
+                out["it%d:gradG:%s" % (it, k)] = sample(gg[k])
+                out["it%d:G:%s" % (it, k)] = sample(dict(netG.named_parameters())[k])
+            for k in TRAIN_D_KEYS:
+                out["it%d:gradD:%s" % (it, k)] = sample(gd[k])
+                out["it%d:D:%s" % (it, k)] = sample(dict(netD.named_parameters())[k])
+            out["it%d:fake" % it] = sample(fake)
+        sdD = netD.state_dict()
+        out["D:running_var"] = sdD["main.layer2.layer2.bn.running_var"].numpy()
+        out["D:nbt"] = sdD["main.layer2.layer2.bn.num_batches_tracked"].numpy()
+        out["G:running_mean"] = netG.state_dict()["dense_block1.denselayer1.norm1.running_mean"].numpy()
+        np.savez_compressed(os.path.join(OUT, "train_step_%s.npz" % tag), **out)
+        print("train step", tag, out["it0:losses"], out["it1:losses"])
+
+
 def main():
     assert R.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -125,6 +192,7 @@ def main():
     gen_d()
     gen_vgg()
     gen_ssim()
+    gen_train_step()
 
 
 if __name__ == "__main__":
