@@ -18,7 +18,9 @@ What each function follows (paths relative to /root/reference):
                            L122-162 / L205-304 recovered in SURVEY Appendix B) --
                            bytecode only, "parity unpinned"
   * ``ssim``               models/pytorch_ssim/__init__.py:7-37
-  * ``train_step``         RECONSTRUCTED; the reference has no train.py -- parity unpinned
+  * ``train_step``         RECONSTRUCTED; the reference has no train.py, so the choice of loss terms
+                           and weights is unpinned; the arithmetic is pinned by tests/golden/train_step_*.npz (two
+                           iterations of the reference's own modules + torch.optim.Adam, make_golden.py:gen_train_step)
 
 BatchNorm always uses batch statistics when ``train=True`` (README.md:38, demo.py
 never calls .eval()).
