@@ -54,6 +54,8 @@ int check_launch(const char* what) {
 }
 
 // ---------------------------------------------------------------- per-launch event profiling
+// A measurement aid for bench.py (one process = one GPU): the event pool is not per device, so profiling must stay off in a
+// process that drives several GPUs (nn.DataParallel).
 struct ProfRec { int family; double flops, bytes; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
@@ -94,6 +96,7 @@ int fdg_profile_enable(int on) {
 // Sums the recorded launches per family (ms, algorithmic flops, algorithmic bytes, launch count) and clears them.
 // Arrays have FDG_PROF_FAMILIES entries.  Synchronises on the recorded events.
 int fdg_profile_collect(double* ms, double* flops, double* bytes, int64_t* launches) {
+  FDG_REQUIRE(ms && flops && bytes && launches, "fdg_profile_collect: null output array");
   std::lock_guard<std::mutex> lk(fdg::g_prof_mu);
   for (int f = 0; f < fdg::PF_COUNT; ++f) { ms[f] = 0; flops[f] = 0; bytes[f] = 0; launches[f] = 0; }
   for (auto& r : fdg::g_prof_recs) {
