@@ -44,7 +44,12 @@ struct WUArgs {
 // 8-channel chunk land in the two 16-byte slots that will hold that chunk's bf16 hi / lo halves, so the conversion is a
 // read-modify-write of the thread's own slots and every ring stage doubles as prefetch buffer: STAGES - 2 chunks of
 // loads are in flight while one chunk is converted and one is consumed by the tensor core.
-template <int NT, int STAGES>
+// FAST (experimental, FDG_WU_FAST=1; off by default until it has been through the GPU parity suite): loader specialised for the
+// dominant call -- 1x1 / stride 1 / no padding, direct gather from a pixel-linear input, split-bf16 gradient -- where a chunk's
+// source address is a running pointer and its validity a comparison, so the per-chunk coordinate arithmetic, tap / border
+// predicates and the shared-memory metadata word of the general loader disappear (~14 instructions per element
+// against ~7.5 of useful work).
+template <int NT, int STAGES, bool FAST = false>
 __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs a) {
   static_assert(NT == 64 || NT == 128 || NT == 256 || NT == 320, "output-channel tile");
   constexpr bool CONCAT = NT <= 128;      // [G_hi | G_lo] as one operand of width 2*NT (see umma_chunk8); wide tiles run
@@ -245,24 +250,102 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(full0 + st * 8);
     };
-    int sl_ = 0, sf = 0;            // stages of the next chunk to load / to convert
-    uint32_t lph = 0;               // parity of the load side's pass over the ring
-#pragma unroll 1
-    for (int q = 0; q < STAGES - 2; ++q) {
-      if (q < nchunks) issue_async(sl_, lph);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
-    }
-#pragma unroll 1
-    for (int q = 0; q < nchunks; ++q) {
-      // refill first (the stage released two chunks ago), then convert chunk q, whose copies have landed when at most
-      // STAGES-2 newer groups are pending
-      if (q + STAGES - 2 < nchunks) issue_async(sl_, lph);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
-      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
-      convert(sf);
-      if (++sf == STAGES) sf = 0;
+    if constexpr (FAST) {
+      // ---- FAST: running pointer, validity by comparison (k == channel, tap 0; the thread's rows are pixels mbeg + pr + 32 q)
+      const bool fv0 = k0 < p.Cin, fv1 = k1 < p.Cin;
+      const float* fx = p.x.p + (mbeg + pr) * p.x.sw;       // pixel-linear view: pixel m lives at m * sw
+      const int64_t fxstep = (int64_t)WU_P * p.x.sw;
+      int64_t fl = mbeg + pr, fc = mbeg + pr;               // pixel of this thread's row in the next chunk to load / to convert
+      auto issue_fast = [&](int st, uint32_t eph) {
+        mbar_wait(empty0 + st * 8, eph ^ 1u);
+        if (fl < mend) {
+          if (fv0) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_a(st, 0, 0)), "l"(fx + k0) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_a(st, 0, 1)), "l"(fx + k0 + 4) : "memory");
+          }
+          if (fv1) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_a(st, 1, 0)), "l"(fx + k1) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_a(st, 1, 1)), "l"(fx + k1 + 4) : "memory");
+          }
+        }
+        if (t == 0) {       // pr == 0: fl is the first pixel of the chunk
+          const uint32_t bar = full0 + st * 8;
+          const uint32_t gbase = smem_base + st * STAGE_BYTES + 2 * WU_A_BYTES;
+          mbar_arrive_expect_tx(bar, 2 * G_BYTES);
+  #pragma unroll
+          for (int q = 0; q < GQ; ++q) {
+            tma_load_2d(gbase + q * WU_BLK, &a.gmap_hi, cot * NT + 64 * q, (int)fl, bar);
+            tma_load_2d(gbase + G_BYTES + q * WU_BLK, &a.gmap_lo, cot * NT + 64 * q, (int)fl, bar);
+          }
+        }
+        fx += fxstep;
+        fl += WU_P;
+      };
+      auto convert_fast = [&](int st) {
+        const bool pv = fc < mend;
+        const float sl = p.slope;
+  #pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+          if (pv && (h ? fv1 : fv0)) {
+            a0 = lds4(slot_a(st, h, 0));
+            a1 = lds4(slot_a(st, h, 1));
+            const float4 sc0 = scv[2 * h], sc1 = scv[2 * h + 1], sh0 = shv[2 * h], sh1 = shv[2 * h + 1];
+            a0.x = prologue_act(fmaf(a0.x, sc0.x, sh0.x), sl); a0.y = prologue_act(fmaf(a0.y, sc0.y, sh0.y), sl);
+            a0.z = prologue_act(fmaf(a0.z, sc0.z, sh0.z), sl); a0.w = prologue_act(fmaf(a0.w, sc0.w, sh0.w), sl);
+            a1.x = prologue_act(fmaf(a1.x, sc1.x, sh1.x), sl); a1.y = prologue_act(fmaf(a1.y, sc1.y, sh1.y), sl);
+            a1.z = prologue_act(fmaf(a1.z, sc1.z, sh1.z), sl); a1.w = prologue_act(fmaf(a1.w, sc1.w, sh1.w), sl);
+          }
+          uint32_t hi[4], lo[4];
+          split2(a0.x, a0.y, hi[0], lo[0]); split2(a0.z, a0.w, hi[1], lo[1]);
+          split2(a1.x, a1.y, hi[2], lo[2]); split2(a1.z, a1.w, hi[3], lo[3]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 0)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a(st, h, 1)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + st * 8);
+        fc += WU_P;
+      };
+      int sl_ = 0, sf = 0;            // stages of the next chunk to load / to convert
+      uint32_t lph = 0;               // parity of the load side's pass over the ring
+  #pragma unroll 1
+      for (int q = 0; q < STAGES - 2; ++q) {
+        if (q < nchunks) issue_fast(sl_, lph);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
+      }
+  #pragma unroll 1
+      for (int q = 0; q < nchunks; ++q) {
+        // refill first (the stage released two chunks ago), then convert chunk q, whose copies have landed when at most
+        // STAGES-2 newer groups are pending
+        if (q + STAGES - 2 < nchunks) issue_fast(sl_, lph);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        convert_fast(sf);
+        if (++sf == STAGES) sf = 0;
+      }
+    } else {
+      int sl_ = 0, sf = 0;            // stages of the next chunk to load / to convert
+      uint32_t lph = 0;               // parity of the load side's pass over the ring
+  #pragma unroll 1
+      for (int q = 0; q < STAGES - 2; ++q) {
+        if (q < nchunks) issue_async(sl_, lph);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
+      }
+  #pragma unroll 1
+      for (int q = 0; q < nchunks; ++q) {
+        // refill first (the stage released two chunks ago), then convert chunk q, whose copies have landed when at most
+        // STAGES-2 newer groups are pending
+        if (q + STAGES - 2 < nchunks) issue_async(sl_, lph);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++sl_ == STAGES) { sl_ = 0; lph ^= 1u; }
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+        convert(sf);
+        if (++sf == STAGES) sf = 0;
+      }
     }
   } else if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
     // =============================================================== MMA issue
@@ -366,13 +449,13 @@ int wgrad_umma_supported(const FdgWgrad* p) {
   return 1;
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, bool FAST = false>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * ((NT + 63) / 64) * WU_BLK) + 1024;
   static int attr_done[64] = {0};           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
-    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d_wgrad[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -390,7 +473,7 @@ static int launch_wu(WUArgs& a, cudaStream_t st) {
   splits = cdiv64(a.M, a.m_per_split);
   ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  wgrad_umma_kernel<NT, STAGES><<<(unsigned)(a.tiles * splits), WU_THREADS, smem, st>>>(a);
+  wgrad_umma_kernel<NT, STAGES, FAST><<<(unsigned)(a.tiles * splits), WU_THREADS, smem, st>>>(a);
   return check_launch("fdg_conv2d_wgrad[tcgen05]");
 }
 
@@ -420,7 +503,13 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   }
   switch (wu_ntile(p->Cout)) {
     case 64: return launch_wu<64, 8>(a, st);      // 8 x 24 KB in-place staging ring
-    case 128: return launch_wu<128, 6>(a, st);    // 6 x 32 KB
+    case 128: {                                   // 6 x 32 KB
+      static const int fast_on = [] { const char* e = getenv("FDG_WU_FAST"); return e ? atoi(e) : 0; }();
+      const FdgTensor& x = p->x;
+      const bool fast = fast_on && a.g_split && !a.dbg && p->R == 1 && p->S == 1 && p->stride == 1 && p->pad == 0 &&
+                        p->gather == FDG_GATHER_DIRECT && x.sh == (int64_t)p->W * x.sw && x.sn == (int64_t)p->H * x.sh;
+      return fast ? launch_wu<128, 6, true>(a, st) : launch_wu<128, 6, false>(a, st);
+    }
     case 256: return launch_wu<256, 4>(a, st);    // 4 x 48 KB
     default: return launch_wu<320, 3>(a, st);     // 3 x 56 KB
   }
