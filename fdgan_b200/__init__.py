@@ -5,5 +5,6 @@ from . import _lib  # noqa: F401  (raises ImportError when libfdgan_b200.so is m
 from .dehaze1113 import D, FDGAN  # noqa: F401
 from .loss import Blur, Laplacian, blur, freq_concat, laplace_filter  # noqa: F401
 from .vgg16 import Vgg16  # noqa: F401
+from . import compat, pytorch_ssim  # noqa: F401  (compat.install(): the reference's import lines, unchanged)
 
 __all__ = ["FDGAN", "D", "Vgg16", "Blur", "Laplacian", "blur", "laplace_filter", "freq_concat"]

@@ -74,6 +74,14 @@ class FdgEwBwd(C.Structure):
     ]
 
 
+class FdgDepthwise(C.Structure):
+    _fields_ = [
+        ("x", FdgTensor), ("y", FdgTensor), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+        ("kernel", C.c_void_p), ("l", C.c_int32), ("pad_mode", C.c_int32), ("mean", C.c_void_p), ("inv_std", C.c_void_p),
+        ("accumulate", C.c_int32),
+    ]
+
+
 class FdgBnBwdFinalize(C.Structure):
     _fields_ = [
         ("stats", C.c_void_p), ("C", C.c_int), ("count", C.c_double),
@@ -111,6 +119,8 @@ _SIGS = {
     "fdg_colsum": ([_P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_fwd": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_bwd": ([_P(FdgTensor), _P(FdgTensor), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    "fdg_depthwise2d_fwd": ([_P(FdgDepthwise), C.c_void_p], C.c_int),
+    "fdg_depthwise2d_bwd": ([_P(FdgDepthwise), C.c_void_p], C.c_int),
     "fdg_ssim_loss_grad": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P(FdgTensor), C.c_int,
                            C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "fdg_image_minmax": ([_P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p], C.c_int),

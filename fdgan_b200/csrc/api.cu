@@ -54,13 +54,14 @@ int check_launch(const char* what) {
 }
 
 // ---------------------------------------------------------------- per-launch event profiling
-// A measurement aid for bench.py (one process = one GPU): the event pool is not per device, so profiling must stay off in a
-// process that drives several GPUs (nn.DataParallel).
+// A measurement aid for bench.py (one process = one GPU).  The event pool belongs to the device that was current when
+// profiling was enabled; launches on any other device (nn.DataParallel worker threads) are simply not recorded.
 struct ProfRec { int family; double flops, bytes; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
 static std::atomic<int> g_prof_on{0};
+static std::atomic<int> g_prof_dev{0};
 
 static cudaEvent_t prof_event() {
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
@@ -70,7 +71,7 @@ static cudaEvent_t prof_event() {
 }
 
 ProfScope::ProfScope(int family, double flops, double bytes, cudaStream_t stream) : idx(-1), st(stream) {
-  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  if (!g_prof_on.load(std::memory_order_relaxed) || current_device() != g_prof_dev.load(std::memory_order_relaxed)) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r{family, flops, bytes, prof_event(), prof_event()};
   cudaEventRecord(r.a, st);
@@ -89,6 +90,7 @@ ProfScope::~ProfScope() {
 extern "C" {
 
 int fdg_profile_enable(int on) {
+  if (on) fdg::g_prof_dev.store(fdg::current_device());
   fdg::g_prof_on.store(on ? 1 : 0);
   return FDG_OK;
 }

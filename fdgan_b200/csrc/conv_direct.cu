@@ -7,6 +7,7 @@
 //    a per-warp shared-memory tile so that the stores are coalesced rows and the BatchNorm statistics are column sums.
 //  * conv_cin1_kernel: Cin == 1 (data gradient of Fusion-D layer 5, 1 -> 288 channels, with the LeakyReLU mask of the
 //    layer input): one thread per (pixel, 4 channels), R*S taps, 128-bit stores.
+#include <atomic>
 #include <cstdlib>
 
 #include "aop.cuh"
@@ -142,7 +143,7 @@ template <int NC4>
 static int launch_thin(const ThinArgs& a, cudaStream_t st) {
   constexpr int CO = 4 * NC4;
   constexpr int smem = (TH_MAXK * CO + 8 * 32 * (CO + 4)) * 4;
-  static int attr_done[64] = {0};           // per device
+  static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(conv_thin_kernel<NC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {

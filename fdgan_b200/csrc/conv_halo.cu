@@ -12,6 +12,7 @@
 // Weights: the same pre-swizzled per-(N tile, tap, chunk) images as conv_umma.cu, streamed through a bulk-TMA ring.
 // Persistent, warp-specialised: warps 0-7 halo loaders, 8-11 epilogue (double-buffered TMEM accumulators),
 // warp 12 MMA issue, warp 13 weight-tile producer.
+#include <atomic>
 #include <cstdlib>
 
 #include "aop.cuh"
@@ -367,7 +368,7 @@ int conv2d_halo_supported(const FdgConv* p) {
 template <int NT, int BSTAGES>
 static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   const int smem = 2 * (2 * a.a_tile) + BSTAGES * (2 * NT * 128) + 1024;
-  static int attr_done[64] = {0};           // per device: largest size configured so far
+  static std::atomic<int> attr_done[64];           // per device: largest size configured so far
   const int adev = current_device();
   if (attr_done[adev] < smem) {
     if (cudaFuncSetAttribute(conv_halo_kernel<NT, BSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {

@@ -11,6 +11,7 @@
 // is a shifted read of a shared-memory tile).  A tile of 16 x 8 A pixels (UMMA M = 128) yields 14 x 8 outputs.
 // Per 64-channel chunk: 3 (kx) x 4 (K slices) x 2 MMAs (A_hi x [B_hi | B_lo], N = 192; A_lo x B_hi, N = 96) instead
 // of 9 x 4 x 2, i.e. one third of the A reads and MMA issues.
+#include <atomic>
 #include <cstdlib>
 
 #include "aop.cuh"
@@ -416,7 +417,7 @@ int conv2d_k1(const FdgConv* p, cudaStream_t st) {
     const uint32_t box[4] = {32, (uint32_t)K1_TW, (uint32_t)K1_OH, 1};
     if (make_tmap_f32(&a.ymap, p->y.p, 4, dims, strides, box)) a.tma_rank = 4;
   }
-  static int attr_done[64] = {0};           // per device
+  static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(conv_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM) != cudaSuccess) {

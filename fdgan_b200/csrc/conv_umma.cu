@@ -17,6 +17,7 @@
 //   releases the smem stage / publishes the accumulator.  Epilogue warps read TMEM with tcgen05.ld
 //   (32x32b.x32), apply alpha/bias/activation/mask, reduce the per-channel BatchNorm statistics with a
 //   butterfly of warp shuffles and store 128-bit rows.
+#include <atomic>
 #include <cstdlib>
 
 #include "aop.cuh"
@@ -683,7 +684,7 @@ int conv2d_umma_supported(const FdgConv* p) {
 template <int NT, int STAGES, int DEPTH, bool BNBWD = false>
 static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + DEPTH * (UM * UKC * 4) + 1024;
-  static int attr_done[64] = {0};           // per device
+  static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES, DEPTH, BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {

@@ -9,6 +9,7 @@
 //    weights (scipy.ndimage.gaussian_filter sigma 1.5: 13 taps, 'reflect' boundary), population covariance, data range
 //    255, K1 .01, K2 .03, 5-pixel crop before the mean (PSNRSSIM.py:46-194).  The kernel accumulates the four sums
 //    (squared error, SSIM map of each channel) in fp64; the host turns them into the two numbers.
+#include <atomic>
 #include "common.cuh"
 
 namespace fdg {
@@ -153,7 +154,7 @@ extern "C" int fdg_image_pack_u8(const FdgTensor* x, int N, int H, int W, int C,
 
 extern "C" int fdg_psnr_ssim_u8(const uint8_t* ref, const uint8_t* res, int H, int W, double* sums4, fdg_stream_t stream) {
   FDG_REQUIRE(ref && res && sums4 && H >= 13 && W >= 13, "fdg_psnr_ssim_u8: bad arguments (images of at least 13x13 after the crops)");
-  static int window_done[64] = {0};         // __constant__ memory is per device
+  static std::atomic<int> window_done[64];         // __constant__ memory is per device
   const int wdev = current_device();
   if (!window_done[wdev]) {   // scipy.ndimage.gaussian_filter(sigma=1.5): radius int(4.0 * 1.5 + 0.5) = 6, normalised exp(-x^2 / (2 sigma^2))
     double w[13], s = 0;

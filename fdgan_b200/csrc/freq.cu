@@ -131,6 +131,91 @@ __global__ void freq_bwd_cols_kernel(FdgTensor dz, const float* scratch, FdgTens
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Generic depth-wise l x l filter (one kernel shared by every (image, channel) plane): the channel-agnostic use of the
+// reference's Laplacian (loss.pyc@L286-301: kernel.repeat(c,1,1,1), groups=c, zero padding) and Blur with a non-default
+// (l, kernel, use_input_norm) (loss.pyc@L123-151: optional ImageNet normalisation, ReflectionPad2d(l//2), one kernel on
+// every plane).  Pure HBM traffic (4 B read + 4 B written per element); a (TY+l-1) x (TX+l-1) halo tile and the filter
+// taps live in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int DW_TX = 32, DW_TY = 16, DW_MAXL = 31;
+
+__device__ __forceinline__ int reflect_multi(int i, int n) {      // ReflectionPad2d for pad < n
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256) depthwise_fwd_kernel(FdgDepthwise d) {
+  extern __shared__ float dsm[];
+  const int l = d.l, r = l / 2;
+  const int TW = DW_TX + l - 1, TH = DW_TY + l - 1;
+  float* kw = dsm;                 // l*l taps
+  float* tile = dsm + l * l;       // TH x (TW+1)
+  const int plane = blockIdx.z, n = plane / d.c, c = plane - n * d.c;
+  const int x0 = blockIdx.x * DW_TX, y0 = blockIdx.y * DW_TY;
+  for (int i = threadIdx.x; i < l * l; i += blockDim.x) kw[i] = __ldg(d.kernel + i);
+  const float mean = d.mean ? __ldg(d.mean + c) : 0.f;
+  const float istd = d.inv_std ? __ldg(d.inv_std + c) : 1.f;
+  const float* xp = d.x.p + (int64_t)n * d.x.sn + (int64_t)c * d.x.sc;
+  for (int i = threadIdx.x; i < TH * TW; i += blockDim.x) {
+    const int ty = i / TW, tx = i - ty * TW;
+    int gy = y0 + ty - r, gx = x0 + tx - r;
+    float v = 0.f;
+    if (d.pad_mode == 1) {
+      gy = reflect_multi(gy, d.h); gx = reflect_multi(gx, d.w);
+      if (gy >= 0 && gy < d.h && gx >= 0 && gx < d.w) v = (__ldg(xp + (int64_t)gy * d.x.sh + (int64_t)gx * d.x.sw) - mean) * istd;
+    } else if (gy >= 0 && gy < d.h && gx >= 0 && gx < d.w) {
+      v = (__ldg(xp + (int64_t)gy * d.x.sh + (int64_t)gx * d.x.sw) - mean) * istd;
+    }
+    tile[ty * (TW + 1) + tx] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DW_TX * DW_TY; i += blockDim.x) {
+    const int ty = i / DW_TX, tx = i - ty * DW_TX;
+    const int gy = y0 + ty, gx = x0 + tx;
+    if (gy >= d.h || gx >= d.w) continue;
+    float s = 0.f;
+    for (int a = 0; a < l; ++a)
+      for (int b = 0; b < l; ++b) s = fmaf(kw[a * l + b], tile[(ty + a) * (TW + 1) + tx + b], s);
+    float* yp = d.y.p + (int64_t)n * d.y.sn + (int64_t)gy * d.y.sh + (int64_t)gx * d.y.sw + (int64_t)c * d.y.sc;
+    *yp = d.accumulate ? *yp + s : s;
+  }
+}
+
+// Adjoint: dx[n,c,fold(y+a-r),fold(x+b-r)] += inv_std[c] * k[a,b] * dy[n,c,y,x] (fold = reflection or drop-outside).
+// dx must hold the values to accumulate onto (zeros for a plain gradient); atomics because folded taps collide.
+__global__ void __launch_bounds__(256) depthwise_bwd_kernel(FdgDepthwise d) {
+  extern __shared__ float dsm[];
+  const int l = d.l, r = l / 2;
+  float* kw = dsm;
+  for (int i = threadIdx.x; i < l * l; i += blockDim.x) kw[i] = __ldg(d.kernel + i);
+  __syncthreads();
+  const int64_t total = (int64_t)d.n * d.c * d.h * d.w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xw = (int)(i % d.w);
+    int64_t q = i / d.w;
+    const int y = (int)(q % d.h); q /= d.h;
+    const int c = (int)(q % d.c);
+    const int n = (int)(q / d.c);
+    // x = dy (the incoming gradient), y = dx (the gradient w.r.t. the filter input)
+    const float g = __ldg(d.x.p + (int64_t)n * d.x.sn + (int64_t)y * d.x.sh + (int64_t)xw * d.x.sw + (int64_t)c * d.x.sc) *
+                    (d.inv_std ? __ldg(d.inv_std + c) : 1.f);
+    float* op = d.y.p + (int64_t)n * d.y.sn + (int64_t)c * d.y.sc;
+    for (int a = 0; a < l; ++a) {
+      int yy = y + a - r;
+      if (d.pad_mode == 1) yy = reflect_multi(yy, d.h);
+      if (yy < 0 || yy >= d.h) continue;
+      for (int b = 0; b < l; ++b) {
+        int xx = xw + b - r;
+        if (d.pad_mode == 1) xx = reflect_multi(xx, d.w);
+        if (xx < 0 || xx >= d.w) continue;
+        atomicAdd(op + (int64_t)yy * d.y.sh + (int64_t)xx * d.y.sw, kw[a * l + b] * g);
+      }
+    }
+  }
+}
+
 // isotropic_gaussian_kernel(l=15, sigma=3) is outer(g, g) with g = exp(-a^2/(2 sigma^2)) / sum (float64 math)
 static Gauss15 make_gauss() {
   double g[15], s = 0.0;
@@ -167,4 +252,36 @@ extern "C" int fdg_freq_concat_bwd(const FdgTensor* dz, const FdgTensor* dx, flo
   if (rc != FDG_OK) return rc;
   freq_bwd_cols_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(*dz, scratch, *dx, N, H, W, gk);
   return check_launch("fdg_freq_concat_bwd[cols]");
+}
+
+static int depthwise_check(const FdgDepthwise* d, const char* who) {
+  FDG_REQUIRE(d && d->x.p && d->y.p && d->kernel && d->n > 0 && d->c > 0 && d->h > 0 && d->w > 0, "%s: bad arguments", who);
+  FDG_REQUIRE(d->l >= 1 && d->l <= DW_MAXL && (d->l & 1), "%s: filter size must be odd and <= %d (got %d)", who, DW_MAXL, d->l);
+  FDG_REQUIRE(d->pad_mode == 0 || d->pad_mode == 1, "%s: pad_mode must be 0 (zero) or 1 (reflect)", who);
+  FDG_REQUIRE(d->pad_mode == 0 || (d->h > d->l / 2 && d->w > d->l / 2), "%s: reflection padding %d needs H, W > %d (got %d x %d)", who,
+              d->l / 2, d->l / 2, d->h, d->w);
+  FDG_REQUIRE((int64_t)d->n * d->c <= 65535, "%s: more than 65535 (image, channel) planes", who);
+  return FDG_OK;
+}
+
+extern "C" int fdg_depthwise2d_fwd(const FdgDepthwise* d, fdg_stream_t stream) {
+  int rc = depthwise_check(d, "fdg_depthwise2d_fwd");
+  if (rc != FDG_OK) return rc;
+  const int TW = DW_TX + d->l - 1, TH = DW_TY + d->l - 1;
+  const size_t smem = sizeof(float) * ((size_t)d->l * d->l + (size_t)TH * (TW + 1));
+  dim3 grid(cdiv(d->w, DW_TX), cdiv(d->h, DW_TY), d->n * d->c);
+  ProfScope prof(PF_FREQ, 2.0 * d->l * d->l * d->n * d->c * (double)d->h * d->w, 8.0 * d->n * d->c * (double)d->h * d->w, (cudaStream_t)stream);
+  depthwise_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(*d);
+  return check_launch("fdg_depthwise2d_fwd");
+}
+
+extern "C" int fdg_depthwise2d_bwd(const FdgDepthwise* d, fdg_stream_t stream) {
+  int rc = depthwise_check(d, "fdg_depthwise2d_bwd");
+  if (rc != FDG_OK) return rc;
+  const int64_t total = (int64_t)d->n * d->c * d->h * d->w;
+  int64_t g = cdiv64(total, 256);
+  if (g > 148 * 16) g = 148 * 16;
+  ProfScope prof(PF_FREQ, 2.0 * d->l * d->l * (double)total, 8.0 * (double)total, (cudaStream_t)stream);
+  depthwise_bwd_kernel<<<(unsigned)g, 256, sizeof(float) * d->l * d->l, (cudaStream_t)stream>>>(*d);
+  return check_launch("fdg_depthwise2d_bwd");
 }

@@ -16,7 +16,6 @@ constexpr int SS_R = 5;               // window radius (11 taps)
 constexpr int SS_I = SS_T + 2 * SS_R; // 42 input rows / columns
 constexpr int SS_P = SS_I + 1;        // padded pitch
 
-__constant__ float c_ssim_w[11];
 
 struct SsimArgs {
   FdgTensor x, y, g;
@@ -25,6 +24,7 @@ struct SsimArgs {
   int accumulate;
   double* loss;
   float* scratch;     // [3][N*C][H][W]
+  float w[11];        // gaussian(11, 1.5): travels with the launch (no __constant__ upload -> legal under stream capture, nothing per device)
 };
 
 __device__ __forceinline__ float tget(const FdgTensor& t, int n, int c, int h, int w) {
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const __grid_constant__ S
     float s1 = 0.f, s2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
 #pragma unroll
     for (int k = 0; k < 11; ++k) {
-      const float w = c_ssim_w[k], xv = xs[r][q + k], yv = ys[r][q + k];
+      const float w = a.w[k], xv = xs[r][q + k], yv = ys[r][q + k];
       s1 = fmaf(w, xv, s1); s2 = fmaf(w, yv, s2);
       s11 = fmaf(w, xv * xv, s11); s22 = fmaf(w, yv * yv, s22); s12 = fmaf(w, xv * yv, s12);
     }
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const __grid_constant__ S
     float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
     for (int k = 0; k < 11; ++k) {
-      const float w = c_ssim_w[k];
+      const float w = a.w[k];
       mu1 = fmaf(w, hq[0][r + k][q], mu1); mu2 = fmaf(w, hq[1][r + k][q], mu2);
       e11 = fmaf(w, hq[2][r + k][q], e11); e22 = fmaf(w, hq[3][r + k][q], e22); e12 = fmaf(w, hq[4][r + k][q], e12);
     }
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(const __grid_constant__ S
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < 11; ++k) {
-      const float w = c_ssim_w[k];
+      const float w = a.w[k];
       s0 = fmaf(w, ds[0][r][q + k], s0); s1 = fmaf(w, ds[1][r][q + k], s1); s2 = fmaf(w, ds[2][r][q + k], s2);
     }
     hq[0][r][q] = s0; hq[1][r][q] = s1; hq[2][r][q] = s2;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(const __grid_constant__ S
     float f0 = 0.f, f1 = 0.f, f2 = 0.f;
 #pragma unroll
     for (int k = 0; k < 11; ++k) {
-      const float w = c_ssim_w[k];
+      const float w = a.w[k];
       f0 = fmaf(w, hq[0][r + k][q], f0); f1 = fmaf(w, hq[1][r + k][q], f1); f2 = fmaf(w, hq[2][r + k][q], f2);
     }
     const float xv = tget(a.x, n, c, oy, ox), yv = tget(a.y, n, c, oy, ox);
@@ -152,21 +152,17 @@ extern "C" int fdg_ssim_loss_grad(const FdgTensor* x, const FdgTensor* y, int N,
                                   const FdgTensor* grad, int accumulate, double* loss, float* scratch, fdg_stream_t stream) {
   FDG_REQUIRE(x && y && x->p && y->p && loss && scratch && N > 0 && H > 0 && W > 0 && C > 0, "fdg_ssim_loss_grad: bad arguments");
   FDG_REQUIRE((int64_t)N * C <= 65535, "fdg_ssim_loss_grad: too many image planes");
-  static int window_done[64] = {0};         // __constant__ memory is per device
-  const int wdev = current_device();
-  if (!window_done[wdev]) {   // gaussian(11, 1.5) in fp32 like the reference (models/pytorch_ssim/__init__.py:7-9)
-    float w[11], s = 0.f;
-    for (int i = 0; i < 11; ++i) { w[i] = expf(-(float)((i - 5) * (i - 5)) / (2.f * 1.5f * 1.5f)); s += w[i]; }
-    for (int i = 0; i < 11; ++i) w[i] /= s;
-    if (cudaMemcpyToSymbol(c_ssim_w, w, sizeof(w)) != cudaSuccess) { set_error("fdg_ssim_loss_grad: cannot upload the window"); return FDG_ECUDA; }
-    window_done[wdev] = 1;
-  }
   SsimArgs a;
   a.x = *x; a.y = *y;
   a.g = grad ? *grad : FdgTensor{nullptr, 0, 0, 0, 0};
   a.N = N; a.H = H; a.W = W; a.C = C;
   a.lscale = lscale; a.gscale = gscale; a.accumulate = accumulate;
   a.loss = loss; a.scratch = scratch;
+  {   // gaussian(11, 1.5) in fp32 like the reference (models/pytorch_ssim/__init__.py:7-9)
+    float sum = 0.f;
+    for (int i = 0; i < 11; ++i) { a.w[i] = expf(-(float)((i - 5) * (i - 5)) / (2.f * 1.5f * 1.5f)); sum += a.w[i]; }
+    for (int i = 0; i < 11; ++i) a.w[i] /= sum;
+  }
   dim3 grid((unsigned)cdiv(W, SS_T), (unsigned)cdiv(H, SS_T), (unsigned)(N * C));
   ssim_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   int rc = check_launch("fdg_ssim_loss_grad[fwd]");

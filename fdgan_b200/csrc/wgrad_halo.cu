@@ -8,6 +8,7 @@
 // hi/lo and store it MN-major (row = halo pixel, 64 channels = 128 B, SWIZZLE_128B from absolute address bits); the
 // gradient block is stored the same way.  Tap (ky,kx) is a descriptor shift of (ky*HC + kx) rows; a K=16 slice is two
 // image rows of 8 pixels (stride between 8-row groups = halo pitch).  Double-buffered over pixel blocks.
+#include <atomic>
 #include <cstdlib>
 
 #include "aop.cuh"
@@ -254,7 +255,7 @@ int wgrad_halo(const FdgWgrad* p, cudaStream_t st) {
   a.ptiles_per_split = cdiv(a.total_ptiles, splits);
   a.splits = cdiv(a.total_ptiles, a.ptiles_per_split);
   constexpr int smem = 2 * WH_STAGE + 1024;
-  static int attr_done[64] = {0};           // per device
+  static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {

@@ -10,6 +10,7 @@
 //   * bf16 hi/lo split of both operands, three MMAs per 16-pixel slice (hi*hi + hi*lo + lo*hi), fp32 accumulate.
 //   * 8 loader warps cp.async the fp32 rows straight into the operand ring and convert them in
 //     place; one thread issues tcgen05.mma; mbarrier ring of STAGES chunks of 32 pixels, STAGES - 2 chunks in flight.
+#include <atomic>
 #include <cstdlib>
 
 #include "aop.cuh"
@@ -452,7 +453,7 @@ int wgrad_umma_supported(const FdgWgrad* p) {
 template <int NT, int STAGES, bool FAST = false>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * ((NT + 63) / 64) * WU_BLK) + 1024;
-  static int attr_done[64] = {0};           // per device
+  static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
     if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {

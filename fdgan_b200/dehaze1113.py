@@ -183,6 +183,9 @@ class _NetFn(torch.autograd.Function):
                 grads = sink                     # caller-owned flat gradient buffer (training step fast path)
             else:
                 _flat, grads = _alloc_grads(named)
+        if ctx.ectx is None:      # the saved activations are released by the first backward (they are tens of MB to GB)
+            raise RuntimeError("fdgan_b200: trying to backward through %s a second time: the saved activations of this forward have already "
+                               "been freed (retain_graph=True is not supported; run the forward again)" % type(mod).__name__)
         dx = mod._run_backward(ctx.ectx, dout, grads, need_dx)
         ctx.ectx = None
         if not need_w or sink is not None:

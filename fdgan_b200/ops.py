@@ -195,11 +195,24 @@ def drop_frozen_in_range(lo: int, hi: int) -> int:
     return len(stale)
 
 
+def invalidate_frozen() -> int:
+    """Forget EVERY cached operand image.  Call after writing frozen parameters through ``param.data`` (``p.data.copy_``, EMA
+    updates, a custom optimiser): such writes do not bump ``_version``, which is the only staleness signal the cache has."""
+    n = len(_FROZEN)
+    _FROZEN.clear()
+    return n
+
+
+_CAPTURE_KEEPALIVE = None      # list that collects every cached operand handed out while a CUDA graph is being captured
+
+
 def pack_weight(w: torch.Tensor, mode: int) -> tuple[torch.Tensor, int]:
     """fdg_pack_weight.  mode 0: OIHW -> [(r,s,ci)][co]; 1: OIHW -> flipped [(r,s,co)][ci]; 2: [Cin][Cout] -> [co][ci]."""
     assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
     key, hit = _frozen_lookup(w, mode)
     if hit is not None:
+        if _CAPTURE_KEEPALIVE is not None:      # a captured graph bakes in the raw pointers of the operand AND its tcgen05 images
+            _CAPTURE_KEEPALIVE.append(hit[1])
         return hit[1], hit[2]
     out, ld = _pack_weight(w, mode)
     if key is not None:
@@ -207,6 +220,8 @@ def pack_weight(w: torch.Tensor, mode: int) -> tuple[torch.Tensor, int]:
             _FROZEN.clear()
         out._fdg_images = {}          # tcgen05 images of this packed operand, filled by conv2d
         _FROZEN[key] = (w._version, out, ld, weakref.ref(w))
+        if _CAPTURE_KEEPALIVE is not None:
+            _CAPTURE_KEEPALIVE.append(out)
     return out, ld
 
 
@@ -312,6 +327,17 @@ def freq_concat_bwd(dz: View, dx: View, scratch: torch.Tensor):
     assert dz.C == 9 and dx.C == 3 and scratch.numel() >= dx.N * 3 * dx.H * dx.W
     a, b = dz.ft(), dx.ft()
     L.check(L.lib.fdg_freq_concat_bwd(_byref(a), _byref(b), scratch.data_ptr(), dx.N, dx.H, dx.W, _stream()), "freq_concat_bwd")
+
+
+def depthwise2d(x: View, y: View, kernel: torch.Tensor, pad_mode: int, mean=None, inv_std=None, accumulate=False, backward=False):
+    """fdg_depthwise2d_fwd / _bwd: one l x l kernel on every (image, channel) plane; pad_mode 0 zero, 1 reflect.
+    backward=True: x is the incoming gradient, y accumulates the gradient w.r.t. the filter input (must be initialised)."""
+    assert (x.N, x.H, x.W, x.C) == (y.N, y.H, y.W, y.C)
+    assert kernel.is_cuda and kernel.dtype == torch.float32 and kernel.is_contiguous() and kernel.dim() == 2 and kernel.shape[0] == kernel.shape[1]
+    d = L.FdgDepthwise(x.ft(), y.ft(), x.N, x.H, x.W, x.C, kernel.data_ptr(), kernel.shape[0], pad_mode, _ptr(mean), _ptr(inv_std),
+                       1 if accumulate else 0)
+    fn = L.lib.fdg_depthwise2d_bwd if backward else L.lib.fdg_depthwise2d_fwd
+    L.check(fn(_byref(d), _stream()), "depthwise2d_bwd" if backward else "depthwise2d_fwd")
 
 
 def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):

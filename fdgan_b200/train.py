@@ -20,6 +20,12 @@ from .ops import View
 DEFAULT_WEIGHTS = dict(l1=1.0, perc=0.5, adv=0.01)
 
 
+def dataparallel_state_dict(module) -> dict:
+    """State dict with the 'module.' prefix nn.DataParallel checkpoints carry: what the reference's demo.py:78-86 expects (it strips
+    the first 7 characters of EVERY key unconditionally, so an un-prefixed checkpoint would be mangled there)."""
+    return {"module." + k: v.detach().clone() for k, v in module.state_dict().items()}
+
+
 class FlatState:
     """Used parameters of one network re-homed into a single flat fp32 buffer (16-byte aligned slices), with a
     flat gradient buffer of the same layout (views by parameter name) and flat Adam moments."""
@@ -132,8 +138,15 @@ class GANTrainer:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._static_fake = self.step(self._static_hazy, self._static_clean, sync_losses=False)
+            # the graph bakes in raw device pointers of the cached operand images of frozen parameters (Vgg16): hold strong
+            # references for the life of the graph, so that evictions from ops._FROZEN cannot free memory a replay still reads
+            self._graph_keepalive = []
+            ops._CAPTURE_KEEPALIVE = self._graph_keepalive
+            try:
+                with torch.cuda.graph(self._graph):
+                    self._static_fake = self.step(self._static_hazy, self._static_clean, sync_losses=False)
+            finally:
+                ops._CAPTURE_KEEPALIVE = None
             self._graph_key = key
             for t_, s_ in zip(state, snap):
                 t_.copy_(s_)
@@ -149,8 +162,10 @@ class GANTrainer:
 
     # ------------------------------------------------------------------ checkpoint / resume
     def state_dict(self):
-        """Everything a resumed run needs: both networks (reference-keyed state dicts, loadable by the reference's modules and
-        by demo.py:78-86), both Adam states by parameter name, and the hyper-parameters for a consistency check."""
+        """Everything a resumed run needs: both networks (reference-keyed state dicts, loadable by the reference's modules'
+        load_state_dict), both Adam states by parameter name, and the hyper-parameters for a consistency check.  The keys carry no
+        'module.' prefix; for a checkpoint the reference's demo.py:78-86 can consume (it strips 7 characters from every key) use
+        ``torch.save(dataparallel_state_dict(trainer.G), path)``."""
         return {"version": 1, "netG": {k: v.detach().clone() for k, v in self.G.state_dict().items()},
                 "netD": {k: v.detach().clone() for k, v in self.D.state_dict().items()},
                 "optG": self.sG.state_dict(), "optD": self.sD.state_dict(),
@@ -181,8 +196,10 @@ class GANTrainer:
         self.last = dict(loss_d=v[0], l1_weighted=v[1], perc_weighted=v[2], adv_weighted=v[3], ssim_weighted=ssim_w,
                          loss_g=v[1] + v[2] + v[3] + ssim_w)
 
-    def step(self, hazy: torch.Tensor, clean: torch.Tensor, sync_losses: bool = True):
-        """One D update and one G update on this rank's shard.  hazy, clean: [b,3,H,W] fp32 CUDA."""
+    def step(self, hazy: torch.Tensor, clean: torch.Tensor, sync_losses: bool = True, apply: bool = True, allreduce: bool = True):
+        """One D update and one G update on this rank's shard.  hazy, clean: [b,3,H,W] fp32 CUDA.
+        ``apply=False`` stops after the gradients (no Adam: ``sD.grad`` / ``sG.grad`` hold the summed-over-ranks gradients of
+        the CURRENT parameters); ``allreduce=False`` keeps them local.  Both exist for bench.py's data-parallel self-check."""
         G, D, V = self.G, self.D, self.V
         dev = hazy.device
         lb = self.loss_buf
@@ -211,8 +228,10 @@ class GANTrainer:
         engine.discriminator_backward(D, ctx_r, dpr, self.sD.grad_views, False)
         engine.discriminator_backward(D, ctx_f, dpf, self.sD.grad_views, False)
         del ctx_r, ctx_f
-        fdist.allreduce_flat_(self.sD.grad, self.group)
-        self.sD.adam(self.lr, b1, b2, self.eps, gscale)
+        if allreduce:
+            fdist.allreduce_flat_(self.sD.grad, self.group)
+        if apply:
+            self.sD.adam(self.lr, b1, b2, self.eps, gscale)
 
         # ---------------- G step (D frozen: data gradient only)
         self.sG.zero_grad()
@@ -245,8 +264,10 @@ class GANTrainer:
             ops.copy4d(View.from_nchw(dxv), View.from_nchw(dfake), accumulate=True)
         engine.generator_backward(G, gctx, dfake, self.sG.grad_views, False)
         del gctx
-        fdist.allreduce_flat_(self.sG.grad, self.group)
-        self.sG.adam(self.lr, b1, b2, self.eps, gscale)
+        if allreduce:
+            fdist.allreduce_flat_(self.sG.grad, self.group)
+        if apply:
+            self.sG.adam(self.lr, b1, b2, self.eps, gscale)
 
         if sync_losses:
             self._read_losses()

@@ -269,6 +269,24 @@ int fdg_freq_concat_fwd(const FdgTensor* x, const FdgTensor* z, int N, int H, in
 int fdg_freq_concat_bwd(const FdgTensor* dz, const FdgTensor* dx, float* scratch /* N*3*H*W floats */, int N, int H,
                         int W, fdg_stream_t stream);
 
+/* Generic depth-wise filter: ONE l x l kernel applied to every (image, channel) plane -- the reference's Laplacian on any
+ * channel count (loss.pyc@L286-301: kernel.repeat(c,1,1,1), F.conv2d(groups=c), zero padding (k-1)/2) and Blur with a
+ * non-default size / kernel / normalisation (loss.pyc@L123-151: optional (x-mean)/std, ReflectionPad2d(l//2), conv per plane).
+ *   fwd: y (=|+=) correlate(pad((x - mean[c]) * inv_std[c]), kernel)      mean / inv_std may be NULL (no normalisation)
+ *   bwd: y += adjoint applied to x, i.e. x is the incoming gradient dL/d(fwd output) and y accumulates dL/d(fwd input)
+ *        (y must be initialised: zeros for a plain gradient).  l odd, 1 <= l <= 31; pad_mode 0 = zero, 1 = reflect. */
+typedef struct FdgDepthwise {
+  FdgTensor x, y;
+  int32_t n, h, w, c;
+  const float* kernel; /* l*l taps, row-major (device) */
+  int32_t l, pad_mode;
+  const float* mean;    /* [c] or NULL (device) */
+  const float* inv_std; /* [c] or NULL (device) */
+  int32_t accumulate;   /* fwd only */
+} FdgDepthwise;
+int fdg_depthwise2d_fwd(const FdgDepthwise* d, fdg_stream_t stream);
+int fdg_depthwise2d_bwd(const FdgDepthwise* d, fdg_stream_t stream);
+
 /* SSIM term of the generator loss and its gradient (reference arithmetic pytorch_ssim._ssim,
  * models/pytorch_ssim/__init__.py:17-37: window 11, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2):
  *   loss[0] += lscale * sum over (n,c,h,w) of ssim_map(x, y);   grad (=|+=) gscale * d(sum ssim_map)/dx   (grad may be NULL)

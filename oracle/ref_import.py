@@ -1,7 +1,7 @@
-"""Import the UNMODIFIED reference modules from /root/reference (authoring container only).
+"""Import the UNMODIFIED reference modules from /root/reference (authoring container) or from the byte-for-byte
+copy under baseline/_ref (GPU box; oracle/vendor_ref.py).
 
-TEST INFRASTRUCTURE ONLY.  The GPU box has no /root/reference: nothing that runs there
-imports this file.  Shims, none of which edit the reference:
+TEST / BASELINE INFRASTRUCTURE ONLY: tests, oracle/make_golden.py and bench.py's baseline legs.  Shims, none of which edit the reference:
   * torchvision.models.densenet121(pretrained=True) would download weights
     (models/dehaze1113.py:707) -> patched to build the architecture with weights=None;
   * class D registers sub-modules with dotted names ('layer1.conv',
@@ -17,7 +17,21 @@ import sys
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("FDGAN_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _find_root() -> str:
+    """/root/reference in the authoring container; on the GPU box the byte-for-byte copy oracle/vendor_ref.py placed under
+    baseline/_ref (git-ignored, travels with the snapshot)."""
+    env = os.environ.get("FDGAN_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "models", "dehaze1113.py")):
+        return "/root/reference"
+    return _VENDORED
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -3,6 +3,7 @@
     python profiles/make_summary.py launches gpurun_out/launches_X.csv profiles/rNN_launches.md "title"
     python profiles/make_summary.py kernel   gpurun_out/Y.ncu-rep      profiles/rNN_kernel_Y.md "title"
     python profiles/make_summary.py traffic  gpurun_out/launches_X.csv profiles/rNN_traffic.md "title" [profiles/rNN_traffic.json]
+    python profiles/make_summary.py sass     fdgan_b200/libfdgan_b200.so profiles/rNN_sass_opcounts.md "title"
 """
 import collections
 import csv
@@ -148,7 +149,8 @@ def traffic(src, dst_md, title, dst_json=None):
     with open(dst_md, "w") as f:
         f.write("\n".join(out) + "\n")
     if dst_json:
-        js = {"source": "ncu launch list of one step of bench.py --steps 1 --warmup 3 --quick (batch 16, 256x256, 1 B200): " + src,
+        js = {"src_sha": kernel_source_sha(),
+              "source": "ncu launch list of one step of bench.py --steps 1 --warmup 3 --quick (batch 16, 256x256, 1 B200): " + src,
               "families": {k: dict(launches=v["launches"], ms_under_ncu=round(v["ms"], 3), dram_bytes_per_launch=round(v["dram"] / v["launches"]),
                                    dram_gbs_under_ncu=round(v["dram"] / v["ms"] / 1e6, 1), tensor_pipe_active_pct=round(100 * v["tc_ms"] / v["ms"], 1))
                            for k, v in fam.items()}}
@@ -156,6 +158,56 @@ def traffic(src, dst_md, title, dst_json=None):
             json.dump(js, f, indent=1)
 
 
+def kernel_source_sha():
+    """Same hash as bench.py:kernel_source_sha (ties a capture to the kernel sources it was taken on)."""
+    import glob
+    import hashlib
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(root, "fdgan_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(root, "include", "*.h"))):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+SASS_OPS = ("UTCHMMA", "UTCQMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "LDGSTS", "HMMA", "FFMA", "RED", "ATOM")
+
+
+def sass(lib, dst, title):
+    """Per-kernel counts of the SASS mnemonics that prove tcgen05 / TMEM / TMA use (B200_PROFILING.md), from `cuobjdump -sass`."""
+    import re
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    filt = subprocess.run(["c++filt"], input="\n".join(re.findall(r"Function : (\S+)", out)), capture_output=True, text=True).stdout.splitlines()
+    names = iter(filt)
+    rows = []
+    cur = None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = {"name": next(names), "n": 0}
+            cur.update({k: 0 for k in SASS_OPS})
+            rows.append(cur)
+            continue
+        if cur is None:
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m:
+            cur["n"] += 1
+            op = m.group(1).split(".")[0]
+            if op in cur:
+                cur[op] += 1
+    md = ["# %s" % title, "", "Source: `cuobjdump -sass %s` (kernel sources %s), counted by `profiles/make_summary.py sass`." % (lib, kernel_source_sha()),
+          "`UTCHMMA` = tcgen05.mma (kind::f16), `LDTM` = tcgen05.ld (TMEM load), `UTMALDG` / `UTMASTG` = TMA tensor load / store,",
+          "`UBLKCP` = cp.async.bulk (1-D bulk copy), `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops, `LDGSTS` = cp.async.", "",
+          "| kernel | SASS instr | " + " | ".join(SASS_OPS) + " |", "|---|---:|" + "---:|" * len(SASS_OPS)]
+    for r in sorted(rows, key=lambda r: (-r["UTCHMMA"], -r["n"])):
+        nm = re.sub(r"^void ", "", r["name"]).split("(")[0]
+        md.append("| `%s` | %d | %s |" % (nm[:80], r["n"], " | ".join(str(r[k]) for k in SASS_OPS)))
+    open(dst, "w").write("\n".join(md) + "\n")
+
+
 if __name__ == "__main__":
     (traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else None) if sys.argv[1] == "traffic" else
-     {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else sys.argv[3]))
+     {"launches": launches, "kernel": kernel, "sass": sass}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else sys.argv[3]))

@@ -1,4 +1,4 @@
-"""CPU checks of bench.py's contract: the reference arm (the oracle port on the host cores) prints one JSON line with the
+"""CPU checks of bench.py's contract: the reference arm (the reference's own modules on the host cores) prints one JSON line with the
 agreed keys on the fdgan_b200 arm's metric / unit / config, only rank 0 works under torchrun, and the fdgan_b200 arm
 refuses to run without a GPU instead of falling back."""
 import json
@@ -24,11 +24,15 @@ def test_reference_arm_line():
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
+    sys.path.insert(0, ROOT)
     assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 2
     assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the reference's own modules (baseline/_ref or /root/reference) when present, else the oracle port -- and the line says which
+    from oracle import ref_step
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_step.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["sample_batch"] == d["sample_batch"] == 4 and "4-image" in d["cpu_baseline"]["sample"]      # the batch it really runs
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    sys.path.insert(0, ROOT)
     import bench
     assert d["metric"] == bench.METRIC
     assert d["config"] == bench.workload_config(16, 2, 64)      # the fdgan_b200 arm's config, key for key

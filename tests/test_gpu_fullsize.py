@@ -61,3 +61,75 @@ def test_train_step_paths_agree_at_256():
     for k in res[True]:
         a, b = float(res[True][k]), float(res[False][k])
         assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (k, a, b)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Against the CPU oracle at BASELINE.json's sizes: the oracle costs 1-15 s per case on the box's host cores.
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _host_mem_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
+
+
+def _bench_pairs(batch, size=256):
+    """bench.py's synthetic pairs: the benchmarked inputs themselves."""
+    import bench
+    prs = [bench.synth_pair(i, size) for i in range(batch)]
+    return torch.stack([p[0] for p in prs]), torch.stack([p[1] for p in prs])
+
+
+@pytest.mark.parametrize("batch", [1, 4, 16])
+def test_train_step_matches_oracle_at_256(batch):
+    """configs[1] (B=1) and configs[2] (B=16, the benchmarked configuration; B=4 as its cheaper sibling): one full G+D+VGG step of
+    GANTrainer on bench.py's inputs vs oracle.train_step.  Bars: generated image <= 1e-3 max-abs (north star), the five loss terms
+    <= 2e-3 relative, every parameter gradient of both networks within the relative-L2 criterion of tests/util.py."""
+    import fdgan_b200
+    from fdgan_b200.train import GANTrainer
+    if batch == 16 and _host_mem_gb() < 120:
+        pytest.skip("the CPU oracle's autograd graph at batch 16 needs ~60 GB of host memory")
+    hazy, clean = _bench_pairs(batch)
+    G, D, V = fdgan_b200.FDGAN(), fdgan_b200.D(9, 36), fdgan_b200.Vgg16()
+    G.load_state_dict(O.make_fdgan_state(0)); D.load_state_dict(O.make_d_state(9, 36, 1)); V.load_state_dict(O.make_vgg_state(2))
+    tr = GANTrainer(G.cuda().train(), D.cuda().train(), V.cuda())
+    fake = tr.step(hazy.cuda(), clean.cuda()).cpu()
+    last = dict(tr.last)
+    gG = {k: v.cpu() for k, v in tr.sG.grad_views.items()}
+    gD = {k: v.cpu() for k, v in tr.sD.grad_views.items()}
+    del tr, G, D, V
+    torch.cuda.empty_cache()
+    g_sd, d_sd, v_sd = O.make_fdgan_state(0), O.make_d_state(9, 36, 1), O.make_vgg_state(2)
+    parts, gd, gg, fake_o = O.train_step(g_sd, d_sd, v_sd, hazy, clean, {}, {})
+    err = maxabs(fake, fake_o)
+    assert err <= 1e-3, err
+    for k in ("loss_d", "loss_g", "l1_weighted", "perc_weighted", "adv_weighted"):
+        assert abs(last[k] - parts[k]) <= 2e-3 * max(1e-6, abs(parts[k])), (k, last[k], parts[k])
+    from tests.util import grad_close
+    worst = 0.0
+    for k, g in gd.items():
+        worst = max(worst, grad_close(gD[k], g, "D " + k, rel_l2=6e-2, rel_max=0.5)[0])
+    for k, g in gg.items():
+        worst = max(worst, grad_close(gG[k], g, "G " + k, rel_l2=6e-2, rel_max=0.5)[0])
+    # all gradients of a network as one vector: mask flips average out, so this is held much tighter than any single parameter
+    for name, mine, ref in (("G", gG, gg), ("D", gD, gd)):
+        num = sum(float((mine[k].double() - ref[k].double()).square().sum()) for k in ref)
+        den = sum(float(ref[k].double().square().sum()) for k in ref)
+        assert (num / den) ** 0.5 <= 2e-2, (name, (num / den) ** 0.5)
+    print("B=%d 256x256 step: fake max-abs %.2e, worst single-parameter gradient rel-L2 %.2e" % (batch, err, worst))
+
+
+def test_fdgan_forward_720p_matches_oracle():
+    """configs[4]: FDGAN forward on one 1280x720 image (train-mode BatchNorm, README.md:38) vs oracle.fdgan_forward, <= 1e-3 max-abs."""
+    net = _net()
+    g = torch.Generator().manual_seed(99)
+    x = torch.rand((1, 3, 720, 1280), generator=g)
+    with torch.no_grad():
+        y = net(x.cuda()).cpu()
+        yo = O.fdgan_forward(O.make_fdgan_state(0), x, True, False)
+    assert tuple(y.shape) == (1, 3, 720, 1280)
+    err = maxabs(y, yo)
+    print("720p forward max-abs vs oracle %.2e" % err)
+    assert err <= 1e-3, err

@@ -233,4 +233,36 @@ def test_blur_laplacian_modules():
     with pytest.raises(ValueError):
         L.laplace_filter(x[0].cuda())
     with pytest.raises(NotImplementedError):
-        L.Blur(l=7)
+        L.Blur(l=8, kernel=torch.ones(8, 8))
+    with pytest.raises(ValueError):
+        L.Blur(l=7)      # no kernel given
+
+
+def test_laplacian_is_channel_agnostic_and_blur_takes_any_kernel():
+    """loss.pyc@L286-301: Laplacian repeats its kernel over however many channels the input has (groups=c); loss.pyc@L123-151:
+    Blur takes any (l, kernel, use_input_norm).  Forward and input gradient against the oracle's restatement (autograd)."""
+    from fdgan_b200 import loss as L
+    for shape, ks in (((2, 5, 20, 27), 3), ((1, 3, 33, 18), 5), ((3, 1, 17, 40), 7), ((1, 9, 16, 16), 3)):
+        x = seeded(shape, 40 + ks)
+        r = seeded(shape, 41, -1.0, 1.0)
+        xo = x.clone().requires_grad_(True)
+        yo = O.laplacian(xo, ks)
+        (yo * r).sum().backward()
+        xd = x.cuda().requires_grad_(True)
+        y = L.Laplacian(ks)(xd)
+        (y * r.cuda()).sum().backward()
+        scale = float(ks * ks)
+        assert maxabs(y, yo) <= 1e-5 * scale and maxabs(xd.grad, xo.grad) <= 1e-5 * scale, (shape, ks)
+    for shape, l, sigma, norm in (((2, 3, 24, 30), 7, 1.5, True), ((1, 4, 40, 21), 9, 2.0, False), ((2, 3, 19, 19), 15, 3.0, False),
+                                  ((1, 2, 36, 50), 31, 6.0, False)):
+        x = seeded(shape, 50 + l)
+        r = seeded(shape, 51, -1.0, 1.0)
+        xo = x.clone().requires_grad_(True)
+        yo = O.blur(xo, l, sigma, norm)
+        (yo * r).sum().backward()
+        xd = x.cuda().requires_grad_(True)
+        y = L.Blur(l, L.isotropic_gaussian_kernel(l, sigma), norm)(xd)
+        (y * r.cuda()).sum().backward()
+        assert maxabs(y, yo) <= 2e-5 and maxabs(xd.grad, xo.grad) <= 2e-5, (shape, l)
+    with pytest.raises(RuntimeError):
+        L.Blur(7, L.isotropic_gaussian_kernel(7, 1.0), True)(seeded((1, 4, 16, 16), 1).cuda())      # ImageNet mean / std are 3-channel
