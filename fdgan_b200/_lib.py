@@ -82,6 +82,16 @@ class FdgDepthwise(C.Structure):
     ]
 
 
+class FdgPackJob(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("kind", C.c_int32), ("cout", C.c_int32), ("cin", C.c_int32), ("r", C.c_int32),
+        ("s", C.c_int32), ("ld", C.c_int32), ("first_block", C.c_int32), ("nblocks", C.c_int32), ("total", C.c_int64),
+    ]
+
+
+PACK_UMMA, PACK_K1 = 3, 4
+
+
 class FdgBnBwdFinalize(C.Structure):
     _fields_ = [
         ("stats", C.c_void_p), ("C", C.c_int), ("count", C.c_double),
@@ -119,6 +129,9 @@ _SIGS = {
     "fdg_colsum": ([_P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_fwd": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_bwd": ([_P(FdgTensor), _P(FdgTensor), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    "fdg_pack_job_items": ([_P(FdgPackJob)], C.c_int64),
+    "fdg_umma_ntile": ([C.c_int], C.c_int),
+    "fdg_pack_batch": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_depthwise2d_fwd": ([_P(FdgDepthwise), C.c_void_p], C.c_int),
     "fdg_depthwise2d_bwd": ([_P(FdgDepthwise), C.c_void_p], C.c_int),
     "fdg_ssim_loss_grad": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P(FdgTensor), C.c_int,

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cstdlib>
 
+#include "pack.cuh"
 #include "aop.cuh"
 #include "umma.cuh"
 #include "umma_epilogue.cuh"
@@ -358,35 +359,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) conv_k1_kernel(const __grid_con
 // out[(chunk, kx)][n = 0..191][64 k, SWIZZLE_128B]: n < 96: hi of (ky = n / 32, co = n % 32); n >= 96: lo of the same.
 // Source: fp32 GEMM operand w[(ky*3 + kx)*Cin + ci][ld].
 __global__ void pack_k1_kernel(const float* __restrict__ w, int ld, int Cin, int Cout, int cchunks, uint8_t* __restrict__ out, int64_t total) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int jj = (int)(i & 7);
-    int64_t r = i >> 3;
-    const int nrow = (int)(r % 96); r /= 96;
-    const int kx = (int)(r % 3);
-    const int cc = (int)(r / 3);
-    const int ky = nrow / 32, co = nrow - ky * 32;
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float f[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int ci = cc * 64 + jj * 8 + 2 * e + q;
-        f[q] = (co < Cout && ci < Cin) ? w[((int64_t)(ky * 3 + kx) * Cin + ci) * ld + co] : 0.f;
-      }
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(f[0], f[1]);
-      const float2 hf = __bfloat1622float2(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(f[0] - hf.x, f[1] - hf.y);
-      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    uint8_t* base = out + (int64_t)(cc * 3 + kx) * K1_B_TILE;
-    const int off_hi = nrow * 128 + ((jj ^ (nrow & 7)) << 4);
-    const int nlo = nrow + 96;
-    const int off_lo = nlo * 128 + ((jj ^ (nlo & 7)) << 4);
-    *reinterpret_cast<uint4*>(base + off_hi) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(base + off_lo) = make_uint4(l[0], l[1], l[2], l[3]);
-  }
+  static_assert(PACK_K1_B_TILE == K1_B_TILE, "pack.cuh and conv_k1.cu disagree on the weight tile size");
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    pack_k1_item(w, ld, Cin, Cout, out, i);
 }
 
 static int g_k1_on = [] { const char* e = getenv("FDG_K1"); return e ? atoi(e) : 1; }();

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "aop.cuh"
+#include "pack.cuh"
 #include "umma.cuh"
 #include "umma_epilogue.cuh"
 
@@ -631,40 +632,11 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
 // out[(ntile, kchunk)] = [hi: NT rows x 128 B, SWIZZLE_128B][lo: same]; source = fp32 [K][ld] GEMM operand
 __global__ void pack_umma_kernel(const float* __restrict__ w, int ld, int taps, int Cin, int Cout, int NT, int cchunks,
                                  uint8_t* __restrict__ out, int64_t total_pairs) {
-  // one thread per (ntile, kchunk, row n, 16-byte chunk j): 8 consecutive k of one output channel
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pairs; i += (int64_t)gridDim.x * blockDim.x) {
-    const int jj = (int)(i & 7);
-    int64_t r = i >> 3;
-    const int nrow = (int)(r % NT); r /= NT;
-    const int nchunks = taps * cchunks;
-    const int kc = (int)(r % nchunks);
-    const int nt = (int)(r / nchunks);
-    const int tap = kc / cchunks;
-    const int cbase = (kc - tap * cchunks) * UKC + jj * 8;
-    const int co = nt * NT + nrow;
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float f[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int ci = cbase + 2 * e + q;
-        f[q] = (co < Cout && ci < Cin) ? w[((int64_t)tap * Cin + ci) * ld + co] : 0.f;
-      }
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(f[0], f[1]);
-      const float2 hf = __bfloat1622float2(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(f[0] - hf.x, f[1] - hf.y);
-      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    uint8_t* base = out + ((int64_t)nt * nchunks + kc) * (2 * NT * 128);
-    const int off = nrow * 128 + ((jj ^ (nrow & 7)) << 4);
-    *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(base + NT * 128 + off) = make_uint4(l[0], l[1], l[2], l[3]);
-  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pairs; i += (int64_t)gridDim.x * blockDim.x)
+    pack_umma_item(w, ld, taps, Cin, Cout, NT, cchunks, out, i);
 }
 
-static inline int umma_ntile(int Cout) {
+int umma_ntile(int Cout) {
   static const int cap = [] { const char* e = getenv("FDG_UMMA_NT_CAP"); return e ? atoi(e) : 128; }();
   const int nt = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
   return nt > cap ? cap : nt;
@@ -766,6 +738,8 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
 }  // namespace fdg
 
 using namespace fdg;
+
+extern "C" int fdg_umma_ntile(int Cout) { return umma_ntile(Cout); }
 
 extern "C" int64_t fdg_umma_weight_bytes(int taps, int Cin, int Cout) {
   const int NT = umma_ntile(Cout);

@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "pack.cuh"
 
 namespace fdg {
 
@@ -427,26 +428,8 @@ __global__ void dgrad_strided_kernel(FdgDgradStrided p, int64_t total) {
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, int mode,
                                    float* __restrict__ out, int out_ld, int64_t total) {
   // total = K * out_ld over the destination; gather from the source layout
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int n = (int)(i % out_ld);
-    const int k = (int)(i / out_ld);
-    float v = 0.f;
-    if (mode == 0) {          // [(r,s,ci)][co] <- W[co][ci][r][s]
-      if (n < Cout) {
-        const int tap = k / Cin, ci = k - tap * Cin;
-        v = w[((int64_t)n * Cin + ci) * (R * S) + tap];
-      }
-    } else if (mode == 1) {   // [(r,s,co)][ci] <- W[co][ci][R-1-r][S-1-s]
-      if (n < Cin) {
-        const int tap = k / Cout, co = k - tap * Cout;
-        const int r = tap / S, s = tap - r * S;
-        v = w[((int64_t)co * Cin + n) * (R * S) + (R - 1 - r) * S + (S - 1 - s)];
-      }
-    } else {                  // [(co)][ci] <- W[ci][co]   (ConvTranspose2d 1x1 data gradient)
-      if (n < Cin) v = w[(int64_t)n * Cout + k];
-    }
-    out[i] = v;
-  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    pack_w_item(w, Cout, Cin, R, S, mode, out, out_ld, i);
 }
 
 // ------------------------------------------------------------------ fused Adam

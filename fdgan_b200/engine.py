@@ -120,6 +120,11 @@ def _transition_fwd(tr, X: View, S, y: View, ystats, ystats_ld, training, fpool,
 
 def generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
     """FDGAN.forward (models/dehaze1113.py:758-801).  x: [B,3,H,W] fp32 CUDA (any strides) -> [B,3,H',W']."""
+    with ops.pack_scope(m, "fwd", x.device):      # all weight-operand repacks of the pass in one launch per level
+        return _generator_forward(m, x, training, need_ctx)
+
+
+def _generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
     if x.dim() != 4 or x.shape[1] != 3:
         raise ValueError("FDGAN expects a [B,3,H,W] input, got %s" % (tuple(x.shape),))
     if not x.is_cuda or x.dtype != torch.float32:
@@ -318,6 +323,11 @@ def _tdy_bwd(tr, prefix, Dv: View, dD: View, gUp: View, grads):
 def generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: bool):
     """Backward of generator_forward.  ``grads`` maps parameter names to pre-zeroed fp32 tensors that the
     kernels accumulate into.  Returns dL/dx (NCHW) or None."""
+    with ops.pack_scope(m, "bwd", dout.device):
+        return _generator_backward(m, ctx, dout, grads, need_dx)
+
+
+def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: bool):
     if not ctx.training:
         raise RuntimeError("fdgan_b200: backward through FDGAN in eval() mode is not implemented (the reference always "
                            "runs BatchNorm on batch statistics, README.md:38)")
@@ -411,6 +421,11 @@ class DCtx:
 
 def discriminator_forward(m, z: torch.Tensor, training: bool, need_ctx: bool):
     """D.forward (models/dehaze1113.py:188-230): z [B,nc,H,W] -> sigmoid patch map [B,1,H/2-2,W/2-2]."""
+    with ops.pack_scope(m, "fwd", z.device):
+        return _discriminator_forward(m, z, training, need_ctx)
+
+
+def _discriminator_forward(m, z: torch.Tensor, training: bool, need_ctx: bool):
     if z.dim() != 4 or z.shape[1] != m.nc:
         raise ValueError("D expects a [B,%d,H,W] input, got %s" % (m.nc, tuple(z.shape)))
     if not z.is_cuda or z.dtype != torch.float32:
@@ -468,6 +483,11 @@ class _NoGrads(dict):
 
 
 def discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bool):
+    with ops.pack_scope(m, "bwd", dout.device):
+        return _discriminator_backward(m, ctx, dout, grads, need_dx)
+
+
+def _discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bool):
     if not ctx.training:
         raise RuntimeError("fdgan_b200: backward through D in eval() mode is not implemented")
     need_w = grads is not None

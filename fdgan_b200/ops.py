@@ -5,8 +5,9 @@ kernels on ``torch.cuda.current_stream()``; nothing here computes with torch ops
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
-
+import threading
 import weakref
 
 import torch
@@ -125,19 +126,27 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
         raise ValueError("conv2d: output view %s does not match %s" % ((y.N, y.H, y.W, y.C), (x.N, mul * OH, mul * OW, Cout)))
     if e is not None and (e.N, e.H, e.W, e.C) != (x.N, OH, OW, Cout):
         raise ValueError("conv2d: mask view shape mismatch")
-    images = getattr(w, "_fdg_images", None)      # packed operand of a frozen parameter: its tcgen05 images are cached
-    if w_umma is None and w_k1 is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and k1_eligible(x, Cout, R, S, stride, pad, gather):
-        w_k1 = images.get(("k1", x.C, Cout)) if images is not None else None
-        if w_k1 is None:
-            w_k1 = pack_weight_k1(w, w_ld, x.C, Cout, x.base.device)
-            if images is not None:
-                images[("k1", x.C, Cout)] = w_k1
-    elif w_umma is None and w_k1 is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA) and umma_eligible(x, Cout, R, S, stride, gather):
-        w_umma = images.get(("umma", R * S, x.C, Cout)) if images is not None else None
-        if w_umma is None:
-            w_umma = pack_weight_umma(w, w_ld, R * S, x.C, Cout, x.base.device)
-            if images is not None:
-                images[("umma", R * S, x.C, Cout)] = w_umma
+    if w_umma is None and w_k1 is None and impl != IMPL_SIMT and (USE_UMMA or impl == IMPL_UMMA):
+        ikey = None
+        if k1_eligible(x, Cout, R, S, stride, pad, gather):
+            ikey = ("k1", x.C, Cout)
+        elif umma_eligible(x, Cout, R, S, stride, gather):
+            ikey = ("umma", R * S, x.C, Cout)
+        if ikey is not None:
+            images = getattr(w, "_fdg_images", None)      # packed operand of a frozen parameter: its tcgen05 images are cached
+            plan = getattr(_TLS, "plan", None) if images is None else None
+            img = images.get(ikey) if images is not None else (plan.image(_ptr(w), w_ld, ikey) if plan is not None else None)
+            if img is None:
+                img = (pack_weight_k1(w, w_ld, x.C, Cout, x.base.device) if ikey[0] == "k1" else
+                       pack_weight_umma(w, w_ld, R * S, x.C, Cout, x.base.device))
+                if images is not None:
+                    images[ikey] = img
+                elif plan is not None:
+                    plan.add_image(_ptr(w), w_ld, ikey, img)
+            if ikey[0] == "k1":
+                w_k1 = img
+            else:
+                w_umma = img
     d = L.FdgConv(
         x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
         _ptr(w), w_ld, R, S, stride, pad, Cout, OH, OW, _ptr(bias), act,
@@ -195,6 +204,123 @@ def drop_frozen_in_range(lo: int, hi: int) -> int:
     return len(stale)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Pack plans: all operand repacks of one network pass in one launch per dependency level (fdg_pack_batch)
+# ----------------------------------------------------------------------------------------------------------------------
+USE_PACK_PLAN = True
+_TLS = threading.local()      # .plan: the PackPlan of the network pass running on this thread (nn.DataParallel workers are threads)
+
+
+class PackPlan:
+    """Operand images of the TRAINABLE parameters one network pass reads.  Parameters keep the PyTorch layout and change every
+    optimiser step, so their GEMM-operand / tcgen05 images are rebuilt per pass.  The first pass under a plan records every repack
+    (and runs it as its own launch); later passes refresh all of them with ONE launch per level -- level 0: fp32 GEMM operands made
+    from parameters, level 1: bf16 hi/lo images made from level-0 operands or directly from 1x1 parameters -- and the pack calls
+    return the plan's persistent tensors.  A lookup that misses (other shapes, re-homed parameters) is served by an individual
+    launch and makes the plan re-record on its next pass."""
+
+    ITEMS_PER_BLOCK = 1024      # 256 threads x 4 items
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.jobs = ([], [])
+        self.packed = {}
+        self.images = {}
+        self.tables = [None, None]
+        self.ready = False
+        self.broken = False
+
+    # -- level 0
+    def packed_operand(self, w: torch.Tensor, mode: int):
+        k = (w.data_ptr(), tuple(w.shape), mode)
+        hit = self.packed.get(k)
+        if hit is not None:
+            return hit
+        out, ld = _pack_weight(w, mode)
+        if self.ready:
+            self.broken = True
+            return out, ld
+        if mode == 2:
+            cin, cout, R, S = w.shape
+        else:
+            cout, cin, R, S = w.shape
+        self.jobs[0].append(L.FdgPackJob(w.data_ptr(), out.data_ptr(), mode, cout, cin, R, S, ld, 0, 0, 0))
+        self.packed[k] = (out, ld)
+        return out, ld
+
+    # -- level 1
+    def image(self, wptr: int, w_ld: int, ikey):
+        return self.images.get((wptr, w_ld, ikey))
+
+    def add_image(self, wptr: int, w_ld: int, ikey, img: torch.Tensor):
+        if self.ready:
+            self.broken = True
+            return
+        if ikey[0] == "k1":
+            _, cin, cout = ikey
+            job = L.FdgPackJob(wptr, img.data_ptr(), L.PACK_K1, cout, cin, 3, 3, w_ld, 0, 0, 0)
+        else:
+            _, taps, cin, cout = ikey
+            job = L.FdgPackJob(wptr, img.data_ptr(), L.PACK_UMMA, cout, cin, taps, int(L.lib.fdg_umma_ntile(cout)), w_ld, 0, 0, 0)
+        self.jobs[1].append(job)
+        self.images[(wptr, w_ld, ikey)] = img
+
+    def finalize(self, device):
+        for lvl in (0, 1):
+            jobs = self.jobs[lvl]
+            if not jobs:
+                continue
+            arr = (L.FdgPackJob * len(jobs))()
+            blk = 0
+            for i, j in enumerate(jobs):
+                total = int(L.lib.fdg_pack_job_items(C.byref(j)))
+                if total <= 0:
+                    raise RuntimeError("fdgan_b200: malformed pack job (kind %d, cout %d, cin %d)" % (j.kind, j.cout, j.cin))
+                j.total, j.first_block = total, blk
+                j.nblocks = (total + self.ITEMS_PER_BLOCK - 1) // self.ITEMS_PER_BLOCK
+                blk += j.nblocks
+                arr[i] = j
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+            self.tables[lvl] = (table, len(jobs), blk)
+        self.ready = True
+
+    def refresh(self):
+        st = _stream()
+        for lvl in (0, 1):
+            if self.tables[lvl] is not None:
+                table, n, blocks = self.tables[lvl]
+                L.check(L.lib.fdg_pack_batch(table.data_ptr(), n, blocks, st), "pack_batch")
+
+
+@contextlib.contextmanager
+def pack_scope(owner, name: str, device):
+    """Run one network pass (``name``: 'fwd' / 'bwd') of module ``owner`` under its pack plan."""
+    if not USE_PACK_PLAN or getattr(owner, "_is_replica", False):
+        yield None
+        return
+    plans = owner.__dict__.setdefault("_fdg_pack_plans", {})
+    key = (name, USE_UMMA, USE_K1, str(device))      # the conv path switches change which images a pass needs
+    plan = plans.get(key)
+    if plan is None:
+        plan = plans[key] = PackPlan()
+    prev = getattr(_TLS, "plan", None)
+    _TLS.plan = plan
+    ok = False
+    try:
+        if plan.ready:
+            plan.refresh()
+        yield plan
+        ok = True
+    finally:
+        _TLS.plan = prev
+        if not ok or plan.broken:
+            plan.reset()
+        elif not plan.ready:
+            plan.finalize(device)
+
+
 def invalidate_frozen() -> int:
     """Forget EVERY cached operand image.  Call after writing frozen parameters through ``param.data`` (``p.data.copy_``, EMA
     updates, a custom optimiser): such writes do not bump ``_version``, which is the only staleness signal the cache has."""
@@ -214,6 +340,9 @@ def pack_weight(w: torch.Tensor, mode: int) -> tuple[torch.Tensor, int]:
         if _CAPTURE_KEEPALIVE is not None:      # a captured graph bakes in the raw pointers of the operand AND its tcgen05 images
             _CAPTURE_KEEPALIVE.append(hit[1])
         return hit[1], hit[2]
+    plan = getattr(_TLS, "plan", None) if key is None else None
+    if plan is not None:
+        return plan.packed_operand(w, mode)
     out, ld = _pack_weight(w, mode)
     if key is not None:
         if len(_FROZEN) > 4096:

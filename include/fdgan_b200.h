@@ -328,6 +328,27 @@ int fdg_adam_flat_dev(float* param, const float* grad, float* exp_avg, float* ex
 int fdg_loss_grad(const float* a, const float* b, float target, int kind, int64_t n, float scale, float* grad,
                   int accumulate, double* loss, fdg_stream_t stream);
 
+/* All weight-operand repacks of one network pass in one launch (replaces the per-layer fdg_pack_weight /
+ * fdg_pack_weight_umma / fdg_pack_weight_k1 launches; the reference has no counterpart -- cuDNN re-reads the PyTorch
+ * layout).  jobs_dev: device array of njobs descriptors sorted by first_block; job j owns blocks
+ * [first_block, first_block + nblocks) of 256 threads, total_blocks = sum of nblocks.  Jobs of one launch must not
+ * depend on each other (an image made from a packed operand goes into a second launch).
+ *   kind 0..2         fdg_pack_weight mode: src = OIHW parameter, dst = fp32 [K][ld];  cout, cin, r, s = filter dims
+ *   FDG_PACK_UMMA     fdg_pack_weight_umma: src = fp32 [K][ld] operand, r = taps, s = N tile (fdg_umma_ntile(cout))
+ *   FDG_PACK_K1       fdg_pack_weight_k1:   src = fp32 [9*cin][ld] operand                                         */
+#define FDG_PACK_UMMA 3
+#define FDG_PACK_K1 4
+typedef struct FdgPackJob {
+  const float* src;
+  void* dst;
+  int32_t kind, cout, cin, r, s, ld;
+  int32_t first_block, nblocks;
+  int64_t total; /* work items = fdg_pack_job_items(job) */
+} FdgPackJob;
+int64_t fdg_pack_job_items(const FdgPackJob* job);
+int fdg_umma_ntile(int Cout);
+int fdg_pack_batch(const FdgPackJob* jobs_dev, int njobs, int total_blocks, fdg_stream_t stream);
+
 /* Live per-launch timing for bench.py's roofline: when enabled every entry point brackets its kernel with CUDA events
  * on the launching stream; collect() sums elapsed ms, algorithmic flops / bytes and launches per kernel family. */
 #define FDG_PROF_FAMILIES 6 /* 0 conv fp32 SIMT, 1 conv tcgen05, 2 weight gradient, 3 element-wise backward, 4 frequency, 5 other */

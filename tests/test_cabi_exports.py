@@ -37,7 +37,7 @@ def test_ctypes_structs_match_the_header_layout(lib, tmp_path):
     import subprocess
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
-    names = ["FdgTensor", "FdgConv", "FdgWgrad", "FdgBnFinalize", "FdgEwBwd", "FdgBnBwdFinalize", "FdgDgradStrided", "FdgDepthwise"]
+    names = ["FdgTensor", "FdgConv", "FdgWgrad", "FdgBnFinalize", "FdgEwBwd", "FdgBnBwdFinalize", "FdgDgradStrided", "FdgDepthwise", "FdgPackJob"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fdgan_b200.h"', "int main(void) {"]
     for n in names:
         cls = getattr(lib, n)
