@@ -86,8 +86,15 @@ constexpr int UTHREADS_P = (ULOAD_WARPS + 1 + 4) * 32;
 
 // DEPTH > 0: the loaders fetch through cp.async into a thread-private shared-memory staging ring (DEPTH chunks in
 // flight, no registers tied up by loads in flight); DEPTH == 0: two-chunk register double buffer.
-template <int NT, int STAGES, int DEPTH, bool BNBWD>
-__global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
+//
+// FAST (1x1 / stride 1 / direct gather over a pixel-linear view, DEPTH >= 2): the fp32 rows reach the staging ring through the
+// bulk-tensor engine instead of per-thread cp.async -- a 14th warp streams [128 pixels x 64 channels] chunks as two SWIZZLE_128B
+// boxes of 32 floats (zero fill past Cin / M comes from the tensor map) and also owns the weight-tile copies; the loader warps
+// only wait on an mbarrier, read their rows conflict-free, run the prologue + bf16 hi/lo split and store the operand tiles: no
+// address arithmetic, bounds predicates or cursor bookkeeping on the LSU-bound warps (ncu r01g: 18 instructions per fp32
+// element in the generic loader against ~6 here).
+template <int NT, int STAGES, int DEPTH, bool BNBWD, bool FAST = false>
+__global__ void __launch_bounds__(FAST ? UTHREADS_P + 32 : UTHREADS_P, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   constexpr int STAGING_BYTES = UM * UKC * 4;          // one raw fp32 chunk
@@ -98,6 +105,8 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   __shared__ __align__(8) uint64_t bar_empty[STAGES];
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_stg_full[DEPTH > 0 ? DEPTH : 1];     // FAST: staging slot filled by the bulk-tensor engine
+  __shared__ __align__(8) uint64_t bar_stg_empty[DEPTH > 0 ? DEPTH : 1];    // FAST: every loader warp has read the slot
   __shared__ uint32_t tmem_base_s;
   __shared__ float sred[2][4][NT];
   __shared__ __align__(1024) uint8_t ep_stage[EP_TILE_BYTES];   // epilogue staging tile: 128 pixels x 32 channels, SWIZZLE_128B box layout
@@ -116,6 +125,9 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
       mbar_init(smem_u32(&bar_full[s]), (BNBWD && a.a_split) ? 1 : ULOAD_WARPS + 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
+    if (FAST) {
+      for (int d = 0; d < DEPTH; ++d) { mbar_init(smem_u32(&bar_stg_full[d]), 1); mbar_init(smem_u32(&bar_stg_empty[d]), ULOAD_WARPS); }
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
       mbar_init(smem_u32(&bar_acc_empty[b]), (BNBWD && a.a_split) ? 8 : 4);   // split input: a second epilogue set (warps 4-7)
@@ -129,9 +141,9 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
   }
   const bool aff_smem = p.has_affine && p.Cin <= UMAX_AFF;
   if (aff_smem) {
-    for (int i = t; i < p.Cin; i += UTHREADS_P) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
+    for (int i = t; i < p.Cin; i += (int)blockDim.x) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
   }
-  for (int i = t; i < 2 * 4 * NT; i += UTHREADS_P) (&sred[0][0][0])[i] = 0.f;
+  for (int i = t; i < 2 * 4 * NT; i += (int)blockDim.x) (&sred[0][0][0])[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -172,6 +184,140 @@ __global__ void __launch_bounds__(UTHREADS_P, 1) conv_umma_kernel(const __grid_c
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
+      }
+    }
+  } else if (FAST && warp == UEPI_WARP0 + 4) {
+    // =============================================================== FAST: bulk-tensor producer (activations + weight tiles)
+    if (lane == 0) {
+      uint32_t held[STAGES];
+#pragma unroll
+      for (int j = 0; j < STAGES; ++j) held[j] = 0xffffffffu;
+      const uint32_t stg0 = smem_base + STAGES * STAGE_BYTES;
+      int my_tiles = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++my_tiles;
+      const int total_chunks = my_tiles * a.nchunks;
+      // cursor of the next chunk to stage (runs DEPTH chunks ahead of the weight-tile cursor)
+      int s_tile = blockIdx.x, s_kc = 0, s_q = 0;
+      auto stage_next = [&]() {
+        const int slot = s_q % DEPTH;
+        if (s_q >= DEPTH) mbar_wait(smem_u32(&bar_stg_empty[slot]), (uint32_t)((s_q / DEPTH) - 1) & 1u);
+        const uint32_t bar = smem_u32(&bar_stg_full[slot]);
+        const uint32_t dst = stg0 + (uint32_t)slot * STAGING_BYTES;
+        const int mt = s_tile % m_tiles;
+        mbar_arrive_expect_tx(bar, STAGING_BYTES);
+        tma_load_2d(dst, &a.xmap_hi, s_kc * UKC, mt * UM, bar);                          // channels [0, 32) of the chunk
+        tma_load_2d(dst + STAGING_BYTES / 2, &a.xmap_hi, s_kc * UKC + 32, mt * UM, bar);   // channels [32, 64)
+        ++s_q;
+        if (++s_kc == a.nchunks) { s_kc = 0; s_tile += gridDim.x; }
+      };
+      for (int q = 0; q < DEPTH && q < total_chunks; ++q) stage_next();
+      int s = 0;
+      uint32_t ph = 0;
+      int q = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / m_tiles;
+        for (int kc = 0; kc < a.nchunks; ++kc, ++q) {
+          // weight tile of chunk q into ring stage s (kept while the same tile is needed again)
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t bar = smem_u32(&bar_full[s]);
+          const uint32_t want = (uint32_t)(nt * a.nchunks + kc);
+          uint32_t have = 0xffffffffu;
+#pragma unroll
+          for (int j = 0; j < STAGES; ++j) if (j == s) have = held[j];
+          if (have != want) {
+            mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
+            bulk_g2s(smem_base + s * STAGE_BYTES + 2 * A_TILE_BYTES, reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)want * (2 * B_TILE_BYTES),
+                     2 * B_TILE_BYTES, bar);
+#pragma unroll
+            for (int j = 0; j < STAGES; ++j) if (j == s) held[j] = want;
+          } else {
+            mbar_arrive(bar);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          if (s_q < total_chunks) stage_next();      // refill the slot the loaders free while they work on chunk q
+        }
+      }
+    }
+  } else if (FAST && warp < ULOAD_WARPS) {
+    // =============================================================== FAST: A loaders fed by the staging ring
+    // thread = 16-byte bf16 chunk j (8 channels) of rows rbase + 32 i; in the fp32 boxes those channels are the two 16-byte
+    // chunks 2(j&3), 2(j&3)+1 of box j>>2, swizzled by row & 7.  Threads j >= 4 read their two chunks in the opposite order,
+    // so that the 8 threads of a row always touch 8 different bank groups (box 0 and box 1 rows alias bank-wise).
+    constexpr int RPT = UM * 8 / (ULOAD_WARPS * 32);   // 4 rows per thread
+    const int j = t & 7, rbase = t >> 3;
+    const uint32_t swz = (uint32_t)(rbase & 7);
+    const uint32_t c_even = ((uint32_t)(2 * (j & 3)) ^ swz) << 4, c_odd = ((uint32_t)(2 * (j & 3) + 1) ^ swz) << 4;
+    const uint32_t src0 = smem_base + STAGES * STAGE_BYTES + (uint32_t)(j >> 2) * (STAGING_BYTES / 2) + (uint32_t)rbase * 128u;
+    const uint32_t dst0 = (uint32_t)rbase * 128u + (((uint32_t)j ^ swz) << 4);
+    const bool flip = (j & 4) != 0;
+    const uint32_t aff0 = smem_u32(&aff_s[0][0]);
+    const float sl = p.slope;
+    auto lds4u = [](uint32_t addr) -> float4 {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+      return v;
+    };
+    int s = 0, q = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % m_tiles;
+      const int64_t mleft = a.M - (int64_t)mt * UM - rbase;      // rows rbase + 32 i exist while 32 i < mleft
+      for (int kc = 0; kc < a.nchunks; ++kc, ++q) {
+        const int slot = q % DEPTH;
+        const int c = kc * UKC + j * 8;
+        const bool cvalid = c < p.Cin;
+        float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+        if (p.has_affine && cvalid) {
+          sc0 = lds4u(aff0 + c * 4); sc1 = lds4u(aff0 + c * 4 + 16);
+          sh0 = lds4u(aff0 + (UMAX_AFF + c) * 4); sh1 = lds4u(aff0 + (UMAX_AFF + c) * 4 + 16);
+        }
+        mbar_wait(smem_u32(&bar_stg_full[slot]), (uint32_t)(q / DEPTH) & 1u);
+        const uint32_t src = src0 + (uint32_t)slot * STAGING_BYTES;
+        float4 v0[RPT], v1[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const uint32_t rs = src + (uint32_t)i * (32u * 128u);
+          if (flip) { v1[i] = lds4u(rs + c_odd); v0[i] = lds4u(rs + c_even); }
+          else { v0[i] = lds4u(rs + c_even); v1[i] = lds4u(rs + c_odd); }
+        }
+        uint32_t h[RPT][4], l[RPT][4];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          float4 x0 = v0[i], x1 = v1[i];
+          if (p.has_affine) {
+            x0.x = fmaf(x0.x, sc0.x, sh0.x); x0.y = fmaf(x0.y, sc0.y, sh0.y); x0.z = fmaf(x0.z, sc0.z, sh0.z); x0.w = fmaf(x0.w, sc0.w, sh0.w);
+            x1.x = fmaf(x1.x, sc1.x, sh1.x); x1.y = fmaf(x1.y, sc1.y, sh1.y); x1.z = fmaf(x1.z, sc1.z, sh1.z); x1.w = fmaf(x1.w, sc1.w, sh1.w);
+          }
+          if (sl == 0.f) {
+            x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
+            x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
+          } else if (sl != 1.f) {
+            x0.x = prologue_act(x0.x, sl); x0.y = prologue_act(x0.y, sl); x0.z = prologue_act(x0.z, sl); x0.w = prologue_act(x0.w, sl);
+            x1.x = prologue_act(x1.x, sl); x1.y = prologue_act(x1.y, sl); x1.z = prologue_act(x1.z, sl); x1.w = prologue_act(x1.w, sl);
+          }
+          if (!cvalid || (int64_t)(32 * i) >= mleft) {      // zero padding AFTER the prologue (a shifted zero is not zero)
+            x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0;
+          }
+          split2(x0.x, x0.y, h[i][0], l[i][0]);
+          split2(x0.z, x0.w, h[i][1], l[i][1]);
+          split2(x1.x, x1.y, h[i][2], l[i][2]);
+          split2(x1.z, x1.w, h[i][3], l[i][3]);
+        }
+        // the slot's values are in registers (consumed by the arithmetic above): hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_stg_empty[slot]));
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        const uint32_t a_hi = smem_base + s * STAGE_BYTES + dst0, a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const uint32_t off = (uint32_t)i * (32u * 128u);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[i][0]), "r"(h[i][1]), "r"(h[i][2]), "r"(h[i][3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[i][0]), "r"(l[i][1]), "r"(l[i][2]), "r"(l[i][3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp < ULOAD_WARPS && !epi2) {
@@ -653,13 +799,13 @@ int conv2d_umma_supported(const FdgConv* p) {
   return 1;
 }
 
-template <int NT, int STAGES, int DEPTH, bool BNBWD = false>
+template <int NT, int STAGES, int DEPTH, bool BNBWD = false, bool FAST = false>
 static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * NT * 128) + DEPTH * (UM * UKC * 4) + 1024;
   static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
-    if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES, DEPTH, BNBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_umma_kernel<NT, STAGES, DEPTH, BNBWD, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -671,7 +817,7 @@ static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
   ProfScope prof(PF_CONV_UMMA, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  conv_umma_kernel<NT, STAGES, DEPTH, BNBWD><<<grid, UTHREADS_P, smem, st>>>(a);
+  conv_umma_kernel<NT, STAGES, DEPTH, BNBWD, FAST><<<grid, FAST ? UTHREADS_P + 32 : UTHREADS_P, smem, st>>>(a);
   return check_launch("fdg_conv2d[tcgen05]");
 }
 
@@ -727,6 +873,16 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
       return FDG_ENOSUPPORT;
     }
     return umma_ntile(p->Cout) == 64 ? launch_umma<64, 2, 3, true>(a, st) : launch_umma<128, 2, 2, true>(a, st);
+  }
+  // 1x1 / stride 1 / direct gather over a pixel-linear view: the staging ring is fed by the bulk-tensor engine (FAST)
+  static const int fast_on = [] { const char* e = getenv("FDG_CONV_FAST"); return e ? atoi(e) : 1; }();
+  if (fast_on && umma_ntile(p->Cout) == 128 && p->R == 1 && p->S == 1 && p->stride == 1 && p->pad == 0 && p->gather == FDG_GATHER_DIRECT &&
+      vec4_ok(p->x) && p->x.sh == (int64_t)p->W * p->x.sw && p->x.sn == (int64_t)p->H * p->x.sh && p->Cin % 8 == 0 &&
+      (!p->has_affine || p->Cin <= UMAX_AFF) && a.M < (1ll << 31)) {
+    const uint64_t dims[2] = {(uint64_t)p->Cin, (uint64_t)a.M};
+    const uint64_t strides[1] = {(uint64_t)p->x.sw * 4};
+    const uint32_t box[2] = {32, 128};
+    if (make_tmap_f32(&a.xmap_hi, p->x.p, 2, dims, strides, box)) return launch_umma<128, 2, 2, false, true>(a, st);   // xmap_hi = the fp32 input view
   }
   switch (umma_ntile(p->Cout)) {
     case 32: return launch_umma<32, 2, 3>(a, st);     // ring 2 x 40 KB + staging 3 x 32 KB

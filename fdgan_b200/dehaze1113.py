@@ -231,7 +231,32 @@ class _KernelNet(nn.Module):
     def load_state_dict(self, state_dict, strict=True, **kw):
         return super().load_state_dict(_remap_checkpoint_keys(state_dict), strict=strict, **kw)
 
+    def _align_replica_tensors(self):
+        """nn.DataParallel replicas on devices other than the first receive their parameters as views into ONE coalesced broadcast
+        buffer (torch.nn.parallel.replicate -> comm.broadcast_coalesced), i.e. at arbitrary 4-byte offsets; the kernels read weights,
+        biases and BatchNorm vectors with 128-bit loads and bulk copies.  The executors read parameters through the attribute path
+        (``lyr.conv1.weight``), so every misaligned tensor of a replica is shadowed there by a 16-byte aligned copy (one multi-tensor
+        copy); the autograd node keeps the broadcast outputs as its inputs, so gradients still flow back to the original."""
+        if getattr(self, "_replica_aligned", False):
+            return
+        mods, keys, src = [], [], []
+        for m in self.modules():
+            for k, v in list(getattr(m, "_former_parameters", {}).items()) + list(m._buffers.items()):
+                if v is not None and v.is_floating_point() and v.data_ptr() % 16 != 0:
+                    mods.append(m); keys.append(k); src.append(v.detach())
+        if src:
+            dst = [torch.empty_like(v, memory_format=torch.contiguous_format) for v in src]
+            torch._foreach_copy_(dst, src)
+            for m, k, d in zip(mods, keys, dst):
+                if k in m._buffers:
+                    m._buffers[k] = d           # running statistics of a replica are scratch (DataParallel keeps the first device's)
+                else:
+                    m.__dict__[k] = d
+        object.__setattr__(self, "_replica_aligned", True)
+
     def _call(self, x):
+        if getattr(self, "_is_replica", False):
+            self._align_replica_tensors()
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for _n, p in self._used_named_parameters())):
             return _NetFn.apply(self, x, *[p for _n, p in self._used_named_parameters()])
         out, _ = self._run_forward(x, False)

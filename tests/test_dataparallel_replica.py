@@ -53,3 +53,30 @@ def test_replica_uses_its_own_parameters(pkg, which):
         mod, attr = n.rsplit(".", 1)
         assert rep.get_submodule(mod).__dict__[attr] is t     # the tensor the executors read through the attribute path
     assert net._used_named_parameters() is named             # the original keeps its cached list
+
+
+def test_replica_shadows_misaligned_tensors_with_aligned_copies(pkg):
+    """Replicas on the other devices get views into one coalesced broadcast buffer (arbitrary 4-byte offsets); the executors must see
+    16-byte aligned tensors of the same values while the autograd inputs stay the broadcast outputs."""
+    net = pkg.D(9, 36)
+    rep = _replicate_like_torch(net)
+    flat = torch.zeros(sum(t.numel() for _n, t in rep._used_named_parameters()) + 64)
+    off = 1                                              # start misaligned, as after a 3-float bias in the real buffer
+    originals = {}
+    for m in rep.modules():
+        for k, v in list(m._former_parameters.items()):
+            view = flat[off:off + v.numel()].view(v.shape)
+            view.copy_(v)
+            off += v.numel()
+            m._former_parameters[k] = view
+            m.__dict__[k] = view
+            originals[(id(m), k)] = view
+    assert any(v.data_ptr() % 16 for v in originals.values())
+    rep._align_replica_tensors()
+    for m in rep.modules():
+        for k, v in m._former_parameters.items():
+            seen = m.__dict__[k]
+            assert seen.data_ptr() % 16 == 0 and torch.equal(seen, v)
+            assert v is originals[(id(m), k)]            # the autograd inputs are untouched
+    named = rep._used_named_parameters()
+    assert all(t is originals[(id(rep.get_submodule(n.rsplit(".", 1)[0])), n.rsplit(".", 1)[1])] for n, t in named)

@@ -53,6 +53,10 @@ CONV_CASES = [
     (144, 288, 4, 1, 2, 21, 19, 0, True, 0.2, False, 0, 0, False, False),  # D layer 4 data-gradient geometry (4x4, pad 2)
     (32, 128, 3, 1, 1, 40, 40, 0, False, 1.0, False, 0, 0, False, True),   # dense-layer conv2 data gradient + ReLU mask
     (64, 64, 3, 1, 1, 5, 3, 0, False, 1.0, True, 1, 0, False, False),      # image smaller than one halo tile
+    (192, 128, 1, 1, 0, 40, 44, 0, True, 0.0, False, 0, 0, True, False),   # bulk-tensor-fed 1x1 loader: many tiles, 3 chunks, statistics
+    (72, 96, 1, 1, 0, 23, 17, 0, True, 0.2, True, 0, 0, False, False),     # ... Cin % 16 == 8 (half K slice), LeakyReLU prologue, bias
+    (512, 300, 1, 1, 0, 13, 10, 0, False, 0.0, False, 1, 0, False, False), # ... several N tiles (BottleneckBlockdy conv1 shape family)
+    (384, 128, 1, 1, 0, 12, 12, 0, False, 0.0, False, 1, 1, False, False), # ... TransitionBlockdy: ReLU prologue, up2 store
 ]
 
 
@@ -119,6 +123,31 @@ def test_conv2d(case, variant):
     if stats:
         tol = 2e-6 * float(N * OH * OW) + 1e-3   # fp32 partial sums over the tile, fp64 across tiles
         assert maxabs(st[:Cout], ysum) <= tol and maxabs(st[Cout + 3:2 * Cout + 3], ysq) <= tol
+
+
+@pytest.mark.parametrize("cin,ctot,c0", [(64, 256, 0), (96, 256, 32), (224, 256, 0), (128, 512, 384)])
+def test_conv2d_1x1_on_channel_slices_of_a_concat_buffer(cin, ctot, c0):
+    """Dense-layer conv1 as the generator runs it: the input is channels [c0, c0+cin) of a wider NHWC concat buffer (the bulk-tensor
+    loader's map clips at cin: the neighbouring channels must not leak in), the output goes into a channel slice of another one."""
+    ops = _ops()
+    N, H, W, Cout = 2, 19, 27, 128
+    buf = seeded((N, H, W, ctot), 1, -1.0, 1.0)
+    w = seeded((Cout, cin, 1, 1), 2, -1.0, 1.0) / math.sqrt(cin)
+    sc, sh = seeded((cin,), 4, 0.5, 1.5), seeded((cin,), 5, -0.3, 0.3)
+    x = buf[..., c0:c0 + cin].permute(0, 3, 1, 2).double()
+    y = F.conv2d(ref_prologue(x, sc.double(), sh.double(), 0.0), w.double())
+    bd = buf.cuda()
+    xv = ops.View.nhwc(bd, N, H, W, ctot).ch(c0, c0 + cin)
+    out = torch.full((N * H * W * 160,), 7.0, dtype=torch.float32, device="cuda")
+    yv = ops.View.nhwc(out, N, H, W, 160).ch(16, 16 + Cout)
+    wp, ld = ops.pack_weight(w.cuda(), 0)
+    st = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    ops.conv2d(xv, wp, ld, 1, 1, 1, 0, Cout, yv, scale=sc.cuda(), shift=sh.cuda(), slope=0.0, stats=st, stats_ld=Cout, impl=ops.IMPL_UMMA)
+    torch.cuda.synchronize()
+    o = out.view(N, H, W, 160)
+    assert maxabs(o[..., 16:16 + Cout].permute(0, 3, 1, 2), y) <= 5e-5
+    assert bool((o[..., :16] == 7.0).all()) and bool((o[..., 16 + Cout:] == 7.0).all())      # neighbours of the output slice untouched
+    assert maxabs(st[:Cout], y.sum((0, 2, 3))) <= 2e-6 * N * H * W + 1e-3
 
 
 @pytest.mark.parametrize("Cout,R,pad,mask", [(288, 4, 2, True), (288, 4, 2, False), (8, 4, 1, True), (288, 3, 1, True)])
