@@ -224,6 +224,8 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st);
 int wgrad_halo_supported(const FdgWgrad* p);
 int wgrad_thin(const FdgWgrad* p, cudaStream_t st);
 int wgrad_halo(const FdgWgrad* p, cudaStream_t st);
+int wgrad_k1_supported(const FdgWgrad* p);
+int wgrad_k1(const FdgWgrad* p, cudaStream_t st);
 }  // namespace fdg
 
 using namespace fdg;
@@ -269,10 +271,11 @@ extern "C" int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream) {
     if (rc == 0) return p->dbias ? fdg_colsum(&p->g, p->N, p->OH, p->OW, p->Cout, p->dbias, 1, stream) : FDG_OK;
   }
   if (p->impl != 1) {
-    const int ok = wgrad_umma_supported(p) || wgrad_halo_supported(p);
+    const int k1 = wgrad_k1_supported(p);      // growth convolutions: filter columns concatenated along N (wgrad_k1.cu)
+    const int ok = k1 || wgrad_umma_supported(p) || wgrad_halo_supported(p);
     if (p->impl == 2 && !ok) { set_error("fdg_conv2d_wgrad: impl=tcgen05 requested but shape/layout unsupported"); return FDG_ENOSUPPORT; }
     if (ok) {
-      const int rc = wgrad_halo_supported(p) ? wgrad_halo(p, st) : wgrad_umma(p, st);
+      const int rc = k1 ? wgrad_k1(p, st) : (wgrad_halo_supported(p) ? wgrad_halo(p, st) : wgrad_umma(p, st));
       if (rc != FDG_OK) return rc;
       if (p->dbias) return fdg_colsum(&p->g, p->N, p->OH, p->OW, p->Cout, p->dbias, 1, stream);
       return FDG_OK;

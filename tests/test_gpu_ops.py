@@ -222,6 +222,9 @@ WGRAD_CASES = [
     (128, 32, 3, 1, 1, 64, 48, 0, True, 0.0, False, False),      # K1, many 8x8 pixel blocks (halo weight-gradient kernel)
     (160, 40, 3, 1, 1, 19, 21, 0, True, 0.2, False, False),      # two channel blocks, two output-channel tiles, ragged blocks
     (64, 24, 4, 1, 1, 12, 12, 0, False, 1.0, False, False),      # 4x4 filter: 16 taps = all 512 TMEM columns
+    (160, 32, 3, 1, 1, 19, 37, 0, True, 0.2, False, False),      # growth-convolution kernel: two channel blocks (second one padded), ragged 16x8 tiles
+    (64, 8, 3, 1, 1, 17, 35, 0, False, 1.0, False, True),        # ... Cout < 32 (zero-padded gradient channels), half-empty channel block, bias gradient
+    (128, 32, 3, 1, 1, 8, 16, 0, True, 0.0, False, False),       # ... exactly one tile per image
 ]
 
 
