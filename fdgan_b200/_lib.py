@@ -96,7 +96,7 @@ class FdgBnBwdFinalize(C.Structure):
     _fields_ = [
         ("stats", C.c_void_p), ("C", C.c_int), ("count", C.c_double),
         ("gamma", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
-        ("coef", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate", C.c_int),
+        ("coef", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate", C.c_int), ("unit_alpha", C.c_int),
     ]
 
 

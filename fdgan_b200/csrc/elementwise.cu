@@ -54,7 +54,7 @@ __global__ void bn_bwd_finalize_kernel(FdgBnBwdFinalize p) {
   const double alpha = g * is;
   const double beta = -alpha * m2 * is;
   const double delta = -alpha * m1 + alpha * m2 * is * mu;
-  p.coef[c] = (float)alpha;
+  p.coef[c] = p.unit_alpha ? 1.f : (float)alpha;
   p.coef[p.C + c] = (float)beta;
   p.coef[2 * p.C + c] = (float)delta;
   if (p.dgamma) p.dgamma[c] = (p.accumulate ? p.dgamma[c] : 0.f) + (float)sum_dz_xhat;

@@ -232,6 +232,11 @@ def _conv_dgrad_w(weight):
 
 
 FUSED_BN1_BWD = True   # norm1 backward inside the conv1 data-gradient epilogue + deferred per-channel affine term
+# norm2 backward with the ReLU mask, alpha and the two reductions inside the conv2 data-gradient epilogue (halo kernel, FdgConv.e_scale with
+# a normal store) instead of the reduce pass.  Correct (test_conv2d_3x3_bn_backward_epilogue, module tests) but measured SLOWER on a B200
+# (76.1 -> 77.9 ms/step): the mask rows are read inside the epilogue's coalesced phase without the prefetch the per-tap kernel has, and the
+# bulk-tensor store is lost; off until the halo epilogue prefetches its mask rows.
+FUSED_BN2_BWD = False
 SPLIT_GRADS = True     # the bottleneck gradient travels as split-bf16 planes: its two consumers are fed by bulk tensor loads
 
 
@@ -264,8 +269,19 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
         g2 = dX.ch(cin, cin + GROWTH)
         ops.wgrad(T, g2, 3, 3, 1, 1, grads[p + ".conv2.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.0)
         wd, ldd = _conv_dgrad_w(lyr.conv2.weight)
-        ops.conv2d(g2, wd, ldd, 3, 3, 1, 1, BOTTLENECK, dA2)
-        _bn_bwd(dA2, T, bn2, dA2, dpool, grads, p + ".norm2", out_split=dA2s)      # dA2 <- dL/d(conv1 output) (in place / planes)
+        if fused and FUSED_BN2_BWD:
+            # the data-gradient epilogue reads the bottleneck tile once: dz = acc * [bn2(T) > 0], stores alpha * dz and reduces
+            # sum dz, sum dz * T; what is left of the BatchNorm backward is one pass dA2 + beta * T + delta (no mask, alpha = 1)
+            st2 = dpool.take(2 * BOTTLENECK)
+            ops.conv2d(g2, wd, ldd, 3, 3, 1, 1, BOTTLENECK, dA2, e=T, eslope=0.0, e_scale=bn2.scale, e_shift=bn2.shift, stats=st2,
+                       stats_ld=BOTTLENECK)
+            coef2 = torch.empty(3 * BOTTLENECK, dtype=torch.float32, device=dev)
+            ops.bn_bwd_finalize(st2, BOTTLENECK, bn2.count, bn2.mod.weight, bn2.mean, bn2.invstd, coef2, grads.get(p + ".norm2.weight"),
+                                grads.get(p + ".norm2.bias"), accumulate=True, unit_alpha=True)
+            ops.ew_bwd(dA2, T, out=None if split else dA2, coef=coef2, slope=1.0, out_split=dA2s)
+        else:
+            ops.conv2d(g2, wd, ldd, 3, 3, 1, 1, BOTTLENECK, dA2)
+            _bn_bwd(dA2, T, bn2, dA2, dpool, grads, p + ".norm2", out_split=dA2s)      # dA2 <- dL/d(conv1 output) (in place / planes)
         ops.wgrad(X.ch(0, cin), dA2sv if split else dA2, 1, 1, 1, 0, grads[p + ".conv1.weight"], scale=bn1.scale, shift=bn1.shift,
                   slope=0.0, g_split=dA2s)
         if fused:

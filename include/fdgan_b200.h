@@ -220,6 +220,7 @@ typedef struct FdgBnBwdFinalize {
   float* dgamma;       /* (+)= or NULL */
   float* dbeta;
   int accumulate;
+  int unit_alpha;      /* write coef[0..C) = 1: the producer of dz already multiplied it by alpha (FdgConv.e_scale epilogue, normal store) */
 } FdgBnBwdFinalize;
 
 int fdg_bn_bwd_finalize(const FdgBnBwdFinalize* p, fdg_stream_t stream);

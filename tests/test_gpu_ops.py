@@ -345,6 +345,42 @@ def test_conv2d_bn_backward_epilogue(shape):
     assert maxabs(dgm, gamma.grad) <= 2e-4 * max(1.0, scale_g) and maxabs(dbt, beta.grad) <= 2e-4 * max(1.0, float(beta.grad.abs().max()))
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 128, 19, 13, 0.0), (1, 32, 128, 40, 24, 0.0), (2, 48, 96, 9, 11, 0.2)])
+def test_conv2d_3x3_bn_backward_epilogue(shape):
+    """3x3 data-gradient conv (halo-tile kernel) with the BatchNorm-backward epilogue and a NORMAL store + fdg_bn_bwd_finalize(unit_alpha) +
+    one mask-free fdg_ew_bwd pass == autograd through conv3x3(leaky_relu(batch_norm(t))) w.r.t. t (dense-layer norm2 / conv2 backward)."""
+    ops = _ops()
+    N, Cout, Ct, H, W, slope = shape
+    t = seeded((N, Ct, H, W), 1, -2, 3).double().requires_grad_(True)
+    gamma = seeded((Ct,), 2, 0.5, 1.5).double().requires_grad_(True)
+    beta = seeded((Ct,), 3, -0.5, 0.5).double().requires_grad_(True)
+    w = (seeded((Cout, Ct, 3, 3), 4, -1, 1) / math.sqrt(9 * Ct)).double()
+    gout = seeded((N, Cout, H, W), 5, -1, 1).double()
+    y = F.conv2d(F.leaky_relu(F.batch_norm(t, None, None, gamma, beta, True, 0.1, 1e-5), slope), w, padding=1)
+    (y * gout).sum().backward()
+    cnt = N * H * W
+    td = cl(t.detach().float())
+    st = torch.stack([t.detach().sum((0, 2, 3)), (t.detach() ** 2).sum((0, 2, 3))]).reshape(-1).cuda()
+    buf = torch.zeros(4 * Ct, device="cuda")
+    ops.bn_finalize(st, Ct, Ct, cnt, gamma.detach().float().cuda(), beta.detach().float().cuda(), 1e-5, 0.1, None, None, True,
+                    buf[:Ct], buf[Ct:2 * Ct], buf[2 * Ct:3 * Ct], buf[3 * Ct:])
+    wd, ld = ops.pack_weight(w.float().cuda(), 1)                  # flipped [(r,s,co)][ci] operand of the data gradient
+    dz = cl(torch.zeros(N, Ct, H, W))
+    st2 = torch.zeros(2 * Ct, dtype=torch.float64, device="cuda")
+    tv = ops.View.from_nchw(td)
+    ops.conv2d(ops.View.from_nchw(cl(gout.float())), wd, ld, 3, 3, 1, 1, Ct, ops.View.from_nchw(dz), e=tv, eslope=slope,
+               e_scale=buf[:Ct], e_shift=buf[Ct:2 * Ct], stats=st2, stats_ld=Ct)
+    coef = torch.empty(3 * Ct, device="cuda")
+    dgm, dbt = torch.zeros(Ct, device="cuda"), torch.zeros(Ct, device="cuda")
+    ops.bn_bwd_finalize(st2, Ct, cnt, gamma.detach().float().cuda(), buf[2 * Ct:3 * Ct], buf[3 * Ct:], coef, dgm, dbt, unit_alpha=True)
+    assert maxabs(coef[:Ct], torch.ones(Ct)) == 0.0
+    dx = cl(torch.zeros(N, Ct, H, W))
+    ops.ew_bwd(ops.View.from_nchw(dz), tv, out=ops.View.from_nchw(dx), coef=coef, slope=1.0)
+    torch.cuda.synchronize()
+    assert maxabs(dx, t.grad) <= 1e-4
+    assert maxabs(dgm, gamma.grad) <= 2e-4 * max(1.0, float(gamma.grad.abs().max())) and maxabs(dbt, beta.grad) <= 2e-4 * max(1.0, float(beta.grad.abs().max()))
+
+
 def test_split_bf16_operands():
     """Split-bf16 planes (fdg_ew_bwd out_split) feeding fdg_conv2d (x_split, BatchNorm-backward epilogue) and
     fdg_conv2d_wgrad (g_split) give the same results as the fp32 tensors they replace: the kernels apply exactly this
