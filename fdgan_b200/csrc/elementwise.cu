@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) ew_bwd_linear_kernel(FdgEwBwd p, int64_t 
               lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
               *reinterpret_cast<uint2*>(hp) = hv;
               *reinterpret_cast<uint2*>(hp + M * p.C) = lv;
-              continue;
+              if (!obase) continue;      // planes only; with `out` given as well the fp32 tensor is written too (a second consumer reads fp32)
             }
             float* op = obase + m * p.out.sw;
             if (p.accumulate) {

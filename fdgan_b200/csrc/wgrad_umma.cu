@@ -488,8 +488,8 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
   a.dbg = dbg_flags();
   a.g_split = 0;
   if (p->g_split) {
-    if (p->Cout % 64 != 0 || a.M >= (1ll << 31)) {
-      set_error("fdg_conv2d_wgrad[tcgen05]: g_split needs Cout %% 64 == 0");
+    if (p->Cout % 8 != 0 || a.M >= (1ll << 31)) {      // rows of the planes must be 16-byte multiples; a partial last 64-channel box is zero-filled
+      set_error("fdg_conv2d_wgrad[tcgen05]: g_split needs Cout %% 8 == 0");
       return FDG_ENOSUPPORT;
     }
     const uint64_t dims[2] = {(uint64_t)p->Cout, (uint64_t)a.M};

@@ -66,9 +66,9 @@ def _bn_run(mod, stats, stats_ld, C, count, training, fpool, nbt_list):
 
 
 def _bn_bwd(g: View, x: View, run: BNRun, out: View, dpool, grads, prefix, *, slope=0.0, accumulate=False,
-            g_gather=GATHER_DIRECT, gscale=1.0, out_split=None):
+            g_gather=GATHER_DIRECT, gscale=1.0, out_split=None, both=False):
     """BatchNorm + (Leaky)ReLU backward: out (=|+=) dL/dx given g = dL/d(act(bn(x))).  With ``out_split`` the result is
-    written as split-bf16 planes (the tensor-core operand format) instead of ``out``."""
+    written as split-bf16 planes (the tensor-core operand format) instead of ``out`` (``both``: in addition to it)."""
     C = run.C
     st = dpool.take(2 * C)
     ops.ew_bwd(g, x, stats=st, scale=run.scale, shift=run.shift, slope=slope, g_gather=g_gather, gscale=gscale)
@@ -76,7 +76,7 @@ def _bn_bwd(g: View, x: View, run: BNRun, out: View, dpool, grads, prefix, *, sl
     dgamma = grads.get(prefix + ".weight") if grads is not None else None
     dbeta = grads.get(prefix + ".bias") if grads is not None else None
     ops.bn_bwd_finalize(st, C, run.count, run.mod.weight, run.mean, run.invstd, coef, dgamma, dbeta, accumulate=True)
-    ops.ew_bwd(g, x, out=None if out_split is not None else out, scale=run.scale, shift=run.shift, slope=slope, coef=coef,
+    ops.ew_bwd(g, x, out=None if (out_split is not None and not both) else out, scale=run.scale, shift=run.shift, slope=slope, coef=coef,
                accumulate=accumulate, g_gather=g_gather, gscale=gscale, out_split=out_split)
 
 
@@ -522,14 +522,23 @@ def _discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bo
     dY4 = View.alloc(Y4.N, Y4.H, Y4.W, Y4.C, dev)
     wd, ldd = ops.pack_weight(l5.weight, 1)
     ops.conv2d(g5, wd, ldd, 4, 4, 1, 2, Y4.C, dY4, e=Y4, eslope=0.2)
-    if need_w:
+    split_g = need_w and ops.USE_UMMA and SPLIT_GRADS
+    if split_g:
+        # layer 4 / layer 3 weight gradients run 18 / 6 CTAs per pixel range, each converting the SAME gradient rows to bf16 hi / lo;
+        # one pass writes them as split planes and the CTAs take them through bulk tensor loads (FdgWgrad.g_split)
+        p4 = torch.empty(dY4.N * dY4.H * dY4.W * dY4.C, dtype=torch.float32, device=dev)
+        ops.ew_bwd(dY4, dY4, slope=1.0, out_split=p4)
+        ops.wgrad(Y3, View.nhwc(p4, dY4.N, dY4.H, dY4.W, dY4.C), 4, 4, 1, 1, grads["main.layer4.conv.weight"], scale=bn3.scale, shift=bn3.shift,
+                  slope=0.2, g_split=p4)
+    elif need_w:
         ops.wgrad(Y3, dY4, 4, 4, 1, 1, grads["main.layer4.conv.weight"], scale=bn3.scale, shift=bn3.shift, slope=0.2)
     dY3 = View.alloc(Y3.N, Y3.H, Y3.W, Y3.C, dev)
     wd, ldd = ops.pack_weight(l4.weight, 1)
     ops.conv2d(dY4, wd, ldd, 4, 4, 1, 2, Y3.C, dY3)
-    _bn_bwd(dY3, Y3, bn3, dY3, dpool, grads if need_w else None, "main.layer3.layer3.bn", slope=0.2)
+    p3 = torch.empty(dY3.N * dY3.H * dY3.W * dY3.C, dtype=torch.float32, device=dev) if split_g else None
+    _bn_bwd(dY3, Y3, bn3, dY3, dpool, grads if need_w else None, "main.layer3.layer3.bn", slope=0.2, out_split=p3, both=True)
     if need_w:
-        ops.wgrad(Y2, dY3, 3, 3, 1, 1, grads["main.layer3.layer3.conv.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.2)
+        ops.wgrad(Y2, dY3, 3, 3, 1, 1, grads["main.layer3.layer3.conv.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.2, g_split=p3)
     dY2 = View.alloc(Y2.N, Y2.H, Y2.W, Y2.C, dev)
     wd, ldd = ops.pack_weight(l3.conv.weight, 1)
     ops.conv2d(dY3, wd, ldd, 3, 3, 1, 1, Y2.C, dY2)

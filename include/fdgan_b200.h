@@ -202,7 +202,8 @@ typedef struct FdgEwBwd {
   FdgTensor out;
   int accumulate;
   double* stats;       /* [2*C] or NULL */
-  void* out_split;     /* apply pass: write the result as split-bf16 planes [N*H*W][C] (hi, then lo) instead of `out`; or NULL */
+  void* out_split;     /* apply pass: write the result as split-bf16 planes [N*H*W][C] (hi, then lo), instead of `out` when out.p is NULL,
+                          in addition to it otherwise; or NULL */
 } FdgEwBwd;
 
 int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream);

@@ -424,6 +424,37 @@ def test_split_bf16_operands():
     assert maxabs(w2, w1) <= 1e-4 * max(1.0, float(w1.abs().max()))
 
 
+@pytest.mark.parametrize("cin,cout,R,pad", [(144, 288, 4, 1), (72, 144, 3, 1), (64, 72, 3, 1)])
+def test_wgrad_wide_tiles_take_split_planes(cin, cout, R, pad):
+    """Fusion-D layer 4 / layer 3 weight gradients (wide output-channel tiles, Cout % 64 != 0): gradient operand from split-bf16 planes
+    written by fdg_ew_bwd (planes AND the fp32 tensor in one pass) == the fp32 gradient operand."""
+    ops = _ops()
+    N, H, W = 2, 13, 11
+    x = seeded((N, cin, H, W), 1, -1, 1)
+    OH = H + 2 * pad - R + 1
+    OW = W + 2 * pad - R + 1
+    g = seeded((N, cout, OH, OW), 2, -1, 1)
+    t = seeded((N, cout, OH, OW), 3, -1, 1)
+    xv, gv, tv = ops.View.from_nchw(cl(x)), ops.View.from_nchw(cl(g)), ops.View.from_nchw(cl(t))
+    P = N * OH * OW
+    planes = torch.empty(P * cout, dtype=torch.float32, device="cuda")
+    d32 = ops.View.alloc(N, OH, OW, cout, "cuda")
+    ops.ew_bwd(gv, tv, out=d32, slope=0.2, out_split=planes)       # LeakyReLU mask; both outputs
+    want = g * torch.where(t > 0, 1.0, 0.2)
+    assert maxabs(d32.as_nchw(), want) <= 1e-6
+    bf = planes.view(torch.bfloat16)
+    assert maxabs((bf[:P * cout].float() + bf[P * cout:].float()).view(N, OH, OW, cout).permute(0, 3, 1, 2), want) <= 1e-5
+    w1 = torch.zeros(cout, cin, R, R, device="cuda")
+    w2 = torch.zeros_like(w1)
+    ops.wgrad(xv, d32, R, R, 1, pad, w1, slope=0.2)
+    ops.wgrad(xv, ops.View.nhwc(planes, N, OH, OW, cout), R, R, 1, pad, w2, slope=0.2, g_split=planes)
+    torch.cuda.synchronize()
+    ref = torch.zeros(cout, cin, R, R, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(F.leaky_relu(x.double(), 0.2), ref, padding=pad) * want.double()).sum().backward()
+    assert maxabs(w1, ref.grad) <= 5e-5 * max(1.0, float(ref.grad.abs().max()))
+    assert maxabs(w2, ref.grad) <= 5e-5 * max(1.0, float(ref.grad.abs().max()))
+
+
 def test_ew_bwd_pooled_gradient_scalar_path():
     ops = _ops()
     N, C, H, W = 2, 9, 6, 8   # C=9: scalar path
