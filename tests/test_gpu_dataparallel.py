@@ -1,7 +1,7 @@
 """nn.DataParallel over TWO GPUs in one process (demo.py:89 as the reference runs on a multi-GPU box): replicas get their own
 parameter copies, worker threads launch on their own device.  Skipped on a single-GPU box (there DataParallel calls the module
 directly); the replica plumbing itself is covered on CPU by tests/test_dataparallel_replica.py.
-NOT YET RUN (written after the GPU budget of round 1 was spent): `gpurun --gpus 2 -- python -m pytest tests/test_gpu_dataparallel.py`."""
+Run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_dataparallel.py` (round 2: passes on 2 x B200; profiles/r02_multigpu.md)."""
 import pytest
 import torch
 
