@@ -45,6 +45,7 @@ struct UmmaArgs {
   int tma_rank;                 // 2: the epilogue stores through ymap {channel, linear pixel}; 0: coalesced stores
   int bn_linear;                // BatchNorm-backward epilogue: y and e are pixel-linear views (pipelined variant)
   int a_split;                  // the A operand arrives as split-bf16 planes through xmap_hi / xmap_lo (no loader work)
+  int pf_ahead;                 // FAST: chunks of L2 prefetch in front of the staging ring (0 = none)
   alignas(64) CUtensorMap xmap_hi;
   alignas(64) CUtensorMap xmap_lo;
   alignas(64) CUtensorMap ymap;
@@ -198,7 +199,21 @@ __global__ void __launch_bounds__(FAST ? UTHREADS_P + 32 : UTHREADS_P, 1) conv_u
       const int total_chunks = my_tiles * a.nchunks;
       // cursor of the next chunk to stage (runs DEPTH chunks ahead of the weight-tile cursor)
       int s_tile = blockIdx.x, s_kc = 0, s_q = 0;
+      // L2 prefetch cursor, a.pf_ahead chunks in front of the staging cursor: two 32 KB slots in flight per SM are ~9.5 MB on the chip,
+      // about what HBM's loaded latency needs, but a slot is refilled only after the loaders drained it -- with the rows already in L2
+      // the refill is an L2 hit
+      int f_tile = blockIdx.x, f_kc = 0, f_q = 0;
+      auto prefetch_to = [&](int upto) {
+        while (f_q < upto && f_q < total_chunks) {
+          const int mt = f_tile % m_tiles;
+          if (f_kc * UKC < p.Cin) tma_prefetch_2d(&a.xmap_hi, f_kc * UKC, mt * UM);
+          if (f_kc * UKC + 32 < p.Cin) tma_prefetch_2d(&a.xmap_hi, f_kc * UKC + 32, mt * UM);
+          ++f_q;
+          if (++f_kc == a.nchunks) { f_kc = 0; f_tile += gridDim.x; }
+        }
+      };
       auto stage_next = [&]() {
+        if (a.pf_ahead > 0) prefetch_to(s_q + 1 + a.pf_ahead);
         const int slot = s_q % DEPTH;
         if (s_q >= DEPTH) mbar_wait(smem_u32(&bar_stg_empty[slot]), (uint32_t)((s_q / DEPTH) - 1) & 1u);
         const uint32_t bar = smem_u32(&bar_stg_full[slot]);
@@ -840,6 +855,8 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
     a.bn_linear = p->e_scale && p->e.p && lin(p->y) && lin(p->e) && vec4_ok(p->y) && vec4_ok(p->e) && p->store != FDG_STORE_UP2;
   }
   a.a_split = 0;
+  static const int pf_ahead = [] { const char* e = getenv("FDG_CONV_PF"); return e ? atoi(e) : 2; }();   // measured: 0.341 -> 0.335 ms (224->128 @256^2), 0.163 -> 0.153 ms (480->128 @128^2); 8 is slower
+  a.pf_ahead = pf_ahead;
   if (p->x_split) {
     if (!(a.bn_linear && p->R == 1 && p->S == 1 && p->stride == 1 && p->pad == 0 && p->gather == FDG_GATHER_DIRECT && !p->has_affine &&
           p->slope == 1.f && p->Cin % 64 == 0 && a.M < (1ll << 31))) {

@@ -21,6 +21,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem, const void* tmap, int
                : "memory");
 }
 
+// L2 prefetch of a box (no shared-memory destination, no completion tracking): issued a few chunks ahead of the real load, it
+// turns that load's DRAM latency into an L2 hit, so fewer bytes have to be in flight per SM to keep HBM busy
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem), "r"(c0), "r"(c1)
                : "memory");
