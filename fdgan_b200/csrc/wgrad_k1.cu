@@ -210,23 +210,51 @@ __global__ void __launch_bounds__(WK_THREADS, 1) wgrad_k1_kernel(const __grid_co
     umma_commit(smem_u32(&bar_acc));
   }
 
-  // =============================================================== epilogue: 3 accumulators [128 x 96] -> atomicAdd into dW (OIHW)
-  if (warp < 4 && ntiles > 0) {
-    mbar_wait(smem_u32(&bar_acc), 0);
+  // =============================================================== epilogue: 3 accumulators [128 x 96] -> dW (OIHW), reduced at L2
+  // For one output channel the CTA's 128 input channels x 9 taps are 1152 CONSECUTIVE floats of dW.  A lane holds one input channel,
+  // so reducing straight from registers is 288 scalar reductions per lane at a 36-byte lane stride (one 32-byte sector per lane and
+  // instruction: ~37 k sector operations per CTA, ~19 us -- more than the main loop at small batches).  The accumulators are
+  // therefore transposed through the (now idle) operand ring into dW's own order and leave as 128-bit reductions, 512 contiguous
+  // bytes per warp instruction (8x fewer sector operations).
+  if (warp < WK_LOAD_WARPS && ntiles > 0) {
+    mbar_wait(smem_u32(&bar_acc), 0);                        // every MMA has retired: the ring is free
     tc_fence_after();
-    const int ci = cb * 128 + warp * 32 + lane;
+    const int quarter = warp & 3;                            // TMEM lanes this warp may read
+    const int cil = quarter * 32 + lane;                     // input channel within the block
+    const uint32_t stg = smem_base;                          // [32 co][128 ci][9 taps] floats = 147456 B <= 2 * WK_STAGE
+    const bool vec = (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;
 #pragma unroll 1
-    for (int q = 0; q < 9; ++q) {                              // q = ky * 3 + view
+    for (int q = (warp >> 2) * 5; q < ((warp >> 2) ? 9 : 5); ++q) {      // warps 0-3: q = 0..4, warps 4-7: q = 5..8 (q = ky * 3 + view)
       const int ky = q / 3, kx = 2 - (q - ky * 3);
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32), v);
-      if (ci < p.Cin) {
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * 32), v);
+      if (vec) {
+        const uint32_t dst = stg + (uint32_t)(cil * 9 + ky * 3 + kx) * 4u;      // lane stride 9 words: conflict-free
 #pragma unroll
-        for (int u = 0; u < 32; ++u)
-          if (u < p.Cout) atomicAdd(p.dw + ((int64_t)u * p.Cin + ci) * 9 + ky * 3 + kx, v[u]);
+        for (int u = 0; u < 32; ++u) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (uint32_t)u * (1152u * 4u)), "f"(v[u]) : "memory");
+      } else {                                               // unaligned dW (a view at an odd offset): scalar reductions
+        const int ci = cb * 128 + cil;
+        if (ci < p.Cin) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+            if (u < p.Cout) atomicAdd(p.dw + ((int64_t)u * p.Cin + ci) * 9 + ky * 3 + kx, v[u]);
+        }
       }
     }
     tc_fence_before();
+    if (vec) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
+      const int valid4 = (p.Cin - cb * 128 < 128 ? p.Cin - cb * 128 : 128) * 9 / 4;      // float4s per output channel that hold data (Cin % 4 == 0)
+      float* base = p.dw + (int64_t)cb * 128 * 9;
+      for (int i = t; i < p.Cout * 288; i += WK_LOAD_WARPS * 32) {
+        const int co = i / 288, r = i - co * 288;
+        if (r < valid4) {
+          float4 val;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(stg + (uint32_t)(co * 1152 + r * 4) * 4u) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + (int64_t)co * p.Cin * 9 + r * 4), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+        }
+      }
+    }
   }
   __syncthreads();
   if (warp == WK_LOAD_WARPS) {
@@ -257,6 +285,15 @@ int wgrad_k1(const FdgWgrad* p, cudaStream_t st) {
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   const int num_sms = device_sm_count();
   int splits = a.cblocks >= num_sms ? 1 : num_sms / a.cblocks;
+  {
+    // every split ends with 128 x 288 atomics into the same addresses: with few pixel tiles (small batches / deep layers) the epilogues
+    // cost more than the tiles.  T(s) = tiles/s * t_tile + s * t_epi is minimal at s = sqrt(tiles * t_tile / t_epi) ~ sqrt(10 tiles)
+    // (measured: ~1.7 us per tile, ~0.17 us of atomics contention per split); batch 16 keeps one split per SM.
+    static const int kfac = [] { const char* e = getenv("FDG_WGRAD_SPLIT_FAC"); return e ? atoi(e) : 10; }();
+    int cap = 1;
+    while ((int64_t)cap * cap < (int64_t)kfac * a.total_ptiles) ++cap;
+    if (kfac > 0 && splits > cap) splits = cap;
+  }
   if (splits > a.total_ptiles) splits = a.total_ptiles;
   if (splits < 1) splits = 1;
   a.ptiles_per_split = cdiv(a.total_ptiles, splits);

@@ -469,6 +469,15 @@ static int launch_wu(WUArgs& a, cudaStream_t st) {
   int64_t splits = a.tiles >= num_sms ? 1 : num_sms / a.tiles;
   const int64_t max_splits = cdiv64(a.M, 8 * WU_P);
   if (splits > max_splits) splits = max_splits;
+  {
+    // every split ends with [128 x NT] atomics into the same addresses; with few pixel chunks the epilogues cost more than the chunks
+    // (see wgrad_k1.cu): cap the splits at ~sqrt(c * chunks)
+    static const int kfac = [] { const char* e = getenv("FDG_WGRAD_SPLIT_FAC"); return e ? atoi(e) : 10; }();
+    const int64_t chunks = cdiv64(a.M, WU_P);
+    int64_t cap = 1;
+    while (cap * cap * 4 < (int64_t)kfac * chunks) ++cap;      // a 32-pixel chunk is a quarter of wgrad_k1's 128-pixel tile
+    if (kfac > 0 && splits > cap) splits = cap;
+  }
   if (splits < 1) splits = 1;
   a.m_per_split = cdiv64(cdiv64(a.M, splits), WU_P) * WU_P;
   splits = cdiv64(a.M, a.m_per_split);
