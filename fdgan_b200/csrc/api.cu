@@ -1,6 +1,7 @@
 // Error reporting, launch accounting and version of the fdgan_b200 C ABI.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -35,6 +36,11 @@ int device_sm_count() {
     sms[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("FDG_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
 }
 
 static int g_dbg = 0;

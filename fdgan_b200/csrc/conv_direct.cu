@@ -25,6 +25,8 @@ struct ThinArgs {
 
 template <int NC4>   // Cout = 4 * NC4
 __global__ void __launch_bounds__(TH_THREADS) conv_thin_kernel(const __grid_constant__ ThinArgs a) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   constexpr int CO = 4 * NC4;
   constexpr int PITCH = CO + 4;                       // floats per tile row (16-byte aligned rows, conflict-free 128-bit access)
   extern __shared__ __align__(16) float smem[];
@@ -155,7 +157,7 @@ static int launch_thin(const ThinArgs& a, cudaStream_t st) {
   int64_t blocks = cdiv64(a.M, 8 * 32);
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope prof(PF_CONV_SIMT, 2.0 * (double)a.M * a.K * CO, 4.0 * ((double)a.M * CO + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  conv_thin_kernel<NC4><<<(unsigned)blocks, TH_THREADS, smem, st>>>(a);
+  launch_k(conv_thin_kernel<NC4>, dim3((unsigned)blocks), dim3(TH_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d[thin]");
 }
 
@@ -180,6 +182,8 @@ struct Cin1Args {
 };
 
 __global__ void __launch_bounds__(256) conv_cin1_kernel(const __grid_constant__ Cin1Args a) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   const FdgConv& p = a.c;
   const int OHW = p.OH * p.OW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -219,6 +223,8 @@ __global__ void __launch_bounds__(256) conv_cin1_kernel(const __grid_constant__ 
 // per thread -- 122 registers leave 16 warps per SM and one mask load in flight per thread.)
 template <int R, int S>
 __global__ void __launch_bounds__(256) conv_cin1_px4_kernel(const __grid_constant__ Cin1Args a, int owg, int64_t total) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   const FdgConv& p = a.c;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c, og, oy, n;
@@ -305,10 +311,10 @@ int conv2d_cin1(const FdgConv* p, cudaStream_t st) {
     int64_t nb = cdiv64(total, 256);
     const int64_t cap = (int64_t)device_sm_count() * 16;
     if (nb > cap) nb = cap;
-    conv_cin1_px4_kernel<4, 4><<<(unsigned)nb, 256, 0, st>>>(a, owg, total);
+    launch_k(conv_cin1_px4_kernel<4, 4>, dim3((unsigned)nb), dim3(256), (size_t)(0), st, a, owg, total);
     return check_launch("fdg_conv2d[cin1]");
   }
-  conv_cin1_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  launch_k(conv_cin1_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, a);
   return check_launch("fdg_conv2d[cin1]");
 }
 
@@ -323,6 +329,8 @@ namespace fdg {
 constexpr int DS_CI = 12;
 
 __global__ void __launch_bounds__(128) dgrad_strided_small_kernel(const __grid_constant__ FdgDgradStrided p, int64_t total) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   extern __shared__ __align__(16) float ws[];      // [R*S][Cout][DS_CI]
   const int taps = p.R * p.S;
   for (int i = threadIdx.x; i < taps * p.Cout * DS_CI; i += blockDim.x) {
@@ -382,7 +390,7 @@ int dgrad_strided_small(const FdgDgradStrided* p, cudaStream_t st) {
   const int64_t total = (int64_t)p->N * p->H * p->W;
   int64_t blocks = cdiv64(total, 128);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  dgrad_strided_small_kernel<<<(unsigned)blocks, 128, smem, st>>>(*p, total);
+  launch_k(dgrad_strided_small_kernel, dim3((unsigned)blocks), dim3(128), (size_t)(smem), st, *p, total);
   return check_launch("fdg_conv2d_dgrad_strided[small]");
 }
 
@@ -402,6 +410,8 @@ struct WThinArgs {
 
 template <int KB>
 __global__ void __launch_bounds__(WT_THREADS) wgrad_thin_kernel(const __grid_constant__ WThinArgs a) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   const FdgWgrad& p = a.c;
   const int K = a.K, Cout = p.Cout;
@@ -531,8 +541,8 @@ int wgrad_thin(const FdgWgrad* p, cudaStream_t st) {
   ctas = cdiv64(a.M, a.m_per_cta);
   const int smem = WT_P * (a.kgroups * kb + a.cgroups * 4) * 4;
   ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * K * p->Cout, 4.0 * ((double)a.M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);
-  if (kb == 3) wgrad_thin_kernel<3><<<(unsigned)ctas, WT_THREADS, smem, st>>>(a);
-  else wgrad_thin_kernel<6><<<(unsigned)ctas, WT_THREADS, smem, st>>>(a);
+  if (kb == 3) launch_k(wgrad_thin_kernel<3>, dim3((unsigned)ctas), dim3(WT_THREADS), (size_t)(smem), st, a);
+  else launch_k(wgrad_thin_kernel<6>, dim3((unsigned)ctas), dim3(WT_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d_wgrad[thin]");
 }
 

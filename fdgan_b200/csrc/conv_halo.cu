@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();      // PDL contract (common.cuh): barriers and TMEM are set up while the previous kernel drains; no global memory before this
+  pdl_trigger();
   const bool aff_smem = p.has_affine && p.Cin <= H_MAX_AFF;
   if (aff_smem)
     for (int i = t; i < p.Cin; i += H_THREADS) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
@@ -382,7 +384,7 @@ static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   const double M = (double)a.c.N * a.c.OH * a.c.OW;
   ProfScope prof(PF_CONV_UMMA, 2.0 * M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * (M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  conv_halo_kernel<NT, BSTAGES><<<grid, H_THREADS, smem, st>>>(a);
+  launch_k(conv_halo_kernel<NT, BSTAGES>, dim3(grid), dim3(H_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d[tcgen05 halo]");
 }
 

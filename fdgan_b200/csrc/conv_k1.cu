@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) conv_k1_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();      // PDL contract (common.cuh): barriers and TMEM are set up while the previous kernel drains; no global memory before this
+  pdl_trigger();
   const bool aff_smem = p.has_affine && p.Cin <= K1_MAX_AFF;
   if (aff_smem)
     for (int i = t; i < p.Cin; i += K1_THREADS) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
@@ -405,7 +407,7 @@ int conv2d_k1(const FdgConv* p, cudaStream_t st) {
   dim3 grid((unsigned)(a.total_tiles < num_sms ? a.total_tiles : num_sms));
   const double M = (double)p->N * p->OH * p->OW;
   ProfScope prof(PF_CONV_UMMA, 2.0 * M * 9 * p->Cin * p->Cout, 4.0 * (M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);
-  conv_k1_kernel<<<grid, K1_THREADS, K1_SMEM, st>>>(a);
+  launch_k(conv_k1_kernel, dim3(grid), dim3(K1_THREADS), (size_t)(K1_SMEM), st, a);
   return check_launch("fdg_conv2d[tcgen05 k1]");
 }
 

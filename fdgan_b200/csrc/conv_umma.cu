@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(FAST ? UTHREADS_P + 32 : UTHREADS_P, 1) conv_u
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();      // PDL contract (common.cuh): barriers and TMEM are set up while the previous kernel drains; no global memory before this
+  pdl_trigger();
   const bool aff_smem = p.has_affine && p.Cin <= UMAX_AFF;
   if (aff_smem) {
     for (int i = t; i < p.Cin; i += (int)blockDim.x) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
@@ -832,7 +834,7 @@ static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
   ProfScope prof(PF_CONV_UMMA, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  conv_umma_kernel<NT, STAGES, DEPTH, BNBWD, FAST><<<grid, FAST ? UTHREADS_P + 32 : UTHREADS_P, smem, st>>>(a);
+  launch_k(conv_umma_kernel<NT, STAGES, DEPTH, BNBWD, FAST>, dim3(grid), dim3(FAST ? UTHREADS_P + 32 : UTHREADS_P), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d[tcgen05]");
 }
 

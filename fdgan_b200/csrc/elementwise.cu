@@ -13,6 +13,8 @@ namespace fdg {
 
 // ------------------------------------------------------------------ BatchNorm finalize (forward)
 __global__ void bn_finalize_kernel(FdgBnFinalize p) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
   float scale, shift;
@@ -45,6 +47,8 @@ __global__ void bn_finalize_kernel(FdgBnFinalize p) {
 // dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  xhat = (x-mu)*invstd
 //    = alpha*dz + beta*x + delta
 __global__ void bn_bwd_finalize_kernel(FdgBnBwdFinalize p) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
   const double s1 = p.stats[c], s2 = p.stats[p.C + c];  // sum dz, sum dz*x
@@ -67,6 +71,8 @@ __global__ void bn_bwd_finalize_kernel(FdgBnBwdFinalize p) {
 // and reduces across the pixel lanes of the CTA in shared memory before the fp64 atomics.
 template <int VW, int UNR>
 __global__ void __launch_bounds__(256) ew_bwd_kernel(FdgEwBwd p, int64_t M, int cgroups, int pix_lanes) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   extern __shared__ float sm[];  // stats: [2][pix_lanes][cgroups*VW] partials
   const int cg = threadIdx.x % cgroups;
   const int pl = threadIdx.x / cgroups;
@@ -172,6 +178,8 @@ __global__ void __launch_bounds__(256) ew_bwd_kernel(FdgEwBwd p, int64_t M, int 
 // thread, four pixels per thread in flight per iteration (8 independent 128-bit loads).
 template <bool STATS>
 __global__ void __launch_bounds__(256) ew_bwd_linear_kernel(FdgEwBwd p, int64_t M, int cgroups, int pix_lanes) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   extern __shared__ float sm[];
   const int cg = threadIdx.x % cgroups;
   const int pl = threadIdx.x / cgroups;
@@ -268,6 +276,8 @@ __global__ void __launch_bounds__(256) ew_bwd_linear_kernel(FdgEwBwd p, int64_t 
 // ------------------------------------------------------------------ deferred affine part of the BatchNorm backward
 __global__ void __launch_bounds__(256) affine_accum_kernel(FdgTensor x, FdgTensor out, int64_t total4, int H, int W, int C4, const float* cb,
                                                            const float* cd) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
     int64_t r = i / C4;
@@ -285,6 +295,8 @@ __global__ void __launch_bounds__(256) affine_accum_kernel(FdgTensor x, FdgTenso
 
 // ------------------------------------------------------------------ max pool 2x2
 __global__ void maxpool2_fwd_kernel(FdgTensor x, FdgTensor y, int64_t total, int OH, int OW, int C) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     int64_t r = i / C;
@@ -299,6 +311,8 @@ __global__ void maxpool2_fwd_kernel(FdgTensor x, FdgTensor y, int64_t total, int
 
 __global__ void maxpool2_bwd_kernel(FdgTensor x, FdgTensor gy, FdgTensor gx, int64_t total, int OH, int OW, int C,
                                     int accumulate) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     int64_t r = i / C;
@@ -325,6 +339,8 @@ __global__ void maxpool2_bwd_kernel(FdgTensor x, FdgTensor gy, FdgTensor gx, int
 // ------------------------------------------------------------------ strided gather-copy with leaky slope
 __global__ void copy4d_kernel(FdgTensor x, FdgTensor y, int64_t total, int H, int W, int C, int gather, float slope,
                               float scale, int accumulate) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     int64_t r = i / C;
@@ -350,6 +366,8 @@ __global__ void copy4d_kernel(FdgTensor x, FdgTensor y, int64_t total, int H, in
 // (channel slices of the NHWC concat buffers: every copy of the generator's forward / backward walk)
 __global__ void __launch_bounds__(256) copy4d_vec4_kernel(FdgTensor x, FdgTensor y, int64_t total4, int H, int W, int C4, int gather,
                                                           float slope, float scale, int accumulate) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     int c, w, h, n;
     if (total4 <= 0x7fffffffLL) {     // 32-bit index arithmetic (a 64-bit division costs ~100 instructions)
@@ -388,6 +406,8 @@ __global__ void __launch_bounds__(256) copy4d_vec4_kernel(FdgTensor x, FdgTensor
 
 __global__ void act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ out, int64_t n,
                                int act) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float yy = y[i];
     out[i] = g[i] * (act == FDG_ACT_TANH ? (1.f - yy * yy) : yy * (1.f - yy));
@@ -436,6 +456,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2_sqrt, float gscale) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gr = g[i] * gscale;
     const float mi = b1 * m[i] + (1.f - b1) * gr;
@@ -449,6 +471,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 // Device-side step counter (CUDA-graph replay: no host value may change between replays).  state = {step, bc1, sqrt(bc2)}
 __global__ void adam_prepare_kernel(float* state, float b1, float b2) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   const float step = state[0] + 1.f;
   state[0] = step;
   state[1] = 1.f - powf(b1, step);
@@ -457,6 +481,8 @@ __global__ void adam_prepare_kernel(float* state, float b1, float b2) {
 
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
                                 float lr, float b1, float b2, float eps, const float* __restrict__ state, float gscale) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   const float bc1 = state[1], bc2_sqrt = state[2];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gr = g[i] * gscale;
@@ -473,6 +499,8 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, float target,
                                                         int kind, int64_t n, float scale, float* __restrict__ grad,
                                                         int accumulate, double* loss) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   float part = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float av = a[i];
@@ -523,14 +551,14 @@ int fdg_bn_finalize(const FdgBnFinalize* p, fdg_stream_t stream) {
   FDG_REQUIRE(p && p->C > 0 && p->gamma && p->beta && p->scale && p->shift, "fdg_bn_finalize: bad arguments");
   FDG_REQUIRE(!p->training || (p->stats && p->count > 0), "fdg_bn_finalize: training mode needs stats and count");
   FDG_REQUIRE(p->training || (p->running_mean && p->running_var), "fdg_bn_finalize: eval mode needs running stats");
-  bn_finalize_kernel<<<cdiv(p->C, 128), 128, 0, (cudaStream_t)stream>>>(*p);
+  launch_k(bn_finalize_kernel, dim3(cdiv(p->C, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, *p);
   return check_launch("fdg_bn_finalize");
 }
 
 int fdg_bn_bwd_finalize(const FdgBnBwdFinalize* p, fdg_stream_t stream) {
   FDG_REQUIRE(p && p->C > 0 && p->stats && p->gamma && p->mean && p->invstd && p->coef && p->count > 0,
               "fdg_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<cdiv(p->C, 128), 128, 0, (cudaStream_t)stream>>>(*p);
+  launch_k(bn_bwd_finalize_kernel, dim3(cdiv(p->C, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, *p);
   return check_launch("fdg_bn_bwd_finalize");
 }
 
@@ -562,15 +590,15 @@ int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
                 "fdg_ew_bwd: out_split needs the pixel-linear 128-bit path (unit channel stride, C %% 4 == 0, direct gather) and no accumulate");
   }
   if (fast) {
-    if (p->stats) ew_bwd_linear_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
-    else ew_bwd_linear_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+    if (p->stats) launch_k(ew_bwd_linear_kernel<true>, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, *p, M, cgroups, pix_lanes);
+    else launch_k(ew_bwd_linear_kernel<false>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, *p, M, cgroups, pix_lanes);
   } else if (vec) {
     // measured on the three transition backward passes (gradient gathered at half resolution): four pixels in flight cost
     // 104 registers and occupancy, 3.16 ms / step against 2.79 ms for the plain loop (profiles/r01h_launches_final.md)
     static const int unr = [] { const char* e = getenv("FDG_EW_UNR"); return e ? atoi(e) : 1; }();
-    if (unr == 4) ew_bwd_kernel<4, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
-    else ew_bwd_kernel<4, 1><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
-  } else ew_bwd_kernel<1, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(*p, M, cgroups, pix_lanes);
+    if (unr == 4) launch_k(ew_bwd_kernel<4, 4>, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, *p, M, cgroups, pix_lanes);
+    else launch_k(ew_bwd_kernel<4, 1>, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, *p, M, cgroups, pix_lanes);
+  } else launch_k(ew_bwd_kernel<1, 4>, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, *p, M, cgroups, pix_lanes);
   return check_launch("fdg_ew_bwd");
 }
 
@@ -581,14 +609,14 @@ int fdg_affine_accum(const FdgTensor* x, const FdgTensor* out, int N, int H, int
               "fdg_affine_accum: needs unit-stride channels, C % 4 == 0 and 16-byte aligned views / vectors");
   const int64_t total4 = (int64_t)N * H * W * (C / 4);
   ProfScope prof(PF_EW, 2.0 * (double)total4 * 4, 4.0 * (double)total4 * 4 * 3.0, (cudaStream_t)stream);
-  affine_accum_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)stream>>>(*x, *out, total4, H, W, C / 4, cb, cd);
+  launch_k(affine_accum_kernel, dim3(grid_for(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *out, total4, H, W, C / 4, cb, cd);
   return check_launch("fdg_affine_accum");
 }
 
 int fdg_maxpool2_fwd(const FdgTensor* x, const FdgTensor* y, int N, int OH, int OW, int C, fdg_stream_t stream) {
   FDG_REQUIRE(x && y && x->p && y->p && N > 0 && OH > 0 && OW > 0 && C > 0, "fdg_maxpool2_fwd: bad arguments");
   const int64_t total = (int64_t)N * OH * OW * C;
-  maxpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y, total, OH, OW, C);
+  launch_k(maxpool2_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *y, total, OH, OW, C);
   return check_launch("fdg_maxpool2_fwd");
 }
 
@@ -597,7 +625,7 @@ int fdg_maxpool2_bwd(const FdgTensor* x, const FdgTensor* gy, const FdgTensor* g
   FDG_REQUIRE(x && gy && gx && x->p && gy->p && gx->p && N > 0 && OH > 0 && OW > 0 && C > 0,
               "fdg_maxpool2_bwd: bad arguments");
   const int64_t total = (int64_t)N * OH * OW * C;
-  maxpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *gy, *gx, total, OH, OW, C, accumulate);
+  launch_k(maxpool2_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *gy, *gx, total, OH, OW, C, accumulate);
   return check_launch("fdg_maxpool2_bwd");
 }
 
@@ -607,17 +635,17 @@ int fdg_copy4d(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int 
   FDG_REQUIRE(gather >= 0 && gather <= 2, "fdg_copy4d: bad gather mode");
   const int64_t total = (int64_t)N * H * W * C;
   if (C % 4 == 0 && fdg::vec4_ok(*x) && fdg::vec4_ok(*y)) {
-    copy4d_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y, total / 4, H, W, C / 4, gather, slope, scale,
+    launch_k(copy4d_vec4_kernel, dim3(grid_for(total / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *y, total / 4, H, W, C / 4, gather, slope, scale,
                                                                                    accumulate);
     return check_launch("fdg_copy4d");
   }
-  copy4d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *y, total, H, W, C, gather, slope, scale, accumulate);
+  launch_k(copy4d_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *y, total, H, W, C, gather, slope, scale, accumulate);
   return check_launch("fdg_copy4d");
 }
 
 int fdg_act_bwd(const float* g, const float* y, float* out, int64_t n, int act, fdg_stream_t stream) {
   FDG_REQUIRE(g && y && out && n > 0 && (act == FDG_ACT_TANH || act == FDG_ACT_SIGMOID), "fdg_act_bwd: bad arguments");
-  act_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(g, y, out, n, act);
+  launch_k(act_bwd_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, g, y, out, n, act);
   return check_launch("fdg_act_bwd");
 }
 
@@ -652,7 +680,7 @@ int fdg_loss_grad(const float* a, const float* b, float target, int kind, int64_
                   int accumulate, double* loss, fdg_stream_t stream) {
   FDG_REQUIRE(a && loss && n > 0 && kind >= 0 && kind <= 2, "fdg_loss_grad: bad arguments");
   FDG_REQUIRE(kind == FDG_LOSS_BCE || b, "fdg_loss_grad: L1/MSE need a second operand");
-  loss_grad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, target, kind, n, scale, grad, accumulate, loss);
+  launch_k(loss_grad_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, b, target, kind, n, scale, grad, accumulate, loss);
   return check_launch("fdg_loss_grad");
 }
 
@@ -661,7 +689,7 @@ int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_av
   FDG_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "fdg_adam_flat: bad arguments");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+  launch_k(adam_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                   bc1, sqrtf(bc2), grad_scale);
   return check_launch("fdg_adam_flat");
 }
@@ -671,10 +699,10 @@ int fdg_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_av
 int fdg_adam_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                       float beta2, float eps, float* state, float grad_scale, fdg_stream_t stream) {
   FDG_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n > 0, "fdg_adam_flat_dev: bad arguments");
-  adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+  launch_k(adam_prepare_kernel, dim3(1), dim3(1), (size_t)(0), (cudaStream_t)stream, state, beta1, beta2);
   int rc = check_launch("fdg_adam_flat_dev[prepare]");
   if (rc != FDG_OK) return rc;
-  adam_dev_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state,
+  launch_k(adam_dev_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state,
                                                                       grad_scale);
   return check_launch("fdg_adam_flat_dev");
 }

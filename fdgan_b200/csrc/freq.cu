@@ -22,6 +22,8 @@ __constant__ float c_std[3] = {0.229f, 0.224f, 0.225f};
 __device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
 
 __global__ void __launch_bounds__(256) freq_fwd_kernel(FdgTensor x, FdgTensor z, int H, int W, const __grid_constant__ Gauss15 gk) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   __shared__ float raw[FH][FH + 1];
   __shared__ float nrm[FH][FH + 1];
   __shared__ float tmp[FH][FT + 1];
@@ -91,6 +93,8 @@ __device__ __forceinline__ float blur_adj_1d(const Gauss15& gk, const float* in,
 
 // pass 1: scratch[n][c][y][x] = adjoint along W of dz[:, 3+c]
 __global__ void freq_bwd_rows_kernel(FdgTensor dz, float* scratch, int N, int H, int W, const __grid_constant__ Gauss15 gk) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   const int64_t total = (int64_t)N * 3 * H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int xw = (int)(i % W);
@@ -106,6 +110,8 @@ __global__ void freq_bwd_rows_kernel(FdgTensor dz, float* scratch, int N, int H,
 // pass 2: dx = dz[:, c] + (1/std) * adjoint along H of scratch + Laplacian(dz[:, 6+c])  (symmetric kernel, zero pad)
 __global__ void freq_bwd_cols_kernel(FdgTensor dz, const float* scratch, FdgTensor dx, int N, int H, int W,
                                      const __grid_constant__ Gauss15 gk) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   const int64_t total = (int64_t)N * 3 * H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int xw = (int)(i % W);
@@ -235,7 +241,7 @@ extern "C" int fdg_freq_concat_fwd(const FdgTensor* x, const FdgTensor* z, int N
   static const Gauss15 gk = make_gauss();
   dim3 grid(cdiv(W, FT), cdiv(H, FT), N * 3);
   ProfScope prof(PF_FREQ, 2.0 * 234.0 * 3.0 * N * H * W, 48.0 * (double)N * H * W, (cudaStream_t)stream);
-  freq_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*x, *z, H, W, gk);
+  launch_k(freq_fwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *z, H, W, gk);
   return check_launch("fdg_freq_concat_fwd");
 }
 
@@ -247,10 +253,10 @@ extern "C" int fdg_freq_concat_bwd(const FdgTensor* dz, const FdgTensor* dx, flo
   const int64_t total = (int64_t)N * 3 * H * W;
   int64_t g = cdiv64(total, 256);
   if (g > 148 * 16) g = 148 * 16;
-  freq_bwd_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(*dz, scratch, N, H, W, gk);
+  launch_k(freq_bwd_rows_kernel, dim3((unsigned)g), dim3(256), (size_t)(0), (cudaStream_t)stream, *dz, scratch, N, H, W, gk);
   int rc = check_launch("fdg_freq_concat_bwd[rows]");
   if (rc != FDG_OK) return rc;
-  freq_bwd_cols_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(*dz, scratch, *dx, N, H, W, gk);
+  launch_k(freq_bwd_cols_kernel, dim3((unsigned)g), dim3(256), (size_t)(0), (cudaStream_t)stream, *dz, scratch, *dx, N, H, W, gk);
   return check_launch("fdg_freq_concat_bwd[cols]");
 }
 

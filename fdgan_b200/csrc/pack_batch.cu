@@ -12,6 +12,8 @@ namespace fdg {
 int umma_ntile(int Cout);
 
 __global__ void __launch_bounds__(256) pack_batch_kernel(const FdgPackJob* __restrict__ jobs, int njobs) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   // job of this block: last job whose first_block <= blockIdx.x (first_block is ascending)
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
@@ -60,6 +62,6 @@ extern "C" int64_t fdg_pack_job_items(const FdgPackJob* j) {
 
 extern "C" int fdg_pack_batch(const FdgPackJob* jobs_dev, int njobs, int total_blocks, fdg_stream_t stream) {
   FDG_REQUIRE(jobs_dev && njobs > 0 && total_blocks > 0, "fdg_pack_batch: bad arguments");
-  pack_batch_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
+  launch_k(pack_batch_kernel, dim3((unsigned)total_blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, jobs_dev, njobs);
   return check_launch("fdg_pack_batch");
 }

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo_kernel(const __grid_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();      // PDL contract (common.cuh): barriers and TMEM are set up while the previous kernel drains; no global memory before this
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -266,7 +268,7 @@ int wgrad_halo(const FdgWgrad* p, cudaStream_t st) {
   }
   const double M = (double)p->N * p->OH * p->OW;
   ProfScope prof(PF_WGRAD, 2.0 * M * p->R * p->S * p->Cin * p->Cout, 4.0 * (M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);
-  wgrad_halo_kernel<<<(unsigned)(groups * a.splits), WH_THREADS, smem, st>>>(a);
+  launch_k(wgrad_halo_kernel, dim3((unsigned)(groups * a.splits)), dim3(WH_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d_wgrad[tcgen05 halo]");
 }
 

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(WK_THREADS, 1) wgrad_k1_kernel(const __grid_co
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();      // PDL contract (common.cuh): barriers and TMEM are set up while the previous kernel drains; no global memory before this
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -310,7 +312,7 @@ int wgrad_k1(const FdgWgrad* p, cudaStream_t st) {
   }
   const double M = (double)p->N * p->OH * p->OW;
   ProfScope prof(PF_WGRAD, 2.0 * M * 9.0 * p->Cin * p->Cout, 4.0 * (M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);
-  wgrad_k1_kernel<<<(unsigned)(a.cblocks * a.splits), WK_THREADS, smem, st>>>(a);
+  launch_k(wgrad_k1_kernel, dim3((unsigned)(a.cblocks * a.splits)), dim3(WK_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d_wgrad[tcgen05 k1]");
 }
 

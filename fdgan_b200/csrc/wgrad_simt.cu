@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(WNT, 2) wgrad_simt_kernel(const __grid_constan
 
 // per-channel sum over all pixels (bias gradient and generic column sums)
 __global__ void colsum_kernel(FdgTensor x, int64_t M, int HW, int W, int C, float* out, int accumulate) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   // grid.x tiles channels by 32, grid.y splits pixels; block (32, 8)
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -181,6 +183,8 @@ __global__ void colsum_kernel(FdgTensor x, int64_t M, int HW, int W, int C, floa
 // iteration, partial sums reduced across the pixel lanes of the CTA in shared memory, one float atomic per channel
 __global__ void __launch_bounds__(256) colsum_vec4_kernel(FdgTensor x, int64_t M, int HW, int W, int C, int cgroups, int pix_lanes,
                                                           float* out) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
   __shared__ float4 red[256];
   const int cg = threadIdx.x % cgroups, pl = threadIdx.x / cgroups;
   const int c = (blockIdx.y * cgroups + cg) * 4;
@@ -246,13 +250,13 @@ extern "C" int fdg_colsum(const FdgTensor* x, int N, int H, int W, int C, float*
     int64_t gx = cdiv64(M, (int64_t)pix_lanes * 16);
     const int64_t cap = (int64_t)device_sm_count() * 8 / gyc + 1;
     if (gx > cap) gx = cap;
-    colsum_vec4_kernel<<<dim3((unsigned)gx, gyc), 256, 0, st>>>(*x, M, H * W, W, C, cgroups, pix_lanes, out);
+    launch_k(colsum_vec4_kernel, dim3(dim3((unsigned)gx, gyc)), dim3(256), (size_t)(0), st, *x, M, H * W, W, C, cgroups, pix_lanes, out);
     return check_launch("fdg_colsum");
   }
   int64_t gy = cdiv64(M, 8 * 64);
   if (gy > 1024) gy = 1024;
   dim3 grid(cdiv(C, 32), (unsigned)gy);
-  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(*x, M, H * W, W, C, out, accumulate);
+  launch_k(colsum_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), st, *x, M, H * W, W, C, out, accumulate);
   return check_launch("fdg_colsum");
 }
 

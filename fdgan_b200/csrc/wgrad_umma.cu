@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();      // PDL contract (common.cuh): barriers and TMEM are set up while the previous kernel drains; no global memory before this
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -483,7 +485,7 @@ static int launch_wu(WUArgs& a, cudaStream_t st) {
   splits = cdiv64(a.M, a.m_per_split);
   ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  wgrad_umma_kernel<NT, STAGES, FAST><<<(unsigned)(a.tiles * splits), WU_THREADS, smem, st>>>(a);
+  launch_k(wgrad_umma_kernel<NT, STAGES, FAST>, dim3((unsigned)(a.tiles * splits)), dim3(WU_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d_wgrad[tcgen05]");
 }
 
