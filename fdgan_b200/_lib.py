@@ -129,6 +129,8 @@ _SIGS = {
     "fdg_colsum": ([_P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_fwd": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_freq_concat_bwd": ([_P(FdgTensor), _P(FdgTensor), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    "fdg_event_record": ([C.c_void_p], C.c_int),
+    "fdg_stream_wait": ([C.c_void_p, C.c_int], C.c_int),
     "fdg_pack_job_items": ([_P(FdgPackJob)], C.c_int64),
     "fdg_umma_ntile": ([C.c_int], C.c_int),
     "fdg_pack_batch": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),

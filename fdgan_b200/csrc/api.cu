@@ -43,6 +43,8 @@ bool pdl_enabled() {
   return on;
 }
 
+static cudaEvent_t* g_event_ring[64] = {nullptr};      // per device: the ring fdg_event_record hands handles out of
+
 static int g_dbg = 0;
 int dbg_flags() { return g_dbg; }
 void set_dbg_flags(int v) { g_dbg = v; }
@@ -117,6 +119,37 @@ int fdg_profile_collect(double* ms, double* flops, double* bytes, int64_t* launc
   }
   fdg::g_prof_recs.clear();
   cudaGetLastError();
+  return FDG_OK;
+}
+
+// Light-weight stream fork / join for the executors (one ctypes call each instead of a torch Event object + context manager):
+// a per-device ring of timing-disabled events.  fdg_event_record enqueues a record on `stream` and returns a handle;
+// fdg_stream_wait makes `stream` wait for that point.  Legal under stream capture (they become graph dependencies).  A handle
+// stays valid for FDG_EVENT_RING further records on its device.
+int fdg_event_record(fdg_stream_t stream) {
+  constexpr int RING = 1024;
+  static cudaEvent_t ring[64][RING];
+  static std::atomic<unsigned> next[64];
+  static std::mutex mu;
+  const int dev = fdg::current_device();
+  const unsigned slot = next[dev].fetch_add(1u) % RING;
+  cudaEvent_t& ev = ring[dev][slot];
+  if (!ev) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { fdg::set_error("fdg_event_record: cannot create an event"); return FDG_ECUDA; }
+  }
+  if (cudaEventRecord(ev, (cudaStream_t)stream) != cudaSuccess) { fdg::set_error("fdg_event_record: cudaEventRecord failed: %s", cudaGetErrorString(cudaGetLastError())); return FDG_ECUDA; }
+  fdg::g_event_ring[dev] = &ring[dev][0];
+  return (int)slot;
+}
+
+int fdg_stream_wait(fdg_stream_t stream, int handle) {
+  const int dev = fdg::current_device();
+  FDG_REQUIRE(handle >= 0 && handle < 1024 && fdg::g_event_ring[dev] && fdg::g_event_ring[dev][handle], "fdg_stream_wait: bad event handle %d", handle);
+  if (cudaStreamWaitEvent((cudaStream_t)stream, fdg::g_event_ring[dev][handle], 0) != cudaSuccess) {
+    fdg::set_error("fdg_stream_wait: cudaStreamWaitEvent failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return FDG_ECUDA;
+  }
   return FDG_OK;
 }
 

@@ -240,6 +240,22 @@ FUSED_BN2_BWD = False
 SPLIT_GRADS = True     # the bottleneck gradient travels as split-bf16 planes: its two consumers are fed by bulk tensor loads
 
 
+# Weight gradients are leaves of the backward graph: nothing downstream reads them before the optimiser.  On small problems (batch 1,
+# deep 64x64 / 32x32 maps) every kernel is latency-bound and leaves most SMs idle, so the dense-block weight gradients are enqueued on a
+# side stream and overlap the data-gradient chain (fork / join through events: legal under CUDA-graph capture, where they become
+# parallel branches).  ``ASYNC_WGRAD_MAX_PIXELS``: largest N*H*W of a block for which this is done (0 = never).
+ASYNC_WGRAD_MAX_PIXELS = int(__import__("os").environ.get("FDG_ASYNC_WGRAD_PIXELS", str(4 * 65536)))
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return s
+
+
 def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, grads, dpool):
     """Backward of one torchvision dense block.  norm1 of layer j reads concat channels [0, cin_j) with the SAME batch
     statistics as every other consumer of those channels, so its backward dx = alpha dz + (beta x + delta) splits into
@@ -250,24 +266,45 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
     N, H, W = X.N, X.H, X.W
     dev = X.base.device
     Ctot = X.C
-    dA2 = View.alloc(N, H, W, BOTTLENECK, dev)
     cmax = c_in + GROWTH * (n_layers - 1)
     fused = FUSED_BN1_BWD and ops.USE_UMMA
     split = fused and SPLIT_GRADS
+    # weight gradients on a side stream (small problems only); the bottleneck-gradient buffers then alternate between two copies, because
+    # the side stream may still read layer i's while the main stream produces layer i-1's
+    # (eager steps at batch < 4 are bound by the host's launch rate -- 15 ms of Python for 10 ms of kernels at batch 1 -- so the extra fork /
+    # join calls would cost more than the overlap returns: there it is used only while a CUDA graph is being captured)
+    async_w = (0 < N * H * W <= ASYNC_WGRAD_MAX_PIXELS and grads is not None and not isinstance(grads, _NoGrads) and
+               (N >= 4 or torch.cuda.is_current_stream_capturing()))
+    nbuf = 2 if async_w else 1
+    main = torch.cuda.current_stream(dev).cuda_stream if async_w else None       # raw handles: fork / join are single C-ABI calls
+    side_t = _side_stream(dev) if async_w else None
+    side = side_t.cuda_stream if async_w else None
+    done1 = {}                                     # layer -> point on the side stream after its conv1 weight gradient
+    dA2_b = [View.alloc(N, H, W, BOTTLENECK, dev) for _ in range(nbuf)]
     # dL/d(conv1 output) after the norm2 backward, as bf16 hi / lo planes [pixels][128] (same bytes as fp32)
-    dA2s = torch.empty(N * H * W * BOTTLENECK, dtype=torch.float32, device=dev) if split else None
-    dA2sv = View.nhwc(dA2s, N, H, W, BOTTLENECK) if split else None
+    dA2s_b = [torch.empty(N * H * W * BOTTLENECK, dtype=torch.float32, device=dev) if split else None for _ in range(nbuf)]
     dA1buf = None if fused else torch.empty(N * H * W * cmax, dtype=torch.float32, device=dev)
     cbd = torch.zeros(2, Ctot, dtype=torch.float32, device=dev) if fused else None   # deferred beta / delta sums
+
+    def wgrad_leaf(*a, **k):
+        if not async_w:
+            return ops.wgrad(*a, **k)
+        ops.stream_wait(side, ops.event_record(main))      # fork: the side stream sees everything enqueued so far
+        ops.wgrad(*a, stream=side, **k)
+
     for i in reversed(range(n_layers)):
         lyr = getattr(block, "denselayer%d" % (i + 1))
         p = "%s.denselayer%d" % (prefix, i + 1)
         cin = c_in + GROWTH * i
         T, bn1, bn2 = layers[i]
+        dA2, dA2s = dA2_b[i % nbuf], dA2s_b[i % nbuf]
+        dA2sv = View.nhwc(dA2s, N, H, W, BOTTLENECK) if split else None
+        if async_w and (i + 2) in done1:
+            ops.stream_wait(main, done1.pop(i + 2))      # the side stream has finished reading this pair of buffers (layer i + 2)
         if fused and i < n_layers - 1:   # the later layers' affine terms for this layer's 32 new channels
             ops.affine_accum(X.ch(cin, cin + GROWTH), dX.ch(cin, cin + GROWTH), cbd[0, cin:cin + GROWTH], cbd[1, cin:cin + GROWTH])
         g2 = dX.ch(cin, cin + GROWTH)
-        ops.wgrad(T, g2, 3, 3, 1, 1, grads[p + ".conv2.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.0)
+        wgrad_leaf(T, g2, 3, 3, 1, 1, grads[p + ".conv2.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.0)
         wd, ldd = _conv_dgrad_w(lyr.conv2.weight)
         if fused and FUSED_BN2_BWD:
             # the data-gradient epilogue reads the bottleneck tile once: dz = acc * [bn2(T) > 0], stores alpha * dz and reduces
@@ -282,8 +319,10 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
         else:
             ops.conv2d(g2, wd, ldd, 3, 3, 1, 1, BOTTLENECK, dA2)
             _bn_bwd(dA2, T, bn2, dA2, dpool, grads, p + ".norm2", out_split=dA2s)      # dA2 <- dL/d(conv1 output) (in place / planes)
-        ops.wgrad(X.ch(0, cin), dA2sv if split else dA2, 1, 1, 1, 0, grads[p + ".conv1.weight"], scale=bn1.scale, shift=bn1.shift,
-                  slope=0.0, g_split=dA2s)
+        wgrad_leaf(X.ch(0, cin), dA2sv if split else dA2, 1, 1, 1, 0, grads[p + ".conv1.weight"], scale=bn1.scale, shift=bn1.shift,
+                   slope=0.0, g_split=dA2s)
+        if async_w:
+            done1[i] = ops.event_record(side)
         if fused:
             st = dpool.take(2 * cin)
             ops.conv2d(dA2sv if split else dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dX.ch(0, cin), store=STORE_ACCUM, e=X.ch(0, cin),
@@ -298,6 +337,8 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
             _bn_bwd(dA1, X.ch(0, cin), bn1, dX.ch(0, cin), dpool, grads, p + ".norm1", accumulate=True)
     if fused:
         ops.affine_accum(X.ch(0, c_in), dX.ch(0, c_in), cbd[0, :c_in], cbd[1, :c_in])
+    if async_w:
+        ops.stream_wait(main, ops.event_record(side))       # join: the buffers above die with this frame; the optimiser reads the gradients on the main stream
 
 
 def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dpool):

@@ -155,8 +155,20 @@ def conv2d(x: View, w, w_ld, R, S, stride, pad, Cout, y: View, *, gather=GATHER_
     L.check(L.lib.fdg_conv2d(_byref(d), _stream()), "conv2d")
 
 
+def event_record(stream: int) -> int:
+    """fdg_event_record: a point on ``stream`` (raw cudaStream_t) as a small integer handle."""
+    h = int(L.lib.fdg_event_record(stream))
+    if h < 0:
+        L.check(h, "event_record")
+    return h
+
+
+def stream_wait(stream: int, handle: int) -> None:
+    L.check(L.lib.fdg_stream_wait(stream, handle), "stream_wait")
+
+
 def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scale=None, shift=None, slope=1.0,
-          transposed=False, dbias=None, impl=None, g_split=None):
+          transposed=False, dbias=None, impl=None, g_split=None, stream=None):
     """fdg_conv2d_wgrad: dw (+)= A^T g in the parameter's own layout (dw must be pre-zeroed or accumulating).
     ``dw is None`` (frozen parameter) skips the launch."""
     if dw is None:
@@ -174,7 +186,7 @@ def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scal
     d = L.FdgWgrad(x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
                    g.ft(), R, S, stride, pad, g.C, OH, OW, _ptr(dw), 1 if transposed else 0, _ptr(dbias),
                    (IMPL_AUTO if USE_UMMA else IMPL_SIMT) if impl is None else impl, _ptr(g_split))
-    L.check(L.lib.fdg_conv2d_wgrad(_byref(d), _stream()), "conv2d_wgrad")
+    L.check(L.lib.fdg_conv2d_wgrad(_byref(d), _stream() if stream is None else stream), "conv2d_wgrad")
 
 
 # Operand images of FROZEN parameters (requires_grad == False: the Vgg16 feature extractor, D during the generator update

@@ -360,6 +360,12 @@ int fdg_profile_collect(double* ms, double* flops, double* bytes, int64_t* launc
 /* Runtime options: "halo" (default 1) = use the halo-tile tcgen05 kernel for stride-1 RxS convolutions. */
 int fdg_set_option(const char* name, int value);
 
+/* Stream fork / join for the host executors (side-stream weight gradients): record a point on `stream` (returns a handle >= 0,
+ * valid for the next 1024 records on the device, or a negative FDG_E* code) and make another stream wait for it.  Legal under
+ * CUDA-graph stream capture. */
+int fdg_event_record(fdg_stream_t stream);
+int fdg_stream_wait(fdg_stream_t stream, int handle);
+
 /* diagnostics */
 const char* fdg_last_error(void);
 int fdg_version(void);
