@@ -383,7 +383,7 @@ static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)(a.total_tiles < num_sms ? a.total_tiles : num_sms));
   const double M = (double)a.c.N * a.c.OH * a.c.OW;
   ProfScope prof(PF_CONV_UMMA, 2.0 * M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
-                 4.0 * (M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
+                 4.0 * (M * a.c.Cout * (1.0 + (a.c.e.p ? 1.0 : 0.0) + (a.c.store == FDG_STORE_ACCUM ? 1.0 : 0.0)) + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
   launch_k(conv_halo_kernel<NT, BSTAGES>, dim3(grid), dim3(H_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d[tcgen05 halo]");
 }

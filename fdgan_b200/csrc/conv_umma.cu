@@ -833,7 +833,9 @@ static int launch_umma(const UmmaArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));
   const double gmul = a.c.gather == FDG_GATHER_AVGPOOL2 ? 4.0 : 1.0;
   ProfScope prof(PF_CONV_UMMA, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
-                 4.0 * ((double)a.M * a.c.Cout + gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
+                 // output + input once, plus what the epilogue reads: the mask tensor (e) and, for accumulating stores, the old values
+                 4.0 * ((double)a.M * a.c.Cout * (1.0 + (a.c.e.p ? 1.0 : 0.0) + (a.c.store == FDG_STORE_ACCUM ? 1.0 : 0.0)) +
+                        gmul * (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
   launch_k(conv_umma_kernel<NT, STAGES, DEPTH, BNBWD, FAST>, dim3(grid), dim3(FAST ? UTHREADS_P + 32 : UTHREADS_P), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d[tcgen05]");
 }

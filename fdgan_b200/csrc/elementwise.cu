@@ -174,6 +174,98 @@ __global__ void __launch_bounds__(256) ew_bwd_kernel(FdgEwBwd p, int64_t M, int 
   }
 }
 
+// Transition backward (gradient at HALF resolution, FDG_GATHER_UP2: the adjoint of the 2x2 average pool folded into the gather):
+// a thread owns 4 channels of one pooled pixel, i.e. a 2x2 block of x / out that shares ONE gradient vector -- one gradient load
+// and four (stats) or eight (accumulating apply) independent 128-bit loads in flight per thread, no per-pixel index division.
+// The generic kernel above ran these six launches at 3.0 TB/s (2.8 ms of the step).
+template <bool STATS>
+__global__ void __launch_bounds__(256) ew_bwd_pool_kernel(FdgEwBwd p, int64_t MP, int cgroups, int pix_lanes) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
+  extern __shared__ float sm[];
+  const int cg = threadIdx.x % cgroups;
+  const int pl = threadIdx.x / cgroups;
+  const int c = (blockIdx.y * cgroups + cg) * 4;
+  const bool cv = c < p.C && pl < pix_lanes;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ca = sc, cb = sh, cd = sh;
+  if (cv) {
+    if (p.has_affine) { sc = *reinterpret_cast<const float4*>(p.scale + c); sh = *reinterpret_cast<const float4*>(p.shift + c); }
+    if (p.coef) {
+      ca = *reinterpret_cast<const float4*>(p.coef + c);
+      cb = *reinterpret_cast<const float4*>(p.coef + p.C + c);
+      cd = *reinterpret_cast<const float4*>(p.coef + 2 * p.C + c);
+    }
+  }
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const float gs = p.gscale, sl = p.slope;
+  const int PH = p.H >> 1, PW = p.W >> 1, PHW = PH * PW;
+  if (cv) {
+    const int64_t step = (int64_t)gridDim.x * pix_lanes;
+    for (int64_t m = (int64_t)blockIdx.x * pix_lanes + pl; m < MP; m += step) {
+      const int n = (int)(m / PHW);
+      const int rem = (int)(m - (int64_t)n * PHW);
+      const int ph = rem / PW, pw = rem - ph * PW;
+      const float4 g = *reinterpret_cast<const float4*>(p.g.p + n * p.g.sn + (int64_t)ph * p.g.sh + (int64_t)pw * p.g.sw + c);
+      const float* xb = p.x.p + n * p.x.sn + (int64_t)(2 * ph) * p.x.sh + (int64_t)(2 * pw) * p.x.sw + c;
+      float4 xv[4];
+      xv[0] = __ldg(reinterpret_cast<const float4*>(xb));
+      xv[1] = __ldg(reinterpret_cast<const float4*>(xb + p.x.sw));
+      xv[2] = __ldg(reinterpret_cast<const float4*>(xb + p.x.sh));
+      xv[3] = __ldg(reinterpret_cast<const float4*>(xb + p.x.sh + p.x.sw));
+      float* ob = nullptr;
+      float4 old[4];
+      if (!STATS) {
+        ob = p.out.p + n * p.out.sn + (int64_t)(2 * ph) * p.out.sh + (int64_t)(2 * pw) * p.out.sw + c;
+        if (p.accumulate) {
+          old[0] = *reinterpret_cast<const float4*>(ob);
+          old[1] = *reinterpret_cast<const float4*>(ob + p.out.sw);
+          old[2] = *reinterpret_cast<const float4*>(ob + p.out.sh);
+          old[3] = *reinterpret_cast<const float4*>(ob + p.out.sh + p.out.sw);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float4 dz;
+        dz.x = gs * g.x * (fmaf(xv[k].x, sc.x, sh.x) > 0.f ? 1.f : sl);
+        dz.y = gs * g.y * (fmaf(xv[k].y, sc.y, sh.y) > 0.f ? 1.f : sl);
+        dz.z = gs * g.z * (fmaf(xv[k].z, sc.z, sh.z) > 0.f ? 1.f : sl);
+        dz.w = gs * g.w * (fmaf(xv[k].w, sc.w, sh.w) > 0.f ? 1.f : sl);
+        if (STATS) {
+          s1.x += dz.x; s1.y += dz.y; s1.z += dz.z; s1.w += dz.w;
+          s2.x = fmaf(dz.x, xv[k].x, s2.x); s2.y = fmaf(dz.y, xv[k].y, s2.y);
+          s2.z = fmaf(dz.z, xv[k].z, s2.z); s2.w = fmaf(dz.w, xv[k].w, s2.w);
+        } else {
+          float4 o;
+          o.x = fmaf(ca.x, dz.x, fmaf(cb.x, xv[k].x, cd.x)); o.y = fmaf(ca.y, dz.y, fmaf(cb.y, xv[k].y, cd.y));
+          o.z = fmaf(ca.z, dz.z, fmaf(cb.z, xv[k].z, cd.z)); o.w = fmaf(ca.w, dz.w, fmaf(cb.w, xv[k].w, cd.w));
+          if (p.accumulate) { o.x += old[k].x; o.y += old[k].y; o.z += old[k].z; o.w += old[k].w; }
+          *reinterpret_cast<float4*>(ob + (int64_t)(k >> 1) * p.out.sh + (int64_t)(k & 1) * p.out.sw) = o;
+        }
+      }
+    }
+  }
+  if (STATS) {
+    const int CW = cgroups * 4;
+    float* r1 = sm;
+    float* r2 = sm + pix_lanes * CW;
+    if (pl < pix_lanes) {
+      *reinterpret_cast<float4*>(&r1[pl * CW + cg * 4]) = s1;
+      *reinterpret_cast<float4*>(&r2[pl * CW + cg * 4]) = s2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CW; i += blockDim.x) {
+      const int cc = blockIdx.y * CW + i;
+      if (cc < p.C) {
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < pix_lanes; ++l) { a += r1[l * CW + i]; b += r2[l * CW + i]; }
+        atomicAdd(p.stats + cc, (double)a);
+        atomicAdd(p.stats + p.C + cc, (double)b);
+      }
+    }
+  }
+}
+
 // Fast path of ew_bwd: all views are pixel-linear (address = base + pixel * row stride + channel), 4 channels per
 // thread, four pixels per thread in flight per iteration (8 independent 128-bit loads).
 template <bool STATS>
@@ -592,6 +684,16 @@ int fdg_ew_bwd(const FdgEwBwd* p, fdg_stream_t stream) {
   if (fast) {
     if (p->stats) launch_k(ew_bwd_linear_kernel<true>, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, *p, M, cgroups, pix_lanes);
     else launch_k(ew_bwd_linear_kernel<false>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, *p, M, cgroups, pix_lanes);
+  } else if (vec && p->g_gather == FDG_GATHER_UP2 && p->H % 2 == 0 && p->W % 2 == 0 && !p->out_split &&
+             (!p->has_affine || (aligned16(p->scale) && aligned16(p->shift))) && (!p->coef || aligned16(p->coef))) {
+    // transition backward: one thread per pooled pixel and 4 channels (2x2 block of x / out)
+    const int64_t MP = M / 4;
+    int64_t gxp = cdiv64(MP, (int64_t)pix_lanes * 4);
+    if (gxp > cap) gxp = cap;
+    if (gxp < 1) gxp = 1;
+    dim3 gridp((unsigned)gxp, gy);
+    if (p->stats) launch_k(ew_bwd_pool_kernel<true>, gridp, dim3(256), smem, (cudaStream_t)stream, *p, MP, cgroups, pix_lanes);
+    else launch_k(ew_bwd_pool_kernel<false>, gridp, dim3(256), (size_t)0, (cudaStream_t)stream, *p, MP, cgroups, pix_lanes);
   } else if (vec) {
     // measured on the three transition backward passes (gradient gathered at half resolution): four pixels in flight cost
     // 104 registers and occupancy, 3.16 ms / step against 2.79 ms for the plain loop (profiles/r01h_launches_final.md)

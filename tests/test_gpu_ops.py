@@ -490,6 +490,33 @@ def test_ew_bwd_pooled_gradient_vector_path():
     assert maxabs(out, out0.double() + a_ * dz + b_ * x.double() + d_) <= 1e-5
 
 
+def test_ew_bwd_pooled_gradient_on_channel_slices():
+    """Same pass on channel slices of wider NHWC buffers (the transition backward accumulates into a dense block's gradient buffer),
+    several CTAs per channel group, LeakyReLU slope, plain (non-accumulating) store."""
+    ops = _ops()
+    N, C, H, W, CT = 2, 256, 36, 28, 320
+    xb = seeded((N, H, W, CT), 1, -1, 1)
+    gb = seeded((N, H // 2, W // 2, CT), 2, -1, 1)
+    sc, sh = seeded((C,), 3, 0.5, 1.5), seeded((C,), 4, -0.3, 0.3)
+    coef = torch.cat([seeded((C,), 5, 0.5, 1.5), seeded((C,), 6, -0.2, 0.2), seeded((C,), 7, -0.1, 0.1)])
+    xd, gd = xb.cuda(), gb.cuda()
+    xv = ops.View.nhwc(xd, N, H, W, CT).ch(32, 32 + C)
+    gv = ops.View.nhwc(gd, N, H // 2, W // 2, CT).ch(64, 64 + C)
+    x = xb[..., 32:32 + C].permute(0, 3, 1, 2).double()
+    g = gb[..., 64:64 + C].permute(0, 3, 1, 2).double()
+    v = x * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1)
+    dz = 0.25 * F.interpolate(g, scale_factor=2, mode="nearest") * torch.where(v > 0, 1.0, 0.1)
+    st = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    ops.ew_bwd(gv, xv, stats=st, scale=sc.cuda(), shift=sh.cuda(), slope=0.1, g_gather=ops.GATHER_UP2, gscale=0.25)
+    assert maxabs(st[:C], dz.sum((0, 2, 3))) <= 2e-4 and maxabs(st[C:], (dz * x).sum((0, 2, 3))) <= 2e-4
+    ob = torch.full((N, H, W, CT), 3.0, device="cuda")
+    ov = ops.View.nhwc(ob, N, H, W, CT).ch(16, 16 + C)
+    ops.ew_bwd(gv, xv, out=ov, scale=sc.cuda(), shift=sh.cuda(), slope=0.1, g_gather=ops.GATHER_UP2, gscale=0.25, coef=coef.cuda())
+    a_, b_, d_ = (coef[i * C:(i + 1) * C].double().view(1, -1, 1, 1) for i in range(3))
+    assert maxabs(ob[..., 16:16 + C].permute(0, 3, 1, 2), a_ * dz + b_ * x + d_) <= 1e-5
+    assert bool((ob[..., :16] == 3.0).all()) and bool((ob[..., 16 + C:] == 3.0).all())
+
+
 def test_maxpool_copy_colsum_actbwd():
     ops = _ops()
     x = seeded((2, 12, 9, 10), 1, -1, 1).requires_grad_(True)
