@@ -33,7 +33,7 @@ constexpr int WK_GITEMS = (WK_HC * WK_HR * 4 + WK_LOAD_WARPS * 32 - 1) / (WK_LOA
 
 struct WKArgs {
   FdgWgrad c;
-  int cblocks, tiles_x, tiles_y, total_ptiles, ptiles_per_split, splits;
+  int cblocks, co_tiles, tiles_x, tiles_y, total_ptiles, ptiles_per_split, splits;
   int gvec;
 };
 
@@ -48,8 +48,9 @@ __global__ void __launch_bounds__(WK_THREADS, 1) wgrad_k1_kernel(const __grid_co
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   int bid = blockIdx.x;
-  const int split = bid % a.splits;
-  const int cb = bid / a.splits;
+  const int split = bid % a.splits; bid /= a.splits;
+  const int cot = bid % a.co_tiles;                        // 32-channel tile of the output channels (Cout <= 96: Fusion-D layer 2)
+  const int cb = bid / a.co_tiles;
   const int pt0 = split * a.ptiles_per_split;
   const int pt1 = pt0 + a.ptiles_per_split < a.total_ptiles ? pt0 + a.ptiles_per_split : a.total_ptiles;
   const int ntiles = pt1 > pt0 ? pt1 - pt0 : 0;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) wgrad_k1_kernel(const __grid_co
       ghx[i] = giv[i] ? hp - ghy[i] * WK_HC : 0;
       g_off[i] = (uint32_t)hp * 64u + (uint32_t)(idx & 3) * 16u;     // linear; the swizzle needs the absolute address (per stage)
     }
-    const int cg = (t & 3) * 8;
+    const int cg = cot * 32 + (t & 3) * 8;
     const float sl = p.slope;
     int buf = 0;
     uint32_t ph = 0;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(WK_THREADS, 1) wgrad_k1_kernel(const __grid_co
         if (ci < p.Cin) {
 #pragma unroll
           for (int u = 0; u < 32; ++u)
-            if (u < p.Cout) atomicAdd(p.dw + ((int64_t)u * p.Cin + ci) * 9 + ky * 3 + kx, v[u]);
+            if (cot * 32 + u < p.Cout) atomicAdd(p.dw + ((int64_t)(cot * 32 + u) * p.Cin + ci) * 9 + ky * 3 + kx, v[u]);
         }
       }
     }
@@ -247,8 +248,9 @@ __global__ void __launch_bounds__(WK_THREADS, 1) wgrad_k1_kernel(const __grid_co
     if (vec) {
       asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps
       const int valid4 = (p.Cin - cb * 128 < 128 ? p.Cin - cb * 128 : 128) * 9 / 4;      // float4s per output channel that hold data (Cin % 4 == 0)
-      float* base = p.dw + (int64_t)cb * 128 * 9;
-      for (int i = t; i < p.Cout * 288; i += WK_LOAD_WARPS * 32) {
+      float* base = p.dw + ((int64_t)cot * 32 * p.Cin + (int64_t)cb * 128) * 9;
+      const int nco = p.Cout - cot * 32 < 32 ? p.Cout - cot * 32 : 32;
+      for (int i = t; i < nco * 288; i += WK_LOAD_WARPS * 32) {
         const int co = i / 288, r = i - co * 288;
         if (r < valid4) {
           float4 val;
@@ -271,7 +273,8 @@ static int g_wgrad_k1_on = [] { const char* e = getenv("FDG_WGRAD_K1"); return e
 int wgrad_k1_supported(const FdgWgrad* p) {
   if (!g_wgrad_k1_on) return 0;
   if (p->gather != FDG_GATHER_DIRECT || p->stride != 1 || p->pad != 1 || p->R != 3 || p->S != 3 || p->transposed) return 0;
-  if (p->Cin % 4 != 0 || p->Cin < 16 || p->Cout < 1 || p->Cout > 32) return 0;
+  // a 32-channel output tile re-reads the activation tile: beyond three tiles the wide kernels of wgrad_umma.cu win (when they apply)
+  if (p->Cin % 4 != 0 || p->Cin < 16 || p->Cout < 1 || p->Cout > (p->Cin % 8 != 0 ? 96 : 32)) return 0;
   AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   if (!aop_vec_ok(ao, p->Cin)) return 0;
   return 1;
@@ -281,12 +284,14 @@ int wgrad_k1(const FdgWgrad* p, cudaStream_t st) {
   WKArgs a;
   a.c = *p;
   a.cblocks = cdiv(p->Cin, 128);
+  a.co_tiles = cdiv(p->Cout, 32);
   a.tiles_x = cdiv(p->OW, WK_TW);
   a.tiles_y = cdiv(p->OH, WK_TH);
   a.total_ptiles = p->N * a.tiles_x * a.tiles_y;
   a.gvec = vec4_ok(p->g) && (p->Cout % 8 == 0);
   const int num_sms = device_sm_count();
-  int splits = a.cblocks >= num_sms ? 1 : num_sms / a.cblocks;
+  const int groups = a.cblocks * a.co_tiles;
+  int splits = groups >= num_sms ? 1 : num_sms / groups;
   {
     // every split ends with 128 x 288 atomics into the same addresses: with few pixel tiles (small batches / deep layers) the epilogues
     // cost more than the tiles.  T(s) = tiles/s * t_tile + s * t_epi is minimal at s = sqrt(tiles * t_tile / t_epi) ~ sqrt(10 tiles)
@@ -312,7 +317,7 @@ int wgrad_k1(const FdgWgrad* p, cudaStream_t st) {
   }
   const double M = (double)p->N * p->OH * p->OW;
   ProfScope prof(PF_WGRAD, 2.0 * M * 9.0 * p->Cin * p->Cout, 4.0 * (M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);
-  launch_k(wgrad_k1_kernel, dim3((unsigned)(a.cblocks * a.splits)), dim3(WK_THREADS), (size_t)(smem), st, a);
+  launch_k(wgrad_k1_kernel, dim3((unsigned)(groups * a.splits)), dim3(WK_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d_wgrad[tcgen05 k1]");
 }
 

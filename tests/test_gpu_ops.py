@@ -424,6 +424,22 @@ def test_split_bf16_operands():
     assert maxabs(w2, w1) <= 1e-4 * max(1.0, float(w1.abs().max()))
 
 
+@pytest.mark.parametrize("cin,cout,H,W", [(36, 72, 21, 19), (36, 40, 16, 32), (20, 96, 9, 17), (132, 24, 12, 12)])
+def test_wgrad_3x3_with_cin_multiple_of_4(cin, cout, H, W):
+    """Fusion-D layer 2 (36 -> 72, 3x3) and relatives: Cin % 8 != 0 shapes run on the growth-convolution weight-gradient kernel with up to
+    three 32-channel output tiles (automatic dispatch), LeakyReLU prologue."""
+    ops = _ops()
+    N = 2
+    x = seeded((N, cin, H, W), 1, -1, 1)
+    g = seeded((N, cout, H, W), 2, -1, 1)
+    ref = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(F.leaky_relu(x.double(), 0.2), ref, padding=1) * g.double()).sum().backward()
+    dw = torch.zeros(cout, cin, 3, 3, device="cuda")
+    ops.wgrad(ops.View.from_nchw(cl(x)), ops.View.from_nchw(cl(g)), 3, 3, 1, 1, dw, slope=0.2)
+    torch.cuda.synchronize()
+    assert maxabs(dw, ref.grad) <= 5e-5 * max(1.0, float(ref.grad.abs().max()))
+
+
 @pytest.mark.parametrize("cin,cout,R,pad", [(144, 288, 4, 1), (72, 144, 3, 1), (64, 72, 3, 1)])
 def test_wgrad_wide_tiles_take_split_planes(cin, cout, R, pad):
     """Fusion-D layer 4 / layer 3 weight gradients (wide output-channel tiles, Cout % 64 != 0): gradient operand from split-bf16 planes
