@@ -536,6 +536,57 @@ __global__ void dgrad_strided_kernel(FdgDgradStrided p, int64_t total) {
   }
 }
 
+// ------------------------------------------------------------------ single-output-channel convolutions by taps
+// A stride-1 RxS convolution with ONE output channel (Fusion-D layer 5: 288 -> 1, 4x4) is a GEMV per pixel; on the implicit-GEMM
+// kernels it pads N to 32 and streams R*S weight tiles.  Re-associated, it is a 1x1 convolution Cin -> R*S (one column per tap:
+// s[p][t] = sum_c a[p][c] w[c][t], a dense GEMM that reads the input once) followed by a sum of the taps over shifted pixels:
+//   fwd:   out(n, oy, ox) = act( sum_t s(n, oy + ky - pad, ox + kx - pad)[t] )                       (fdg_tap_sum)
+//   wgrad: dW[c][t] = sum_p a[p][c] G(p)[t],  G(n, y, x)[t] = g(n, y - ky + pad, x - kx + pad)        (fdg_tap_spread + 1x1 wgrad)
+__global__ void __launch_bounds__(256) tap_sum_kernel(FdgTensor s, FdgTensor out, int64_t total, int H, int W, int R, int S, int pad, int OH,
+                                                      int OW, int act) {
+  pdl_wait();      // PDL contract (common.cuh)
+  pdl_trigger();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW);
+    int64_t q = i / OW;
+    const int oy = (int)(q % OH);
+    const int n = (int)(q / OH);
+    float acc = 0.f;
+    for (int ky = 0; ky < R; ++ky) {
+      const int y = oy + ky - pad;
+      if (y < 0 || y >= H) continue;
+      for (int kx = 0; kx < S; ++kx) {
+        const int x = ox + kx - pad;
+        if (x < 0 || x >= W) continue;
+        acc += __ldg(s.p + n * s.sn + (int64_t)y * s.sh + (int64_t)x * s.sw + (int64_t)(ky * S + kx) * s.sc);
+      }
+    }
+    if (act == FDG_ACT_RELU) acc = fmaxf(acc, 0.f);
+    else if (act == FDG_ACT_TANH) acc = tanhf(acc);
+    else if (act == FDG_ACT_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+    out.p[n * out.sn + (int64_t)oy * out.sh + (int64_t)ox * out.sw] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) tap_spread_kernel(FdgTensor g, FdgTensor gs, int64_t total, int H, int W, int R, int S, int pad, int OH,
+                                                         int OW) {
+  pdl_wait();      // PDL contract (common.cuh)
+  pdl_trigger();
+  const int T = R * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    int64_t q = i / T;
+    const int x = (int)(q % W); q /= W;
+    const int y = (int)(q % H);
+    const int n = (int)(q / H);
+    const int ky = t / S, kx = t - ky * S;
+    const int oy = y - ky + pad, ox = x - kx + pad;
+    float v = 0.f;
+    if (oy >= 0 && oy < OH && ox >= 0 && ox < OW) v = __ldg(g.p + n * g.sn + (int64_t)oy * g.sh + (int64_t)ox * g.sw);
+    gs.p[n * gs.sn + (int64_t)y * gs.sh + (int64_t)x * gs.sw + (int64_t)t * gs.sc] = v;
+  }
+}
+
 // ------------------------------------------------------------------ weight repack
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S, int mode,
                                    float* __restrict__ out, int out_ld, int64_t total) {
@@ -743,6 +794,24 @@ int fdg_copy4d(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int 
   }
   launch_k(copy4d_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *y, total, H, W, C, gather, slope, scale, accumulate);
   return check_launch("fdg_copy4d");
+}
+
+int fdg_tap_sum(const FdgTensor* s, const FdgTensor* out, int N, int H, int W, int R, int S, int pad, int act, fdg_stream_t stream) {
+  FDG_REQUIRE(s && out && s->p && out->p && N > 0 && H > 0 && W > 0 && R > 0 && S > 0 && pad >= 0, "fdg_tap_sum: bad arguments");
+  const int OH = H + 2 * pad - R + 1, OW = W + 2 * pad - S + 1;
+  FDG_REQUIRE(OH > 0 && OW > 0, "fdg_tap_sum: empty output");
+  const int64_t total = (int64_t)N * OH * OW;
+  launch_k(tap_sum_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, *s, *out, total, H, W, R, S, pad, OH, OW, act);
+  return check_launch("fdg_tap_sum");
+}
+
+int fdg_tap_spread(const FdgTensor* g, const FdgTensor* gs, int N, int H, int W, int R, int S, int pad, fdg_stream_t stream) {
+  FDG_REQUIRE(g && gs && g->p && gs->p && N > 0 && H > 0 && W > 0 && R > 0 && S > 0 && pad >= 0, "fdg_tap_spread: bad arguments");
+  const int OH = H + 2 * pad - R + 1, OW = W + 2 * pad - S + 1;
+  FDG_REQUIRE(OH > 0 && OW > 0, "fdg_tap_spread: empty gradient");
+  const int64_t total = (int64_t)N * H * W * R * S;
+  launch_k(tap_spread_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, *g, *gs, total, H, W, R, S, pad, OH, OW);
+  return check_launch("fdg_tap_spread");
 }
 
 int fdg_act_bwd(const float* g, const float* y, float* out, int64_t n, int act, fdg_stream_t stream) {

@@ -231,6 +231,7 @@ def _conv_dgrad_w(weight):
     return ops.pack_weight(weight, 1)
 
 
+TAP_DECOMPOSE_L5 = True   # Fusion-D layer 5 (one output channel) as a 1x1 convolution over taps + shifted sum (fdg_tap_sum / fdg_tap_spread)
 FUSED_BN1_BWD = True   # norm1 backward inside the conv1 data-gradient epilogue + deferred per-channel affine term
 # norm2 backward with the ReLU mask, alpha and the two reductions inside the conv2 data-gradient epilogue (halo kernel, FdgConv.e_scale with
 # a normal store) instead of the reduce pass.  Correct (test_conv2d_3x3_bn_backward_epilogue, module tests) but measured SLOWER on a B200
@@ -516,8 +517,16 @@ def _discriminator_forward(m, z: torch.Tensor, training: bool, need_ctx: bool):
     w, ld = ops.pack_weight(l4.weight, 0)
     ops.conv2d(Y3, w, ld, 4, 4, 1, 1, 8 * nf, Y4, scale=bn3.scale, shift=bn3.shift, slope=0.2)
     out = torch.empty((B, 1, H1 - 2, W1 - 2), dtype=torch.float32, device=dev)
-    w, ld = ops.pack_weight(l5.weight, 0)
-    ops.conv2d(Y4, w, ld, 4, 4, 1, 1, 1, View.from_nchw(out), slope=0.2, act=ACT_SIGMOID)
+    if ops.USE_UMMA and TAP_DECOMPOSE_L5 and (8 * nf) % 8 == 0:
+        # one output channel: 1x1 convolution 8nf -> 16 (a column per filter tap; the OIHW weight [1][8nf][4][4] is that operand as it
+        # stands) on the tensor cores, then the 16 taps are summed over shifted pixels -- the input is read once instead of 16 weight tiles
+        # being streamed against an N = 32 tile of which one column is used
+        S5 = View.alloc(B, Y4.H, Y4.W, 16, dev)
+        ops.conv2d(Y4, l5.weight, 16, 1, 1, 1, 0, 16, S5, slope=0.2)
+        ops.tap_sum(S5, View.from_nchw(out), 4, 4, 1, act=ACT_SIGMOID)
+    else:
+        w, ld = ops.pack_weight(l5.weight, 0)
+        ops.conv2d(Y4, w, ld, 4, 4, 1, 1, 1, View.from_nchw(out), slope=0.2, act=ACT_SIGMOID)
     if nbt:
         torch._foreach_add_(nbt, 1)
     if not need_ctx:
@@ -558,7 +567,11 @@ def _discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bo
     dpre = torch.empty_like(ctx.out)
     ops.act_bwd(dout.contiguous(), ctx.out, dpre, ACT_SIGMOID)
     g5 = View.from_nchw(dpre)
-    if need_w:
+    if need_w and ops.USE_UMMA and TAP_DECOMPOSE_L5:
+        G5 = View.alloc(Y4.N, Y4.H, Y4.W, 16, dev)           # the patch-map gradient spread over the 16 taps
+        ops.tap_spread(g5, G5, 4, 4, 1)
+        ops.wgrad(Y4, G5, 1, 1, 1, 0, grads["main.layer5.conv.weight"], slope=0.2, transposed=True)      # [8nf][16] = OIHW [1][8nf][4][4]
+    elif need_w:
         ops.wgrad(Y4, g5, 4, 4, 1, 1, grads["main.layer5.conv.weight"], slope=0.2)
     dY4 = View.alloc(Y4.N, Y4.H, Y4.W, Y4.C, dev)
     wd, ldd = ops.pack_weight(l5.weight, 1)

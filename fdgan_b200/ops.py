@@ -440,6 +440,20 @@ def copy4d(x: View, y: View, *, gather=GATHER_DIRECT, slope=1.0, scale=1.0, accu
                              1 if accumulate else 0, _stream()), "copy4d")
 
 
+def tap_sum(s: View, out: View, R, S, pad, act=ACT_NONE):
+    """fdg_tap_sum: out(n,oy,ox) = act(sum over taps t of s(n, oy+ky-pad, ox+kx-pad)[t])."""
+    assert s.C == R * S and out.C == 1 and (out.N, out.H, out.W) == (s.N, s.H + 2 * pad - R + 1, s.W + 2 * pad - S + 1)
+    st, ot = s.ft(), out.ft()
+    L.check(L.lib.fdg_tap_sum(_byref(st), _byref(ot), s.N, s.H, s.W, R, S, pad, act, _stream()), "tap_sum")
+
+
+def tap_spread(g: View, gs: View, R, S, pad):
+    """fdg_tap_spread: gs(n,y,x)[t] = g(n, y-ky+pad, x-kx+pad)."""
+    assert gs.C == R * S and g.C == 1 and (g.N, g.H, g.W) == (gs.N, gs.H + 2 * pad - R + 1, gs.W + 2 * pad - S + 1)
+    gt, st = g.ft(), gs.ft()
+    L.check(L.lib.fdg_tap_spread(_byref(gt), _byref(st), gs.N, gs.H, gs.W, R, S, pad, _stream()), "tap_spread")
+
+
 def act_bwd(g: torch.Tensor, y: torch.Tensor, out: torch.Tensor, act: int):
     assert g.is_contiguous() and y.is_contiguous() and out.is_contiguous() and g.numel() == y.numel() == out.numel()
     L.check(L.lib.fdg_act_bwd(g.data_ptr(), y.data_ptr(), out.data_ptr(), g.numel(), act, _stream()), "act_bwd")

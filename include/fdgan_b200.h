@@ -237,6 +237,15 @@ int fdg_maxpool2_bwd(const FdgTensor* x, const FdgTensor* gy, const FdgTensor* g
 int fdg_copy4d(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int C, int gather, float slope, float scale,
                int accumulate, fdg_stream_t stream);
 
+/* Single-output-channel stride-1 convolutions by taps (Fusion-D layer 5, dehaze1113.py:222: 8nf -> 1, 4x4): the convolution is run as
+ * a 1x1 convolution Cin -> R*S (column t = filter tap t; the OIHW weight [1][Cin][R][S] IS that [Cin][R*S] operand) followed by
+ *   fdg_tap_sum:     out(n,oy,ox) = act( sum_t s(n, oy+ky-pad, ox+kx-pad)[t] ),  s: [N,H,W,R*S], out: [N,OH,OW,1]
+ * and its weight gradient as a 1x1 weight gradient (transposed layout) against
+ *   fdg_tap_spread:  gs(n,y,x)[t] = g(n, y-ky+pad, x-kx+pad) (0 outside),          g: [N,OH,OW,1], gs: [N,H,W,R*S]
+ * with OH = H + 2 pad - R + 1, OW = W + 2 pad - S + 1. */
+int fdg_tap_sum(const FdgTensor* s, const FdgTensor* out, int N, int H, int W, int R, int S, int pad, int act, fdg_stream_t stream);
+int fdg_tap_spread(const FdgTensor* g, const FdgTensor* gs, int N, int H, int W, int R, int S, int pad, fdg_stream_t stream);
+
 /* out = g * act'(y) for contiguous arrays: act = FDG_ACT_TANH (1 - y^2) or FDG_ACT_SIGMOID (y (1 - y)). */
 int fdg_act_bwd(const float* g, const float* y, float* out, int64_t n, int act, fdg_stream_t stream);
 

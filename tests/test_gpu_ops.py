@@ -533,6 +533,33 @@ def test_ew_bwd_pooled_gradient_on_channel_slices():
     assert bool((ob[..., :16] == 3.0).all()) and bool((ob[..., 16 + C:] == 3.0).all())
 
 
+@pytest.mark.parametrize("cin,R,pad,H,W", [(288, 4, 1, 15, 13), (64, 3, 1, 9, 20), (72, 4, 2, 8, 8)])
+def test_single_output_channel_conv_by_taps(cin, R, pad, H, W):
+    """Fusion-D layer 5 re-associated: 1x1 convolution Cin -> R*S on the tensor cores + fdg_tap_sum == conv2d with one output channel;
+    fdg_tap_spread + transposed 1x1 weight gradient == its weight gradient (the OIHW parameter is used as the [Cin][R*S] operand as is)."""
+    ops = _ops()
+    N, T = 2, R * R
+    x = seeded((N, cin, H, W), 1, -1, 1)
+    w = (seeded((1, cin, R, R), 2, -1, 1) / math.sqrt(cin * T)).requires_grad_(True)
+    y = torch.sigmoid(F.conv2d(F.leaky_relu(x.double(), 0.2), w.double(), padding=pad))
+    OH, OW = y.shape[-2:]
+    g = seeded((N, 1, OH, OW), 3, -1, 1)
+    (F.conv2d(F.leaky_relu(x.double(), 0.2), w.double(), padding=pad) * g.double()).sum().backward()
+    xv = ops.View.from_nchw(cl(x))
+    wd = w.detach().cuda().contiguous()
+    s = ops.View.alloc(N, H, W, T, "cuda")
+    ops.conv2d(xv, wd, T, 1, 1, 1, 0, T, s, slope=0.2, impl=ops.IMPL_UMMA)
+    out = torch.empty(N, 1, OH, OW, device="cuda")
+    ops.tap_sum(s, ops.View.from_nchw(out), R, R, pad, act=ops.ACT_SIGMOID)
+    assert maxabs(out, y) <= 5e-5
+    gs = ops.View.alloc(N, H, W, T, "cuda")
+    ops.tap_spread(ops.View.from_nchw(g.cuda()), gs, R, R, pad)
+    dw = torch.zeros(1, cin, R, R, device="cuda")
+    ops.wgrad(xv, gs, 1, 1, 1, 0, dw, slope=0.2, transposed=True)
+    torch.cuda.synchronize()
+    assert maxabs(dw, w.grad) <= 5e-5 * max(1.0, float(w.grad.abs().max()))
+
+
 def test_maxpool_copy_colsum_actbwd():
     ops = _ops()
     x = seeded((2, 12, 9, 10), 1, -1, 1).requires_grad_(True)
