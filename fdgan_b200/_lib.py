@@ -97,6 +97,7 @@ class FdgBnBwdFinalize(C.Structure):
         ("stats", C.c_void_p), ("C", C.c_int), ("count", C.c_double),
         ("gamma", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
         ("coef", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate", C.c_int), ("unit_alpha", C.c_int),
+        ("acc_beta", C.c_void_p), ("acc_delta", C.c_void_p),
     ]
 
 

@@ -61,6 +61,8 @@ __global__ void bn_bwd_finalize_kernel(FdgBnBwdFinalize p) {
   p.coef[c] = p.unit_alpha ? 1.f : (float)alpha;
   p.coef[p.C + c] = (float)beta;
   p.coef[2 * p.C + c] = (float)delta;
+  if (p.acc_beta) p.acc_beta[c] += (float)beta;
+  if (p.acc_delta) p.acc_delta[c] += (float)delta;
   if (p.dgamma) p.dgamma[c] = (p.accumulate ? p.dgamma[c] : 0.f) + (float)sum_dz_xhat;
   if (p.dbeta) p.dbeta[c] = (p.accumulate ? p.dbeta[c] : 0.f) + (float)s1;
 }

@@ -286,6 +286,7 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
     dA2s_b = [torch.empty(N * H * W * BOTTLENECK, dtype=torch.float32, device=dev) if split else None for _ in range(nbuf)]
     dA1buf = None if fused else torch.empty(N * H * W * cmax, dtype=torch.float32, device=dev)
     cbd = torch.zeros(2, Ctot, dtype=torch.float32, device=dev) if fused else None   # deferred beta / delta sums
+    coef_scratch = torch.empty(3 * Ctot, dtype=torch.float32, device=dev) if fused else None
 
     def wgrad_leaf(*a, **k):
         if not async_w:
@@ -328,10 +329,9 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
             st = dpool.take(2 * cin)
             ops.conv2d(dA2sv if split else dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dX.ch(0, cin), store=STORE_ACCUM, e=X.ch(0, cin),
                        eslope=0.0, e_scale=bn1.scale, e_shift=bn1.shift, stats=st, stats_ld=cin, x_split=dA2s)
-            coef = torch.empty(3, cin, dtype=torch.float32, device=dev)
-            ops.bn_bwd_finalize(st, cin, bn1.count, bn1.mod.weight, bn1.mean, bn1.invstd, coef,
-                                grads.get(p + ".norm1.weight"), grads.get(p + ".norm1.bias"), accumulate=True)
-            cbd[:, :cin] += coef[1:]
+            # beta / delta of this layer go straight into the running sums of the deferred affine term (no torch add, no allocation)
+            ops.bn_bwd_finalize(st, cin, bn1.count, bn1.mod.weight, bn1.mean, bn1.invstd, coef_scratch,
+                                grads.get(p + ".norm1.weight"), grads.get(p + ".norm1.bias"), accumulate=True, acc_beta=cbd[0], acc_delta=cbd[1])
         else:
             dA1 = View.nhwc(dA1buf, N, H, W, cin)
             ops.conv2d(dA2, lyr.conv1.weight, cin, 1, 1, 1, 0, cin, dA1)

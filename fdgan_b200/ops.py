@@ -408,9 +408,10 @@ def affine_accum(x: View, out: View, cb, cd):
     L.check(L.lib.fdg_affine_accum(_byref(xt), _byref(ot), x.N, x.H, x.W, x.C, _ptr(cb), _ptr(cd), _stream()), "affine_accum")
 
 
-def bn_bwd_finalize(stats, Cc, count, gamma, mean, invstd, coef, dgamma=None, dbeta=None, accumulate=True, unit_alpha=False):
+def bn_bwd_finalize(stats, Cc, count, gamma, mean, invstd, coef, dgamma=None, dbeta=None, accumulate=True, unit_alpha=False,
+                    acc_beta=None, acc_delta=None):
     d = L.FdgBnBwdFinalize(_ptr(stats), Cc, float(count), _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(coef),
-                           _ptr(dgamma), _ptr(dbeta), 1 if accumulate else 0, 1 if unit_alpha else 0)
+                           _ptr(dgamma), _ptr(dbeta), 1 if accumulate else 0, 1 if unit_alpha else 0, _ptr(acc_beta), _ptr(acc_delta))
     L.check(L.lib.fdg_bn_bwd_finalize(_byref(d), _stream()), "bn_bwd_finalize")
 
 

@@ -222,6 +222,8 @@ typedef struct FdgBnBwdFinalize {
   float* dbeta;
   int accumulate;
   int unit_alpha;      /* write coef[0..C) = 1: the producer of dz already multiplied it by alpha (FdgConv.e_scale epilogue, normal store) */
+  float* acc_beta;     /* += beta  [C], or NULL: running sums of the deferred affine term over the consumers of a concat channel */
+  float* acc_delta;    /* += delta [C], or NULL */
 } FdgBnBwdFinalize;
 
 int fdg_bn_bwd_finalize(const FdgBnBwdFinalize* p, fdg_stream_t stream);
