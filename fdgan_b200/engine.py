@@ -257,6 +257,44 @@ def _side_stream(dev):
     return s
 
 
+class _SideQueue:
+    """Leaf weight gradients of one backward pass on the side stream (see ASYNC_WGRAD_MAX_PIXELS).  ``wgrad`` forks (the side stream waits
+    for everything enqueued on the main stream so far), launches there and keeps the operand buffers alive; ``join`` makes the main stream
+    wait for the side stream -- called before the pass returns, i.e. before any buffer dies and before the optimiser reads the gradients."""
+
+    def __init__(self, dev, pixels, batch, grads):
+        self.on = (0 < pixels <= ASYNC_WGRAD_MAX_PIXELS and grads is not None and not isinstance(grads, _NoGrads) and
+                   (batch >= 4 or torch.cuda.is_current_stream_capturing()))
+        if self.on:
+            self.main = torch.cuda.current_stream(dev).cuda_stream
+            self.side = _side_stream(dev).cuda_stream
+        self.keep = []
+        self.used = False
+
+    def wgrad(self, x, g, *a, **k):
+        if not self.on or a[4] is None:      # a[4] = dw: a frozen parameter skips the launch
+            return ops.wgrad(x, g, *a, **k)
+        ops.stream_wait(self.side, ops.event_record(self.main))
+        ops.wgrad(x, g, *a, stream=self.side, **k)
+        self.keep.append((x.base, g.base))
+        self.used = True
+
+    def join(self):
+        if self.on and self.used:
+            ops.stream_wait(self.main, ops.event_record(self.side))
+        self.keep.clear()
+        self.used = False
+
+
+_TLS_Q = __import__("threading").local()
+
+
+def _wgrad(*a, **k):
+    """ops.wgrad, through the pass's side queue when there is one."""
+    q = getattr(_TLS_Q, "q", None)
+    return q.wgrad(*a, **k) if q is not None else ops.wgrad(*a, **k)
+
+
 def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, grads, dpool):
     """Backward of one torchvision dense block.  norm1 of layer j reads concat channels [0, cin_j) with the SAME batch
     statistics as every other consumer of those channels, so its backward dx = alpha dz + (beta x + delta) splits into
@@ -344,7 +382,7 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
 
 def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dpool):
     """torchvision transition backward; g = dL/d(output) at the pooled resolution; accumulates into dX."""
-    ops.wgrad(X, g, 1, 1, 1, 0, grads[prefix + ".conv.weight"], gather=GATHER_AVGPOOL2, scale=bn.scale, shift=bn.shift,
+    _wgrad(X, g, 1, 1, 1, 0, grads[prefix + ".conv.weight"], gather=GATHER_AVGPOOL2, scale=bn.scale, shift=bn.shift,
               slope=0.0)
     dP = View.alloc(g.N, g.H, g.W, X.C, X.base.device)
     ops.conv2d(g, tr.conv.weight, X.C, 1, 1, 1, 0, X.C, dP)
@@ -358,11 +396,11 @@ def _bdy_bwd(blk, prefix, Dv: View, dD: View, T: View, c_in, grads):
     on return dD[:, :c_in] is dL/d(pre-ReLU x)."""
     c_out = Dv.C - c_in
     g = dD.ch(c_in, Dv.C)
-    ops.wgrad(T, g, 3, 3, 1, 1, grads[prefix + ".conv2.weight"], slope=0.0)
+    _wgrad(T, g, 3, 3, 1, 1, grads[prefix + ".conv2.weight"], slope=0.0)
     dT = View.alloc(T.N, T.H, T.W, T.C, T.base.device)
     wd, ldd = _conv_dgrad_w(blk.conv2.weight)
     ops.conv2d(g, wd, ldd, 3, 3, 1, 1, T.C, dT, e=T, eslope=0.0)
-    ops.wgrad(Dv.ch(0, c_in), dT, 1, 1, 1, 0, grads[prefix + ".conv1.weight"])
+    _wgrad(Dv.ch(0, c_in), dT, 1, 1, 1, 0, grads[prefix + ".conv1.weight"])
     ops.conv2d(dT, blk.conv1.weight, c_in, 1, 1, 1, 0, c_in, dD.ch(0, c_in), e=Dv.ch(0, c_in), eslope=0.0,
                store=STORE_ACCUM)
     del c_out
@@ -373,7 +411,7 @@ def _tdy_bwd(tr, prefix, Dv: View, dD: View, gUp: View, grads):
     c_out = gUp.C
     dU = View.alloc(Dv.N, Dv.H, Dv.W, c_out, Dv.base.device)
     ops.copy4d(gUp, dU, gather=GATHER_AVGPOOL2, scale=4.0)              # adjoint of nearest x2
-    ops.wgrad(Dv, dU, 1, 1, 1, 0, grads[prefix + ".conv1.weight"], slope=0.0, transposed=True)
+    _wgrad(Dv, dU, 1, 1, 1, 0, grads[prefix + ".conv1.weight"], slope=0.0, transposed=True)
     wd, ldd = ops.pack_weight(tr.conv1.weight, 2)
     ops.conv2d(dU, wd, ldd, 1, 1, 1, 0, Dv.C, dD, e=Dv, eslope=0.0)
 
@@ -381,8 +419,14 @@ def _tdy_bwd(tr, prefix, Dv: View, dD: View, gUp: View, grads):
 def generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: bool):
     """Backward of generator_forward.  ``grads`` maps parameter names to pre-zeroed fp32 tensors that the
     kernels accumulate into.  Returns dL/dx (NCHW) or None."""
-    with ops.pack_scope(m, "bwd", dout.device):
-        return _generator_backward(m, ctx, dout, grads, need_dx)
+    q = _SideQueue(dout.device, ctx.out.shape[0] * ctx.out.shape[2] * ctx.out.shape[3], ctx.out.shape[0], grads)
+    _TLS_Q.q = q if q.on else None
+    try:
+        with ops.pack_scope(m, "bwd", dout.device):
+            return _generator_backward(m, ctx, dout, grads, need_dx)
+    finally:
+        _TLS_Q.q = None
+        q.join()
 
 
 def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: bool):
@@ -400,7 +444,7 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     dpre = torch.empty_like(ctx.out)
     ops.act_bwd(dout.contiguous(), ctx.out, dpre, ACT_TANH)
     gpre = View.from_nchw(dpre)
-    ops.wgrad(X6, gpre, 3, 3, 1, 1, grads["conv_refin3.weight"], dbias=grads["conv_refin3.bias"])
+    _wgrad(X6, gpre, 3, 3, 1, 1, grads["conv_refin3.weight"], dbias=grads["conv_refin3.bias"])
     dX6 = View.alloc(X6.N, X6.H, X6.W, 16, dev)
     wd, ldd = _conv_dgrad_w(m.conv_refin3.weight)
     ops.conv2d(gpre, wd, ldd, 3, 3, 1, 1, 16, dX6)
@@ -420,13 +464,13 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     _tdy_bwd(m.trans_block4, "trans_block4", D4, dD4, dX42.ch(0, 128), grads)
     _bdy_bwd(m.dense_block4, "dense_block4", D4, dD4, T4, 512, grads)
     g6 = dD4.ch(0, 512)                                                   # dL/d(conv_refin6 pre-ReLU output)
-    ops.wgrad(C6, g6, 3, 3, 1, 1, grads["conv_refin6.weight"], dbias=grads["conv_refin6.bias"])
+    _wgrad(C6, g6, 3, 3, 1, 1, grads["conv_refin6.weight"], dbias=grads["conv_refin6.bias"])
     dC6 = View.alloc(C6.N, C6.H, C6.W, 640, dev)
     wd, ldd = _conv_dgrad_w(m.conv_refin6.weight)
     ops.conv2d(g6, wd, ldd, 3, 3, 1, 1, 640, dC6)
     # ---- conv_refin5 branch (x22)
     g5 = dC6.ch(512, 640)
-    ops.wgrad(X3.ch(0, 256), g5, 1, 1, 1, 0, grads["conv_refin5.weight"], gather=GATHER_AVGPOOL2,
+    _wgrad(X3.ch(0, 256), g5, 1, 1, 1, 0, grads["conv_refin5.weight"], gather=GATHER_AVGPOOL2,
               dbias=grads["conv_refin5.bias"])
     dP = View.alloc(g5.N, g5.H, g5.W, 256, dev)
     ops.conv2d(g5, m.conv_refin5.weight, 256, 1, 1, 1, 0, 256, dP)
@@ -439,7 +483,7 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     _transition_bwd(m.trans_block2, "trans_block2", X2, dX2, dX3.ch(0, 256), ctx.bn_t2, grads, dpool)
     _dense_block_bwd(m.dense_block2, "dense_block2", 12, 128, X2, dX2, ctx.saved["dense_block2"], grads, dpool)
     g4 = dX2.ch(0, 128)
-    ops.wgrad(C4, g4, 3, 3, 1, 1, grads["conv_refine4.weight"], dbias=grads["conv_refine4.bias"])
+    _wgrad(C4, g4, 3, 3, 1, 1, grads["conv_refine4.weight"], dbias=grads["conv_refine4.bias"])
     dC4 = View.alloc(C4.N, C4.H, C4.W, 160, dev)
     wd, ldd = _conv_dgrad_w(m.conv_refine4.weight)
     ops.conv2d(g4, wd, ldd, 3, 3, 1, 1, 160, dC4)
@@ -447,7 +491,7 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     dX1 = View.alloc(X1.N, X1.H, X1.W, 256, dev, zero=True)
     _transition_bwd(m.trans_block1, "trans_block1", X1, dX1, dC4.ch(32, 160), ctx.bn_t1, grads, dpool)
     g2 = dC4.ch(0, 32)
-    ops.wgrad(X1.ch(0, 64), g2, 1, 1, 1, 0, grads["conv_refin2.weight"], gather=GATHER_AVGPOOL2,
+    _wgrad(X1.ch(0, 64), g2, 1, 1, 1, 0, grads["conv_refin2.weight"], gather=GATHER_AVGPOOL2,
               dbias=grads["conv_refin2.bias"])
     dP = View.alloc(g2.N, g2.H, g2.W, 64, dev)
     ops.conv2d(g2, m.conv_refin2.weight, 64, 1, 1, 1, 0, 64, dP)
@@ -459,7 +503,7 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     g0 = dX1.ch(0, 64)
     ops.ew_bwd(g0, X1.ch(0, 64), out=g0, slope=0.0)
     xin = View.from_nchw(ctx.x)
-    ops.wgrad(xin, g0, 3, 3, 1, 1, grads["conv_refin1.weight"], dbias=grads["conv_refin1.bias"])
+    _wgrad(xin, g0, 3, 3, 1, 1, grads["conv_refin1.weight"], dbias=grads["conv_refin1.bias"])
     if not need_dx:
         return None
     dx = torch.empty((B, 3, xin.H, xin.W), dtype=torch.float32, device=dev)
@@ -549,8 +593,14 @@ class _NoGrads(dict):
 
 
 def discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bool):
-    with ops.pack_scope(m, "bwd", dout.device):
-        return _discriminator_backward(m, ctx, dout, grads, need_dx)
+    q = _SideQueue(dout.device, ctx.z.shape[0] * ctx.z.shape[2] * ctx.z.shape[3], ctx.z.shape[0], grads)
+    _TLS_Q.q = q if q.on else None
+    try:
+        with ops.pack_scope(m, "bwd", dout.device):
+            return _discriminator_backward(m, ctx, dout, grads, need_dx)
+    finally:
+        _TLS_Q.q = None
+        q.join()
 
 
 def _discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bool):
@@ -570,9 +620,9 @@ def _discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bo
     if need_w and ops.USE_UMMA and TAP_DECOMPOSE_L5:
         G5 = View.alloc(Y4.N, Y4.H, Y4.W, 16, dev)           # the patch-map gradient spread over the 16 taps
         ops.tap_spread(g5, G5, 4, 4, 1)
-        ops.wgrad(Y4, G5, 1, 1, 1, 0, grads["main.layer5.conv.weight"], slope=0.2, transposed=True)      # [8nf][16] = OIHW [1][8nf][4][4]
+        _wgrad(Y4, G5, 1, 1, 1, 0, grads["main.layer5.conv.weight"], slope=0.2, transposed=True)      # [8nf][16] = OIHW [1][8nf][4][4]
     elif need_w:
-        ops.wgrad(Y4, g5, 4, 4, 1, 1, grads["main.layer5.conv.weight"], slope=0.2)
+        _wgrad(Y4, g5, 4, 4, 1, 1, grads["main.layer5.conv.weight"], slope=0.2)
     dY4 = View.alloc(Y4.N, Y4.H, Y4.W, Y4.C, dev)
     wd, ldd = ops.pack_weight(l5.weight, 1)
     ops.conv2d(g5, wd, ldd, 4, 4, 1, 2, Y4.C, dY4, e=Y4, eslope=0.2)
@@ -582,29 +632,29 @@ def _discriminator_backward(m, ctx: DCtx, dout: torch.Tensor, grads, need_dx: bo
         # one pass writes them as split planes and the CTAs take them through bulk tensor loads (FdgWgrad.g_split)
         p4 = torch.empty(dY4.N * dY4.H * dY4.W * dY4.C, dtype=torch.float32, device=dev)
         ops.ew_bwd(dY4, dY4, slope=1.0, out_split=p4)
-        ops.wgrad(Y3, View.nhwc(p4, dY4.N, dY4.H, dY4.W, dY4.C), 4, 4, 1, 1, grads["main.layer4.conv.weight"], scale=bn3.scale, shift=bn3.shift,
+        _wgrad(Y3, View.nhwc(p4, dY4.N, dY4.H, dY4.W, dY4.C), 4, 4, 1, 1, grads["main.layer4.conv.weight"], scale=bn3.scale, shift=bn3.shift,
                   slope=0.2, g_split=p4)
     elif need_w:
-        ops.wgrad(Y3, dY4, 4, 4, 1, 1, grads["main.layer4.conv.weight"], scale=bn3.scale, shift=bn3.shift, slope=0.2)
+        _wgrad(Y3, dY4, 4, 4, 1, 1, grads["main.layer4.conv.weight"], scale=bn3.scale, shift=bn3.shift, slope=0.2)
     dY3 = View.alloc(Y3.N, Y3.H, Y3.W, Y3.C, dev)
     wd, ldd = ops.pack_weight(l4.weight, 1)
     ops.conv2d(dY4, wd, ldd, 4, 4, 1, 2, Y3.C, dY3)
     p3 = torch.empty(dY3.N * dY3.H * dY3.W * dY3.C, dtype=torch.float32, device=dev) if split_g else None
     _bn_bwd(dY3, Y3, bn3, dY3, dpool, grads if need_w else None, "main.layer3.layer3.bn", slope=0.2, out_split=p3, both=True)
     if need_w:
-        ops.wgrad(Y2, dY3, 3, 3, 1, 1, grads["main.layer3.layer3.conv.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.2, g_split=p3)
+        _wgrad(Y2, dY3, 3, 3, 1, 1, grads["main.layer3.layer3.conv.weight"], scale=bn2.scale, shift=bn2.shift, slope=0.2, g_split=p3)
     dY2 = View.alloc(Y2.N, Y2.H, Y2.W, Y2.C, dev)
     wd, ldd = ops.pack_weight(l3.conv.weight, 1)
     ops.conv2d(dY3, wd, ldd, 3, 3, 1, 1, Y2.C, dY2)
     _bn_bwd(dY2, Y2, bn2, dY2, dpool, grads if need_w else None, "main.layer2.layer2.bn", slope=0.2)
     if need_w:
-        ops.wgrad(Y1, dY2, 3, 3, 1, 1, grads["main.layer2.layer2.conv.weight"], slope=0.2)
+        _wgrad(Y1, dY2, 3, 3, 1, 1, grads["main.layer2.layer2.conv.weight"], slope=0.2)
     dY1 = View.alloc(Y1.N, Y1.H, Y1.W, Y1.C, dev)
     wd, ldd = ops.pack_weight(l2.conv.weight, 1)
     ops.conv2d(dY2, wd, ldd, 3, 3, 1, 1, Y1.C, dY1, e=Y1, eslope=0.2)
     zin = View.from_nchw(ctx.z)
     if need_w:
-        ops.wgrad(zin, dY1, 4, 4, 2, 1, grads["main.layer1.conv.weight"])
+        _wgrad(zin, dY1, 4, 4, 2, 1, grads["main.layer1.conv.weight"])
     if not need_dx:
         return None
     # channels-last memory, returned as a logical NCHW tensor
