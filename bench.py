@@ -444,6 +444,10 @@ def run_ours(args):
     # ---- live roofline of the dominant kernel family (profiled pass over the same steps; events on the launch stream)
     pk = peaks()
     roof = None
+    # per-launch durations need launches that do not overlap: the side-stream weight gradients (engine.ASYNC_WGRAD_MAX_PIXELS) are
+    # switched off for this pass (the events between launches already serialise programmatic dependent launches)
+    from fdgan_b200 import engine as _engine
+    async_px, _engine.ASYNC_WGRAD_MAX_PIXELS = _engine.ASYNC_WGRAD_MAX_PIXELS, 0
     L.profile_enable(True)
     prof_steps = min(args.steps, 3)
     for i in range(prof_steps):
@@ -451,6 +455,7 @@ def run_ours(args):
         tr.step(h, c, sync_losses=False)
     torch.cuda.synchronize()
     L.profile_enable(False)
+    _engine.ASYNC_WGRAD_MAX_PIXELS = async_px
     fam = L.profile_collect()
     tot_ms = sum(v["ms"] for v in fam.values())
     dom = max(fam, key=lambda k: fam[k]["ms"])
