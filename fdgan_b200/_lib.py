@@ -124,6 +124,7 @@ _SIGS = {
     "fdg_maxpool2_fwd": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_maxpool2_bwd": ([_P(FdgTensor), _P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_copy4d": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p], C.c_int),
+    "fdg_pool2_bn_act": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p], C.c_int),
     "fdg_tap_sum": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_tap_spread": ([_P(FdgTensor), _P(FdgTensor), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_act_bwd": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p], C.c_int),

@@ -538,6 +538,39 @@ __global__ void dgrad_strided_kernel(FdgDgradStrided p, int64_t total) {
   }
 }
 
+// ------------------------------------------------------------------ pooled BatchNorm + activation (transition blocks)
+// y(n, h, w, c) = mean over the 2x2 block of act(x * scale[c] + shift[c]): the input of a torchvision transition's 1x1 convolution
+// with the average pool commuted in front of it (models/densenet.py:214-221), materialised ONCE.  Forward convolution and weight
+// gradient then run as plain 1x1 kernels on a quarter of the pixels instead of gathering 2x2 blocks through their loaders
+// (four loads + prologue per operand element).  128-bit accesses; x, y: unit channel stride, 16-byte aligned, C % 4 == 0.
+__global__ void __launch_bounds__(256) pool2_bn_act_kernel(FdgTensor x, FdgTensor y, int64_t total4, int OH, int OW, int C4, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, float slope) {
+  pdl_wait();      // PDL contract (common.cuh)
+  pdl_trigger();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    int64_t r = i / C4;
+    const int w = (int)(r % OW); r /= OW;
+    const int h = (int)(r % OH);
+    const int n = (int)(r / OH);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) { sc = __ldg(reinterpret_cast<const float4*>(scale + c)); sh = __ldg(reinterpret_cast<const float4*>(shift + c)); }
+    const float* b = x.p + n * x.sn + (int64_t)(2 * h) * x.sh + (int64_t)(2 * w) * x.sw + c;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(b)), v1 = __ldg(reinterpret_cast<const float4*>(b + x.sw));
+    const float4 v2 = __ldg(reinterpret_cast<const float4*>(b + x.sh)), v3 = __ldg(reinterpret_cast<const float4*>(b + x.sh + x.sw));
+    float4 o;   // same association as the gather of the convolution loaders (aop.cuh:fetch4): (v0 + v1) + (v2 + v3)
+    o.x = 0.25f * ((prologue_act(fmaf(v0.x, sc.x, sh.x), slope) + prologue_act(fmaf(v1.x, sc.x, sh.x), slope)) +
+                   (prologue_act(fmaf(v2.x, sc.x, sh.x), slope) + prologue_act(fmaf(v3.x, sc.x, sh.x), slope)));
+    o.y = 0.25f * ((prologue_act(fmaf(v0.y, sc.y, sh.y), slope) + prologue_act(fmaf(v1.y, sc.y, sh.y), slope)) +
+                   (prologue_act(fmaf(v2.y, sc.y, sh.y), slope) + prologue_act(fmaf(v3.y, sc.y, sh.y), slope)));
+    o.z = 0.25f * ((prologue_act(fmaf(v0.z, sc.z, sh.z), slope) + prologue_act(fmaf(v1.z, sc.z, sh.z), slope)) +
+                   (prologue_act(fmaf(v2.z, sc.z, sh.z), slope) + prologue_act(fmaf(v3.z, sc.z, sh.z), slope)));
+    o.w = 0.25f * ((prologue_act(fmaf(v0.w, sc.w, sh.w), slope) + prologue_act(fmaf(v1.w, sc.w, sh.w), slope)) +
+                   (prologue_act(fmaf(v2.w, sc.w, sh.w), slope) + prologue_act(fmaf(v3.w, sc.w, sh.w), slope)));
+    *reinterpret_cast<float4*>(y.p + n * y.sn + (int64_t)h * y.sh + (int64_t)w * y.sw + c) = o;
+  }
+}
+
 // ------------------------------------------------------------------ single-output-channel convolutions by taps
 // A stride-1 RxS convolution with ONE output channel (Fusion-D layer 5: 288 -> 1, 4x4) is a GEMV per pixel; on the implicit-GEMM
 // kernels it pads N to 32 and streams R*S weight tiles.  Re-associated, it is a 1x1 convolution Cin -> R*S (one column per tap:
@@ -796,6 +829,20 @@ int fdg_copy4d(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int 
   }
   launch_k(copy4d_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *y, total, H, W, C, gather, slope, scale, accumulate);
   return check_launch("fdg_copy4d");
+}
+
+int fdg_pool2_bn_act(const FdgTensor* x, const FdgTensor* y, int N, int OH, int OW, int C, const float* scale, const float* shift, float slope,
+                     fdg_stream_t stream) {
+  FDG_REQUIRE(x && y && x->p && y->p && N > 0 && OH > 0 && OW > 0 && C > 0, "fdg_pool2_bn_act: bad arguments");
+  FDG_REQUIRE((scale == nullptr) == (shift == nullptr), "fdg_pool2_bn_act: scale and shift come together");
+  if (!(C % 4 == 0 && fdg::vec4_ok(*x) && fdg::vec4_ok(*y) && (!scale || (fdg::aligned16(scale) && fdg::aligned16(shift))))) {
+    fdg::set_error("fdg_pool2_bn_act: needs unit channel stride, 16-byte aligned views and C %% 4 == 0");
+    return FDG_ENOSUPPORT;
+  }
+  const int64_t total4 = (int64_t)N * OH * OW * (C / 4);
+  ProfScope prof(PF_OTHER, 0.0, 4.0 * 5.0 * (double)N * OH * OW * C, (cudaStream_t)stream);
+  launch_k(pool2_bn_act_kernel, dim3(grid_for(total4, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, *x, *y, total4, OH, OW, C / 4, scale, shift, slope);
+  return check_launch("fdg_pool2_bn_act");
 }
 
 int fdg_tap_sum(const FdgTensor* s, const FdgTensor* out, int N, int H, int W, int R, int S, int pad, int act, fdg_stream_t stream) {

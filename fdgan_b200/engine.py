@@ -110,12 +110,23 @@ def _dense_block_fwd(block, prefix, n_layers, c_in, X: View, S, training, fpool,
     saved[prefix] = layers
 
 
+POOL_FIRST = True      # transitions: materialise avg_pool(relu(bn(x))) once; conv and weight gradient run as plain 1x1 kernels on it
+
+
 def _transition_fwd(tr, X: View, S, y: View, ystats, ystats_ld, training, fpool, nbt):
+    """torchvision transition (BatchNorm, ReLU, 1x1 conv, AvgPool2d(2)) with the pool commuted in front of the convolution.
+    Returns (BatchNorm state, pooled activation or None)."""
     bn = _bn_run(tr.norm, S, X.C, X.C, X.N * X.H * X.W, training, fpool, nbt)
+    if POOL_FIRST and ops.USE_UMMA and X.H % 2 == 0 and X.W % 2 == 0:
+        P = View.alloc(X.N, X.H // 2, X.W // 2, X.C, X.base.device)
+        ops.pool2_bn_act(X, P, bn.scale, bn.shift, 0.0)
+        w, ld = ops.pack_weight(tr.conv.weight, 0)
+        ops.conv2d(P, w, ld, 1, 1, 1, 0, y.C, y, stats=ystats, stats_ld=ystats_ld)
+        return bn, P
     w, ld = ops.pack_weight(tr.conv.weight, 0)
     ops.conv2d(X, w, ld, 1, 1, 1, 0, y.C, y, gather=GATHER_AVGPOOL2, scale=bn.scale, shift=bn.shift, slope=0.0,
                stats=ystats, stats_ld=ystats_ld)
-    return bn
+    return bn, None
 
 
 def generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
@@ -156,7 +167,7 @@ def _generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
     ops.conv2d(X1.ch(0, 64), w, ld, 1, 1, 1, 0, 32, C4.ch(0, 32), gather=GATHER_AVGPOOL2, bias=m.conv_refin2.bias)
     # ---- dense_block1 + trans_block1
     _dense_block_fwd(m.dense_block1, "dense_block1", 6, 64, X1, S1, training, fpool, spool, nbt, saved)
-    bn_t1 = _transition_fwd(m.trans_block1, X1, S1, C4.ch(32, 160), None, 0, training, fpool, nbt)
+    bn_t1, P_t1 = _transition_fwd(m.trans_block1, X1, S1, C4.ch(32, 160), None, 0, training, fpool, nbt)
     # ---- x10 = conv_refine4(cat[x01, x1])
     X2 = View.alloc(B, H2, W2, 512, dev)
     S2 = spool.take(2 * 512)
@@ -166,10 +177,10 @@ def _generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
     _dense_block_fwd(m.dense_block2, "dense_block2", 12, 128, X2, S2, training, fpool, spool, nbt, saved)
     X3 = View.alloc(B, H3, W3, 1024, dev)
     S3 = spool.take(2 * 1024)
-    bn_t2 = _transition_fwd(m.trans_block2, X2, S2, X3.ch(0, 256), S3 if training else None, 1024, training, fpool, nbt)
+    bn_t2, P_t2 = _transition_fwd(m.trans_block2, X2, S2, X3.ch(0, 256), S3 if training else None, 1024, training, fpool, nbt)
     _dense_block_fwd(m.dense_block3, "dense_block3", 24, 256, X3, S3, training, fpool, spool, nbt, saved)
     C6 = View.alloc(B, H4, W4, 640, dev)
-    bn_t3 = _transition_fwd(m.trans_block3, X3, S3, C6.ch(0, 512), None, 0, training, fpool, nbt)
+    bn_t3, P_t3 = _transition_fwd(m.trans_block3, X3, S3, C6.ch(0, 512), None, 0, training, fpool, nbt)
     # ---- x22 = conv_refin5(avg_pool2d(x2, 2))
     w, ld = ops.pack_weight(m.conv_refin5.weight, 0)
     ops.conv2d(X3.ch(0, 256), w, ld, 1, 1, 1, 0, 128, C6.ch(512, 640), gather=GATHER_AVGPOOL2, bias=m.conv_refin5.bias)
@@ -217,6 +228,7 @@ def _generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
     ctx.X1, ctx.C4, ctx.X2, ctx.X3, ctx.C6, ctx.D4, ctx.T4 = X1, C4, X2, X3, C6, D4, T4
     ctx.X42, ctx.T5, ctx.D6, ctx.T6, ctx.X6 = X42, T5, D6, T6, X6
     ctx.bn_t1, ctx.bn_t2, ctx.bn_t3 = bn_t1, bn_t2, bn_t3
+    ctx.P_t = (P_t1, P_t2, P_t3)      # pooled transition inputs (saved for the weight gradients)
     ctx.saved = saved
     ctx.keep = (fpool, spool)
     ctx.training = training
@@ -380,10 +392,14 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
         ops.stream_wait(main, ops.event_record(side))       # join: the buffers above die with this frame; the optimiser reads the gradients on the main stream
 
 
-def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dpool):
-    """torchvision transition backward; g = dL/d(output) at the pooled resolution; accumulates into dX."""
-    _wgrad(X, g, 1, 1, 1, 0, grads[prefix + ".conv.weight"], gather=GATHER_AVGPOOL2, scale=bn.scale, shift=bn.shift,
-              slope=0.0)
+def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dpool, P: View | None = None):
+    """torchvision transition backward; g = dL/d(output) at the pooled resolution; accumulates into dX.  ``P``: the pooled activation
+    the forward pass materialised (POOL_FIRST): the weight gradient is then a plain 1x1 one on a quarter of the pixels."""
+    if P is not None:
+        _wgrad(P, g, 1, 1, 1, 0, grads[prefix + ".conv.weight"])
+    else:
+        _wgrad(X, g, 1, 1, 1, 0, grads[prefix + ".conv.weight"], gather=GATHER_AVGPOOL2, scale=bn.scale, shift=bn.shift,
+               slope=0.0)
     dP = View.alloc(g.N, g.H, g.W, X.C, X.base.device)
     ops.conv2d(g, tr.conv.weight, X.C, 1, 1, 1, 0, X.C, dP)
     if (X.H, X.W) != (2 * g.H, 2 * g.W):
@@ -476,11 +492,11 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     ops.conv2d(g5, m.conv_refin5.weight, 256, 1, 1, 1, 0, 256, dP)
     ops.copy4d(dP, dX3.ch(0, 256), gather=GATHER_UP2, scale=0.25, accumulate=True)
     # ---- encoder level 3
-    _transition_bwd(m.trans_block3, "trans_block3", X3, dX3, dC6.ch(0, 512), ctx.bn_t3, grads, dpool)
+    _transition_bwd(m.trans_block3, "trans_block3", X3, dX3, dC6.ch(0, 512), ctx.bn_t3, grads, dpool, ctx.P_t[2])
     _dense_block_bwd(m.dense_block3, "dense_block3", 24, 256, X3, dX3, ctx.saved["dense_block3"], grads, dpool)
     # ---- encoder level 2
     dX2 = View.alloc(X2.N, X2.H, X2.W, 512, dev, zero=True)
-    _transition_bwd(m.trans_block2, "trans_block2", X2, dX2, dX3.ch(0, 256), ctx.bn_t2, grads, dpool)
+    _transition_bwd(m.trans_block2, "trans_block2", X2, dX2, dX3.ch(0, 256), ctx.bn_t2, grads, dpool, ctx.P_t[1])
     _dense_block_bwd(m.dense_block2, "dense_block2", 12, 128, X2, dX2, ctx.saved["dense_block2"], grads, dpool)
     g4 = dX2.ch(0, 128)
     _wgrad(C4, g4, 3, 3, 1, 1, grads["conv_refine4.weight"], dbias=grads["conv_refine4.bias"])
@@ -489,7 +505,7 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     ops.conv2d(g4, wd, ldd, 3, 3, 1, 1, 160, dC4)
     # ---- encoder level 1
     dX1 = View.alloc(X1.N, X1.H, X1.W, 256, dev, zero=True)
-    _transition_bwd(m.trans_block1, "trans_block1", X1, dX1, dC4.ch(32, 160), ctx.bn_t1, grads, dpool)
+    _transition_bwd(m.trans_block1, "trans_block1", X1, dX1, dC4.ch(32, 160), ctx.bn_t1, grads, dpool, ctx.P_t[0])
     g2 = dC4.ch(0, 32)
     _wgrad(X1.ch(0, 64), g2, 1, 1, 1, 0, grads["conv_refin2.weight"], gather=GATHER_AVGPOOL2,
               dbias=grads["conv_refin2.bias"])

@@ -441,6 +441,13 @@ def copy4d(x: View, y: View, *, gather=GATHER_DIRECT, slope=1.0, scale=1.0, accu
                              1 if accumulate else 0, _stream()), "copy4d")
 
 
+def pool2_bn_act(x: View, y: View, scale=None, shift=None, slope=1.0):
+    """fdg_pool2_bn_act: y = avg_pool2(leaky(x * scale + shift, slope))."""
+    assert (y.N, y.H, y.W, y.C) == (x.N, x.H // 2, x.W // 2, x.C)
+    xt, yt = x.ft(), y.ft()
+    L.check(L.lib.fdg_pool2_bn_act(_byref(xt), _byref(yt), y.N, y.H, y.W, y.C, _ptr(scale), _ptr(shift), slope, _stream()), "pool2_bn_act")
+
+
 def tap_sum(s: View, out: View, R, S, pad, act=ACT_NONE):
     """fdg_tap_sum: out(n,oy,ox) = act(sum over taps t of s(n, oy+ky-pad, ox+kx-pad)[t])."""
     assert s.C == R * S and out.C == 1 and (out.N, out.H, out.W) == (s.N, s.H + 2 * pad - R + 1, s.W + 2 * pad - S + 1)

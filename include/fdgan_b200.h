@@ -239,6 +239,13 @@ int fdg_maxpool2_bwd(const FdgTensor* x, const FdgTensor* gy, const FdgTensor* g
 int fdg_copy4d(const FdgTensor* x, const FdgTensor* y, int N, int H, int W, int C, int gather, float slope, float scale,
                int accumulate, fdg_stream_t stream);
 
+/* y(n,h,w,c) = mean over the 2x2 block of leaky(x * scale[c] + shift[c], slope): BatchNorm + ReLU + AvgPool2d(2) of a torchvision
+ * transition (models/densenet.py:214-221) with the pool commuted in front of the 1x1 convolution, materialised once so that the
+ * convolution and its weight gradient run on a quarter of the pixels without gather.  scale / shift may both be NULL.
+ * x: [N,2OH,2OW,C], y: [N,OH,OW,C]; unit channel stride, 16-byte aligned, C % 4 == 0 (else FDG_ENOSUPPORT). */
+int fdg_pool2_bn_act(const FdgTensor* x, const FdgTensor* y, int N, int OH, int OW, int C, const float* scale, const float* shift, float slope,
+                     fdg_stream_t stream);
+
 /* Single-output-channel stride-1 convolutions by taps (Fusion-D layer 5, dehaze1113.py:222: 8nf -> 1, 4x4): the convolution is run as
  * a 1x1 convolution Cin -> R*S (column t = filter tap t; the OIHW weight [1][Cin][R][S] IS that [Cin][R*S] operand) followed by
  *   fdg_tap_sum:     out(n,oy,ox) = act( sum_t s(n, oy+ky-pad, ox+kx-pad)[t] ),  s: [N,H,W,R*S], out: [N,OH,OW,1]

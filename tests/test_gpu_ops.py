@@ -533,6 +533,22 @@ def test_ew_bwd_pooled_gradient_on_channel_slices():
     assert bool((ob[..., :16] == 3.0).all()) and bool((ob[..., 16 + C:] == 3.0).all())
 
 
+def test_pool2_bn_act():
+    """fdg_pool2_bn_act == avg_pool2d(leaky_relu(x * scale + shift)) on a channel slice of a wider buffer, with and without the affine."""
+    ops = _ops()
+    N, H, W, C, CT = 2, 12, 20, 64, 96
+    xb = seeded((N, H, W, CT), 1, -1, 1)
+    sc, sh = seeded((C,), 2, 0.5, 1.5), seeded((C,), 3, -0.3, 0.3)
+    x = xb[..., 16:16 + C].permute(0, 3, 1, 2).double()
+    xv = ops.View.nhwc(xb.cuda(), N, H, W, CT).ch(16, 16 + C)
+    for affine, slope in ((True, 0.0), (False, 1.0), (True, 0.2)):
+        v = x * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1) if affine else x
+        want = F.avg_pool2d(torch.where(v > 0, v, slope * v), 2)
+        y = ops.View.alloc(N, H // 2, W // 2, C, "cuda")
+        ops.pool2_bn_act(xv, y, sc.cuda() if affine else None, sh.cuda() if affine else None, slope)
+        assert maxabs(y.as_nchw(), want) <= 1e-6
+
+
 @pytest.mark.parametrize("cin,R,pad,H,W", [(288, 4, 1, 15, 13), (64, 3, 1, 9, 20), (72, 4, 2, 8, 8)])
 def test_single_output_channel_conv_by_taps(cin, R, pad, H, W):
     """Fusion-D layer 5 re-associated: 1x1 convolution Cin -> R*S on the tensor cores + fdg_tap_sum == conv2d with one output channel;
