@@ -164,7 +164,14 @@ def _generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
     # ---- x01 = conv_refin2(avg_pool2d(x0, 2)) -> first 32 channels of the conv_refine4 input
     C4 = View.alloc(B, H2, W2, 160, dev)
     w, ld = ops.pack_weight(m.conv_refin2.weight, 0)
-    ops.conv2d(X1.ch(0, 64), w, ld, 1, 1, 1, 0, 32, C4.ch(0, 32), gather=GATHER_AVGPOOL2, bias=m.conv_refin2.bias)
+    pool_first = POOL_FIRST and ops.USE_UMMA and H1 % 2 == 0 and W1 % 2 == 0
+    P01 = P22 = None
+    if pool_first:      # avg_pool2d(x0, 2) materialised once (dehaze1113.py:763): plain 1x1 convolution / weight gradient on it
+        P01 = View.alloc(B, H2, W2, 64, dev)
+        ops.pool2_bn_act(X1.ch(0, 64), P01)
+        ops.conv2d(P01, w, ld, 1, 1, 1, 0, 32, C4.ch(0, 32), bias=m.conv_refin2.bias)
+    else:
+        ops.conv2d(X1.ch(0, 64), w, ld, 1, 1, 1, 0, 32, C4.ch(0, 32), gather=GATHER_AVGPOOL2, bias=m.conv_refin2.bias)
     # ---- dense_block1 + trans_block1
     _dense_block_fwd(m.dense_block1, "dense_block1", 6, 64, X1, S1, training, fpool, spool, nbt, saved)
     bn_t1, P_t1 = _transition_fwd(m.trans_block1, X1, S1, C4.ch(32, 160), None, 0, training, fpool, nbt)
@@ -183,7 +190,12 @@ def _generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
     bn_t3, P_t3 = _transition_fwd(m.trans_block3, X3, S3, C6.ch(0, 512), None, 0, training, fpool, nbt)
     # ---- x22 = conv_refin5(avg_pool2d(x2, 2))
     w, ld = ops.pack_weight(m.conv_refin5.weight, 0)
-    ops.conv2d(X3.ch(0, 256), w, ld, 1, 1, 1, 0, 128, C6.ch(512, 640), gather=GATHER_AVGPOOL2, bias=m.conv_refin5.bias)
+    if pool_first and H3 % 2 == 0 and W3 % 2 == 0:
+        P22 = View.alloc(B, H4, W4, 256, dev)
+        ops.pool2_bn_act(X3.ch(0, 256), P22)
+        ops.conv2d(P22, w, ld, 1, 1, 1, 0, 128, C6.ch(512, 640), bias=m.conv_refin5.bias)
+    else:
+        ops.conv2d(X3.ch(0, 256), w, ld, 1, 1, 1, 0, 128, C6.ch(512, 640), gather=GATHER_AVGPOOL2, bias=m.conv_refin5.bias)
     # ---- decoder level 4: conv_refin6 -> BottleneckBlockdy(512,256) -> TransitionBlockdy(768,128)
     D4 = View.alloc(B, H4, W4, 768, dev)
     w, ld = ops.pack_weight(m.conv_refin6.weight, 0)
@@ -229,6 +241,7 @@ def _generator_forward(m, x: torch.Tensor, training: bool, need_ctx: bool):
     ctx.X42, ctx.T5, ctx.D6, ctx.T6, ctx.X6 = X42, T5, D6, T6, X6
     ctx.bn_t1, ctx.bn_t2, ctx.bn_t3 = bn_t1, bn_t2, bn_t3
     ctx.P_t = (P_t1, P_t2, P_t3)      # pooled transition inputs (saved for the weight gradients)
+    ctx.P01, ctx.P22 = P01, P22
     ctx.saved = saved
     ctx.keep = (fpool, spool)
     ctx.training = training
@@ -486,8 +499,10 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     ops.conv2d(g6, wd, ldd, 3, 3, 1, 1, 640, dC6)
     # ---- conv_refin5 branch (x22)
     g5 = dC6.ch(512, 640)
-    _wgrad(X3.ch(0, 256), g5, 1, 1, 1, 0, grads["conv_refin5.weight"], gather=GATHER_AVGPOOL2,
-              dbias=grads["conv_refin5.bias"])
+    if ctx.P22 is not None:
+        _wgrad(ctx.P22, g5, 1, 1, 1, 0, grads["conv_refin5.weight"], dbias=grads["conv_refin5.bias"])
+    else:
+        _wgrad(X3.ch(0, 256), g5, 1, 1, 1, 0, grads["conv_refin5.weight"], gather=GATHER_AVGPOOL2, dbias=grads["conv_refin5.bias"])
     dP = View.alloc(g5.N, g5.H, g5.W, 256, dev)
     ops.conv2d(g5, m.conv_refin5.weight, 256, 1, 1, 1, 0, 256, dP)
     ops.copy4d(dP, dX3.ch(0, 256), gather=GATHER_UP2, scale=0.25, accumulate=True)
@@ -507,8 +522,10 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     dX1 = View.alloc(X1.N, X1.H, X1.W, 256, dev, zero=True)
     _transition_bwd(m.trans_block1, "trans_block1", X1, dX1, dC4.ch(32, 160), ctx.bn_t1, grads, dpool, ctx.P_t[0])
     g2 = dC4.ch(0, 32)
-    _wgrad(X1.ch(0, 64), g2, 1, 1, 1, 0, grads["conv_refin2.weight"], gather=GATHER_AVGPOOL2,
-              dbias=grads["conv_refin2.bias"])
+    if ctx.P01 is not None:
+        _wgrad(ctx.P01, g2, 1, 1, 1, 0, grads["conv_refin2.weight"], dbias=grads["conv_refin2.bias"])
+    else:
+        _wgrad(X1.ch(0, 64), g2, 1, 1, 1, 0, grads["conv_refin2.weight"], gather=GATHER_AVGPOOL2, dbias=grads["conv_refin2.bias"])
     dP = View.alloc(g2.N, g2.H, g2.W, 64, dev)
     ops.conv2d(g2, m.conv_refin2.weight, 64, 1, 1, 1, 0, 64, dP)
     if (X1.H, X1.W) != (2 * dP.H, 2 * dP.W):
