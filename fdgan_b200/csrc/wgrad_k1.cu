@@ -222,6 +222,10 @@ __global__ void __launch_bounds__(WK_THREADS, 1) wgrad_k1_kernel(const __grid_co
   if (warp < WK_LOAD_WARPS && ntiles > 0) {
     mbar_wait(smem_u32(&bar_acc), 0);                        // every MMA has retired: the ring is free
     tc_fence_after();
+    // The ring is about to be overwritten by OTHER threads than those that filled it.  The mbarrier chain (loader stores -> arrive ->
+    // tcgen05.mma -> commit -> this wait) already orders that; the CTA barrier among the eight loader warps makes the hand-over explicit
+    // (and visible to compute-sanitizer's racecheck, which does not model mbarrier / tensor-core completion).
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const int quarter = warp & 3;                            // TMEM lanes this warp may read
     const int cil = quarter * 32 + lane;                     // input channel within the block
     const uint32_t stg = smem_base;                          // [32 co][128 ci][9 taps] floats = 147456 B <= 2 * WK_STAGE
