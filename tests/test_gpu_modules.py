@@ -266,3 +266,23 @@ def test_laplacian_is_channel_agnostic_and_blur_takes_any_kernel():
         assert maxabs(y, yo) <= 2e-5 and maxabs(xd.grad, xo.grad) <= 2e-5, (shape, l)
     with pytest.raises(RuntimeError):
         L.Blur(7, L.isotropic_gaussian_kernel(7, 1.0), True)(seeded((1, 4, 16, 16), 1).cuda())      # ImageNet mean / std are 3-channel
+
+
+def test_pytorch_ssim_surface_matches_reference_arithmetic():
+    """fdgan_b200.pytorch_ssim.ssim / SSIM (the models/pytorch_ssim surface, :39-73): value for size_average True / False and the gradient
+    w.r.t. BOTH images against the oracle's restatement (pinned to the reference module by tests/test_oracle_golden.py) under autograd."""
+    from fdgan_b200 import pytorch_ssim as PS
+    a, b = seeded((3, 3, 40, 28), 60), seeded((3, 3, 40, 28), 61)
+    ao, bo = a.clone().double().requires_grad_(True), b.clone().double().requires_grad_(True)
+    vo = O.ssim(ao, bo)
+    (1 - vo).backward()
+    ad, bd = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    v = PS.ssim(ad, bd)
+    (1 - v).backward()
+    assert abs(float(v) - float(vo)) <= 2e-6
+    assert maxabs(ad.grad, ao.grad) <= 1e-6 and maxabs(bd.grad, bo.grad) <= 1e-6
+    per = PS.SSIM(size_average=False)(a.cuda(), b.cuda())
+    want = torch.stack([O.ssim(a[i:i + 1].double(), b[i:i + 1].double()) for i in range(3)])
+    assert tuple(per.shape) == (3,) and maxabs(per, want) <= 2e-6
+    with pytest.raises(NotImplementedError):
+        PS.ssim(a.cuda(), b.cuda(), window_size=7)
