@@ -46,13 +46,14 @@ template <int NT, int BSTAGES>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   const int A_STAGE = 2 * a.a_tile;
-  static_assert(NT <= 128, "two double-width accumulators must fit the 512 TMEM columns");
-  constexpr int TMEM_COLS = 4 * NT;        // two accumulator buffers of [hi*hi | hi*lo + lo*hi] halves
+  static_assert(NT <= 128 && NT % 16 == 0, "two double-width accumulators must fit the 512 TMEM columns");
+  constexpr int TMEM_COLS = 4 * NT <= 128 ? 128 : (4 * NT <= 256 ? 256 : 512);   // two accumulator buffers of [hi*hi | hi*lo + lo*hi] halves (power of two)
+  constexpr int NTP = (NT + 31) / 32 * 32;  // 32-channel epilogue groups; the last one of an 80-wide tile holds 16 channels
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full[2], bar_a_empty[2], bar_b_full[BSTAGES], bar_b_empty[BSTAGES];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float sred[2][4][NT];
+  __shared__ float sred[2][4][NTP];
   __shared__ __align__(1024) uint8_t ep_stage[EP_TILE_BYTES];   // epilogue staging tile (SWIZZLE_128B box layout)
   __shared__ __align__(16) float aff_s[2][H_MAX_AFF];
 
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   const bool aff_smem = p.has_affine && p.Cin <= H_MAX_AFF;
   if (aff_smem)
     for (int i = t; i < p.Cin; i += H_THREADS) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
-  for (int i = t; i < 2 * 4 * NT; i += H_THREADS) (&sred[0][0][0])[i] = 0.f;
+  for (int i = t; i < 2 * 4 * NTP; i += H_THREADS) (&sred[0][0][0])[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, ox0, oy0, n};
       const int cbase = ntile * NT;
 #pragma unroll 1
-      for (int g = 0; g < NT / 32; ++g) {
+      for (int g = 0; g < NTP / 32; ++g) {
         const int c0 = cbase + g * 32;
         if (c0 < p.Cout && !(a.dbg & 8)) {
           float v[32];
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             for (int u = 0; u < 32; ++u) v[u] += v2[u];
           }
           umma_epilogue_group<true>(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, &sred[0][quarter][g * 32],
-                              &sred[1][quarter][g * 32]);
+                              &sred[1][quarter][g * 32], NT - g * 32);
         }
       }
       tc_fence_before();
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
 }
 
 static int g_halo_on = [] { const char* e = getenv("FDG_HALO"); return e ? atoi(e) : 1; }();
+int halo_enabled() { return g_halo_on; }
 
 int conv2d_halo_supported(const FdgConv* p) {
   if (!g_halo_on || !p->w_umma) return 0;
@@ -413,6 +415,8 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
   switch (nt) {
     case 32: return launch_halo<32, 10>(a, st);
     case 64: return launch_halo<64, 5>(a, st);
+    case 80: return launch_halo<80, 4>(a, st);     // 144 = 2 x 80, 72, 160 (Fusion-D layer 3, data gradients of layers 3 / 4, conv_refine4)
+    case 96: return launch_halo<96, 3>(a, st);     // 288 = 3 x 96 (Fusion-D layer 4)
     default: return a.a_tile <= 23 * 1024 ? launch_halo<128, 3>(a, st) : launch_halo<128, 2>(a, st);
   }
 }

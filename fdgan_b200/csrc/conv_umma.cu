@@ -799,9 +799,25 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, int ld, int taps, 
     pack_umma_item(w, ld, taps, Cin, Cout, NT, cchunks, out, i);
 }
 
-int umma_ntile(int Cout) {
+int halo_enabled();
+
+// Output-channel tile of the packed weight images.  Per-tap kernel (1x1 and everything the halo kernel does not take): 32 / 64 / 128.
+// Filters with >= 4 taps run on the halo-tile kernel, which also has 80- and 96-wide instantiations: the MMAs of a partly filled
+// tile are issued at full width, so 144 = 2 x 80 (not 2 x 128), 288 = 3 x 96, 72 -> 80, 160 = 2 x 80 (Fusion-D layers 3 / 4 and
+// their data gradients: 25-44 % fewer tensor-core cycles).  Cost model: cycles per K = 16 slice of the concatenated-B pair
+// (N = 2NT and N = NT; below N = 128 the shared-memory read of the A operand, 32 cycles, is the floor of an MMA).
+int umma_ntile(int taps, int Cout) {
   static const int cap = [] { const char* e = getenv("FDG_UMMA_NT_CAP"); return e ? atoi(e) : 128; }();
-  const int nt = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+  static const int fine = [] { const char* e = getenv("FDG_UMMA_NT_FINE"); return e ? atoi(e) : 1; }();
+  int nt = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+  if (fine && taps >= 4 && Cout > 64 && halo_enabled()) {
+    const int cand[3] = {128, 96, 80}, cost[3] = {192, 152, 132};
+    int best = 1 << 30;
+    for (int i = 0; i < 3; ++i) {
+      const int c = cdiv(Cout, cand[i]) * cost[i];
+      if (c < best) { best = c; nt = cand[i]; }
+    }
+  }
   return nt > cap ? cap : nt;
 }
 
@@ -810,6 +826,10 @@ int conv2d_halo_supported(const FdgConv* p);
 int conv2d_umma_supported(const FdgConv* p) {
   if (!p->w_umma) return 0;
   if (p->Cin % 8 != 0) return p->Cin % 4 == 0 && conv2d_halo_supported(p);   // only the halo kernel takes half chunks
+  {
+    const int nt = umma_ntile(p->R * p->S, p->Cout);
+    if (nt != 32 && nt != 64 && nt != 128 && !conv2d_halo_supported(p)) return 0;   // 80 / 96-wide images exist for the halo kernel only
+  }
   if (p->Cin < 16 || p->Cout < 1) return 0;
   AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
   if (!aop_vec_ok(ao, p->Cin)) return 0;
@@ -844,7 +864,8 @@ int conv2d_halo_supported(const FdgConv* p);
 int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st);
 
 int conv2d_umma(const FdgConv* p, cudaStream_t st) {
-  if (umma_ntile(p->Cout) <= 128 && conv2d_halo_supported(p)) return conv2d_halo(p, umma_ntile(p->Cout), st);
+  const int ntile = umma_ntile(p->R * p->S, p->Cout);
+  if (ntile <= 128 && conv2d_halo_supported(p)) return conv2d_halo(p, ntile, st);
   UmmaArgs a;
   a.c = *p;
   a.ao = AOp{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
@@ -887,17 +908,17 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
     if (make_tmap_f32(&a.ymap, p->y.p, 2, dims, strides, box)) a.tma_rank = 2;
   }
   static const int reg_path = [] { const char* e = getenv("FDG_CONV_REG"); return e ? atoi(e) : 0; }();
-  if (reg_path && umma_ntile(p->Cout) == 128) return launch_umma<128, 3, 0>(a, st);   // register double buffer, no staging ring
+  if (reg_path && ntile == 128) return launch_umma<128, 3, 0>(a, st);   // register double buffer, no staging ring
   if (p->e_scale) {   // BatchNorm-backward epilogue: own instantiation (pixel-linear 128-bit views, wide outputs)
-    if (!a.bn_linear || umma_ntile(p->Cout) < 64) {
+    if (!a.bn_linear || ntile < 64) {
       set_error("fdg_conv2d[tcgen05]: the BatchNorm-backward epilogue of the per-tap kernel needs pixel-linear y / e views and Cout > 32");
       return FDG_ENOSUPPORT;
     }
-    return umma_ntile(p->Cout) == 64 ? launch_umma<64, 2, 3, true>(a, st) : launch_umma<128, 2, 2, true>(a, st);
+    return ntile == 64 ? launch_umma<64, 2, 3, true>(a, st) : launch_umma<128, 2, 2, true>(a, st);
   }
   // 1x1 / stride 1 / direct gather over a pixel-linear view: the staging ring is fed by the bulk-tensor engine (FAST)
   static const int fast_on = [] { const char* e = getenv("FDG_CONV_FAST"); return e ? atoi(e) : 1; }();
-  if (fast_on && umma_ntile(p->Cout) == 128 && p->R == 1 && p->S == 1 && p->stride == 1 && p->pad == 0 && p->gather == FDG_GATHER_DIRECT &&
+  if (fast_on && ntile == 128 && p->R == 1 && p->S == 1 && p->stride == 1 && p->pad == 0 && p->gather == FDG_GATHER_DIRECT &&
       vec4_ok(p->x) && p->x.sh == (int64_t)p->W * p->x.sw && p->x.sn == (int64_t)p->H * p->x.sh && p->Cin % 8 == 0 &&
       (!p->has_affine || p->Cin <= UMAX_AFF) && a.M < (1ll << 31)) {
     const uint64_t dims[2] = {(uint64_t)p->Cin, (uint64_t)a.M};
@@ -905,7 +926,11 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
     const uint32_t box[2] = {32, 128};
     if (make_tmap_f32(&a.xmap_hi, p->x.p, 2, dims, strides, box)) return launch_umma<128, 2, 2, false, true>(a, st);   // xmap_hi = the fp32 input view
   }
-  switch (umma_ntile(p->Cout)) {
+  if (ntile != 32 && ntile != 64 && ntile != 128) {
+    set_error("fdg_conv2d[tcgen05]: the %d-wide weight image of this filter belongs to the halo-tile kernel, which does not take the shape", ntile);
+    return FDG_ENOSUPPORT;
+  }
+  switch (ntile) {
     case 32: return launch_umma<32, 2, 3>(a, st);     // ring 2 x 40 KB + staging 3 x 32 KB
     case 64: return launch_umma<64, 2, 3>(a, st);     // ring 2 x 48 KB + staging 3 x 32 KB
     default: return launch_umma<128, 2, 2>(a, st);    // ring 2 x 64 KB + staging 2 x 32 KB
@@ -916,17 +941,17 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
 
 using namespace fdg;
 
-extern "C" int fdg_umma_ntile(int Cout) { return umma_ntile(Cout); }
+extern "C" int fdg_umma_ntile(int taps, int Cout) { return umma_ntile(taps, Cout); }
 
 extern "C" int64_t fdg_umma_weight_bytes(int taps, int Cin, int Cout) {
-  const int NT = umma_ntile(Cout);
+  const int NT = umma_ntile(taps, Cout);
   return (int64_t)cdiv(Cout, NT) * taps * cdiv(Cin, UKC) * 2 * NT * 128;
 }
 
 extern "C" int fdg_pack_weight_umma(const float* w, int w_ld, int taps, int Cin, int Cout, void* out, fdg_stream_t stream) {
   FDG_REQUIRE(w && out && taps > 0 && Cin > 0 && Cout > 0 && w_ld >= Cout, "fdg_pack_weight_umma: bad arguments");
   FDG_REQUIRE(aligned16(out), "fdg_pack_weight_umma: output must be 16-byte aligned");
-  const int NT = umma_ntile(Cout);
+  const int NT = umma_ntile(taps, Cout);
   const int cch = cdiv(Cin, UKC);
   const int64_t total = (int64_t)cdiv(Cout, NT) * taps * cch * NT * 8;
   int64_t g = cdiv64(total, 256);

@@ -9,7 +9,7 @@
 
 namespace fdg {
 
-int umma_ntile(int Cout);
+int umma_ntile(int taps, int Cout);
 
 __global__ void __launch_bounds__(256) pack_batch_kernel(const FdgPackJob* __restrict__ jobs, int njobs) {
   pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
@@ -50,7 +50,7 @@ extern "C" int64_t fdg_pack_job_items(const FdgPackJob* j) {
     return K * j->ld;
   }
   if (j->kind == FDG_PACK_UMMA) {   // r = taps, s = NT (must equal the kernel's tile choice for this Cout)
-    if (j->r <= 0 || j->s != umma_ntile(j->cout) || j->ld < j->cout) return -1;
+    if (j->r <= 0 || j->s != umma_ntile(j->r, j->cout) || j->ld < j->cout) return -1;
     return (int64_t)cdiv(j->cout, j->s) * j->r * cdiv(j->cin, 64) * j->s * 8;
   }
   if (j->kind == FDG_PACK_K1) {

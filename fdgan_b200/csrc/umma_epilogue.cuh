@@ -32,8 +32,10 @@ struct EpiTma {
 template <bool BN>   // BN: the BatchNorm-backward mode (p.e_scale) is compiled in
 __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec, bool evec, float (&v)[32], bool mv, int64_t yoff,
                                                     int64_t eoff, int c0, int lane, int quarter, int et, uint32_t tile, const EpiTma& tm,
-                                                    float* st1, float* st2) {
-  const int nvalid = p.Cout - c0 < 32 ? p.Cout - c0 : 32;
+                                                    float* st1, float* st2, int ncap = 32) {
+  // ncap < 32: the group is the 16-channel tail of an 80-wide tile; channels beyond it belong to the NEXT tile and are not touched
+  const int nrem = p.Cout - c0 < ncap ? p.Cout - c0 : ncap;
+  const int nvalid = nrem < 32 ? nrem : 32;
   const bool full = nvalid == 32;
   // ---- alpha, bias
   if (p.bias) {
@@ -67,8 +69,8 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
 #pragma unroll
     for (int u = 0; u < 32; ++u) if (!mv || u >= nvalid) v[u] = 0.f;
   }
-  const bool use_tma = tm.map != nullptr;
-  if (use_tma) {
+  const bool use_tma = tm.map != nullptr && ncap >= 32;   // a tile-tail group leaves through the coalesced path (a 32-channel box would overrun)
+  if (tm.map != nullptr) {
     // the previous group's bulk store must have finished READING the staging tile before it is overwritten
     if (et == 0) bulk_wait_read0();
     asm volatile("bar.sync 2, 128;" ::: "memory");

@@ -354,7 +354,7 @@ int fdg_loss_grad(const float* a, const float* b, float target, int kind, int64_
  * [first_block, first_block + nblocks) of 256 threads, total_blocks = sum of nblocks.  Jobs of one launch must not
  * depend on each other (an image made from a packed operand goes into a second launch).
  *   kind 0..2         fdg_pack_weight mode: src = OIHW parameter, dst = fp32 [K][ld];  cout, cin, r, s = filter dims
- *   FDG_PACK_UMMA     fdg_pack_weight_umma: src = fp32 [K][ld] operand, r = taps, s = N tile (fdg_umma_ntile(cout))
+ *   FDG_PACK_UMMA     fdg_pack_weight_umma: src = fp32 [K][ld] operand, r = taps, s = N tile (fdg_umma_ntile(taps, cout))
  *   FDG_PACK_K1       fdg_pack_weight_k1:   src = fp32 [9*cin][ld] operand                                         */
 #define FDG_PACK_UMMA 3
 #define FDG_PACK_K1 4
@@ -366,7 +366,7 @@ typedef struct FdgPackJob {
   int64_t total; /* work items = fdg_pack_job_items(job) */
 } FdgPackJob;
 int64_t fdg_pack_job_items(const FdgPackJob* job);
-int fdg_umma_ntile(int Cout);
+int fdg_umma_ntile(int taps, int Cout); /* output-channel tile of the packed image: 32 / 64 / 128, or 80 / 96 for filters of >= 4 taps (halo-tile kernel) */
 int fdg_pack_batch(const FdgPackJob* jobs_dev, int njobs, int total_blocks, fdg_stream_t stream);
 
 /* Live per-launch timing for bench.py's roofline: when enabled every entry point brackets its kernel with CUDA events

@@ -24,6 +24,11 @@ SHAPES = [
     ("dgrad 1x1 128->224 @256", "conv", 128, 224, 1, 0, 256, False, False),
     ("vgg 3x3 64->64 @256", "conv", 64, 64, 3, 1, 256, False, False),
     ("D L4 4x4 144->288 @128", "conv", 144, 288, 4, 1, 128, True, False),
+    ("D L4 dgrad 4x4 288->144 @127", "conv", 288, 144, 4, 2, 127, False, False),
+    ("D L3 3x3 72->144 @128", "conv", 72, 144, 3, 1, 128, True, False),
+    ("vgg 3x3 128->128 @128", "conv", 128, 128, 3, 1, 128, False, False),
+    ("vgg 3x3 256->256 @64", "conv", 256, 256, 3, 1, 64, False, False),
+    ("vgg 3x3 512->512 @32", "conv", 512, 512, 3, 1, 32, False, False),
     ("wgrad K1 3x3 128->32 @256", "wgrad", 128, 32, 3, 1, 256, True, False),
     ("wgrad K2 1x1 224->128 @256", "wgrad", 224, 128, 1, 0, 256, True, False),
     ("wgrad K2 1x1 992->128 @64", "wgrad", 992, 128, 1, 0, 64, True, False),
@@ -47,7 +52,7 @@ def main():
     dev = "cuda"
     print("%-30s" % "shape" + "".join("  dbg=%-2d  " % m for m in MODES) + "   (ms; TF/s at dbg=0)")
     for name, kind, Cin, Cout, R, pad, H, affine, stats in SHAPES:
-        if only and only not in name:
+        if only and not any(f in name for f in only.split(",")):
             continue
         x = View.alloc(B, H, H, Cin, dev); x.base.normal_()
         OH = H + 2 * pad - R + 1

@@ -57,6 +57,11 @@ CONV_CASES = [
     (72, 96, 1, 1, 0, 23, 17, 0, True, 0.2, True, 0, 0, False, False),     # ... Cin % 16 == 8 (half K slice), LeakyReLU prologue, bias
     (512, 300, 1, 1, 0, 13, 10, 0, False, 0.0, False, 1, 0, False, False), # ... several N tiles (BottleneckBlockdy conv1 shape family)
     (384, 128, 1, 1, 0, 12, 12, 0, False, 0.0, False, 1, 1, False, False), # ... TransitionBlockdy: ReLU prologue, up2 store
+    (72, 144, 3, 1, 1, 19, 21, 0, True, 0.2, False, 0, 0, True, False),    # D layer 3: two 80-wide N tiles (16-channel tail groups), statistics
+    (288, 144, 4, 1, 2, 13, 11, 0, False, 1.0, False, 0, 0, False, True),  # D layer 4 data gradient: 80-wide tiles + LeakyReLU mask
+    (144, 72, 3, 1, 1, 17, 9, 0, False, 1.0, False, 0, 0, False, True),    # D layer 3 data gradient: one 80-wide tile, Cout tail inside it
+    (128, 160, 3, 1, 1, 9, 10, 0, False, 1.0, True, 1, 2, False, False),   # conv_refine4 data-gradient geometry: 160 = 2 x 80, accumulate
+    (144, 288, 4, 1, 1, 20, 18, 0, True, 0.2, False, 0, 0, True, False),   # D layer 4: three 96-wide N tiles, bulk tensor stores, statistics
 ]
 
 
