@@ -23,8 +23,12 @@ struct ThinArgs {
   int K;
 };
 
-template <int NC4>   // Cout = 4 * NC4
-__global__ void __launch_bounds__(TH_THREADS) conv_thin_kernel(const __grid_constant__ ThinArgs a) {
+// FR, FS, FC > 0: filter extent and input channels are compile-time (stem / Vgg16 conv1_1 3x3x3, Fusion-D layer 1 4x4x9): the
+// input values of a whole filter (K <= 32) or of one filter row are fetched into registers FIRST -- independent loads in flight --
+// and multiplied afterwards.  The generic form below issues one dependent load per k, which left the kernel latency-bound at
+// 16 warps per SM (stem: 0.29 ms against a 0.06 ms FMA floor).
+template <int NC4, int FR = 0, int FS = 0, int FC = 0>   // Cout = 4 * NC4
+__global__ void __launch_bounds__(TH_THREADS, 2) conv_thin_kernel(const __grid_constant__ ThinArgs a) {
   pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
   pdl_trigger();
   constexpr int CO = 4 * NC4;
@@ -57,6 +61,44 @@ __global__ void __launch_bounds__(TH_THREADS) conv_thin_kernel(const __grid_cons
       yoff = n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox * p.y.sw;
       const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
       const float* xb = p.x.p + n * p.x.sn;
+      if constexpr (FR > 0) {
+        constexpr int KROW = FS * FC;
+        constexpr int RCH = (FR * KROW <= 32) ? FR : 1;      // filter rows per register chunk
+        const float sl = p.slope;
+#pragma unroll 1
+        for (int r0 = 0; r0 < FR; r0 += RCH) {
+          float xin[RCH * KROW];
+#pragma unroll
+          for (int rr = 0; rr < RCH; ++rr) {
+            const int iy = iy0 + r0 + rr;
+            const bool yin = iy >= 0 && iy < p.H;
+            const float* xr = xb + (int64_t)iy * p.x.sh;
+#pragma unroll
+            for (int s = 0; s < FS; ++s) {
+              const int ix = ix0 + s;
+              const bool in = yin && ix >= 0 && ix < p.W;
+#pragma unroll
+              for (int ci = 0; ci < FC; ++ci)
+                xin[(rr * FS + s) * FC + ci] = in ? __ldg(xr + (int64_t)ix * p.x.sw + (int64_t)ci * p.x.sc) : 0.f;
+            }
+          }
+          if (sl != 1.f) {
+#pragma unroll
+            for (int i = 0; i < RCH * KROW; ++i) xin[i] = prologue_act(xin[i], sl);
+          }
+          const float4* wr = reinterpret_cast<const float4*>(ws + r0 * KROW * CO);
+#pragma unroll
+          for (int i = 0; i < RCH * KROW; ++i) {
+            const float xv = xin[i];
+#pragma unroll
+            for (int q = 0; q < NC4; ++q) {
+              const float4 wv = wr[i * NC4 + q];                 // same address in every lane: broadcast
+              v[4 * q] = fmaf(xv, wv.x, v[4 * q]); v[4 * q + 1] = fmaf(xv, wv.y, v[4 * q + 1]);
+              v[4 * q + 2] = fmaf(xv, wv.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(xv, wv.w, v[4 * q + 3]);
+            }
+          }
+        }
+      } else {
       int k = 0;
       for (int r = 0; r < p.R; ++r) {
         const int iy = iy0 + r;
@@ -76,6 +118,7 @@ __global__ void __launch_bounds__(TH_THREADS) conv_thin_kernel(const __grid_cons
             }
           }
         }
+      }
       }
 #pragma unroll
       for (int u = 0; u < CO; ++u) {
@@ -131,6 +174,151 @@ __global__ void __launch_bounds__(TH_THREADS) conv_thin_kernel(const __grid_cons
   }
 }
 
+// Stem form (3x3 / stride 1 / pad 1, 3 -> 64: conv_refin1 and Vgg16 conv1_1).  With one pixel per thread every k costs 16 warp-wide
+// 128-bit weight broadcasts for 64 FMAs per lane: the shared-memory pipe (4 cycles per 128-bit warp load) bounds the kernel at
+// ~0.2 ms.  Here a thread owns FOUR horizontally adjacent pixels x 16 channels (channels 16q + 4*cg .. +3, q = 0..3, so that the
+// four lanes of a pixel group store 64 contiguous bytes per instruction): 4 weight loads per 64 FMAs, the 18 x 3 input values of
+// the four pixels are fetched into registers first.  BatchNorm statistics are per-thread sums folded by shuffles.
+constexpr int ST_THREADS = 128;
+
+struct StemArgs {
+  FdgConv c;
+  int owg;           // groups of four pixels per row
+  int64_t groups;    // N * OH * owg
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(ST_THREADS, 3) conv_stem4_kernel(const __grid_constant__ StemArgs a) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
+  __shared__ __align__(16) float ws[27 * 64];
+  __shared__ __align__(16) float bs[64];
+  __shared__ float red[2][64];
+  const FdgConv& p = a.c;
+  const int t = threadIdx.x, lane = t & 31;
+  for (int i = t; i < 27 * 64; i += ST_THREADS) ws[i] = __ldg(p.w + (int64_t)(i >> 6) * p.w_ld + (i & 63));
+  if (t < 128) (&red[0][0])[t] = 0.f;
+  if (t < 64) bs[t] = p.bias ? __ldg(p.bias + t) : 0.f;
+  __syncthreads();
+  const int cg = t & 3;
+  const bool relu = p.act == FDG_ACT_RELU;
+  float s1[STATS ? 16 : 1], s2[STATS ? 16 : 1];     // per-thread statistics of its 16 channels (kept in registers: 3 CTAs of 128 threads per SM)
+#pragma unroll
+  for (int u = 0; u < (STATS ? 16 : 1); ++u) { s1[u] = 0.f; s2[u] = 0.f; }
+  const int64_t gstep = (int64_t)gridDim.x * (ST_THREADS / 4);
+  for (int64_t gi = (int64_t)blockIdx.x * (ST_THREADS / 4) + (t >> 2); gi < a.groups; gi += gstep) {
+    const int og = (int)(gi % a.owg);
+    const int64_t r_ = gi / a.owg;
+    const int oy = (int)(r_ % p.OH), n = (int)(r_ / p.OH);
+    const int ox0 = og * 4;
+    const float* xb = p.x.p + n * p.x.sn;
+    // ---- the 3 x 6 x 3 input patch of the four pixels (zero outside the image)
+    float xin[3][6][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy - 1 + r;
+      const bool yin = iy >= 0 && iy < p.H;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int ix = ox0 - 1 + c;
+        const bool in = yin && ix >= 0 && ix < p.W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+          xin[r][c][ci] = in ? __ldg(xb + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw + (int64_t)ci * p.x.sc) : 0.f;
+      }
+    }
+    if (p.slope != 1.f) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) xin[r][c][ci] = prologue_act(xin[r][c][ci], p.slope);
+    }
+    float v[4][16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[j][u] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float* wk = ws + ((r * 3 + sx) * 3 + ci) * 64 + 4 * cg;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = *reinterpret_cast<const float4*>(wk + 16 * q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float xv = xin[r][sx + j][ci];
+              v[j][4 * q] = fmaf(xv, wv.x, v[j][4 * q]); v[j][4 * q + 1] = fmaf(xv, wv.y, v[j][4 * q + 1]);
+              v[j][4 * q + 2] = fmaf(xv, wv.z, v[j][4 * q + 2]); v[j][4 * q + 3] = fmaf(xv, wv.w, v[j][4 * q + 3]);
+            }
+          }
+        }
+    float* yb = p.y.p + n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox0 * p.y.sw + 4 * cg;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bs + 16 * q + 4 * cg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o[4];
+        o[0] = fmaf(v[j][4 * q], p.alpha, b4.x); o[1] = fmaf(v[j][4 * q + 1], p.alpha, b4.y);
+        o[2] = fmaf(v[j][4 * q + 2], p.alpha, b4.z); o[3] = fmaf(v[j][4 * q + 3], p.alpha, b4.w);
+        if (relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+        if (ox0 + j < p.OW) {
+          *reinterpret_cast<float4*>(yb + (int64_t)j * p.y.sw + 16 * q) = make_float4(o[0], o[1], o[2], o[3]);
+          if (STATS) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s1[4 * q + u] += o[u]; s2[4 * q + u] = fmaf(o[u], o[u], s2[4 * q + u]); }
+          }
+        }
+      }
+    }
+  }
+  if (STATS) {
+    // all lanes are here (the loop has ended for everyone): the eight lanes with equal cg (lane & 3) fold their sums
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+#pragma unroll
+      for (int off = 4; off <= 16; off <<= 1) {
+        s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], off);
+        s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], off);
+      }
+    }
+    if (lane < 4) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int c = 16 * (u >> 2) + 4 * cg + (u & 3);
+        atomicAdd(&red[0][c], s1[u]);
+        atomicAdd(&red[1][c], s2[u]);
+      }
+    }
+    __syncthreads();
+    if (t < 64) {
+      atomicAdd(p.stats + t, (double)red[0][t]);
+      atomicAdd(p.stats + p.stats_ld + t, (double)red[1][t]);
+    }
+  }
+}
+
+static int conv2d_stem4(const FdgConv* p, cudaStream_t st) {
+  StemArgs a;
+  a.c = *p;
+  a.owg = cdiv(p->OW, 4);
+  a.groups = (int64_t)p->N * p->OH * a.owg;
+  int64_t blocks = cdiv64(a.groups, ST_THREADS / 4);
+  const int64_t cap = (int64_t)device_sm_count() * 12;
+  if (blocks > cap) blocks = cap;
+  const double M = (double)p->N * p->OH * p->OW;
+  ProfScope prof(PF_CONV_SIMT, 2.0 * M * 27 * 64, 4.0 * (M * 64 + (double)p->N * p->H * p->W * 3), st);
+  if (p->stats) launch_k(conv_stem4_kernel<true>, dim3((unsigned)blocks), dim3(ST_THREADS), (size_t)(0), st, a);
+  else launch_k(conv_stem4_kernel<false>, dim3((unsigned)blocks), dim3(ST_THREADS), (size_t)(0), st, a);
+  return check_launch("fdg_conv2d[thin]");
+}
+
 int conv2d_thin_supported(const FdgConv* p) {
   static const int on = [] { const char* e = getenv("FDG_THIN"); return e ? atoi(e) : 1; }();
   if (!on || p->impl != 0) return 0;                  // impl = 1 keeps the generic SIMT kernel (the tests' fp32 arbiter)
@@ -141,14 +329,14 @@ int conv2d_thin_supported(const FdgConv* p) {
   return 1;
 }
 
-template <int NC4>
+template <int NC4, int FR = 0, int FS = 0, int FC = 0>
 static int launch_thin(const ThinArgs& a, cudaStream_t st) {
   constexpr int CO = 4 * NC4;
   constexpr int smem = (TH_MAXK * CO + 8 * 32 * (CO + 4)) * 4;
   static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
-    if (cudaFuncSetAttribute(conv_thin_kernel<NC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_thin_kernel<NC4, FR, FS, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[thin]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -157,19 +345,23 @@ static int launch_thin(const ThinArgs& a, cudaStream_t st) {
   int64_t blocks = cdiv64(a.M, 8 * 32);
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope prof(PF_CONV_SIMT, 2.0 * (double)a.M * a.K * CO, 4.0 * ((double)a.M * CO + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  launch_k(conv_thin_kernel<NC4>, dim3((unsigned)blocks), dim3(TH_THREADS), (size_t)(smem), st, a);
+  launch_k(conv_thin_kernel<NC4, FR, FS, FC>, dim3((unsigned)blocks), dim3(TH_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d[thin]");
 }
 
 int conv2d_thin(const FdgConv* p, cudaStream_t st) {
+  static const int stem4 = [] { const char* e = getenv("FDG_STEM4"); return e ? atoi(e) : 1; }();
+  if (stem4 && p->Cout == 64 && p->Cin == 3 && p->R == 3 && p->S == 3 && p->stride == 1 && p->pad == 1 &&
+      (p->act == FDG_ACT_NONE || p->act == FDG_ACT_RELU))
+    return conv2d_stem4(p, st);
   ThinArgs a;
   a.c = *p;
   a.M = (int64_t)p->N * p->OH * p->OW;
   a.K = p->R * p->S * p->Cin;
   switch (p->Cout) {
     case 16: return launch_thin<4>(a, st);
-    case 36: return launch_thin<9>(a, st);
-    default: return launch_thin<16>(a, st);
+    case 36: return (p->R == 4 && p->S == 4 && p->Cin == 9) ? launch_thin<9, 4, 4, 9>(a, st) : launch_thin<9>(a, st);
+    default: return (p->R == 3 && p->S == 3 && p->Cin == 3) ? launch_thin<16, 3, 3, 3>(a, st) : launch_thin<16>(a, st);
   }
 }
 
@@ -520,11 +712,243 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_thin_kernel(const __grid_con
   }
 }
 
+// Tiled form (default; FDG_WTHIN_TILE=0 selects the batch kernel above).  The batch kernel materialises im2col rows of 32 pixels
+// with one scalar load and a tap decode per element and synchronises twice per 32 pixels: 0.74 ms for the head conv_refin3
+// (16 -> 3), 0.33 ms for the stem, 0.28 ms for Fusion-D layer 1, 5-15x above their FMA / HBM floors.  Here a CTA owns tiles of
+// WTL_TH x WTL_TW output pixels: the INPUT tile with its halo is staged once (prologue applied, zero padding after it), the
+// gradient tile as 128-bit rows; a thread owns a KB x CB block of dW in registers for the whole kernel, its KB filter elements
+// are fixed offsets into the input tile, and the tile's pixels are dealt round-robin to `nslices` thread groups.  Partial sums
+// meet in shared memory (one atomic per element per CTA, two CTAs per SM).
+constexpr int WTL_TW = 32, WTL_TH = 4, WTL_PX = WTL_TW * WTL_TH;
+constexpr int WTL_KB = 6;
+
+struct WTileArgs {
+  FdgWgrad c;
+  int K, kgroups, cgroups, nslices, CP;
+  int HR, HC;                    // input tile rows / columns (with halo)
+  int tiles_x, tiles_y, total_tiles;
+  int gvec;
+};
+
+__device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+
+template <int CB>
+__global__ void __launch_bounds__(256, 2) wgrad_tile_kernel(const __grid_constant__ WTileArgs a) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
+  extern __shared__ __align__(16) float sm[];
+  const FdgWgrad& p = a.c;
+  const int Cin = p.Cin, Cout = p.Cout, CP = a.CP;
+  const int xs_n = a.HR * a.HC * Cin;
+  const int xs_p = (xs_n + 3) & ~3;
+  const int buf_words = xs_p + WTL_PX * CP;        // one stage: input tile [HR][HC][Cin] + gradient tile [WTL_PX][CP]
+  const int t = threadIdx.x;
+  const int per_slice = a.kgroups * a.cgroups;
+  const int slice = t / per_slice;
+  const bool worker = slice < a.nslices;
+  const int wi = t - slice * per_slice;
+  const int kg = worker ? wi / a.cgroups : 0, cg = worker ? wi - kg * a.cgroups : 0;
+  int off[WTL_KB];
+#pragma unroll
+  for (int i = 0; i < WTL_KB; ++i) {
+    const int k = kg * WTL_KB + i;
+    off[i] = 0;
+    if (k < a.K) {
+      const int tap = k / Cin, ci = k - tap * Cin;
+      const int r = tap / p.S, s2 = tap - r * p.S;
+      off[i] = (r * a.HC + s2) * Cin + ci;
+    }
+  }
+  float acc[WTL_KB][CB];
+#pragma unroll
+  for (int i = 0; i < WTL_KB; ++i)
+#pragma unroll
+    for (int u = 0; u < CB; ++u) acc[i][u] = 0.f;
+  const int tiles_img = a.tiles_x * a.tiles_y;
+  const bool nhwc = p.x.sc == 1;
+  const int rowlen = a.HC * Cin, plane = a.HR * a.HC;
+  const float sl = p.slope;
+  const bool prologue = p.has_affine || sl != 1.f;
+
+  // element e of the input tile -> (halo row, halo column, channel); the order follows the memory layout (NHWC: channel fastest,
+  // NCHW planes: column fastest) so that the copies coalesce
+  auto xdecode = [&](int e, int& hy, int& hx, int& ci) {
+    if (nhwc) { hy = e / rowlen; const int q = e - hy * rowlen; hx = q / Cin; ci = q - hx * Cin; }
+    else { ci = e / plane; const int q = e - ci * plane; hy = q / a.HC; hx = q - hy * a.HC; }
+  };
+  auto tile_origin = [&](int tile, int& n, int& oy0, int& ox0) {
+    n = tile / tiles_img;
+    const int rr = tile - n * tiles_img;
+    const int tyi = rr / a.tiles_x;
+    oy0 = tyi * WTL_TH;
+    ox0 = (rr - tyi * a.tiles_x) * WTL_TW;
+  };
+  // asynchronous copies of one tile into stage `b` (zero-filled outside the image / past Cout): no registers held in flight
+  auto stage = [&](int tile, int b) {
+    float* xs = sm + b * buf_words;
+    float* gs = xs + xs_p;
+    int n, oy0, ox0;
+    tile_origin(tile, n, oy0, ox0);
+    const int iy0 = oy0 * p.stride - p.pad, ix0 = ox0 * p.stride - p.pad;
+    const float* xb = p.x.p + n * p.x.sn;
+    for (int e = t; e < xs_n; e += 256) {
+      int hy, hx, ci;
+      xdecode(e, hy, hx, ci);
+      const int iy = iy0 + hy, ix = ix0 + hx;
+      const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      cp_async4_zfill(xs + (hy * a.HC + hx) * Cin + ci, in ? xb + (int64_t)iy * p.x.sh + (int64_t)ix * p.x.sw + (int64_t)ci * p.x.sc : xb, in);
+    }
+    const float* gb = p.g.p + n * p.g.sn;
+    if (a.gvec) {
+      const int c4n = CP >> 2;
+      for (int e = t; e < WTL_PX * c4n; e += 256) {
+        const int pi = e / c4n, c = (e - pi * c4n) * 4;
+        const int oy = oy0 + (pi >> 5), ox = ox0 + (pi & 31);
+        const bool in = oy < p.OH && ox < p.OW && c < Cout;
+        cp_async16_zfill(gs + pi * CP + c, in ? gb + (int64_t)oy * p.g.sh + (int64_t)ox * p.g.sw + c : gb, in);
+      }
+    } else {
+      // channel-planar gradients (NCHW head): pixel fastest so that the copies coalesce
+      for (int e = t; e < WTL_PX * CP; e += 256) {
+        const int c = e >> 7, pi = e & (WTL_PX - 1);
+        const int oy = oy0 + (pi >> 5), ox = ox0 + (pi & 31);
+        const bool in = oy < p.OH && ox < p.OW && c < Cout;
+        cp_async4_zfill(gs + pi * CP + c, in ? gb + (int64_t)oy * p.g.sh + (int64_t)ox * p.g.sw + (int64_t)c * p.g.sc : gb, in);
+      }
+    }
+  };
+
+  int b = 0;
+  if ((int)blockIdx.x < a.total_tiles) stage(blockIdx.x, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    const int next = tile + gridDim.x;
+    if (next < a.total_tiles) stage(next, b ^ 1);            // stage b ^ 1 was released by the barrier that ended the previous tile
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");     // this thread's copies of the current tile have landed
+    float* xs = sm + b * buf_words;
+    const float* gs = xs + xs_p;
+    if (prologue) {
+      // BatchNorm scale/shift + activation in place, by the thread that copied the element; padding stays exactly zero
+      int n, oy0, ox0;
+      tile_origin(tile, n, oy0, ox0);
+      const int iy0 = oy0 * p.stride - p.pad, ix0 = ox0 * p.stride - p.pad;
+      for (int e = t; e < xs_n; e += 256) {
+        int hy, hx, ci;
+        xdecode(e, hy, hx, ci);
+        const int iy = iy0 + hy, ix = ix0 + hx;
+        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          float* q = xs + (hy * a.HC + hx) * Cin + ci;
+          float v = *q;
+          if (p.has_affine) v = fmaf(v, __ldg(p.scale + ci), __ldg(p.shift + ci));
+          *q = prologue_act(v, sl);
+        }
+      }
+    }
+    __syncthreads();
+    if (worker) {
+      const float* gcol = gs + cg * CB;
+#pragma unroll 2
+      for (int pi = slice; pi < WTL_PX; pi += a.nslices) {
+        const float* xr = xs + (((pi >> 5) * p.stride) * a.HC + (pi & 31) * p.stride) * Cin;
+        float gv[CB];
+#pragma unroll
+        for (int u = 0; u < CB; u += 4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gcol + pi * CP + u);
+          gv[u] = g4.x; gv[u + 1] = g4.y; gv[u + 2] = g4.z; gv[u + 3] = g4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < WTL_KB; ++i) {
+          const float xv = xr[off[i]];
+#pragma unroll
+          for (int u = 0; u < CB; ++u) acc[i][u] = fmaf(xv, gv[u], acc[i][u]);
+        }
+      }
+    }
+    __syncthreads();
+    b ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // ---- partial sums of the slices meet in shared memory, then one atomic per element and CTA
+  float* red = sm;                                 // [K][Cout] (fits: K * Cout <= 160 * 64 floats <= the stages)
+  for (int e = t; e < a.K * Cout; e += 256) red[e] = 0.f;
+  __syncthreads();
+  if (worker) {
+#pragma unroll
+    for (int i = 0; i < WTL_KB; ++i) {
+      const int k = kg * WTL_KB + i;
+      if (k < a.K) {
+#pragma unroll
+        for (int u = 0; u < CB; ++u) {
+          const int co = cg * CB + u;
+          if (co < Cout) atomicAdd(red + k * Cout + co, acc[i][u]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int RS = p.R * p.S;
+  for (int e = t; e < a.K * Cout; e += 256) {
+    const int k = e / Cout, co = e - k * Cout;
+    const int tap = k / Cin, ci = k - tap * Cin;
+    atomicAdd(p.dw + ((int64_t)co * Cin + ci) * RS + tap, red[e]);
+  }
+}
+
+static int wgrad_tile(const FdgWgrad* p, cudaStream_t st) {
+  WTileArgs a;
+  a.c = *p;
+  a.K = p->R * p->S * p->Cin;
+  const int cb = p->Cout > 36 ? 8 : 4;
+  a.kgroups = cdiv(a.K, WTL_KB);
+  a.cgroups = cdiv(p->Cout, cb);
+  if (a.kgroups * a.cgroups > 256) return 1;
+  a.nslices = 256 / (a.kgroups * a.cgroups);
+  if (a.nslices > 16) a.nslices = 16;
+  a.CP = a.cgroups * cb;
+  a.HR = (WTL_TH - 1) * p->stride + p->R;
+  a.HC = (WTL_TW - 1) * p->stride + p->S;
+  a.tiles_x = cdiv(p->OW, WTL_TW);
+  a.tiles_y = cdiv(p->OH, WTL_TH);
+  a.total_tiles = p->N * a.tiles_x * a.tiles_y;
+  a.gvec = vec4_ok(p->g) && p->Cout % 4 == 0;
+  const int xs_n = (a.HR * a.HC * p->Cin + 3) & ~3;
+  int words = 2 * (xs_n + WTL_PX * a.CP);          // two stages (asynchronous copies of the next tile during the current one)
+  if (words < a.K * p->Cout) words = a.K * p->Cout;
+  const int smem = words * 4;
+  if (smem > 110 * 1024) return 1;
+  static std::atomic<int> attr_done[64][2];           // per device and instantiation: largest size configured so far
+  const int adev = current_device();
+  if (attr_done[adev][cb == 8] < smem) {
+    const cudaError_t e = cb == 8 ? cudaFuncSetAttribute(wgrad_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                  : cudaFuncSetAttribute(wgrad_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("fdg_conv2d_wgrad[thin]: cannot raise dynamic shared memory to %d bytes", smem); return FDG_ECUDA; }
+    attr_done[adev][cb == 8] = smem;
+  }
+  int ctas = device_sm_count() * 2;
+  if (ctas > a.total_tiles) ctas = a.total_tiles;
+  const double M = (double)p->N * p->OH * p->OW;
+  ProfScope prof(PF_WGRAD, 2.0 * M * a.K * p->Cout, 4.0 * (M * p->Cout + (double)p->N * p->H * p->W * p->Cin), st);
+  if (cb == 8) launch_k(wgrad_tile_kernel<8>, dim3((unsigned)ctas), dim3(256), (size_t)(smem), st, a);
+  else launch_k(wgrad_tile_kernel<4>, dim3((unsigned)ctas), dim3(256), (size_t)(smem), st, a);
+  return check_launch("fdg_conv2d_wgrad[thin]");
+}
+
 // returns 1 when the shape is not taken by this path
 int wgrad_thin(const FdgWgrad* p, cudaStream_t st) {
   static const int on = [] { const char* e = getenv("FDG_THIN"); return e ? atoi(e) : 1; }();
   const int K = p->R * p->S * p->Cin;
   if (!on || p->impl != 0 || K > TH_MAXK || p->Cin > 16 || p->Cout > 64 || p->gather != FDG_GATHER_DIRECT || p->transposed) return 1;
+  static const int tile_on = [] { const char* e = getenv("FDG_WTHIN_TILE"); return e ? atoi(e) : 1; }();
+  if (tile_on && p->stride <= 2) {
+    const int rc = wgrad_tile(p, st);
+    if (rc != 1) return rc;
+  }
   WThinArgs a;
   a.c = *p;
   a.M = (int64_t)p->N * p->OH * p->OW;

@@ -33,6 +33,12 @@ SHAPES = [
     ("wgrad K2 1x1 224->128 @256", "wgrad", 224, 128, 1, 0, 256, True, False),
     ("wgrad K2 1x1 992->128 @64", "wgrad", 992, 128, 1, 0, 64, True, False),
     ("wgrad vgg 3x3 64->64 @256", "wgrad", 64, 64, 3, 1, 256, False, False),
+    ("wgrad W D L4 4x4 144->288 @128", "wgrad", 144, 288, 4, 1, 128, True, False),
+    ("wgrad W D L3 3x3 72->144 @128", "wgrad", 72, 144, 3, 1, 128, True, False),
+    ("wgrad W refine4 3x3 160->128 @128", "wgrad", 160, 128, 3, 1, 128, False, False),
+    ("wgrad W bdy5 3x3 512->128 @64", "wgrad", 512, 128, 3, 1, 64, False, False),
+    ("wgrad W bdy4 3x3 1024->256 @32", "wgrad", 1024, 256, 3, 1, 32, False, False),
+    ("wgrad W refin6 3x3 640->512 @32", "wgrad", 640, 512, 3, 1, 32, False, False),
 ]
 MODES = [int(m) for m in os.environ.get("ABL_MODES", "0,1,3,4,8,12,7,15").split(",")]
 
@@ -50,7 +56,7 @@ def timeit(fn, iters=5):
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     dev = "cuda"
-    print("%-30s" % "shape" + "".join("  dbg=%-2d  " % m for m in MODES) + "   (ms; TF/s at dbg=0)")
+    print("%-34s" % "shape" + "".join("  dbg=%-2d  " % m for m in MODES) + "   (ms; TF/s at dbg=0)")
     for name, kind, Cin, Cout, R, pad, H, affine, stats in SHAPES:
         if only and not any(f in name for f in only.split(",")):
             continue
@@ -63,7 +69,7 @@ def main():
         sh = torch.rand(Cin, device=dev) - 0.5 if affine else None
         st = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if stats else None
         flops = 2.0 * B * OH * OH * Cout * Cin * R * R
-        out = "%-30s" % name
+        out = "%-34s" % name
         t0 = None
         for m in MODES:
             _lib.set_option("dbg", m)

@@ -51,3 +51,9 @@ print("D L5 wgrad 288->1   %.3f ms" % timeit(lambda: ops.wgrad(y4, View.from_nch
 y5 = torch.empty(B, 1, 126, 126, device=dev)
 w5f, ld5f = ops.pack_weight(w5, 0)
 print("D L5 fwd 288->1     %.3f ms" % timeit(lambda: ops.conv2d(y4, w5f, ld5f, 4, 4, 1, 1, 1, View.from_nchw(y5), slope=0.2, act=ops.ACT_SIGMOID)))
+
+x6 = View.alloc(B, 256, 256, 16, dev); x6.base.normal_()
+gh = torch.randn(B, 3, 256, 256, device=dev)
+dwh = torch.zeros(3, 16, 3, 3, device=dev); dbh = torch.zeros(3, device=dev)
+print("head wgrad 16->3    %.3f ms" % timeit(lambda: ops.wgrad(x6, View.from_nchw(gh), 3, 3, 1, 1, dwh, dbias=dbh)))
+print("head colsum only    %.3f ms" % timeit(lambda: ops.colsum(View.from_nchw(gh), dbh, accumulate=True)))

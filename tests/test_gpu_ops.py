@@ -695,3 +695,57 @@ def test_adam_flat():
         opt.step()
         ops.adam_flat(pd, (2 * g).cuda(), m, v, 2e-4, 0.5, 0.999, 1e-8, step, grad_scale=0.5)
     assert maxabs(pd, ref.detach()) <= 1e-6
+
+
+THIN_CASES = [
+    # Cin, Cout, R, stride, pad, H, W, x_nchw, g_nchw, affine, slope, dbias
+    (3, 64, 3, 1, 1, 37, 70, True, False, False, 1.0, True),      # stem conv_refin1 / Vgg16 conv1_1: NCHW image, ragged 4x32 tiles
+    (9, 36, 4, 2, 1, 22, 74, False, False, False, 1.0, False),    # Fusion-D layer 1: 4x4 stride 2, NHWC 9-channel input
+    (16, 3, 3, 1, 1, 21, 45, False, True, False, 1.0, True),      # head conv_refin3: NCHW 3-channel gradient, bias gradient by planes
+    (12, 16, 3, 1, 1, 9, 33, False, False, True, 0.2, False),     # BatchNorm + LeakyReLU prologue, zero padding after it
+    (3, 64, 3, 1, 1, 128, 96, True, False, False, 1.0, True),     # many tiles per CTA (every slice group accumulates)
+]
+
+
+@pytest.mark.parametrize("case", THIN_CASES)
+def test_thin_layers_auto_dispatch(case):
+    """The direct kernels of the thin layers (conv_direct.cu: compile-time-filter forward, tiled weight gradient, planar bias
+    gradient) are reached only with impl = auto; forward and weight gradient against fp64 torch."""
+    ops = _ops()
+    Cin, Cout, R, stride, pad, H, W, x_nchw, g_nchw, affine, slope, dbias = case
+    N = 3
+    x = seeded((N, Cin, H, W), 1, -1, 1).double()
+    sc = seeded((Cin,), 4, 0.5, 1.5).double() if affine else None
+    sh = seeded((Cin,), 5, -0.3, 0.3).double() if affine else None
+    a = ref_prologue(x, sc, sh, slope)
+    w = (seeded((Cout, Cin, R, R), 2, -1, 1) / math.sqrt(Cin * R * R)).double().requires_grad_(True)
+    b = seeded((Cout,), 3, -0.5, 0.5).double()
+    y = F.conv2d(a, w, b, stride=stride, padding=pad)
+    g = seeded(tuple(y.shape), 8, -1, 1).double()
+    (y * g).sum().backward()
+    xd = x.float().cuda() if x_nchw else cl(x.float())
+    xv = ops.View.from_nchw(xd)
+    # forward (the prologue of the thin forward kernel is an activation only)
+    if not affine and Cout in (16, 36, 64):
+        wp, ld = ops.pack_weight(w.detach().float().cuda(), 0)
+        yd = cl(torch.zeros(tuple(y.shape)))
+        ops.conv2d(xv, wp, ld, R, R, stride, pad, Cout, ops.View.from_nchw(yd), slope=slope, bias=b.float().cuda())
+        assert maxabs(yd, y.detach()) <= 2e-5
+    gd = g.float().cuda() if g_nchw else cl(g.float())
+    dw = torch.zeros(Cout, Cin, R, R, device="cuda")
+    db = torch.zeros(Cout, device="cuda") if dbias else None
+    ops.wgrad(xv, ops.View.from_nchw(gd), R, R, stride, pad, dw, scale=sc.float().cuda() if affine else None,
+              shift=sh.float().cuda() if affine else None, slope=slope, dbias=db)
+    scale = float(w.grad.abs().max())
+    assert maxabs(dw, w.grad) <= 2e-5 * max(1.0, scale)
+    if dbias:
+        assert maxabs(db, g.sum((0, 2, 3))) <= 2e-5 * max(1.0, float(g.sum((0, 2, 3)).abs().max()))
+
+
+def test_colsum_nchw_planes():
+    ops = _ops()
+    for shape in ((4, 3, 64, 64), (2, 5, 70, 91)):
+        b_ = seeded(shape, 7, -1, 1)
+        cs = torch.ones(shape[1], device="cuda")
+        ops.colsum(ops.View.from_nchw(b_.cuda()), cs, accumulate=True)
+        assert maxabs(cs, 1 + b_.double().sum((0, 2, 3))) <= 5e-4
