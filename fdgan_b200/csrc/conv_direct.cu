@@ -193,11 +193,10 @@ __global__ void __launch_bounds__(ST_THREADS, 3) conv_stem4_kernel(const __grid_
   pdl_trigger();
   __shared__ __align__(16) float ws[27 * 64];
   __shared__ __align__(16) float bs[64];
-  __shared__ float red[2][64];
+  __shared__ float red[ST_THREADS / 32][2][64];      // per-warp sums, added in a fixed order (fp32 partial sums stay reproducible)
   const FdgConv& p = a.c;
   const int t = threadIdx.x, lane = t & 31;
   for (int i = t; i < 27 * 64; i += ST_THREADS) ws[i] = __ldg(p.w + (int64_t)(i >> 6) * p.w_ld + (i & 63));
-  if (t < 128) (&red[0][0])[t] = 0.f;
   if (t < 64) bs[t] = p.bias ? __ldg(p.bias + t) : 0.f;
   __syncthreads();
   const int cg = t & 3;
@@ -292,14 +291,17 @@ __global__ void __launch_bounds__(ST_THREADS, 3) conv_stem4_kernel(const __grid_
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int c = 16 * (u >> 2) + 4 * cg + (u & 3);
-        atomicAdd(&red[0][c], s1[u]);
-        atomicAdd(&red[1][c], s2[u]);
+        red[t >> 5][0][c] = s1[u];
+        red[t >> 5][1][c] = s2[u];
       }
     }
     __syncthreads();
     if (t < 64) {
-      atomicAdd(p.stats + t, (double)red[0][t]);
-      atomicAdd(p.stats + p.stats_ld + t, (double)red[1][t]);
+      double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < ST_THREADS / 32; ++w) { d1 += (double)red[w][0][t]; d2 += (double)red[w][1][t]; }
+      atomicAdd(p.stats + t, d1);
+      atomicAdd(p.stats + p.stats_ld + t, d2);
     }
   }
 }
