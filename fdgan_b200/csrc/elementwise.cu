@@ -424,9 +424,71 @@ __global__ void maxpool2_bwd_kernel(FdgTensor x, FdgTensor gy, FdgTensor gx, int
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
       float* q = o + (d >> 1) * gx.sh + (d & 1) * gx.sw;
-      const float val = d == arg ? g : 0.f;
-      *q = accumulate ? *q + val : val;
+      const float val = (d == arg && (!(accumulate & 2) || best > 0.f)) ? g : 0.f;
+      *q = (accumulate & 1) ? *q + val : val;
     }
+  }
+}
+
+// 128-bit variants (unit channel stride, C % 4 == 0): thread = four channels of one pooled pixel, 32-bit index arithmetic.
+// Backward flags: bit 0 accumulate, bit 1 multiply by [max > 0] (the ReLU mask of the pooled tensor: Vgg16 pools post-ReLU stages,
+// so the separate mask pass over the un-pooled gradient disappears).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(256) maxpool2_fwd_vec4_kernel(FdgTensor x, FdgTensor y, int total4, int OH, int OW, int C4) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int c = (i % C4) * 4;
+    int r = i / C4;
+    const int ow = r % OW; r /= OW;
+    const int oh = r % OH, n = r / OH;
+    const float* b = x.p + n * x.sn + (int64_t)(2 * oh) * x.sh + (int64_t)(2 * ow) * x.sw + c;
+    const float4 v0 = ldg4(b), v1 = ldg4(b + x.sw), v2 = ldg4(b + x.sh), v3 = ldg4(b + x.sh + x.sw);
+    float4 m;
+    m.x = fmaxf(fmaxf(v0.x, v1.x), fmaxf(v2.x, v3.x)); m.y = fmaxf(fmaxf(v0.y, v1.y), fmaxf(v2.y, v3.y));
+    m.z = fmaxf(fmaxf(v0.z, v1.z), fmaxf(v2.z, v3.z)); m.w = fmaxf(fmaxf(v0.w, v1.w), fmaxf(v2.w, v3.w));
+    *reinterpret_cast<float4*>(y.p + n * y.sn + (int64_t)oh * y.sh + (int64_t)ow * y.sw + c) = m;
+  }
+}
+
+__device__ __forceinline__ void maxpool_route(float a, float b, float c, float d, float g, bool mask, float& o0, float& o1, float& o2, float& o3) {
+  int arg = 0;
+  float best = a;
+  if (b > best) { best = b; arg = 1; }      // first maximum, scan order
+  if (c > best) { best = c; arg = 2; }
+  if (d > best) { best = d; arg = 3; }
+  if (mask && !(best > 0.f)) g = 0.f;
+  o0 = arg == 0 ? g : 0.f; o1 = arg == 1 ? g : 0.f; o2 = arg == 2 ? g : 0.f; o3 = arg == 3 ? g : 0.f;
+}
+
+__global__ void __launch_bounds__(256) maxpool2_bwd_vec4_kernel(FdgTensor x, FdgTensor gy, FdgTensor gx, int total4, int OH, int OW, int C4,
+                                                                int flags) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
+  const bool acc = flags & 1, mask = flags & 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int c = (i % C4) * 4;
+    int r = i / C4;
+    const int ow = r % OW; r /= OW;
+    const int oh = r % OH, n = r / OH;
+    const float* b = x.p + n * x.sn + (int64_t)(2 * oh) * x.sh + (int64_t)(2 * ow) * x.sw + c;
+    const float4 v0 = ldg4(b), v1 = ldg4(b + x.sw), v2 = ldg4(b + x.sh), v3 = ldg4(b + x.sh + x.sw);
+    const float4 g = ldg4(gy.p + n * gy.sn + (int64_t)oh * gy.sh + (int64_t)ow * gy.sw + c);
+    float4 o0, o1, o2, o3;
+    maxpool_route(v0.x, v1.x, v2.x, v3.x, g.x, mask, o0.x, o1.x, o2.x, o3.x);
+    maxpool_route(v0.y, v1.y, v2.y, v3.y, g.y, mask, o0.y, o1.y, o2.y, o3.y);
+    maxpool_route(v0.z, v1.z, v2.z, v3.z, g.z, mask, o0.z, o1.z, o2.z, o3.z);
+    maxpool_route(v0.w, v1.w, v2.w, v3.w, g.w, mask, o0.w, o1.w, o2.w, o3.w);
+    float* o = gx.p + n * gx.sn + (int64_t)(2 * oh) * gx.sh + (int64_t)(2 * ow) * gx.sw + c;
+    float4* q0 = reinterpret_cast<float4*>(o), *q1 = reinterpret_cast<float4*>(o + gx.sw);
+    float4* q2 = reinterpret_cast<float4*>(o + gx.sh), *q3 = reinterpret_cast<float4*>(o + gx.sh + gx.sw);
+    if (acc) {
+      const float4 p0 = *q0, p1 = *q1, p2 = *q2, p3 = *q3;
+      o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w; o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+      o2.x += p2.x; o2.y += p2.y; o2.z += p2.z; o2.w += p2.w; o3.x += p3.x; o3.y += p3.y; o3.z += p3.z; o3.w += p3.w;
+    }
+    *q0 = o0; *q1 = o1; *q2 = o2; *q3 = o3;
   }
 }
 
@@ -804,6 +866,10 @@ int fdg_affine_accum(const FdgTensor* x, const FdgTensor* out, int N, int H, int
 int fdg_maxpool2_fwd(const FdgTensor* x, const FdgTensor* y, int N, int OH, int OW, int C, fdg_stream_t stream) {
   FDG_REQUIRE(x && y && x->p && y->p && N > 0 && OH > 0 && OW > 0 && C > 0, "fdg_maxpool2_fwd: bad arguments");
   const int64_t total = (int64_t)N * OH * OW * C;
+  if (C % 4 == 0 && fdg::vec4_ok(*x) && fdg::vec4_ok(*y) && total / 4 < (1ll << 31)) {
+    launch_k(maxpool2_fwd_vec4_kernel, dim3(grid_for(total / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *y, (int)(total / 4), OH, OW, C / 4);
+    return check_launch("fdg_maxpool2_fwd");
+  }
   launch_k(maxpool2_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *y, total, OH, OW, C);
   return check_launch("fdg_maxpool2_fwd");
 }
@@ -813,6 +879,11 @@ int fdg_maxpool2_bwd(const FdgTensor* x, const FdgTensor* gy, const FdgTensor* g
   FDG_REQUIRE(x && gy && gx && x->p && gy->p && gx->p && N > 0 && OH > 0 && OW > 0 && C > 0,
               "fdg_maxpool2_bwd: bad arguments");
   const int64_t total = (int64_t)N * OH * OW * C;
+  if (C % 4 == 0 && fdg::vec4_ok(*x) && fdg::vec4_ok(*gy) && fdg::vec4_ok(*gx) && total / 4 < (1ll << 31)) {
+    launch_k(maxpool2_bwd_vec4_kernel, dim3(grid_for(total / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *gy, *gx, (int)(total / 4), OH, OW, C / 4,
+             accumulate);
+    return check_launch("fdg_maxpool2_bwd");
+  }
   launch_k(maxpool2_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, *x, *gy, *gx, total, OH, OW, C, accumulate);
   return check_launch("fdg_maxpool2_bwd");
 }

@@ -405,9 +405,10 @@ def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, g
         ops.stream_wait(main, ops.event_record(side))       # join: the buffers above die with this frame; the optimiser reads the gradients on the main stream
 
 
-def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dpool, P: View | None = None):
-    """torchvision transition backward; g = dL/d(output) at the pooled resolution; accumulates into dX.  ``P``: the pooled activation
-    the forward pass materialised (POOL_FIRST): the weight gradient is then a plain 1x1 one on a quarter of the pixels."""
+def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dpool, P: View | None = None, accumulate=True):
+    """torchvision transition backward; g = dL/d(output) at the pooled resolution; accumulates into dX (``accumulate=False``: dX is
+    uninitialised and this is its first writer -- every element is written, no zero fill and no read of the old value).  ``P``: the pooled
+    activation the forward pass materialised (POOL_FIRST): the weight gradient is then a plain 1x1 one on a quarter of the pixels."""
     if P is not None:
         _wgrad(P, g, 1, 1, 1, 0, grads[prefix + ".conv.weight"])
     else:
@@ -417,7 +418,7 @@ def _transition_bwd(tr, prefix, X: View, dX: View, g: View, bn: BNRun, grads, dp
     ops.conv2d(g, tr.conv.weight, X.C, 1, 1, 1, 0, X.C, dP)
     if (X.H, X.W) != (2 * g.H, 2 * g.W):
         raise RuntimeError("fdgan_b200 backward needs even feature-map sizes at every transition (got %dx%d)" % (X.H, X.W))
-    _bn_bwd(dP, X, bn, dX, dpool, grads, prefix + ".norm", accumulate=True, g_gather=GATHER_UP2, gscale=0.25)
+    _bn_bwd(dP, X, bn, dX, dpool, grads, prefix + ".norm", accumulate=accumulate, g_gather=GATHER_UP2, gscale=0.25)
 
 
 def _bdy_bwd(blk, prefix, Dv: View, dD: View, T: View, c_in, grads):
@@ -485,9 +486,9 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     dX42 = View.alloc(X42.N, X42.H, X42.W, 512, dev)
     _tdy_bwd(m.trans_block5, "trans_block5", X42, dX42, dD6.ch(0, 64), grads)
     _bdy_bwd(m.dense_block5, "dense_block5", X42, dX42, T5, 384, grads)
-    # gradient buffers of the encoder blocks (zero-initialised, everything accumulates)
-    dX3 = View.alloc(X3.N, X3.H, X3.W, 1024, dev, zero=True)
-    ops.copy4d(dX42.ch(128, 384), dX3.ch(0, 256), accumulate=True)       # x2 skip (already masked by relu(x2) > 0)
+    # gradient buffers of the encoder blocks: the transition backward is the first writer of every element (no zero fill), everything
+    # else accumulates afterwards
+    dX3 = View.alloc(X3.N, X3.H, X3.W, 1024, dev)
     # ---- level 4
     dD4 = View.alloc(D4.N, D4.H, D4.W, 768, dev)
     _tdy_bwd(m.trans_block4, "trans_block4", D4, dD4, dX42.ch(0, 128), grads)
@@ -505,13 +506,14 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
         _wgrad(X3.ch(0, 256), g5, 1, 1, 1, 0, grads["conv_refin5.weight"], gather=GATHER_AVGPOOL2, dbias=grads["conv_refin5.bias"])
     dP = View.alloc(g5.N, g5.H, g5.W, 256, dev)
     ops.conv2d(g5, m.conv_refin5.weight, 256, 1, 1, 1, 0, 256, dP)
-    ops.copy4d(dP, dX3.ch(0, 256), gather=GATHER_UP2, scale=0.25, accumulate=True)
     # ---- encoder level 3
-    _transition_bwd(m.trans_block3, "trans_block3", X3, dX3, dC6.ch(0, 512), ctx.bn_t3, grads, dpool, ctx.P_t[2])
+    _transition_bwd(m.trans_block3, "trans_block3", X3, dX3, dC6.ch(0, 512), ctx.bn_t3, grads, dpool, ctx.P_t[2], accumulate=False)
+    ops.copy4d(dX42.ch(128, 384), dX3.ch(0, 256), accumulate=True)       # x2 skip (already masked by relu(x2) > 0)
+    ops.copy4d(dP, dX3.ch(0, 256), gather=GATHER_UP2, scale=0.25, accumulate=True)
     _dense_block_bwd(m.dense_block3, "dense_block3", 24, 256, X3, dX3, ctx.saved["dense_block3"], grads, dpool)
     # ---- encoder level 2
-    dX2 = View.alloc(X2.N, X2.H, X2.W, 512, dev, zero=True)
-    _transition_bwd(m.trans_block2, "trans_block2", X2, dX2, dX3.ch(0, 256), ctx.bn_t2, grads, dpool, ctx.P_t[1])
+    dX2 = View.alloc(X2.N, X2.H, X2.W, 512, dev)
+    _transition_bwd(m.trans_block2, "trans_block2", X2, dX2, dX3.ch(0, 256), ctx.bn_t2, grads, dpool, ctx.P_t[1], accumulate=False)
     _dense_block_bwd(m.dense_block2, "dense_block2", 12, 128, X2, dX2, ctx.saved["dense_block2"], grads, dpool)
     g4 = dX2.ch(0, 128)
     _wgrad(C4, g4, 3, 3, 1, 1, grads["conv_refine4.weight"], dbias=grads["conv_refine4.bias"])
@@ -519,8 +521,8 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     wd, ldd = _conv_dgrad_w(m.conv_refine4.weight)
     ops.conv2d(g4, wd, ldd, 3, 3, 1, 1, 160, dC4)
     # ---- encoder level 1
-    dX1 = View.alloc(X1.N, X1.H, X1.W, 256, dev, zero=True)
-    _transition_bwd(m.trans_block1, "trans_block1", X1, dX1, dC4.ch(32, 160), ctx.bn_t1, grads, dpool, ctx.P_t[0])
+    dX1 = View.alloc(X1.N, X1.H, X1.W, 256, dev)
+    _transition_bwd(m.trans_block1, "trans_block1", X1, dX1, dC4.ch(32, 160), ctx.bn_t1, grads, dpool, ctx.P_t[0], accumulate=False)
     g2 = dC4.ch(0, 32)
     if ctx.P01 is not None:
         _wgrad(ctx.P01, g2, 1, 1, 1, 0, grads["conv_refin2.weight"], dbias=grads["conv_refin2.bias"])
@@ -755,12 +757,22 @@ def vgg_backward(m, ctx: VCtx, gouts, grads, need_dx: bool):
         top = acts[-1]
         if g_next is None and gouts[si] is None:
             continue
-        dF = View.alloc(top.N, top.H, top.W, top.C, dev, zero=True)
-        if gouts[si] is not None:
-            ops.copy4d(View.from_nchw(gouts[si]), dF, accumulate=True)
-        if g_next is not None:
+        # dF = (gouts + unpool(g_next)) * [top > 0], every element written exactly once by its first contributor (no zero fill, no
+        # separate mask pass): the un-pooling routes to the block maximum and applies the mask itself (top is post-ReLU)
+        if g_next is None:
+            dF = View.alloc(top.N, top.H, top.W, top.C, dev)
+            ops.ew_bwd(View.from_nchw(gouts[si]), top, out=dF, slope=0.0)
+        elif top.H % 2 == 0 and top.W % 2 == 0:
+            dF = View.alloc(top.N, top.H, top.W, top.C, dev)
+            ops.maxpool2_bwd(top, g_next, dF, accumulate=False, relu_mask=True)
+            if gouts[si] is not None:
+                ops.ew_bwd(View.from_nchw(gouts[si]), top, out=dF, slope=0.0, accumulate=True)
+        else:       # odd sizes: the last row / column is not covered by the 2x2 blocks
+            dF = View.alloc(top.N, top.H, top.W, top.C, dev, zero=True)
+            if gouts[si] is not None:
+                ops.copy4d(View.from_nchw(gouts[si]), dF, accumulate=True)
             ops.maxpool2_bwd(top, g_next, dF, accumulate=True)
-        ops.ew_bwd(dF, top, out=dF, slope=0.0)       # ReLU mask of the stage output
+            ops.ew_bwd(dF, top, out=dF, slope=0.0)       # ReLU mask of the stage output
         g = dF
         for li in reversed(range(len(stage))):
             name = stage[li]

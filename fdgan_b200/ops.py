@@ -421,11 +421,14 @@ def maxpool2_fwd(x: View, y: View):
     L.check(L.lib.fdg_maxpool2_fwd(_byref(xt), _byref(yt), y.N, y.H, y.W, y.C, _stream()), "maxpool2_fwd")
 
 
-def maxpool2_bwd(x: View, gy: View, gx: View, accumulate=True):
+def maxpool2_bwd(x: View, gy: View, gx: View, accumulate=True, relu_mask=False):
+    """gx (=|+=) the pooled gradient gy routed to the first maximum of every 2x2 block of x; ``relu_mask``: times [max > 0]
+    (x is a post-ReLU tensor: the mask of its ReLU comes for free).  Without ``accumulate`` the 2x2 blocks are written in full,
+    i.e. all of gx when H and W are even."""
     assert (gy.N, gy.H, gy.W, gy.C) == (x.N, x.H // 2, x.W // 2, x.C) and (gx.H, gx.W, gx.C) == (x.H, x.W, x.C)
     xt, gyt, gxt = x.ft(), gy.ft(), gx.ft()
     L.check(L.lib.fdg_maxpool2_bwd(_byref(xt), _byref(gyt), _byref(gxt), gy.N, gy.H, gy.W, gy.C,
-                                   1 if accumulate else 0, _stream()), "maxpool2_bwd")
+                                   (1 if accumulate else 0) | (2 if relu_mask else 0), _stream()), "maxpool2_bwd")
 
 
 def copy4d(x: View, y: View, *, gather=GATHER_DIRECT, slope=1.0, scale=1.0, accumulate=False):

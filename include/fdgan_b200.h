@@ -228,7 +228,9 @@ typedef struct FdgBnBwdFinalize {
 
 int fdg_bn_bwd_finalize(const FdgBnBwdFinalize* p, fdg_stream_t stream);
 
-/* 2x2 max pooling (F.max_pool2d(h, 2, 2), vgg16.py:31,36,42) and its gradient (routed to the first maximum). */
+/* 2x2 max pooling (F.max_pool2d(h, 2, 2), vgg16.py:31,36,42) and its gradient (routed to the first maximum).
+ * Backward `accumulate` is a bit set: 1 = add to gx (otherwise every element of the 2x2 blocks is written), 2 = multiply the routed
+ * gradient by [max > 0], the ReLU mask of a post-ReLU input (saves the separate mask pass over gx). */
 int fdg_maxpool2_fwd(const FdgTensor* x, const FdgTensor* y, int N, int OH, int OW, int C, fdg_stream_t stream);
 int fdg_maxpool2_bwd(const FdgTensor* x, const FdgTensor* gy, const FdgTensor* gx, int N, int OH, int OW, int C,
                      int accumulate, fdg_stream_t stream);

@@ -594,6 +594,16 @@ def test_maxpool_copy_colsum_actbwd():
     gx = cl(torch.zeros_like(x))
     ops.maxpool2_bwd(ops.View.from_nchw(xd), ops.View.from_nchw(cl(g)), ops.View.from_nchw(gx), accumulate=True)
     assert maxabs(gx, x.grad) == 0.0
+    gx2 = cl(torch.full_like(x.detach(), 7.0))       # first-writer mode with the ReLU mask of a post-ReLU input
+    ops.maxpool2_bwd(ops.View.from_nchw(xd), ops.View.from_nchw(cl(g)), ops.View.from_nchw(gx2), accumulate=False, relu_mask=True)
+    assert maxabs(gx2[:, :, :8, :], (x.grad * (x.detach() > 0))[:, :, :8, :]) == 0.0
+    x3 = seeded((2, 3, 8, 6), 9, -1, 1)              # scalar kernels (C = 3, NCHW)
+    g3 = seeded((2, 3, 4, 3), 10, -1, 1)
+    gx3 = torch.full((2, 3, 8, 6), 7.0, device="cuda")
+    ops.maxpool2_bwd(ops.View.from_nchw(x3.cuda()), ops.View.from_nchw(g3.cuda()), ops.View.from_nchw(gx3), accumulate=False, relu_mask=True)
+    x3r = x3.clone().requires_grad_(True)
+    (F.max_pool2d(x3r, 2, 2) * g3).sum().backward()
+    assert maxabs(gx3, x3r.grad * (x3 > 0)) == 0.0
     # copy4d: adjoint of nearest x2 and of avg-pool
     a = seeded((2, 8, 6, 6), 3, -1, 1)
     o = cl(torch.zeros(2, 8, 3, 3))
