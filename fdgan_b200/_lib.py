@@ -137,6 +137,7 @@ _SIGS = {
     "fdg_stream_wait": ([C.c_void_p, C.c_int], C.c_int),
     "fdg_pack_job_items": ([_P(FdgPackJob)], C.c_int64),
     "fdg_umma_ntile": ([C.c_int, C.c_int], C.c_int),
+    "fdg_umma_tile_code": ([C.c_int, C.c_int, C.c_int], C.c_int),
     "fdg_pack_batch": ([C.c_void_p, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "fdg_depthwise2d_fwd": ([_P(FdgDepthwise), C.c_void_p], C.c_int),
     "fdg_depthwise2d_bwd": ([_P(FdgDepthwise), C.c_void_p], C.c_int),

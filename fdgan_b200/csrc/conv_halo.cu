@@ -38,6 +38,8 @@ struct HaloArgs {
   int a_tile;      // bytes of one bf16 halo tile (hi or lo), multiple of 1024
   int yvec;
   int dbg;   // ablation: 1 no global loads, 2 no split/stores, 4 no MMA, 8 no epilogue
+  int pair;  // weight image holds two filter taps per 64-deep chunk (Cin <= 32, pack.cuh)
+  int wstages;   // weight stages per tile: taps * cchunks, or ceil(taps / 2) in pair mode
   int tma_rank;                 // 4: the epilogue stores through ymap {channel, x, y, image}; 0: coalesced stores
   alignas(64) CUtensorMap ymap;
 };
@@ -287,6 +289,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       const uint32_t bfull0 = smem_u32(&bar_b_full[0]), bempty0 = smem_u32(&bar_b_empty[0]);
       int buf = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
+      uint32_t tshift[16];                               // pair mode: A-descriptor row shift of every filter tap (rows * 128 B in 16-byte units)
+#pragma unroll
+      for (int tp = 0; tp < 16; ++tp) {
+        const int ky = tp / p.S, kx = tp - ky * p.S;
+        tshift[tp] = (uint32_t)(ky * a.HC + kx) * 8u;
+      }
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
         const int b = it & 1;
         mbar_wait(smem_u32(&bar_acc_empty[b]), (((uint32_t)it >> 1) & 1u) ^ 1u);
@@ -299,6 +307,39 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
           const uint32_t ah_lo0 = umma_desc_lo(a_hi, 16), al_lo0 = umma_desc_lo(a_lo, 16), a_hw = umma_desc_hi(sbo);
           const int cleft = p.Cin - cc * UKC_H;
           const int kslices = cleft >= UKC_H ? 4 : (cleft + 15) / 16;     // K = 16 slices of this chunk that hold channels
+          if (a.pair) {
+            // two filter taps per weight stage: tap 2s in bytes 0..63 of the rows, tap 2s + 1 in bytes 64..127 (K slices 2, 3 of the
+            // B descriptor); the A operand is the same halo tile at each tap's own row shift, channels 0..31.  The issuing thread's
+            // instruction latency bounds the MMA rate: shifts come from a table, a stage is ONE block of eight MMAs.
+#pragma unroll
+            for (int st = 0; st < 8; ++st) {
+              if (st < a.wstages) {
+                mbar_wait(bfull0 + bs * 8, bph);
+                tc_fence_after();
+                const uint32_t bl = umma_desc_lo(b_base + bs * (2 * B_TILE_BYTES), 16);
+                if (!(a.dbg & 4)) {
+                  if (kslices == 2 && 2 * st + 1 < taps) {
+                    umma_pair8(d_tmem, ah_lo0 + tshift[2 * st], al_lo0 + tshift[2 * st], ah_lo0 + tshift[2 * st + 1], al_lo0 + tshift[2 * st + 1], a_hw,
+                               bl, b_hw, idesc2, idesc1, st > 0 ? 1u : 0u, (uint32_t)NT);
+                  } else {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                      if (2 * st + half < taps) {
+                        for (int sl = 0; sl < kslices; ++sl)
+                          umma_concat_slice(d_tmem, ah_lo0 + tshift[2 * st + half] + 2u * sl, al_lo0 + tshift[2 * st + half] + 2u * sl, a_hw,
+                                            bl + 4u * half + 2u * sl, b_hw, idesc2, idesc1, (st > 0 || half > 0 || sl > 0) ? 1u : 0u, (uint32_t)NT);
+                      }
+                    }
+                  }
+                }
+                umma_commit(bempty0 + bs * 8);
+                if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
+              }
+            }
+            umma_commit(smem_u32(&bar_a_empty[buf]));
+            if (++buf == 2) { buf = 0; aph ^= 1u; }
+            continue;
+          }
           int ky = 0, kx = 0;
           for (int tap = 0; tap < taps; ++tap) {
             const uint32_t shift = (uint32_t)(ky * a.HC + kx) * 8u;            // rows * 128 B, in 16-byte descriptor units
@@ -331,17 +372,19 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     if (lane == 0) {
       int bs = 0;
       uint32_t bph = 0;
-      const int nchunks = taps * a.cchunks;
+      const int nchunks = a.wstages;
+      const int inner = a.pair ? a.wstages : taps;       // stages per channel chunk (pair mode: a single chunk)
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         int ntile, n, oy0, ox0;
         decode(tile, ntile, n, oy0, ox0);
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.w_umma) + (size_t)ntile * nchunks * (2 * B_TILE_BYTES);
         for (int cc = 0; cc < a.cchunks; ++cc)
-          for (int tap = 0; tap < taps; ++tap) {
+          for (int tap = 0; tap < inner; ++tap) {
             mbar_wait(smem_u32(&bar_b_empty[bs]), bph ^ 1u);
             const uint32_t bar = smem_u32(&bar_b_full[bs]);
             mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
-            bulk_g2s(b_base + bs * (2 * B_TILE_BYTES), wimg + (size_t)(tap * a.cchunks + cc) * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+            const int idx = a.pair ? tap : tap * a.cchunks + cc;
+            bulk_g2s(b_base + bs * (2 * B_TILE_BYTES), wimg + (size_t)idx * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
             if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
           }
       }
@@ -356,6 +399,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   }
 }
 
+int umma_tap_pair(int taps, int Cin);
 static int g_halo_on = [] { const char* e = getenv("FDG_HALO"); return e ? atoi(e) : 1; }();
 int halo_enabled() { return g_halo_on; }
 
@@ -403,6 +447,8 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
   a.a_tile = ((a.HR * a.HC * 128 + 1023) / 1024) * 1024;
   a.yvec = vec4_ok(p->y);
   a.dbg = dbg_flags();
+  a.pair = umma_tap_pair(p->R * p->S, p->Cin);
+  a.wstages = a.pair ? (p->R * p->S + 1) / 2 : p->R * p->S * a.cchunks;
   a.tma_rank = 0;
   static const int tma_on = [] { const char* e = getenv("FDG_TMA_STORE"); return e ? atoi(e) : 1; }();
   if (tma_on && a.yvec && p->store == FDG_STORE_NORMAL && !p->e.p) {

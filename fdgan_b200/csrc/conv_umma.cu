@@ -794,9 +794,9 @@ __global__ void __launch_bounds__(FAST ? UTHREADS_P + 32 : UTHREADS_P, 1) conv_u
 // ------------------------------------------------------------------------------------------------ weight image
 // out[(ntile, kchunk)] = [hi: NT rows x 128 B, SWIZZLE_128B][lo: same]; source = fp32 [K][ld] GEMM operand
 __global__ void pack_umma_kernel(const float* __restrict__ w, int ld, int taps, int Cin, int Cout, int NT, int cchunks,
-                                 uint8_t* __restrict__ out, int64_t total_pairs) {
+                                 uint8_t* __restrict__ out, int64_t total_pairs, int pair) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pairs; i += (int64_t)gridDim.x * blockDim.x)
-    pack_umma_item(w, ld, taps, Cin, Cout, NT, cchunks, out, i);
+    pack_umma_item(w, ld, taps, Cin, Cout, NT, cchunks, out, i, pair);
 }
 
 int halo_enabled();
@@ -821,6 +821,13 @@ int umma_ntile(int taps, int Cout) {
   return nt > cap ? cap : nt;
 }
 
+// Two filter taps per 64-deep weight chunk (pack.cuh): filters of >= 4 taps over at most 32 input channels, halo kernel only.
+int umma_tap_pair(int taps, int Cin) {
+  static const int on = [] { const char* e = getenv("FDG_UMMA_TAP_PAIR"); return e ? atoi(e) : 1; }();
+  return on && taps >= 4 && Cin <= 32 && halo_enabled();
+}
+int umma_nchunks(int taps, int Cin) { return umma_tap_pair(taps, Cin) ? (taps + 1) / 2 : taps * cdiv(Cin, UKC); }
+
 int conv2d_halo_supported(const FdgConv* p);
 
 int conv2d_umma_supported(const FdgConv* p) {
@@ -829,6 +836,7 @@ int conv2d_umma_supported(const FdgConv* p) {
   {
     const int nt = umma_ntile(p->R * p->S, p->Cout);
     if (nt != 32 && nt != 64 && nt != 128 && !conv2d_halo_supported(p)) return 0;   // 80 / 96-wide images exist for the halo kernel only
+    if (umma_tap_pair(p->R * p->S, p->Cin) && !conv2d_halo_supported(p)) return 0;  // so do tap-pair images
   }
   if (p->Cin < 16 || p->Cout < 1) return 0;
   AOp ao{p->x, p->H, p->W, p->gather, p->has_affine, p->scale, p->shift, p->slope};
@@ -942,10 +950,11 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
 using namespace fdg;
 
 extern "C" int fdg_umma_ntile(int taps, int Cout) { return umma_ntile(taps, Cout); }
+extern "C" int fdg_umma_tile_code(int taps, int Cin, int Cout) { return umma_ntile(taps, Cout) | (umma_tap_pair(taps, Cin) << 16); }
 
 extern "C" int64_t fdg_umma_weight_bytes(int taps, int Cin, int Cout) {
   const int NT = umma_ntile(taps, Cout);
-  return (int64_t)cdiv(Cout, NT) * taps * cdiv(Cin, UKC) * 2 * NT * 128;
+  return (int64_t)cdiv(Cout, NT) * umma_nchunks(taps, Cin) * 2 * NT * 128;
 }
 
 extern "C" int fdg_pack_weight_umma(const float* w, int w_ld, int taps, int Cin, int Cout, void* out, fdg_stream_t stream) {
@@ -953,9 +962,10 @@ extern "C" int fdg_pack_weight_umma(const float* w, int w_ld, int taps, int Cin,
   FDG_REQUIRE(aligned16(out), "fdg_pack_weight_umma: output must be 16-byte aligned");
   const int NT = umma_ntile(taps, Cout);
   const int cch = cdiv(Cin, UKC);
-  const int64_t total = (int64_t)cdiv(Cout, NT) * taps * cch * NT * 8;
+  const int pair = umma_tap_pair(taps, Cin);
+  const int64_t total = (int64_t)cdiv(Cout, NT) * umma_nchunks(taps, Cin) * NT * 8;
   int64_t g = cdiv64(total, 256);
   if (g > 148 * 8) g = 148 * 8;
-  pack_umma_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, w_ld, taps, Cin, Cout, NT, cch, (uint8_t*)out, total);
+  pack_umma_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, w_ld, taps, Cin, Cout, NT, cch, (uint8_t*)out, total, pair);
   return check_launch("fdg_pack_weight_umma");
 }

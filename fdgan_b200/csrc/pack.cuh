@@ -49,22 +49,25 @@ __device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo
 
 // tcgen05 image of the per-tap kernels: out[(ntile, kchunk)] = [hi: NT rows x 128 B, SWIZZLE_128B][lo: same]; source = fp32
 // [K][ld] GEMM operand.  Item i = (ntile, kchunk, row n, 16-byte chunk j): 8 consecutive k of one output channel.
+// pair (halo kernel, Cin <= 32 and >= 4 taps: the 32 -> 128 data gradients of the growth convolutions): a 64-deep chunk holds TWO
+// filter taps, channels 0..31 of tap 2c in its first 64 bytes and of tap 2c + 1 in the second -- no padding streams through the ring.
 __device__ __forceinline__ void pack_umma_item(const float* __restrict__ w, int ld, int taps, int Cin, int Cout, int NT, int cchunks,
-                                               uint8_t* __restrict__ out, int64_t i) {
+                                               uint8_t* __restrict__ out, int64_t i, int pair = 0) {
   const int jj = (int)(i & 7);
   int64_t r = i >> 3;
   const int nrow = (int)(r % NT); r /= NT;
-  const int nchunks = taps * cchunks;
+  const int nchunks = pair ? (taps + 1) / 2 : taps * cchunks;
   const int kc = (int)(r % nchunks);
   const int nt = (int)(r / nchunks);
-  const int tap = kc / cchunks;
-  const int cbase = (kc - tap * cchunks) * 64 + jj * 8;
+  int tap, cbase;
+  if (pair) { tap = 2 * kc + (jj >> 2); cbase = (jj & 3) * 8; }
+  else { tap = kc / cchunks; cbase = (kc - tap * cchunks) * 64 + jj * 8; }
   const int co = nt * NT + nrow;
   float f[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int ci = cbase + e;
-    f[e] = (co < Cout && ci < Cin) ? w[((int64_t)tap * Cin + ci) * ld + co] : 0.f;
+    f[e] = (co < Cout && ci < Cin && tap < taps) ? w[((int64_t)tap * Cin + ci) * ld + co] : 0.f;
   }
   uint4 hi, lo;
   split8(f, hi, lo);

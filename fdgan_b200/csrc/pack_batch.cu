@@ -10,6 +10,8 @@
 namespace fdg {
 
 int umma_ntile(int taps, int Cout);
+int umma_tap_pair(int taps, int Cin);
+int umma_nchunks(int taps, int Cin);
 
 __global__ void __launch_bounds__(256) pack_batch_kernel(const FdgPackJob* __restrict__ jobs, int njobs) {
   pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const FdgPackJob* __res
   } else if (j.kind == FDG_PACK_UMMA) {
     uint8_t* __restrict__ dst = static_cast<uint8_t*>(j.dst);
     const int cch = (j.cin + 63) / 64;
-    for (int64_t i = i0; i < j.total; i += step) pack_umma_item(src, j.ld, j.r, j.cin, j.cout, j.s, cch, dst, i);
+    for (int64_t i = i0; i < j.total; i += step) pack_umma_item(src, j.ld, j.r, j.cin, j.cout, j.s & 0xffff, cch, dst, i, j.s >> 16);
   } else {
     uint8_t* __restrict__ dst = static_cast<uint8_t*>(j.dst);
     for (int64_t i = i0; i < j.total; i += step) pack_k1_item(src, j.ld, j.cin, j.cout, dst, i);
@@ -49,9 +51,11 @@ extern "C" int64_t fdg_pack_job_items(const FdgPackJob* j) {
     const int64_t K = j->kind == 0 ? (int64_t)j->r * j->s * j->cin : (j->kind == 1 ? (int64_t)j->r * j->s * j->cout : j->cout);
     return K * j->ld;
   }
-  if (j->kind == FDG_PACK_UMMA) {   // r = taps, s = NT (must equal the kernel's tile choice for this Cout)
-    if (j->r <= 0 || j->s != umma_ntile(j->r, j->cout) || j->ld < j->cout) return -1;
-    return (int64_t)cdiv(j->cout, j->s) * j->r * cdiv(j->cin, 64) * j->s * 8;
+  if (j->kind == FDG_PACK_UMMA) {   // r = taps, s = fdg_umma_tile_code (must equal the kernel's tile / chunk choice for this filter)
+    const int code = umma_ntile(j->r, j->cout) | (umma_tap_pair(j->r, j->cin) << 16);
+    if (j->r <= 0 || j->s != code || j->ld < j->cout) return -1;
+    const int nt = code & 0xffff;
+    return (int64_t)cdiv(j->cout, nt) * umma_nchunks(j->r, j->cin) * nt * 8;
   }
   if (j->kind == FDG_PACK_K1) {
     if (j->cout > 32 || j->ld < j->cout) return -1;

@@ -359,6 +359,52 @@ __device__ __forceinline__ void umma_concat_slice(uint32_t d_tmem, uint32_t a_hi
       : "memory");
 }
 
+// Two filter taps x two K = 16 slices of the concatenated-B scheme in one block (conv_halo pair mode, 32 input channels): the B
+// descriptor walks the four 32-byte K slices of the stage, the A descriptors are the halo tile at tap 0's / tap 1's row shift.
+__device__ __forceinline__ void umma_pair8(uint32_t d_tmem, uint32_t a0_hi, uint32_t a0_lo, uint32_t a1_hi, uint32_t a1_lo, uint32_t a_hw,
+                                           uint32_t b_lo, uint32_t b_hw, uint32_t idesc2, uint32_t idesc1, uint32_t accumulate_first,
+                                           uint32_t nt_cols) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ta, tb, d2;\n\t"
+      ".reg .pred p, pt;\n\t"
+      "setp.ne.b32 p, %10, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.u32 d2, %0, %11;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%6, %7};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %8, p;\n\t"
+      "mov.b64 da, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %9, pt;\n\t"
+      "add.u32 ta, %1, 2;\n\t"
+      "add.u32 tb, %6, 2;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "mov.b64 db, {tb, %7};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %8, pt;\n\t"
+      "add.u32 ta, %2, 2;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %9, pt;\n\t"
+      "add.u32 tb, %6, 4;\n\t"
+      "mov.b64 da, {%3, %5};\n\t"
+      "mov.b64 db, {tb, %7};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %8, pt;\n\t"
+      "mov.b64 da, {%4, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %9, pt;\n\t"
+      "add.u32 ta, %3, 2;\n\t"
+      "add.u32 tb, %6, 6;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "mov.b64 db, {tb, %7};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %8, pt;\n\t"
+      "add.u32 ta, %4, 2;\n\t"
+      "mov.b64 da, {ta, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [d2], da, db, %9, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a0_hi), "r"(a0_lo), "r"(a1_hi), "r"(a1_lo), "r"(a_hw), "r"(b_lo), "r"(b_hw), "r"(idesc2), "r"(idesc1),
+        "r"(accumulate_first), "r"(nt_cols)
+      : "memory");
+}
+
 // one tcgen05.mma from 32-bit descriptor halves
 __device__ __forceinline__ void umma_single(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hw, uint32_t b_lo, uint32_t b_hw, uint32_t idesc,
                                             uint32_t accumulate) {

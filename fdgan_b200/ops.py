@@ -275,7 +275,7 @@ class PackPlan:
             job = L.FdgPackJob(wptr, img.data_ptr(), L.PACK_K1, cout, cin, 3, 3, w_ld, 0, 0, 0)
         else:
             _, taps, cin, cout = ikey
-            job = L.FdgPackJob(wptr, img.data_ptr(), L.PACK_UMMA, cout, cin, taps, int(L.lib.fdg_umma_ntile(taps, cout)), w_ld, 0, 0, 0)
+            job = L.FdgPackJob(wptr, img.data_ptr(), L.PACK_UMMA, cout, cin, taps, int(L.lib.fdg_umma_tile_code(taps, cin, cout)), w_ld, 0, 0, 0)
         self.jobs[1].append(job)
         self.images[(wptr, w_ld, ikey)] = img
 

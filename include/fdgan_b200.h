@@ -356,7 +356,7 @@ int fdg_loss_grad(const float* a, const float* b, float target, int kind, int64_
  * [first_block, first_block + nblocks) of 256 threads, total_blocks = sum of nblocks.  Jobs of one launch must not
  * depend on each other (an image made from a packed operand goes into a second launch).
  *   kind 0..2         fdg_pack_weight mode: src = OIHW parameter, dst = fp32 [K][ld];  cout, cin, r, s = filter dims
- *   FDG_PACK_UMMA     fdg_pack_weight_umma: src = fp32 [K][ld] operand, r = taps, s = N tile (fdg_umma_ntile(taps, cout))
+ *   FDG_PACK_UMMA     fdg_pack_weight_umma: src = fp32 [K][ld] operand, r = taps, s = fdg_umma_tile_code(taps, cin, cout)
  *   FDG_PACK_K1       fdg_pack_weight_k1:   src = fp32 [9*cin][ld] operand                                         */
 #define FDG_PACK_UMMA 3
 #define FDG_PACK_K1 4
@@ -368,6 +368,7 @@ typedef struct FdgPackJob {
   int64_t total; /* work items = fdg_pack_job_items(job) */
 } FdgPackJob;
 int64_t fdg_pack_job_items(const FdgPackJob* job);
+int fdg_umma_tile_code(int taps, int Cin, int Cout); /* fdg_umma_ntile | (two taps per 64-deep chunk: filters of >= 4 taps over <= 32 channels) << 16 */
 int fdg_umma_ntile(int taps, int Cout); /* output-channel tile of the packed image: 32 / 64 / 128, or 80 / 96 for filters of >= 4 taps (halo-tile kernel) */
 int fdg_pack_batch(const FdgPackJob* jobs_dev, int njobs, int total_blocks, fdg_stream_t stream);
 
