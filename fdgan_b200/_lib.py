@@ -53,6 +53,7 @@ class FdgWgrad(C.Structure):
         ("R", C.c_int), ("S", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
         ("Cout", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
         ("dw", C.c_void_p), ("transposed", C.c_int), ("dbias", C.c_void_p), ("impl", C.c_int), ("g_split", C.c_void_p),
+        ("x_split", C.c_void_p),
     ]
 
 

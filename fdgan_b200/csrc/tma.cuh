@@ -21,6 +21,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem, const void* tmap, int
                : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t smem, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem),
+               "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // L2 prefetch of a box (no shared-memory destination, no completion tracking): issued a few chunks ahead of the real load, it
 // turns that load's DRAM latency into an L2 hit, so fewer bytes have to be in flight per SM to keep HBM busy
 __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {

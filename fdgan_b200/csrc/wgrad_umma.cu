@@ -37,8 +37,11 @@ struct WUArgs {
   int dbg;           // ablation: 1 no global loads, 2 no split/stores, 4 no MMA
   int gvec;          // gradient rows loadable as float4 (unit channel stride, aligned, Cout % 8 == 0)
   int g_split;       // the gradient operand arrives as split-bf16 planes through gmap_hi / gmap_lo (bulk tensor loads)
+  int upt;           // XS: 64-channel units per filter tap, ceil(Cin / 64); the 128 rows of a k block are units 2 kb, 2 kb + 1
   alignas(64) CUtensorMap gmap_hi;
   alignas(64) CUtensorMap gmap_lo;
+  alignas(64) CUtensorMap xmap_hi;   // XS: the post-prologue input as split-bf16 planes, {Cin, W, H, N}
+  alignas(64) CUtensorMap xmap_lo;
 };
 
 // In-place staging: the fp32 rows are cp.async'ed straight into the operand ring.  Each thread's 32 bytes of fp32 per
@@ -50,7 +53,12 @@ struct WUArgs {
 // source address is a running pointer and its validity a comparison, so the per-chunk coordinate arithmetic, tap / border
 // predicates and the shared-memory metadata word of the general loader disappear (~14 instructions per element
 // against ~7.5 of useful work).
-template <int NT, int STAGES, bool FAST = false>
+// XS (wide RxS weight gradients, stride 1, OW % 32 == 0): BOTH operands arrive as split-bf16 planes through the bulk-tensor engine.
+// The generic loader converts every input element once per filter tap and every gradient element once per k block (10x redundant for
+// a 160 -> 128 3x3 layer: the kernel ran at 12-40 % of the tensor pipe with the MMAs waiting on the eight loader warps); here the
+// planes are written once by an element-wise pass, a filter tap is a coordinate offset of a [64 channels x 32 pixels] box (borders
+// zero-filled by the tensor map) and one thread feeds the ring.
+template <int NT, int STAGES, bool FAST = false, bool XS = false>
 __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs a) {
   static_assert(NT == 64 || NT == 128 || NT == 256 || NT == 320, "output-channel tile");
   constexpr bool CONCAT = NT <= 128;      // [G_hi | G_lo] as one operand of width 2*NT (see umma_chunk8); wide tiles run
@@ -81,7 +89,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
 
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), WU_LOAD_WARPS + (a.g_split ? 1 : 0));
+      mbar_init(smem_u32(&bar_full[s]), XS ? 1 : WU_LOAD_WARPS + (a.g_split ? 1 : 0));
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
@@ -99,7 +107,49 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < WU_LOAD_WARPS && nchunks > 0) {
+  if (XS) {
+    if (t == 0 && nchunks > 0) {
+      // =============================================================== bulk-tensor producer (both operands)
+      const int total_units = p.R * p.S * a.upt;
+      int xc[2], xdx[2], xdy[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int u = kb * 2 + h;
+        if (u < total_units) {
+          const int tap = u / a.upt, fr = tap / p.S;
+          xc[h] = (u - tap * a.upt) * 64; xdy[h] = fr - p.pad; xdx[h] = tap - fr * p.S - p.pad;
+        } else {
+          xc[h] = a.upt * 64; xdy[h] = 0; xdx[h] = 0;       // past the last channel: the box is zero-filled
+        }
+      }
+      int n = (int)(mbeg / OHW);
+      const int rem = (int)(mbeg - (int64_t)n * OHW);
+      int oy = rem / p.OW, ox = rem - oy * p.OW;              // first pixel of the chunk: OW % 32 == 0, a chunk never leaves its image row
+      int64_t lm = mbeg;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int q = 0; q < nchunks; ++q) {
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        const uint32_t bar = smem_u32(&bar_full[s]);
+        const uint32_t abase = smem_base + s * STAGE_BYTES, gbase = abase + 2 * WU_A_BYTES;
+        mbar_arrive_expect_tx(bar, 2 * WU_A_BYTES + 2 * G_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tma_load_4d(abase + h * WU_BLK, &a.xmap_hi, xc[h], ox + xdx[h], oy + xdy[h], n, bar);
+          tma_load_4d(abase + WU_A_BYTES + h * WU_BLK, &a.xmap_lo, xc[h], ox + xdx[h], oy + xdy[h], n, bar);
+        }
+#pragma unroll
+        for (int g = 0; g < GQ; ++g) {
+          tma_load_2d(gbase + g * WU_BLK, &a.gmap_hi, cot * NT + 64 * g, (int)lm, bar);
+          tma_load_2d(gbase + G_BYTES + g * WU_BLK, &a.gmap_lo, cot * NT + 64 * g, (int)lm, bar);
+        }
+        lm += WU_P;
+        ox += WU_P;
+        if (ox >= p.OW) { ox = 0; if (++oy == p.OH) { oy = 0; ++n; } }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp < WU_LOAD_WARPS && nchunks > 0) {
     // =============================================================== loaders
     const int pr = t >> 3, seg = t & 7;         // pixel row of the chunk, 8-channel chunk within a 64-channel block
     const bool direct = p.gather == FDG_GATHER_DIRECT;
@@ -350,7 +400,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
         if (++sf == STAGES) sf = 0;
       }
     }
-  } else if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
+  }
+  if (warp == WU_LOAD_WARPS && lane == 0 && nchunks > 0) {
     // =============================================================== MMA issue
     constexpr uint32_t idesc1 = umma_idesc_bf16_mn(WU_K, CONCAT ? NT : N1), idesc2 = umma_idesc_bf16_mn(WU_K, CONCAT ? 2 * NT : N2);
     const uint32_t mn_hw = umma_desc_hi(1024);
@@ -393,11 +444,19 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   // =============================================================== epilogue: TMEM -> atomicAdd into the parameter layout
   if (warp < 4 && nchunks > 0) {
     mbar_wait(smem_u32(&bar_acc), 0);
+    __syncwarp();                                 // XS: lane 0 of warp 0 arrives from the producer loop; tcgen05.ld is warp-aligned
     tc_fence_after();
     const int krow = kb * WU_K + warp * 32 + lane;
-    const bool kvalid = krow < Ktot;
-    const int tap = kvalid ? krow / p.Cin : 0;
-    const int ci = kvalid ? krow - tap * p.Cin : 0;
+    bool kvalid = krow < Ktot;
+    int tap = kvalid ? krow / p.Cin : 0;
+    int ci = kvalid ? krow - tap * p.Cin : 0;
+    if (XS) {                                     // rows = two 64-channel units of (tap, channel block), channels padded per tap
+      const int u = kb * 2 + (warp >> 1);
+      tap = u / a.upt;
+      ci = (u - tap * a.upt) * 64 + (warp & 1) * 32 + lane;
+      kvalid = u < p.R * p.S * a.upt && ci < p.Cin;
+      if (!kvalid) { tap = 0; ci = 0; }
+    }
     const int RS = p.R * p.S;
 #pragma unroll 1
     for (int g = 0; g < NT / 32; ++g) {
@@ -452,13 +511,13 @@ int wgrad_umma_supported(const FdgWgrad* p) {
   return 1;
 }
 
-template <int NT, int STAGES, bool FAST = false>
+template <int NT, int STAGES, bool FAST = false, bool XS = false>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * ((NT + 63) / 64) * WU_BLK) + 1024;
   static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
-    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, FAST, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d_wgrad[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -485,7 +544,7 @@ static int launch_wu(WUArgs& a, cudaStream_t st) {
   splits = cdiv64(a.M, a.m_per_split);
   ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  launch_k(wgrad_umma_kernel<NT, STAGES, FAST>, dim3((unsigned)(a.tiles * splits)), dim3(WU_THREADS), (size_t)(smem), st, a);
+  launch_k(wgrad_umma_kernel<NT, STAGES, FAST, XS>, dim3((unsigned)(a.tiles * splits)), dim3(WU_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d_wgrad[tcgen05]");
 }
 
@@ -512,6 +571,28 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
       return FDG_ECUDA;
     }
     a.g_split = 1;
+  }
+  a.upt = 0;
+  if (p->x_split) {
+    // both operands as planes: stride-1 RxS filters whose output rows are whole 32-pixel chunks (see the kernel comment)
+    const int nt = wu_ntile(p->Cout);
+    if (!(a.g_split && p->stride == 1 && p->gather == FDG_GATHER_DIRECT && p->OW % WU_P == 0 && p->Cin % 8 == 0 && !p->transposed &&
+          (nt == 128 || nt == 256) && !a.dbg)) {
+      set_error("fdg_conv2d_wgrad[tcgen05]: x_split needs g_split, stride 1, a direct gather, OW %% 32 == 0, Cin %% 8 == 0 and 64 < Cout");
+      return FDG_ENOSUPPORT;
+    }
+    const uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
+    const uint64_t strides[3] = {(uint64_t)p->Cin * 2, (uint64_t)p->W * p->Cin * 2, (uint64_t)p->H * p->W * p->Cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)WU_P, 1, 1};
+    const uint8_t* hi = reinterpret_cast<const uint8_t*>(p->x_split);
+    const size_t plane = (size_t)p->N * p->H * p->W * p->Cin * 2;
+    if (!make_tmap_bf16(&a.xmap_hi, hi, 4, dims, strides, box) || !make_tmap_bf16(&a.xmap_lo, hi + plane, 4, dims, strides, box)) {
+      set_error("fdg_conv2d_wgrad[tcgen05]: cannot build the tensor maps of the split-bf16 input");
+      return FDG_ECUDA;
+    }
+    a.upt = cdiv(p->Cin, 64);
+    a.kblocks = cdiv(p->R * p->S * a.upt, 2);
+    return nt == 128 ? launch_wu<128, 6, false, true>(a, st) : launch_wu<256, 4, false, true>(a, st);
   }
   switch (wu_ntile(p->Cout)) {
     case 64: return launch_wu<64, 8>(a, st);      // 8 x 24 KB in-place staging ring

@@ -301,7 +301,7 @@ class _SideQueue:
             return ops.wgrad(x, g, *a, **k)
         ops.stream_wait(self.side, ops.event_record(self.main))
         ops.wgrad(x, g, *a, stream=self.side, **k)
-        self.keep.append((x.base, g.base))
+        self.keep.append((x.base, g.base, k.get("x_split"), k.get("g_split")))
         self.used = True
 
     def join(self):
@@ -318,6 +318,20 @@ def _wgrad(*a, **k):
     """ops.wgrad, through the pass's side queue when there is one."""
     q = getattr(_TLS_Q, "q", None)
     return q.wgrad(*a, **k) if q is not None else ops.wgrad(*a, **k)
+
+
+WIDE_WGRAD_PLANES = True     # wide stride-1 RxS weight gradients: both operands as split-bf16 planes (FdgWgrad.x_split)
+
+
+def _wgrad_wide(x: View, g: View, R, S, stride, pad, dw, *, slope=1.0, dbias=None):
+    """Weight gradient of a wide RxS convolution (decoder / fusion 3x3 layers).  The generic tensor-core kernel converts every input element
+    once per filter tap and every gradient element once per 128-row block of dW; here act(x) and g are written once as split-bf16 planes
+    and the kernel is fed by bulk tensor loads alone."""
+    if dw is not None and WIDE_WGRAD_PLANES and ops.wgrad_planes_ok(x, g, R, S, stride, pad):
+        xs = ops.split_planes(x, slope)
+        gs = ops.split_planes(g, 1.0)
+        return _wgrad(x, g, R, S, stride, pad, dw, slope=slope, dbias=dbias, x_split=xs, g_split=gs)
+    return _wgrad(x, g, R, S, stride, pad, dw, slope=slope, dbias=dbias)
 
 
 def _dense_block_bwd(block, prefix, n_layers, c_in, X: View, dX: View, layers, grads, dpool):
@@ -426,7 +440,7 @@ def _bdy_bwd(blk, prefix, Dv: View, dD: View, T: View, c_in, grads):
     on return dD[:, :c_in] is dL/d(pre-ReLU x)."""
     c_out = Dv.C - c_in
     g = dD.ch(c_in, Dv.C)
-    _wgrad(T, g, 3, 3, 1, 1, grads[prefix + ".conv2.weight"], slope=0.0)
+    _wgrad_wide(T, g, 3, 3, 1, 1, grads[prefix + ".conv2.weight"], slope=0.0)
     dT = View.alloc(T.N, T.H, T.W, T.C, T.base.device)
     wd, ldd = _conv_dgrad_w(blk.conv2.weight)
     ops.conv2d(g, wd, ldd, 3, 3, 1, 1, T.C, dT, e=T, eslope=0.0)
@@ -494,7 +508,7 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     _tdy_bwd(m.trans_block4, "trans_block4", D4, dD4, dX42.ch(0, 128), grads)
     _bdy_bwd(m.dense_block4, "dense_block4", D4, dD4, T4, 512, grads)
     g6 = dD4.ch(0, 512)                                                   # dL/d(conv_refin6 pre-ReLU output)
-    _wgrad(C6, g6, 3, 3, 1, 1, grads["conv_refin6.weight"], dbias=grads["conv_refin6.bias"])
+    _wgrad_wide(C6, g6, 3, 3, 1, 1, grads["conv_refin6.weight"], dbias=grads["conv_refin6.bias"])
     dC6 = View.alloc(C6.N, C6.H, C6.W, 640, dev)
     wd, ldd = _conv_dgrad_w(m.conv_refin6.weight)
     ops.conv2d(g6, wd, ldd, 3, 3, 1, 1, 640, dC6)
@@ -516,7 +530,7 @@ def _generator_backward(m, ctx: GCtx, dout: torch.Tensor, grads: dict, need_dx: 
     _transition_bwd(m.trans_block2, "trans_block2", X2, dX2, dX3.ch(0, 256), ctx.bn_t2, grads, dpool, ctx.P_t[1], accumulate=False)
     _dense_block_bwd(m.dense_block2, "dense_block2", 12, 128, X2, dX2, ctx.saved["dense_block2"], grads, dpool)
     g4 = dX2.ch(0, 128)
-    _wgrad(C4, g4, 3, 3, 1, 1, grads["conv_refine4.weight"], dbias=grads["conv_refine4.bias"])
+    _wgrad_wide(C4, g4, 3, 3, 1, 1, grads["conv_refine4.weight"], dbias=grads["conv_refine4.bias"])
     dC4 = View.alloc(C4.N, C4.H, C4.W, 160, dev)
     wd, ldd = _conv_dgrad_w(m.conv_refine4.weight)
     ops.conv2d(g4, wd, ldd, 3, 3, 1, 1, 160, dC4)

@@ -168,7 +168,7 @@ def stream_wait(stream: int, handle: int) -> None:
 
 
 def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scale=None, shift=None, slope=1.0,
-          transposed=False, dbias=None, impl=None, g_split=None, stream=None):
+          transposed=False, dbias=None, impl=None, g_split=None, x_split=None, stream=None):
     """fdg_conv2d_wgrad: dw (+)= A^T g in the parameter's own layout (dw must be pre-zeroed or accumulating).
     ``dw is None`` (frozen parameter) skips the launch."""
     if dw is None:
@@ -185,8 +185,25 @@ def wgrad(x: View, g: View, R, S, stride, pad, dw, *, gather=GATHER_DIRECT, scal
         raise ValueError("wgrad: gradient view %s does not match output extent %s" % ((g.N, g.H, g.W), (x.N, OH, OW)))
     d = L.FdgWgrad(x.ft(), x.N, H, W, x.C, gather, 1 if scale is not None else 0, _ptr(scale), _ptr(shift), slope,
                    g.ft(), R, S, stride, pad, g.C, OH, OW, _ptr(dw), 1 if transposed else 0, _ptr(dbias),
-                   (IMPL_AUTO if USE_UMMA else IMPL_SIMT) if impl is None else impl, _ptr(g_split))
+                   (IMPL_AUTO if USE_UMMA else IMPL_SIMT) if impl is None else impl, _ptr(g_split), _ptr(x_split))
     L.check(L.lib.fdg_conv2d_wgrad(_byref(d), _stream() if stream is None else stream), "conv2d_wgrad")
+
+
+def split_planes(x: View, slope=1.0) -> torch.Tensor:
+    """act(x) as split-bf16 planes [pixels][C] (hi plane, then lo plane; the bytes of an fp32 tensor of the same extent): the operand
+    format the tensor-core kernels take through bulk tensor loads.  One element-wise pass (fdg_ew_bwd with the tensor as its own mask:
+    x * [x > 0 ? 1 : slope])."""
+    out = torch.empty(x.N * x.H * x.W * x.C, dtype=torch.float32, device=x.base.device)
+    ew_bwd(x, x, slope=slope, out_split=out)
+    return out
+
+
+def wgrad_planes_ok(x: View, g: View, R, S, stride, pad) -> bool:
+    """Shapes the all-planes weight-gradient path takes (FdgWgrad.x_split)."""
+    OW = x.W + 2 * pad - S + 1
+    lin = lambda v: v.sc == 1 and v.sh == v.W * v.sw and v.sn == v.H * v.sh
+    return (USE_UMMA and stride == 1 and R >= 2 and S >= 2 and OW % 32 == 0 and x.C % 8 == 0 and g.C % 8 == 0 and 64 < g.C and
+            (g.C <= 256 or g.C % 128 == 0) and lin(x) and lin(g))
 
 
 # Operand images of FROZEN parameters (requires_grad == False: the Vgg16 feature extractor, D during the generator update

@@ -132,6 +132,9 @@ typedef struct FdgWgrad {
   float* dbias;         /* [Cout] (+)= sum_pixels g, or NULL */
   int impl;             /* 0 auto, 1 force SIMT fp32, 2 force tcgen05 (error if unsupported) */
   const void* g_split;  /* the gradient as split-bf16 planes [N*OH*OW][Cout] (see FdgConv.x_split) or NULL; Cout % 64 == 0 */
+  const void* x_split;  /* the conv input AFTER its prologue as split-bf16 planes [N*H*W][Cin] (hi plane, then lo plane) or NULL:
+                         * wide stride-1 RxS weight gradients feed both operands through the bulk-tensor engine (needs g_split,
+                         * OW % 32 == 0, Cin % 8 == 0, 64 < Cout; x / scale / shift / slope are then not read) */
 } FdgWgrad;
 
 int fdg_conv2d_wgrad(const FdgWgrad* p, fdg_stream_t stream);

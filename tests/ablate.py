@@ -82,7 +82,13 @@ def main():
             else:
                 y.base.normal_()
                 dw = torch.zeros_like(w)
-                ms = timeit(lambda: ops.wgrad(x, y, R, R, 1, pad, dw, scale=sc, shift=sh, slope=0.0 if affine else 1.0), iters=3)
+                if os.environ.get("ABL_PLANES") and ops.wgrad_planes_ok(x, y, R, R, 1, pad) and not affine:
+                    def run():
+                        xs, gs = ops.split_planes(x, 1.0), ops.split_planes(y, 1.0)
+                        ops.wgrad(x, y, R, R, 1, pad, dw, x_split=xs, g_split=gs)
+                    ms = timeit(run, iters=3)
+                else:
+                    ms = timeit(lambda: ops.wgrad(x, y, R, R, 1, pad, dw, scale=sc, shift=sh, slope=0.0 if affine else 1.0), iters=3)
             if m == 0:
                 t0 = ms
             out += " %8.3f " % ms

@@ -759,3 +759,34 @@ def test_colsum_nchw_planes():
         cs = torch.ones(shape[1], device="cuda")
         ops.colsum(ops.View.from_nchw(b_.cuda()), cs, accumulate=True)
         assert maxabs(cs, 1 + b_.double().sum((0, 2, 3))) <= 5e-4
+
+
+@pytest.mark.parametrize("cin,cout,R,pad,H,W,slope", [
+    (160, 128, 3, 1, 7, 32, 1.0),      # conv_refine4: 2.5 channel units per tap (padded rows), one output tile
+    (512, 128, 3, 1, 5, 64, 0.0),      # dense_block5.conv2: ReLU prologue folded into the planes, two chunks per row
+    (192, 256, 3, 1, 4, 32, 0.0),      # 256-wide output tile
+    (640, 512, 3, 1, 3, 32, 1.0),      # conv_refin6: two 256-wide output tiles
+    (72, 136, 4, 1, 6, 33, 0.2),       # 4x4 filter, OW = 32, channel tail inside a unit, Cout tail inside the 256-wide tile
+])
+def test_wgrad_both_operands_from_split_planes(cin, cout, R, pad, H, W, slope):
+    """FdgWgrad.x_split: wide stride-1 RxS weight gradients fed by bulk tensor loads alone (filter taps = box coordinates, borders
+    zero-filled by the tensor map) == fp64 torch; also through a channel slice of a wider gradient buffer."""
+    ops = _ops()
+    N = 2
+    x = seeded((N, cin, H, W), 1, -1, 1)
+    OH, OW = H + 2 * pad - R + 1, W + 2 * pad - R + 1
+    assert OW % 32 == 0
+    g = seeded((N, cout + 8, OH, OW), 2, -1, 1)
+    xv = ops.View.from_nchw(cl(x))
+    gv = ops.View.from_nchw(cl(g)).ch(8, cout + 8)
+    assert ops.wgrad_planes_ok(xv, gv, R, R, 1, pad)
+    xs, gs = ops.split_planes(xv, slope), ops.split_planes(gv, 1.0)
+    dw = torch.zeros(cout, cin, R, R, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    ops.wgrad(xv, gv, R, R, 1, pad, dw, slope=slope, dbias=db, x_split=xs, g_split=gs)
+    torch.cuda.synchronize()
+    ref = torch.zeros(cout, cin, R, R, dtype=torch.float64, requires_grad=True)
+    gd = g[:, 8:].double()
+    (F.conv2d(F.leaky_relu(x.double(), slope), ref, padding=pad) * gd).sum().backward()
+    assert maxabs(dw, ref.grad) <= 5e-5 * max(1.0, float(ref.grad.abs().max()))
+    assert maxabs(db, gd.sum((0, 2, 3))) <= 1e-4 * max(1.0, float(gd.sum((0, 2, 3)).abs().max()))
