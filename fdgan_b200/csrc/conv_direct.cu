@@ -577,10 +577,96 @@ __global__ void __launch_bounds__(128) dgrad_strided_small_kernel(const __grid_c
   }
 }
 
+// Stride-2 form (Fusion-D layer 1): the one-pixel kernel above fetches three 128-bit weight vectors per (tap, output channel) for 12
+// FMAs -- the shared-memory pipe bounds it (0.35 ms against a 0.05 ms FMA floor).  Input pixels of equal column parity use the SAME
+// filter taps, so a thread takes FOUR of them (x, x + 2, x + 4, x + 6: consecutive output columns) and every weight vector feeds 48 FMAs.
+__global__ void __launch_bounds__(128) dgrad_stride2_px4_kernel(const __grid_constant__ FdgDgradStrided p, int xgroups, int64_t total) {
+  pdl_wait();      // PDL contract (common.cuh): nothing of an earlier kernel is read before this returns
+  pdl_trigger();
+  extern __shared__ __align__(16) float ws[];      // [R*S][Cout][DS_CI]
+  const int taps = p.R * p.S;
+  for (int i = threadIdx.x; i < taps * p.Cout * DS_CI; i += blockDim.x) {
+    const int ci = i % DS_CI;
+    const int co = (i / DS_CI) % p.Cout;
+    const int tap = i / (DS_CI * p.Cout);
+    ws[i] = ci < p.Cin ? __ldg(p.w + ((int64_t)co * p.Cin + ci) * taps + tap) : 0.f;
+  }
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i -> (image, row, group of eight columns, column parity)
+    const int par = (int)(i & 1);
+    int64_t r = i >> 1;
+    const int xg = (int)(r % xgroups); r /= xgroups;
+    const int y = (int)(r % p.H);
+    const int n = (int)(r / p.H);
+    const int x0 = xg * 8 + par;                   // the thread's pixels: x0 + 2 j
+    float acc[4][DS_CI];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < DS_CI; ++c) acc[j][c] = 0.f;
+    for (int kr = 0; kr < p.R; ++kr) {
+      const int ty = y + p.pad - kr;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= p.OH) continue;
+      for (int ks = (x0 + p.pad) & 1; ks < p.S; ks += 2) {       // taps with (x + pad - ks) even
+        const int ox0 = (x0 + p.pad - ks) >> 1;                   // may be -1 for the first group (arithmetic shift); pixel j reads ox0 + j
+        const float* gp = p.g.p + n * p.g.sn + (int64_t)oy * p.g.sh;
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ok[j] = ox0 + j >= 0 && ox0 + j < p.OW && x0 + 2 * j < p.W;
+        const float4* wt = reinterpret_cast<const float4*>(ws + (size_t)(kr * p.S + ks) * p.Cout * DS_CI);
+        for (int co = 0; co < p.Cout; co += 4) {
+          float gq[4][4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 g4 = ok[j] ? ld4(gp + (int64_t)(ox0 + j) * p.g.sw + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gq[j][0] = g4.x; gq[j][1] = g4.y; gq[j][2] = g4.z; gq[j][3] = g4.w;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 w0 = wt[(co + u) * 3], w1 = wt[(co + u) * 3 + 1], w2 = wt[(co + u) * 3 + 2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float gv = gq[j][u];
+              acc[j][0] = fmaf(gv, w0.x, acc[j][0]); acc[j][1] = fmaf(gv, w0.y, acc[j][1]); acc[j][2] = fmaf(gv, w0.z, acc[j][2]); acc[j][3] = fmaf(gv, w0.w, acc[j][3]);
+              acc[j][4] = fmaf(gv, w1.x, acc[j][4]); acc[j][5] = fmaf(gv, w1.y, acc[j][5]); acc[j][6] = fmaf(gv, w1.z, acc[j][6]); acc[j][7] = fmaf(gv, w1.w, acc[j][7]);
+              acc[j][8] = fmaf(gv, w2.x, acc[j][8]); acc[j][9] = fmaf(gv, w2.y, acc[j][9]); acc[j][10] = fmaf(gv, w2.z, acc[j][10]); acc[j][11] = fmaf(gv, w2.w, acc[j][11]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + 2 * j;
+      if (x < p.W) {
+        float* o = p.dx.p + n * p.dx.sn + (int64_t)y * p.dx.sh + (int64_t)x * p.dx.sw;
+#pragma unroll
+        for (int c = 0; c < DS_CI; ++c)
+          if (c < p.Cin) {
+            float* oc = o + (int64_t)c * p.dx.sc;
+            *oc = p.accumulate ? *oc + acc[j][c] : acc[j][c];
+          }
+      }
+    }
+  }
+}
+
 int dgrad_strided_small(const FdgDgradStrided* p, cudaStream_t st) {
   static const int on = [] { const char* e = getenv("FDG_THIN"); return e ? atoi(e) : 1; }();
   const int smem = p->R * p->S * p->Cout * DS_CI * 4;
   if (!on || p->Cin > DS_CI || p->Cout % 4 != 0 || smem > 48 * 1024 || !vec4_ok(p->g)) return 1;   // 1 = not taken
+  static const int px4 = [] { const char* e = getenv("FDG_DGRAD_S2_PX4"); return e ? atoi(e) : 1; }();
+  if (px4 && p->stride == 2) {
+    const int xgroups = cdiv(p->W, 8);
+    const int64_t total4 = (int64_t)p->N * p->H * xgroups * 2;
+    int64_t blocks = cdiv64(total4, 128);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    launch_k(dgrad_stride2_px4_kernel, dim3((unsigned)blocks), dim3(128), (size_t)(smem), st, *p, xgroups, total4);
+    return check_launch("fdg_conv2d_dgrad_strided[small]");
+  }
   const int64_t total = (int64_t)p->N * p->H * p->W;
   int64_t blocks = cdiv64(total, 128);
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -653,6 +653,16 @@ def test_dgrad_strided():
     dx = torch.zeros(2, 9, 16, 18, device="cuda")
     ops.dgrad_strided(ops.View.from_nchw(cl(g)), w.cuda(), 2, 1, ops.View.from_nchw(dx))
     assert maxabs(dx, x.grad) <= 1e-5
+    # four same-parity pixels per thread: ragged column groups, odd sizes, channels-last output
+    for shape in ((1, 9, 15, 21), (3, 9, 34, 40), (2, 5, 9, 7)):
+        x = seeded(shape, 4, -1, 1).requires_grad_(True)
+        w = seeded((36, shape[1], 4, 4), 5, -1, 1) / 12
+        y = F.conv2d(x, w, stride=2, padding=1)
+        g = seeded(tuple(y.shape), 6, -1, 1)
+        (y * g).sum().backward()
+        dx = cl(torch.full(shape, 3.0))
+        ops.dgrad_strided(ops.View.from_nchw(cl(g)), w.cuda(), 2, 1, ops.View.from_nchw(dx))
+        assert maxabs(dx, x.grad) <= 1e-5, shape
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 40, 56), (1, 3, 8, 9), (1, 3, 33, 65)])
