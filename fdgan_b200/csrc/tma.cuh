@@ -21,6 +21,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem, const void* tmap, int
                : "memory");
 }
 
+// multicast form: the box lands at the same shared-memory offset in every CTA of `mask`, each one's mbarrier (same offset) counts the bytes
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t smem, const void* tmap, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem),
+               "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t smem, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem),
                "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)

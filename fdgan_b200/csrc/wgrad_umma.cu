@@ -37,6 +37,7 @@ struct WUArgs {
   int dbg;           // ablation: 1 no global loads, 2 no split/stores, 4 no MMA
   int gvec;          // gradient rows loadable as float4 (unit channel stride, aligned, Cout % 8 == 0)
   int g_split;       // the gradient operand arrives as split-bf16 planes through gmap_hi / gmap_lo (bulk tensor loads)
+  int pf_ahead;      // FAST: chunks of L2 prefetch in front of the ring (0 = none)
   int upt;           // XS: 64-channel units per filter tap, ceil(Cin / 64); the 128 rows of a k block are units 2 kb, 2 kb + 1
   alignas(64) CUtensorMap gmap_hi;
   alignas(64) CUtensorMap gmap_lo;
@@ -58,7 +59,11 @@ struct WUArgs {
 // a 160 -> 128 3x3 layer: the kernel ran at 12-40 % of the tensor pipe with the MMAs waiting on the eight loader warps); here the
 // planes are written once by an element-wise pass, a filter tap is a coordinate offset of a [64 channels x 32 pixels] box (borders
 // zero-filled by the tensor map) and one thread feeds the ring.
-template <int NT, int STAGES, bool FAST = false, bool XS = false>
+// CL (wide tiles with a split-plane gradient, even number of k blocks): CTAs 2i, 2i + 1 (k blocks 2i, 2i + 1 of the same output tile and pixel
+// range) form a cluster and SHARE the gradient operand: rank 0 fetches the hi plane's boxes, rank 1 the lo plane's, each multicast
+// into both CTAs.  The 320-wide tile moves 56 KB per 32-pixel chunk through the L2 -> SM path (60 B / clock / SM at the MMA rate, more
+// than the L2 sustains): the gradient is 40 KB of it.  A stage is free when BOTH CTAs' MMAs have retired (multicast commits).
+template <int NT, int STAGES, bool FAST = false, bool XS = false, bool CL = false>
 __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs a) {
   static_assert(NT == 64 || NT == 128 || NT == 256 || NT == 320, "output-channel tile");
   constexpr bool CONCAT = NT <= 128;      // [G_hi | G_lo] as one operand of width 2*NT (see umma_chunk8); wide tiles run
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), XS ? 1 : WU_LOAD_WARPS + (a.g_split ? 1 : 0));
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), CL ? 2 : 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
     fence_barrier_init();
@@ -106,6 +111,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  const uint32_t crank = CL ? cluster_ctarank() : 0u;
+  if (CL) cluster_sync_all();      // the peer's barriers are initialised before anything of this CTA can signal them
 
   if (XS) {
     if (t == 0 && nchunks > 0) {
@@ -246,10 +253,17 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
         const uint32_t bar = full0 + st * 8;
         const uint32_t gbase = smem_base + st * STAGE_BYTES + 2 * WU_A_BYTES;
         mbar_arrive_expect_tx(bar, 2 * G_BYTES);
+        if (CL) {
+          // this CTA's half of the shared gradient operand (rank 0: hi plane, rank 1: lo plane), delivered to both CTAs
 #pragma unroll
-        for (int q = 0; q < GQ; ++q) {
-          tma_load_2d(gbase + q * WU_BLK, &a.gmap_hi, cot * NT + 64 * q, (int)lm, bar);
-          tma_load_2d(gbase + G_BYTES + q * WU_BLK, &a.gmap_lo, cot * NT + 64 * q, (int)lm, bar);
+          for (int q = 0; q < GQ; ++q)
+            tma_load_2d_multicast(gbase + crank * G_BYTES + q * WU_BLK, crank ? &a.gmap_lo : &a.gmap_hi, cot * NT + 64 * q, (int)lm, bar, (uint16_t)3);
+        } else {
+#pragma unroll
+          for (int q = 0; q < GQ; ++q) {
+            tma_load_2d(gbase + q * WU_BLK, &a.gmap_hi, cot * NT + 64 * q, (int)lm, bar);
+            tma_load_2d(gbase + G_BYTES + q * WU_BLK, &a.gmap_lo, cot * NT + 64 * q, (int)lm, bar);
+          }
         }
       }
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta0 + st * (NLT * 4)), "r"(ok) : "memory");
@@ -304,6 +318,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
       if (lane == 0) mbar_arrive(full0 + st * 8);
     };
     if constexpr (FAST) {
+      const int wu_pf = a.pf_ahead;
       // ---- FAST: running pointer, validity by comparison (k == channel, tap 0; the thread's rows are pixels mbeg + pr + 32 q)
       const bool fv0 = k0 < p.Cin, fv1 = k1 < p.Cin;
       const float* fx = p.x.p + (mbeg + pr) * p.x.sw;       // pixel-linear view: pixel m lives at m * sw
@@ -320,6 +335,13 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_a(st, 1, 0)), "l"(fx + k1) : "memory");
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slot_a(st, 1, 1)), "l"(fx + k1 + 4) : "memory");
           }
+        }
+        if (wu_pf > 0 && fl + (int64_t)wu_pf * WU_P < mend) {
+          // L2 prefetch of this thread's rows wu_pf chunks ahead: the ring holds STAGES - 2 chunks of 16 KB in flight, too few bytes per
+          // SM to cover the DRAM latency at full bandwidth; with the lines already in L2 the same ring covers the (shorter) L2 latency
+          const float* pf = fx + (int64_t)wu_pf * fxstep;
+          if (fv0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + k0) : "memory");
+          if (fv1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + k1) : "memory");
         }
         if (t == 0) {       // pr == 0: fl is the first pixel of the chunk
           const uint32_t bar = full0 + st * 8;
@@ -435,7 +457,8 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
           }
         }
       }
-      umma_commit(smem_u32(&bar_empty[s]));
+      if (CL) umma_commit_multicast(smem_u32(&bar_empty[s]), (uint16_t)3);
+      else umma_commit(smem_u32(&bar_empty[s]));
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     umma_commit(smem_u32(&bar_acc));
@@ -486,6 +509,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
     tc_fence_before();
   }
   __syncthreads();
+  if (CL) cluster_sync_all();      // shared memory and barriers stay alive until the peer's last multicast copy / commit has landed
   if (warp == WU_LOAD_WARPS) {
     __syncwarp();
     tc_fence_after();
@@ -511,13 +535,13 @@ int wgrad_umma_supported(const FdgWgrad* p) {
   return 1;
 }
 
-template <int NT, int STAGES, bool FAST = false, bool XS = false>
+template <int NT, int STAGES, bool FAST = false, bool XS = false, bool CL = false>
 static int launch_wu(WUArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * WU_A_BYTES + 2 * ((NT + 63) / 64) * WU_BLK) + 1024;
   static std::atomic<int> attr_done[64];           // per device
   const int adev = current_device();
   if (!attr_done[adev]) {
-    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, FAST, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(wgrad_umma_kernel<NT, STAGES, FAST, XS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d_wgrad[tcgen05]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -544,7 +568,8 @@ static int launch_wu(WUArgs& a, cudaStream_t st) {
   splits = cdiv64(a.M, a.m_per_split);
   ProfScope prof(PF_WGRAD, 2.0 * (double)a.M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * ((double)a.M * a.c.Cout + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  launch_k(wgrad_umma_kernel<NT, STAGES, FAST, XS>, dim3((unsigned)(a.tiles * splits)), dim3(WU_THREADS), (size_t)(smem), st, a);
+  if (CL) launch_k_cluster(wgrad_umma_kernel<NT, STAGES, FAST, XS, CL>, dim3((unsigned)(a.tiles * splits)), dim3(WU_THREADS), (size_t)(smem), st, 2, a);
+  else launch_k(wgrad_umma_kernel<NT, STAGES, FAST, XS, CL>, dim3((unsigned)(a.tiles * splits)), dim3(WU_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d_wgrad[tcgen05]");
 }
 
@@ -573,6 +598,8 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
     a.g_split = 1;
   }
   a.upt = 0;
+  static const int pf_ahead = [] { const char* e = getenv("FDG_WU_PF"); return e ? atoi(e) : 0; }();   // measured: 0.341 ms without, 0.356 ms with 4 / 8 / 16 chunks (224 -> 128 @256^2): DRAM latency is not what bounds the loaders
+  a.pf_ahead = pf_ahead;
   if (p->x_split) {
     // both operands as planes: stride-1 RxS filters whose output rows are whole 32-pixel chunks (see the kernel comment)
     const int nt = wu_ntile(p->Cout);
@@ -594,6 +621,7 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
     a.kblocks = cdiv(p->R * p->S * a.upt, 2);
     return nt == 128 ? launch_wu<128, 6, false, true>(a, st) : launch_wu<256, 4, false, true>(a, st);
   }
+  static const int cl_on = [] { const char* e = getenv("FDG_WU_CLUSTER"); return e ? atoi(e) : 1; }();
   switch (wu_ntile(p->Cout)) {
     case 64: return launch_wu<64, 8>(a, st);      // 8 x 24 KB in-place staging ring
     case 128: {                                   // 6 x 32 KB
@@ -603,8 +631,14 @@ int wgrad_umma(const FdgWgrad* p, cudaStream_t st) {
                         p->gather == FDG_GATHER_DIRECT && x.sh == (int64_t)p->W * x.sw && x.sn == (int64_t)p->H * x.sh;
       return fast ? launch_wu<128, 6, true>(a, st) : launch_wu<128, 6, false>(a, st);
     }
-    case 256: return launch_wu<256, 4>(a, st);    // 4 x 48 KB
-    default: return launch_wu<320, 3>(a, st);     // 3 x 56 KB
+    case 256: {                                   // 4 x 48 KB
+      if (cl_on && a.g_split && !a.dbg && cdiv(p->Cout, 256) == 1 && a.kblocks % 2 == 0) return launch_wu<256, 4, false, false, true>(a, st);
+      return launch_wu<256, 4>(a, st);
+    }
+    default: {                                    // 3 x 56 KB
+      if (cl_on && a.g_split && !a.dbg && a.kblocks % 2 == 0) return launch_wu<320, 3, false, false, true>(a, st);
+      return launch_wu<320, 3>(a, st);
+    }
   }
 }
 

@@ -67,7 +67,8 @@ def main():
         if which in ("both", "wgrad") or os.environ.get("BENCH_WGRAD"):
             g = View.alloc(B, OH, OH, Cout, dev); g.base.normal_()
             dw = torch.zeros_like(w)
-            ms = timeit(lambda: ops.wgrad(x, g, R, R, 1, pad, dw, scale=sc, shift=sh, slope=0.0 if affine else 1.0), iters=3)
+            gs = ops.split_planes(g, 1.0) if (os.environ.get("BENCH_GSPLIT") and Cout % 8 == 0) else None    # FAST 1x1 loader needs planes
+            ms = timeit(lambda: ops.wgrad(x, g, R, R, 1, pad, dw, scale=sc, shift=sh, slope=0.0 if affine else 1.0, g_split=gs), iters=5)
             out += "  wgrad %8.3f ms %7.1f TF/s" % (ms, flops / ms / 1e9)
         print(out, flush=True)
 
