@@ -448,6 +448,8 @@ def run_ours(args):
     # switched off for this pass (the events between launches already serialise programmatic dependent launches)
     from fdgan_b200 import engine as _engine
     async_px, _engine.ASYNC_WGRAD_MAX_PIXELS = _engine.ASYNC_WGRAD_MAX_PIXELS, 0
+    from fdgan_b200 import train as _train
+    ovl, _train.OVERLAP_CLEAN_BRANCH = _train.OVERLAP_CLEAN_BRANCH, False      # likewise the clean-image branch on its auxiliary stream
     L.profile_enable(True)
     prof_steps = min(args.steps, 3)
     for i in range(prof_steps):
@@ -456,6 +458,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     L.profile_enable(False)
     _engine.ASYNC_WGRAD_MAX_PIXELS = async_px
+    _train.OVERLAP_CLEAN_BRANCH = ovl
     fam = L.profile_collect()
     tot_ms = sum(v["ms"] for v in fam.values())
     dom = max(fam, key=lambda k: fam[k]["ms"])

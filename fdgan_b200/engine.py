@@ -262,7 +262,7 @@ FUSED_BN1_BWD = True   # norm1 backward inside the conv1 data-gradient epilogue 
 # a normal store) instead of the reduce pass.  Correct (test_conv2d_3x3_bn_backward_epilogue, module tests) but measured SLOWER on a B200
 # (76.1 -> 77.9 ms/step): the mask rows are read inside the epilogue's coalesced phase without the prefetch the per-tap kernel has, and the
 # bulk-tensor store is lost; off until the halo epilogue prefetches its mask rows.
-FUSED_BN2_BWD = False
+FUSED_BN2_BWD = bool(int(__import__("os").environ.get("FDG_FUSED_BN2_BWD", "0")))
 SPLIT_GRADS = True     # the bottleneck gradient travels as split-bf16 planes: its two consumers are fed by bulk tensor loads
 
 

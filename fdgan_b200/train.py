@@ -96,6 +96,18 @@ class FlatState:
             self.dev_state[0] = float(self.step)
 
 
+OVERLAP_CLEAN_BRANCH = bool(int(__import__("os").environ.get("FDG_OVERLAP", "1")))
+_AUX_STREAMS = {}
+
+
+def _aux_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    s = _AUX_STREAMS.get(key)
+    if s is None:
+        s = _AUX_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return s
+
+
 class GANTrainer:
     def __init__(self, netG, netD, vgg, lr=2e-4, betas=(0.5, 0.999), eps=1e-8, weights=None, perc_layers=(1, 3),
                  process_group=None):
@@ -207,19 +219,44 @@ class GANTrainer:
         b1, b2 = self.betas
         gscale = 1.0 / self.world
 
+        if tuple(clean.shape) != tuple(hazy.shape):
+            raise ValueError("clean %s does not match hazy %s" % (tuple(clean.shape), tuple(hazy.shape)))
+        clean = clean.contiguous()
+        B, _, H, W = clean.shape
+        want_perc = self.w["perc"] != 0.0 and bool(self.perc_layers)
+        # Everything that depends on the clean image only -- its frequency decomposition, D(real) forward, Vgg16(clean) -- runs on an
+        # auxiliary stream beside the generator forward: the generator's small-map kernels (64x64 / 32x32 maps, one-CTA BatchNorm
+        # finalisations) leave SMs idle that these tensor-bound kernels fill; at batch 1 the two chains simply run side by side.
+        # Ordering: the auxiliary stream starts after everything enqueued so far (previous optimiser steps) and is joined before the
+        # first consumer; tensors it allocates are reused only by its own later allocations, i.e. after the next fork.
+        overlap = OVERLAP_CLEAN_BRANCH and dev.type == "cuda"
+        main = torch.cuda.current_stream(dev) if overlap else None
+        aux = _aux_stream(dev) if overlap else None
+        cctx = None
+
+        def clean_branch():
+            z_real = View.alloc(B, H, W, 9, dev)
+            ops.freq_concat_fwd(View.from_nchw(clean), z_real)
+            pr_, ctx_r_ = engine.discriminator_forward(D, z_real.as_nchw(), True, True)
+            cc = engine.vgg_forward(V, clean, False)[1] if want_perc else None
+            return z_real, pr_, ctx_r_, cc
+
+        if overlap:
+            aux.wait_stream(main)
+            with torch.cuda.stream(aux):
+                z_real, pr, ctx_r, cctx = clean_branch()
         fake, gctx = engine.generator_forward(G, hazy, True, True)
-        B, _, H, W = fake.shape
         if tuple(clean.shape) != tuple(fake.shape):
             raise ValueError("clean %s does not match G(hazy) %s" % (tuple(clean.shape), tuple(fake.shape)))
-        clean = clean.contiguous()
-        z_real = View.alloc(B, H, W, 9, dev)
         z_fake = View.alloc(B, H, W, 9, dev)
-        ops.freq_concat_fwd(View.from_nchw(clean), z_real)
         ops.freq_concat_fwd(View.from_nchw(fake), z_fake)
 
         # ---------------- D step
         self.sD.zero_grad()
-        pr, ctx_r = engine.discriminator_forward(D, z_real.as_nchw(), True, True)
+        if overlap:
+            main.wait_stream(aux)
+        else:
+            z_real, pr, ctx_r, cctx = clean_branch()
         pf, ctx_f = engine.discriminator_forward(D, z_fake.as_nchw(), True, True)
         n_p = pr.numel()
         dpr, dpf = torch.empty_like(pr), torch.empty_like(pf)
@@ -251,7 +288,6 @@ class GANTrainer:
                                View.from_nchw(dfake), accumulate=True)
         if self.w["perc"] != 0.0 and self.perc_layers:
             _fo, vctx = engine.vgg_forward(V, fake, True)
-            _co, cctx = engine.vgg_forward(V, clean, False)
             gouts = [None, None, None, None]
             for k in self.perc_layers:
                 fk, ck = vctx.feats[k], cctx.feats[k]
