@@ -289,6 +289,16 @@ __global__ void __launch_bounds__(FAST ? UTHREADS_P + 32 : UTHREADS_P, 1) conv_u
           sh0 = lds4u(aff0 + (UMAX_AFF + c) * 4); sh1 = lds4u(aff0 + (UMAX_AFF + c) * 4 + 16);
         }
         mbar_wait(smem_u32(&bar_stg_full[slot]), (uint32_t)(q / DEPTH) & 1u);
+        if (a.dbg & 2) {      // ablation: barrier protocol only (no shared-memory reads, arithmetic or operand stores)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_stg_empty[slot]));
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          continue;
+        }
         const uint32_t src = src0 + (uint32_t)slot * STAGING_BYTES;
         float4 v0[RPT], v1[RPT];
 #pragma unroll
