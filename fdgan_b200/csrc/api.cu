@@ -43,6 +43,11 @@ bool pdl_enabled() {
   return on;
 }
 
+bool epi_warp_stores() {
+  static const bool on = [] { const char* e = getenv("FDG_EPI_WARP"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
 static cudaEvent_t* g_event_ring[64] = {nullptr};      // per device: the ring fdg_event_record hands handles out of
 
 static int g_dbg = 0;

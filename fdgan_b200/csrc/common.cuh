@@ -13,6 +13,7 @@ void count_launch(int n = 1);
 int check_launch(const char* what);
 int current_device();         // cudaGetDevice clamped to [0, 63]: index of per-device one-time state
 int device_sm_count();        // SM count of the current device (cached per device)
+bool epi_warp_stores();      // tcgen05 epilogues: one bulk tensor store per WARP and group (FDG_EPI_WARP=0: one per group, 128-thread barriers)
 int dbg_flags();             // ablation switches for the tcgen05 kernels (fdg_set_option("dbg", v)); 0 in production
 void set_dbg_flags(int v);  // cudaGetLastError -> FDG_ECUDA
 

@@ -41,6 +41,7 @@ struct HaloArgs {
   int pair;  // weight image holds two filter taps per 64-deep chunk (Cin <= 32, pack.cuh)
   int wstages;   // weight stages per tile: taps * cchunks, or ceil(taps / 2) in pair mode
   int tma_rank;                 // 4: the epilogue stores through ymap {channel, x, y, image}; 0: coalesced stores
+  int epi_wrows;                // EpiTma.wrows: 4 = every epilogue warp stores its own 4 tile rows (box {32, 8, 4, 1}); 0 = one box per group
   alignas(64) CUtensorMap ymap;
 };
 
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         yoff = n * p.y.sn + (int64_t)(us * oy) * p.y.sh + (int64_t)(us * ox) * p.y.sw;
         if (p.e.p) eoff = n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw;
       }
-      const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, ox0, oy0, n};
+      const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, ox0, oy0, n, a.epi_wrows};
       const int cbase = ntile * NT;
 #pragma unroll 1
       for (int g = 0; g < NTP / 32; ++g) {
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         }
       }
     }
-    if (a.tma_rank && et == 0) bulk_wait_read0();
+    if (a.tma_rank && (a.epi_wrows ? lane == 0 : et == 0)) bulk_wait_read0();
   } else if (warp == H_MMA_WARP) {
     // =============================================================== MMA issue
     if (lane == 0) {
@@ -450,11 +451,13 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
   a.pair = umma_tap_pair(p->R * p->S, p->Cin);
   a.wstages = a.pair ? (p->R * p->S + 1) / 2 : p->R * p->S * a.cchunks;
   a.tma_rank = 0;
+  a.epi_wrows = 0;
   static const int tma_on = [] { const char* e = getenv("FDG_TMA_STORE"); return e ? atoi(e) : 1; }();
   if (tma_on && a.yvec && p->store == FDG_STORE_NORMAL && !p->e.p) {
     const uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)p->OW, (uint64_t)p->OH, (uint64_t)p->N};
     const uint64_t strides[3] = {(uint64_t)p->y.sw * 4, (uint64_t)p->y.sh * 4, (uint64_t)p->y.sn * 4};
-    const uint32_t box[4] = {32, (uint32_t)HT_W, (uint32_t)HT_H, 1};
+    a.epi_wrows = epi_warp_stores() ? 32 / HT_W : 0;
+    const uint32_t box[4] = {32, (uint32_t)HT_W, a.epi_wrows ? (uint32_t)a.epi_wrows : (uint32_t)HT_H, 1};
     if (make_tmap_f32(&a.ymap, p->y.p, 4, dims, strides, box)) a.tma_rank = 4;
   }
   // weight-tile ring depth: as deep as shared memory allows (the ring hides the L2 latency of the bulk copies)

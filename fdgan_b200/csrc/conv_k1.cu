@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) conv_k1_kernel(const __grid_con
         yoff = n * p.y.sn + (int64_t)(us * oy) * p.y.sh + (int64_t)(us * ox) * p.y.sw;
         if (p.e.p) eoff = n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw;
       }
-      const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, ox0, oy0, n};
+      const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, ox0, oy0, n, 0};   // 14 of the tile's 16 rows are outputs: one box for the tile
       umma_epilogue_group<true>(p, a.yvec, evec, v, mv, yoff, eoff, 0, lane, quarter, et, so, tm, &sred[0][quarter][0], &sred[1][quarter][0]);
       asm volatile("bar.sync 4, 128;" ::: "memory");          // every warp is done reading the shift tiles
     }

@@ -43,6 +43,7 @@ struct UmmaArgs {
   int yvec;
   int dbg;   // ablation: 1 no global loads, 2 no split/stores, 4 no MMA, 8 no epilogue
   int tma_rank;                 // 2: the epilogue stores through ymap {channel, linear pixel}; 0: coalesced stores
+  int epi_wrows;                // EpiTma.wrows: 32 = every epilogue warp stores its own 32 pixels (box {32, 32}); 0 = one {32, 128} box per group
   int bn_linear;                // BatchNorm-backward epilogue: y and e are pixel-linear views (pipelined variant)
   int a_split;                  // the A operand arrives as split-bf16 planes through xmap_hi / xmap_lo (no loader work)
   int pf_ahead;                 // FAST: chunks of L2 prefetch in front of the staging ring (0 = none)
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(FAST ? UTHREADS_P + 32 : UTHREADS_P, 1) conv_u
         yoff = n * p.y.sn + (int64_t)(us * oy) * p.y.sh + (int64_t)(us * ox) * p.y.sw;
         if (p.e.p) eoff = n * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw;
       }
-      const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, mt * UM, 0, 0};
+      const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, mt * UM, 0, 0, a.epi_wrows};
       const int cbase = ntile * NT;
       if constexpr (BNBWD) {
         const int ngroups = (p.Cout - cbase + 31) / 32 < NT / 32 ? (p.Cout - cbase + 31) / 32 : NT / 32;
@@ -790,7 +791,7 @@ __global__ void __launch_bounds__(FAST ? UTHREADS_P + 32 : UTHREADS_P, 1) conv_u
         }
       }
     }
-    if (a.tma_rank && et == 0 && !epi2) bulk_wait_read0();   // the staging tile must outlive the last bulk store's read
+    if (a.tma_rank && (a.epi_wrows ? lane == 0 : et == 0) && !epi2) bulk_wait_read0();   // the staging tile must outlive the last bulk store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -893,6 +894,7 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
   a.yvec = vec4_ok(p->y);
   a.dbg = dbg_flags();
   a.tma_rank = 0;
+  a.epi_wrows = 0;
   {
     auto lin = [&](const FdgTensor& t) { return t.sh == (int64_t)p->OW * t.sw && t.sn == (int64_t)p->OH * t.sh; };
     a.bn_linear = p->e_scale && p->e.p && lin(p->y) && lin(p->e) && vec4_ok(p->y) && vec4_ok(p->e) && p->store != FDG_STORE_UP2;
@@ -922,7 +924,8 @@ int conv2d_umma(const FdgConv* p, cudaStream_t st) {
       p->y.sn == (int64_t)p->OH * p->y.sh && a.M < (1ll << 31)) {
     const uint64_t dims[2] = {(uint64_t)p->Cout, (uint64_t)a.M};
     const uint64_t strides[1] = {(uint64_t)p->y.sw * 4};
-    const uint32_t box[2] = {32, 128};
+    a.epi_wrows = epi_warp_stores() ? 32 : 0;
+    const uint32_t box[2] = {32, a.epi_wrows ? 32u : 128u};
     if (make_tmap_f32(&a.ymap, p->y.p, 2, dims, strides, box)) a.tma_rank = 2;
   }
   static const int reg_path = [] { const char* e = getenv("FDG_CONV_REG"); return e ? atoi(e) : 0; }();

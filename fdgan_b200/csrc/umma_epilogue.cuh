@@ -20,6 +20,8 @@ struct EpiTma {
   const void* map;   // tensor map in kernel-parameter space, or nullptr: coalesced path
   int rank;          // 2: {channel, linear pixel}; 4: {channel, x, y, image}
   int c1, c2, c3;    // pixel coordinates of the tile (c1 only for rank 2)
+  int wrows;         // 0: one store per group for the whole tile (thread 0, 128-thread barriers); > 0: every warp stores its own 32 staging rows
+                     // (rank 2: 32 pixels; rank 4: wrows image rows of the tile) and synchronises with nobody else
 };
 
 // v:      the lane's pixel (tile row quarter*32 + lane), channels c0 .. c0+31 (accumulator values)
@@ -72,8 +74,13 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
   const bool use_tma = tm.map != nullptr && ncap >= 32;   // a tile-tail group leaves through the coalesced path (a 32-channel box would overrun)
   if (tm.map != nullptr) {
     // the previous group's bulk store must have finished READING the staging tile before it is overwritten
-    if (et == 0) bulk_wait_read0();
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (tm.wrows) {
+      if (lane == 0) bulk_wait_read0();      // the warp's own rows, its own bulk group
+      __syncwarp();
+    } else {
+      if (et == 0) bulk_wait_read0();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
   }
   // ---- staging tile row of this lane's pixel
   const uint32_t wrow0 = tile + (uint32_t)(quarter * 32) * 128u;      // first row of this warp
@@ -88,11 +95,22 @@ __device__ __forceinline__ void umma_epilogue_group(const FdgConv& p, bool yvec,
   const bool bnbwd = BN && p.e_scale != nullptr;
   if (use_tma) {
     fence_proxy_async();                                   // generic-proxy writes -> visible to the bulk-copy engine
-    asm volatile("bar.sync 3, 128;" ::: "memory");
-    if (et == 0) {
-      if (tm.rank == 2) tma_store_2d(tm.map, tile, c0, tm.c1);
-      else tma_store_4d(tm.map, tile, c0, tm.c1, tm.c2, tm.c3);
-      bulk_commit();
+    if (tm.wrows) {
+      // per-warp stores: four 4 KB boxes per group instead of one 16 KB box, but no warp waits for another one's accumulator reads,
+      // staging stores or statistics, and a warp only waits for the bulk engine to have read ITS rows
+      __syncwarp();
+      if (lane == 0) {
+        if (tm.rank == 2) tma_store_2d(tm.map, wrow0, c0, tm.c1 + quarter * 32);
+        else tma_store_4d(tm.map, wrow0, c0, tm.c1, tm.c2 + quarter * tm.wrows, tm.c3);
+        bulk_commit();
+      }
+    } else {
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      if (et == 0) {
+        if (tm.rank == 2) tma_store_2d(tm.map, tile, c0, tm.c1);
+        else tma_store_4d(tm.map, tile, c0, tm.c1, tm.c2, tm.c3);
+        bulk_commit();
+      }
     }
   } else {
     __syncwarp();
