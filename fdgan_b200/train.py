@@ -97,6 +97,7 @@ class FlatState:
 
 
 OVERLAP_CLEAN_BRANCH = bool(int(__import__("os").environ.get("FDG_OVERLAP", "1")))
+OVERLAP_PERC_BRANCH = bool(int(__import__("os").environ.get("FDG_OVERLAP_PERC", "1")))     # Vgg16(fake) forward / backward beside the D step
 _AUX_STREAMS = {}
 
 
@@ -257,6 +258,27 @@ class GANTrainer:
             main.wait_stream(aux)
         else:
             z_real, pr, ctx_r, cctx = clean_branch()
+
+        # The perceptual branch -- Vgg16(fake), the feature-space MSE gradients, the Vgg16 data gradient -- needs `fake` only: it runs on
+        # the auxiliary stream beside the whole discriminator step and the adversarial gradient (second fork; joined where dfake takes
+        # the perceptual gradient).  At batch 1 this hides ~45 latency-bound launches; at batch 16 the kernels just interleave.
+        def perc_branch():
+            _fo, vctx = engine.vgg_forward(V, fake, True)
+            gouts = [None, None, None, None]
+            for k in self.perc_layers:
+                fk, ck = vctx.feats[k], cctx.feats[k]
+                n_k = fk.N * fk.H * fk.W * fk.C
+                gk = View.alloc(fk.N, fk.H, fk.W, fk.C, dev)
+                ops.loss_grad(ops.LOSS_MSE, fk.base, ck.base, n_k, self.w["perc"] / n_k, lb[2:3], gk.base)
+                gouts[k] = gk.as_nchw()
+            return engine.vgg_backward(V, vctx, gouts, None, True)
+
+        overlap_p = overlap and want_perc and OVERLAP_PERC_BRANCH
+        dxv = None
+        if overlap_p:
+            aux.wait_stream(main)
+            with torch.cuda.stream(aux):
+                dxv = perc_branch()
         pf, ctx_f = engine.discriminator_forward(D, z_fake.as_nchw(), True, True)
         n_p = pr.numel()
         dpr, dpf = torch.empty_like(pr), torch.empty_like(pf)
@@ -286,17 +308,12 @@ class GANTrainer:
         if w_ssim != 0.0:      # w * (1 - mean ssim_map(fake, clean)), models/pytorch_ssim/__init__.py:17-37
             ops.ssim_loss_grad(View.from_nchw(fake), View.from_nchw(clean), -w_ssim / n_img, -w_ssim / n_img, lb[4:5],
                                View.from_nchw(dfake), accumulate=True)
-        if self.w["perc"] != 0.0 and self.perc_layers:
-            _fo, vctx = engine.vgg_forward(V, fake, True)
-            gouts = [None, None, None, None]
-            for k in self.perc_layers:
-                fk, ck = vctx.feats[k], cctx.feats[k]
-                n_k = fk.N * fk.H * fk.W * fk.C
-                gk = View.alloc(fk.N, fk.H, fk.W, fk.C, dev)
-                ops.loss_grad(ops.LOSS_MSE, fk.base, ck.base, n_k, self.w["perc"] / n_k, lb[2:3], gk.base)
-                gouts[k] = gk.as_nchw()
-            dxv = engine.vgg_backward(V, vctx, gouts, None, True)
-            del vctx, cctx
+        if want_perc:
+            if overlap_p:
+                main.wait_stream(aux)
+            else:
+                dxv = perc_branch()
+            cctx = None
             ops.copy4d(View.from_nchw(dxv), View.from_nchw(dfake), accumulate=True)
         engine.generator_backward(G, gctx, dfake, self.sG.grad_views, False)
         del gctx
