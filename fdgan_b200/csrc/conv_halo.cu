@@ -45,7 +45,10 @@ struct HaloArgs {
   alignas(64) CUtensorMap ymap;
 };
 
-template <int NT, int BSTAGES>
+// BN2 (own instantiation, NT = 128): the BatchNorm-backward epilogue (FdgConv.e_scale) with the mask-tensor rows of the NEXT 32-channel
+// group (or of the next tile's first group) in flight while the current group is processed -- the dense-layer norm2 backward inside the
+// conv2 data gradient: dz = acc * [e_scale * e + e_shift > 0], y = e_scale * dz, stats += (sum dz, sum dz * e).
+template <int NT, int BSTAGES, bool BN2 = false>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   const int A_STAGE = 2 * a.a_tile;
@@ -224,7 +227,24 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     const int et = t - H_EPI_WARP0 * 32;
     const uint32_t stage = smem_u32(ep_stage);
     const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
+    // BN2: lane -> (row of four, 4-channel chunk) of the coalesced phase; evn[i] = mask-tensor values of row 4 i + brs of this warp's 32 pixels
+    float4 evn[BN2 ? 8 : 1];
+    const int bq = lane & 7, bc4 = bq * 4, brs = lane >> 3;
+    auto bn_prefetch = [&](int tile_, int g_) {
+      if constexpr (BN2) {
+        int nt_, n_, oy_, ox_;
+        decode(tile_, nt_, n_, oy_, ox_);
+        const int c_ = nt_ * NT + g_ * 32 + bc4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int oy = oy_ + quarter * 4 + (i >> 1), ox = ox_ + 4 * (i & 1) + brs;
+          evn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (oy < p.OH && ox < p.OW && c_ < p.Cout) evn[i] = ld4(p.e.p + n_ * p.e.sn + (int64_t)oy * p.e.sh + (int64_t)ox * p.e.sw + c_);
+        }
+      }
+    };
     int it = 0;
+    if (BN2 && (int)blockIdx.x < a.total_tiles) bn_prefetch(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       int ntile, n, oy0, ox0;
       decode(tile, ntile, n, oy0, ox0);
@@ -242,6 +262,73 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       }
       const EpiTma tm{a.tma_rank ? (const void*)&a.ymap : nullptr, a.tma_rank, ox0, oy0, n, a.epi_wrows};
       const int cbase = ntile * NT;
+      if constexpr (BN2) {
+        const int ngroups = (p.Cout - cbase + 31) / 32 < NT / 32 ? (p.Cout - cbase + 31) / 32 : NT / 32;
+        const uint32_t wrow0 = stage + (uint32_t)(quarter * 32) * 128u;
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+          const int c0 = cbase + g * 32;
+          {
+            float v[32], v2[32];
+            const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 * NT + g * 32);
+            tmem_ld32_nowait(tcol, v);
+            tmem_ld32_nowait(tcol + NT, v2);
+            tmem_ld_wait();
+            const uint32_t trow = wrow0 + (uint32_t)lane * 128u;
+            const int sw = lane & 7;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (uint32_t)((qq ^ sw) << 4)), "f"(v[4 * qq] + v2[4 * qq]),
+                           "f"(v[4 * qq + 1] + v2[4 * qq + 1]), "f"(v[4 * qq + 2] + v2[4 * qq + 2]), "f"(v[4 * qq + 3] + v2[4 * qq + 3]) : "memory");
+          }
+          __syncwarp();
+          const bool cv = c0 + bc4 < p.Cout;
+          float4 bsc = make_float4(0.f, 0.f, 0.f, 0.f), bsh = bsc, ps1 = bsc, ps2 = bsc;
+          if (cv) { bsc = ld4(p.e_scale + c0 + bc4); bsh = ld4(p.e_shift + c0 + bc4); }
+          const float al = p.alpha, als = p.alpha * p.eslope;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + brs;
+            const int oy = oy0 + quarter * 4 + (i >> 1), ox = ox0 + 4 * (i & 1) + brs;
+            if (oy < p.OH && ox < p.OW && cv) {
+              float4 val;
+              const uint32_t ta = wrow0 + (uint32_t)row * 128u + (uint32_t)((bq ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(ta) : "memory");
+              const float4 ev = evn[i];
+              val.x *= fmaf(ev.x, bsc.x, bsh.x) > 0.f ? al : als; val.y *= fmaf(ev.y, bsc.y, bsh.y) > 0.f ? al : als;
+              val.z *= fmaf(ev.z, bsc.z, bsh.z) > 0.f ? al : als; val.w *= fmaf(ev.w, bsc.w, bsh.w) > 0.f ? al : als;
+              ps1.x += val.x; ps1.y += val.y; ps1.z += val.z; ps1.w += val.w;
+              ps2.x = fmaf(val.x, ev.x, ps2.x); ps2.y = fmaf(val.y, ev.y, ps2.y); ps2.z = fmaf(val.z, ev.z, ps2.z); ps2.w = fmaf(val.w, ev.w, ps2.w);
+              val.x *= bsc.x; val.y *= bsc.y; val.z *= bsc.z; val.w *= bsc.w;
+              float* yp = p.y.p + n * p.y.sn + (int64_t)oy * p.y.sh + (int64_t)ox * p.y.sw + c0 + bc4;
+              if (p.store == FDG_STORE_ACCUM)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yp), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+              else
+                *reinterpret_cast<float4*>(yp) = val;
+            }
+          }
+          // mask rows of the next group / of the next tile's first group: in flight during the statistics fold, the next tcgen05.ld and
+          // staging stores and, across tiles, the wait for the accumulator
+          if (g + 1 < ngroups) bn_prefetch(tile, g + 1);
+          else if (tile + (int)gridDim.x < a.total_tiles) bn_prefetch(tile + gridDim.x, 0);
+          if (p.stats) {
+#pragma unroll
+            for (int off = 8; off <= 16; off <<= 1) {
+              ps1.x += __shfl_xor_sync(0xffffffffu, ps1.x, off); ps1.y += __shfl_xor_sync(0xffffffffu, ps1.y, off);
+              ps1.z += __shfl_xor_sync(0xffffffffu, ps1.z, off); ps1.w += __shfl_xor_sync(0xffffffffu, ps1.w, off);
+              ps2.x += __shfl_xor_sync(0xffffffffu, ps2.x, off); ps2.y += __shfl_xor_sync(0xffffffffu, ps2.y, off);
+              ps2.z += __shfl_xor_sync(0xffffffffu, ps2.z, off); ps2.w += __shfl_xor_sync(0xffffffffu, ps2.w, off);
+            }
+            if (lane < 8 && cv) {
+              float* st1 = &sred[0][quarter][g * 32 + bc4];
+              float* st2 = &sred[1][quarter][g * 32 + bc4];
+              st1[0] += ps1.x; st1[1] += ps1.y; st1[2] += ps1.z; st1[3] += ps1.w;
+              st2[0] += ps2.x; st2[1] += ps2.y; st2[2] += ps2.z; st2[3] += ps2.w;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
 #pragma unroll 1
       for (int g = 0; g < NTP / 32; ++g) {
         const int c0 = cbase + g * 32;
@@ -259,6 +346,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
           umma_epilogue_group<true>(p, a.yvec, evec, v, mv, yoff, eoff, c0, lane, quarter, et, stage, tm, &sred[0][quarter][g * 32],
                               &sred[1][quarter][g * 32], NT - g * 32);
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -414,13 +502,13 @@ int conv2d_halo_supported(const FdgConv* p) {
   return 1;
 }
 
-template <int NT, int BSTAGES>
+template <int NT, int BSTAGES, bool BN2 = false>
 static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   const int smem = 2 * (2 * a.a_tile) + BSTAGES * (2 * NT * 128) + 1024;
   static std::atomic<int> attr_done[64];           // per device: largest size configured so far
   const int adev = current_device();
   if (attr_done[adev] < smem) {
-    if (cudaFuncSetAttribute(conv_halo_kernel<NT, BSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_halo_kernel<NT, BSTAGES, BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05 halo]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -431,7 +519,7 @@ static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   const double M = (double)a.c.N * a.c.OH * a.c.OW;
   ProfScope prof(PF_CONV_UMMA, 2.0 * M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * (M * a.c.Cout * (1.0 + (a.c.e.p ? 1.0 : 0.0) + (a.c.store == FDG_STORE_ACCUM ? 1.0 : 0.0)) + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  launch_k(conv_halo_kernel<NT, BSTAGES>, dim3(grid), dim3(H_THREADS), (size_t)(smem), st, a);
+  launch_k(conv_halo_kernel<NT, BSTAGES, BN2>, dim3(grid), dim3(H_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d[tcgen05 halo]");
 }
 
@@ -466,7 +554,12 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
     case 64: return launch_halo<64, 5>(a, st);
     case 80: return launch_halo<80, 4>(a, st);     // 144 = 2 x 80, 72, 160 (Fusion-D layer 3, data gradients of layers 3 / 4, conv_refine4)
     case 96: return launch_halo<96, 3>(a, st);     // 288 = 3 x 96 (Fusion-D layer 4)
-    default: return a.a_tile <= 23 * 1024 ? launch_halo<128, 3>(a, st) : launch_halo<128, 2>(a, st);
+    default: {
+      static const int bn2_on = [] { const char* e = getenv("FDG_HALO_BN2"); return e ? atoi(e) : 1; }();
+      // BatchNorm-backward epilogue on 128-bit views (validated by fdg_conv2d): the instantiation that prefetches its mask rows
+      if (bn2_on && p->e_scale && a.a_tile <= 23 * 1024) return launch_halo<128, 3, true>(a, st);
+      return a.a_tile <= 23 * 1024 ? launch_halo<128, 3>(a, st) : launch_halo<128, 2>(a, st);
+    }
   }
 }
 
