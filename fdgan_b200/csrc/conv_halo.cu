@@ -45,9 +45,12 @@ struct HaloArgs {
   alignas(64) CUtensorMap ymap;
 };
 
-// BN2 (own instantiation, NT = 128): the BatchNorm-backward epilogue (FdgConv.e_scale) with the mask-tensor rows of the NEXT 32-channel
-// group (or of the next tile's first group) in flight while the current group is processed -- the dense-layer norm2 backward inside the
-// conv2 data gradient: dz = acc * [e_scale * e + e_shift > 0], y = e_scale * dz, stats += (sum dz, sum dz * e).
+// BN2 (own instantiation, NT = 128, Cin <= 32, no prologue): the BatchNorm-backward epilogue (FdgConv.e_scale) with the mask-tensor rows of
+// the NEXT 32-channel group (or of the next tile's first group) in flight while the current group is processed -- the dense-layer norm2
+// backward inside the conv2 data gradient: dz = acc * [e_scale * e + e_shift > 0], y = e_scale * dz, stats += (sum dz, sum dz * e).
+// A 32 -> 128 data gradient is bound by its epilogue (K = 288 against 128 output channels), and a 32-channel halo is half the loader
+// work: warps 0-3 load (4 eight-channel chunks per halo pixel instead of 8), warps 4-7 become a SECOND set of epilogue warps with its
+// own staging tile; set s takes the 32-channel groups g = s (mod 2).
 template <int NT, int BSTAGES, bool BN2 = false>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
@@ -61,7 +64,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   __shared__ uint32_t tmem_base_s;
   __shared__ float sred[2][4][NTP];
   __shared__ __align__(1024) uint8_t ep_stage[EP_TILE_BYTES];   // epilogue staging tile (SWIZZLE_128B box layout)
-  __shared__ __align__(16) float aff_s[2][H_MAX_AFF];
+  __shared__ __align__(1024) uint8_t ep_stage2[BN2 ? EP_TILE_BYTES : 16];   // BN2: staging tile of the second epilogue set
+  __shared__ __align__(16) float aff_s[2][BN2 ? 4 : H_MAX_AFF];             // (BN2 runs without a prologue: the space goes to ep_stage2)
+  constexpr int LW = BN2 ? 4 : H_LOAD_WARPS;          // loader warps
+  constexpr int JB = BN2 ? 2 : 3;                     // log2 of the 8-channel chunks per halo pixel a pass of the loaders covers
 
   const FdgConv& p = a.c;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -73,10 +79,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
 
   if (t == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bar_a_full[s]), H_LOAD_WARPS);
+      mbar_init(smem_u32(&bar_a_full[s]), LW);
       mbar_init(smem_u32(&bar_a_empty[s]), 1);
       mbar_init(smem_u32(&bar_acc_full[s]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[s]), 4);
+      mbar_init(smem_u32(&bar_acc_empty[s]), BN2 ? 8 : 4);
     }
     for (int s = 0; s < BSTAGES; ++s) {
       mbar_init(smem_u32(&bar_b_full[s]), 1);
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   }
   pdl_wait();      // PDL contract (common.cuh): barriers and TMEM are set up while the previous kernel drains; no global memory before this
   pdl_trigger();
-  const bool aff_smem = p.has_affine && p.Cin <= H_MAX_AFF;
+  const bool aff_smem = !BN2 && p.has_affine && p.Cin <= H_MAX_AFF;
   if (aff_smem)
     for (int i = t; i < p.Cin; i += H_THREADS) { aff_s[0][i] = __ldg(p.scale + i); aff_s[1][i] = __ldg(p.shift + i); }
   for (int i = t; i < 2 * 4 * NTP; i += H_THREADS) (&sred[0][0][0])[i] = 0.f;
@@ -111,15 +117,16 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     ox0 = (r - tyi * a.tiles_x) * HT_W;
   };
 
-  if (warp < H_LOAD_WARPS) {
+  const bool epi2 = BN2 && warp >= LW && warp < H_LOAD_WARPS;      // BN2: second epilogue set
+  if (warp < LW) {
     // =============================================================== halo loaders
     // item i of this thread: halo row (pixel) hrow[i], 16-byte bf16 chunk j (8 channels); fixed for the whole kernel
-    const int j = t & 7;
+    const int j = t & ((1 << JB) - 1);
     int hy[H_ITEMS], hx[H_ITEMS];
     bool iv[H_ITEMS];
 #pragma unroll
     for (int i = 0; i < H_ITEMS; ++i) {
-      const int row = (t >> 3) + i * (H_LOAD_WARPS * 4);
+      const int row = (t >> JB) + i * 32;
       iv[i] = row < HP;
       hy[i] = iv[i] ? row / a.HC : 0;
       hx[i] = iv[i] ? row - hy[i] * a.HC : 0;
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < H_ITEMS; ++i) {
           if (iv[i] && !(a.dbg & 2)) {
-            const int row = (t >> 3) + i * (H_LOAD_WARPS * 4);
+            const int row = (t >> JB) + i * 32;
             const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
             uint32_t h[4], l[4];
             split2(v0[i].x, v0[i].y, h[0], l[0]);
@@ -221,11 +228,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         if (++buf == 2) { buf = 0; ph ^= 1u; }
       }
     }
-  } else if (warp >= H_EPI_WARP0) {
+  } else if (warp >= H_EPI_WARP0 || epi2) {
     // =============================================================== epilogue warps (TMEM lane quarter = warp & 3, two per quarter)
     const int quarter = warp & 3;
-    const int et = t - H_EPI_WARP0 * 32;
-    const uint32_t stage = smem_u32(ep_stage);
+    const int wset = epi2 ? 1 : 0;                      // BN2: epilogue set, 32-channel groups g = wset (mod 2)
+    constexpr int NSETS = BN2 ? 2 : 1;
+    const int et = epi2 ? t : t - H_EPI_WARP0 * 32;     // set 1 (threads 128..255) keeps its thread index
+    const uint32_t stage = epi2 ? smem_u32(ep_stage2) : smem_u32(ep_stage);
     const bool evec = p.e.p && p.e.sc == 1 && aligned16_dev(p.e.p) && (p.e.sn % 4 == 0) && (p.e.sh % 4 == 0) && (p.e.sw % 4 == 0);
     // BN2: lane -> (row of four, 4-channel chunk) of the coalesced phase; evn[i] = mask-tensor values of row 4 i + brs of this warp's 32 pixels
     float4 evn[BN2 ? 8 : 1];
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       }
     };
     int it = 0;
-    if (BN2 && (int)blockIdx.x < a.total_tiles) bn_prefetch(blockIdx.x, 0);
+    if (BN2 && (int)blockIdx.x < a.total_tiles) bn_prefetch(blockIdx.x, wset);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       int ntile, n, oy0, ox0;
       decode(tile, ntile, n, oy0, ox0);
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         const int ngroups = (p.Cout - cbase + 31) / 32 < NT / 32 ? (p.Cout - cbase + 31) / 32 : NT / 32;
         const uint32_t wrow0 = stage + (uint32_t)(quarter * 32) * 128u;
 #pragma unroll 1
-        for (int g = 0; g < ngroups; ++g) {
+        for (int g = wset; g < ngroups; g += NSETS) {      // Cout % 64 == 0: every tile has groups for both sets
           const int c0 = cbase + g * 32;
           {
             float v[32], v2[32];
@@ -309,8 +318,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
           }
           // mask rows of the next group / of the next tile's first group: in flight during the statistics fold, the next tcgen05.ld and
           // staging stores and, across tiles, the wait for the accumulator
-          if (g + 1 < ngroups) bn_prefetch(tile, g + 1);
-          else if (tile + (int)gridDim.x < a.total_tiles) bn_prefetch(tile + gridDim.x, 0);
+          if (g + NSETS < ngroups) bn_prefetch(tile, g + NSETS);
+          else if (tile + (int)gridDim.x < a.total_tiles) bn_prefetch(tile + gridDim.x, wset);
           if (p.stats) {
 #pragma unroll
             for (int off = 8; off <= 16; off <<= 1) {
@@ -354,7 +363,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       if (p.stats) {
         const int next = tile + gridDim.x;
         if (next >= a.total_tiles || next / (p.N * tiles_img) != ntile) {
+          if (BN2) asm volatile("bar.sync 1, 256;" ::: "memory"); else
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (!epi2)
           for (int cidx = et; cidx < NT; cidx += 128) {
             const int c = ntile * NT + cidx;
             if (c < p.Cout) {
@@ -364,11 +375,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             sred[0][0][cidx] = 0.f; sred[0][1][cidx] = 0.f; sred[0][2][cidx] = 0.f; sred[0][3][cidx] = 0.f;
             sred[1][0][cidx] = 0.f; sred[1][1][cidx] = 0.f; sred[1][2][cidx] = 0.f; sred[1][3][cidx] = 0.f;
           }
+          if (BN2) asm volatile("bar.sync 1, 256;" ::: "memory"); else
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
     }
-    if (a.tma_rank && (a.epi_wrows ? lane == 0 : et == 0)) bulk_wait_read0();
+    if (a.tma_rank && !epi2 && (a.epi_wrows ? lane == 0 : et == 0)) bulk_wait_read0();
   } else if (warp == H_MMA_WARP) {
     // =============================================================== MMA issue
     if (lane == 0) {
@@ -557,7 +569,8 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
     default: {
       static const int bn2_on = [] { const char* e = getenv("FDG_HALO_BN2"); return e ? atoi(e) : 1; }();
       // BatchNorm-backward epilogue on 128-bit views (validated by fdg_conv2d): the instantiation that prefetches its mask rows
-      if (bn2_on && p->e_scale && a.a_tile <= 23 * 1024) return launch_halo<128, 3, true>(a, st);
+      if (bn2_on && p->e_scale && a.a_tile <= 23 * 1024 && a.pair && a.cchunks == 1 && !p->has_affine && p->Cout % 64 == 0)
+        return launch_halo<128, 3, true>(a, st);
       return a.a_tile <= 23 * 1024 ? launch_halo<128, 3>(a, st) : launch_halo<128, 2>(a, st);
     }
   }

@@ -259,10 +259,12 @@ def _conv_dgrad_w(weight):
 TAP_DECOMPOSE_L5 = True   # Fusion-D layer 5 (one output channel) as a 1x1 convolution over taps + shifted sum (fdg_tap_sum / fdg_tap_spread)
 FUSED_BN1_BWD = True   # norm1 backward inside the conv1 data-gradient epilogue + deferred per-channel affine term
 # norm2 backward with the ReLU mask, alpha and the two reductions inside the conv2 data-gradient epilogue (halo kernel, FdgConv.e_scale with
-# a normal store) instead of the reduce pass.  Correct (test_conv2d_3x3_bn_backward_epilogue, module tests) but measured SLOWER on a B200
-# (76.1 -> 77.9 ms/step): the mask rows are read inside the epilogue's coalesced phase without the prefetch the per-tap kernel has, and the
-# bulk-tensor store is lost; off until the halo epilogue prefetches its mask rows.
-FUSED_BN2_BWD = bool(int(__import__("os").environ.get("FDG_FUSED_BN2_BWD", "0")))
+# a normal store) instead of the reduce pass over dA2 and T.  Round-2 history: through the generic epilogue it was SLOWER (76.1 -> 77.9
+# ms/step: mask rows fetched inside the coalesced phase, no bulk-tensor store); conv_halo<128,3,BN2> prefetches the mask rows of the next
+# group (level with the reduce pass: the 32 -> 128 data gradient is bound by its four epilogue warps) and runs TWO epilogue sets on the
+# warps a 32-channel halo does not need for loading: 65.27 -> 64.90 ms/step at batch 16, 7.61 -> 7.46 ms graphed at batch 1, 42 launches
+# and 2.7 GB of DRAM traffic per step less.  FDG_FUSED_BN2_BWD=0 restores the reduce pass.
+FUSED_BN2_BWD = bool(int(__import__("os").environ.get("FDG_FUSED_BN2_BWD", "1")))
 SPLIT_GRADS = True     # the bottleneck gradient travels as split-bf16 planes: its two consumers are fed by bulk tensor loads
 
 

@@ -350,7 +350,9 @@ def test_conv2d_bn_backward_epilogue(shape):
     assert maxabs(dgm, gamma.grad) <= 2e-4 * max(1.0, scale_g) and maxabs(dbt, beta.grad) <= 2e-4 * max(1.0, float(beta.grad.abs().max()))
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 128, 19, 13, 0.0), (1, 32, 128, 40, 24, 0.0), (2, 48, 96, 9, 11, 0.2)])
+@pytest.mark.parametrize("shape", [(2, 32, 128, 19, 13, 0.0), (1, 32, 128, 40, 24, 0.0), (2, 48, 96, 9, 11, 0.2),
+                                   # two output-channel tiles / LeakyReLU / a 16-channel gradient on the two-epilogue-set instantiation (conv_halo<128,3,BN2>)
+                                   (1, 32, 256, 17, 9, 0.2), (3, 16, 128, 8, 8, 0.0), (16, 32, 128, 32, 32, 0.0)])
 def test_conv2d_3x3_bn_backward_epilogue(shape):
     """3x3 data-gradient conv (halo-tile kernel) with the BatchNorm-backward epilogue and a NORMAL store + fdg_bn_bwd_finalize(unit_alpha) +
     one mask-free fdg_ew_bwd pass == autograd through conv3x3(leaky_relu(batch_norm(t))) w.r.t. t (dense-layer norm2 / conv2 backward)."""
