@@ -51,7 +51,12 @@ struct HaloArgs {
 // A 32 -> 128 data gradient is bound by its epilogue (K = 288 against 128 output channels), and a 32-channel halo is half the loader
 // work: warps 0-3 load (4 eight-channel chunks per halo pixel instead of 8), warps 4-7 become a SECOND set of epilogue warps with its
 // own staging tile; set s takes the 32-channel groups g = s (mod 2).
-template <int NT, int BSTAGES, bool BN2 = false>
+// CL (one output-channel tile, even tile count): CTAs 2i, 2i + 1 form a cluster and SHARE the weight stream.  Every 128-pixel tile needs the
+// whole filter (160 KB for a 3x3 32 -> 128 data gradient), streamed from L2 because it does not fit beside the halo ring: 1.3 GB of L2 -> SM
+// traffic for 0.5 GB of output, the kernel runs at the L2 fabric's rate (0.169 ms with MMAs and epilogue switched off).  Rank 0 fetches the
+// hi half of each stage, rank 1 the lo half, each multicast into both CTAs (same shared-memory offset, each CTA's own full barrier counts
+// all bytes); a stage is refilled when BOTH CTAs' MMAs have retired (multicast commits on an empty barrier that counts two arrivals).
+template <int NT, int BSTAGES, bool BN2 = false, bool CL = false>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   constexpr int B_TILE_BYTES = NT * 128;
   const int A_STAGE = 2 * a.a_tile;
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     }
     for (int s = 0; s < BSTAGES; ++s) {
       mbar_init(smem_u32(&bar_b_full[s]), 1);
-      mbar_init(smem_u32(&bar_b_empty[s]), 1);
+      mbar_init(smem_u32(&bar_b_empty[s]), CL ? 2 : 1);
     }
     fence_barrier_init();
   }
@@ -105,6 +110,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  const uint32_t crank = CL ? cluster_ctarank() : 0u;
+  if (CL) cluster_sync_all();      // the peer's barriers are initialised before anything of this CTA can signal them
 
   // tile id -> (output-channel tile, image, tile row, tile column)
   auto decode = [&](int tile, int& ntile, int& n, int& oy0, int& ox0) {
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
                     }
                   }
                 }
-                umma_commit(bempty0 + bs * 8);
+                if (CL) umma_commit_multicast(bempty0 + bs * 8, (uint16_t)3); else umma_commit(bempty0 + bs * 8);
                 if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
               }
             }
@@ -458,7 +465,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
                                     (cc > 0 || tap > 0 || sl > 0) ? 1u : 0u, (uint32_t)NT);
               }
             }
-            umma_commit(bempty0 + bs * 8);
+            if (CL) umma_commit_multicast(bempty0 + bs * 8, (uint16_t)3); else umma_commit(bempty0 + bs * 8);
             if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
             if (++kx == p.S) { kx = 0; ++ky; }
           }
@@ -485,7 +492,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             const uint32_t bar = smem_u32(&bar_b_full[bs]);
             mbar_arrive_expect_tx(bar, 2 * B_TILE_BYTES);
             const int idx = a.pair ? tap : tap * a.cchunks + cc;
-            bulk_g2s(b_base + bs * (2 * B_TILE_BYTES), wimg + (size_t)idx * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+            if (CL) {
+              // this CTA's half of the stage (rank 0: hi tile, rank 1: lo tile), delivered to both CTAs of the pair
+              bulk_g2s_multicast(b_base + bs * (2 * B_TILE_BYTES) + crank * B_TILE_BYTES, wimg + (size_t)idx * (2 * B_TILE_BYTES) + crank * B_TILE_BYTES,
+                                 B_TILE_BYTES, bar, (uint16_t)3);
+            } else {
+              bulk_g2s(b_base + bs * (2 * B_TILE_BYTES), wimg + (size_t)idx * (2 * B_TILE_BYTES), 2 * B_TILE_BYTES, bar);
+            }
             if (++bs == BSTAGES) { bs = 0; bph ^= 1u; }
           }
       }
@@ -498,6 +511,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
+  if (CL) cluster_sync_all();      // neither CTA leaves while the other may still multicast into it or signal its barriers
 }
 
 int umma_tap_pair(int taps, int Cin);
@@ -514,13 +528,13 @@ int conv2d_halo_supported(const FdgConv* p) {
   return 1;
 }
 
-template <int NT, int BSTAGES, bool BN2 = false>
+template <int NT, int BSTAGES, bool BN2 = false, bool CL = false>
 static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   const int smem = 2 * (2 * a.a_tile) + BSTAGES * (2 * NT * 128) + 1024;
   static std::atomic<int> attr_done[64];           // per device: largest size configured so far
   const int adev = current_device();
   if (attr_done[adev] < smem) {
-    if (cudaFuncSetAttribute(conv_halo_kernel<NT, BSTAGES, BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_halo_kernel<NT, BSTAGES, BN2, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("fdg_conv2d[tcgen05 halo]: cannot raise dynamic shared memory to %d bytes", smem);
       return FDG_ECUDA;
     }
@@ -531,7 +545,29 @@ static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   const double M = (double)a.c.N * a.c.OH * a.c.OW;
   ProfScope prof(PF_CONV_UMMA, 2.0 * M * a.c.R * a.c.S * a.c.Cin * a.c.Cout,
                  4.0 * (M * a.c.Cout * (1.0 + (a.c.e.p ? 1.0 : 0.0) + (a.c.store == FDG_STORE_ACCUM ? 1.0 : 0.0)) + (double)a.c.N * a.c.H * a.c.W * a.c.Cin), st);
-  launch_k(conv_halo_kernel<NT, BSTAGES, BN2>, dim3(grid), dim3(H_THREADS), (size_t)(smem), st, a);
+  if (CL) {
+    // persistent pairs: as many CTAs as clusters can be resident at once (a cluster that waits for a free pair of SMs would run its
+    // whole share of the tiles after everybody else)
+    static std::atomic<int> max_clusters[64];
+    if (!max_clusters[adev]) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(num_sms & ~1));
+      cfg.blockDim = dim3(H_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, conv_halo_kernel<NT, BSTAGES, BN2, CL>, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = num_sms / 2 - 2; }
+      max_clusters[adev] = nc;
+    }
+    int g = 2 * max_clusters[adev];
+    if (g > a.total_tiles) g = a.total_tiles;      // even (checked by the caller)
+    launch_k_cluster(conv_halo_kernel<NT, BSTAGES, BN2, CL>, dim3((unsigned)g), dim3(H_THREADS), (size_t)(smem), st, 2, a);
+  } else
+  launch_k(conv_halo_kernel<NT, BSTAGES, BN2, CL>, dim3(grid), dim3(H_THREADS), (size_t)(smem), st, a);
   return check_launch("fdg_conv2d[tcgen05 halo]");
 }
 
@@ -561,6 +597,11 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
     if (make_tmap_f32(&a.ymap, p->y.p, 4, dims, strides, box)) a.tma_rank = 4;
   }
   // weight-tile ring depth: as deep as shared memory allows (the ring hides the L2 latency of the bulk copies)
+  static const int cl_on = [] { const char* e = getenv("FDG_HALO_CLUSTER"); return e ? atoi(e) : 1; }();
+  // pairs of CTAs share the weight stream (CL) when tiles 2i, 2i + 1 always lie in the same output-channel tile.  Measured on the plain
+  // instantiations (3x3 32 -> 128, 64 -> 64, 72 -> 144, 128 -> 128 ...): no difference, so only the epilogue-bound BN2 kernel takes it
+  // (0.450 -> 0.388 ms at 256^2: its mask-tensor reads compete with the weight stream for the L2 -> SM path)
+  const bool cl = cl_on && (p->N * a.tiles_x * a.tiles_y) % 2 == 0 && a.total_tiles >= 4 && !a.dbg;
   switch (nt) {
     case 32: return launch_halo<32, 10>(a, st);
     case 64: return launch_halo<64, 5>(a, st);
@@ -570,7 +611,7 @@ int conv2d_halo(const FdgConv* p, int nt, cudaStream_t st) {
       static const int bn2_on = [] { const char* e = getenv("FDG_HALO_BN2"); return e ? atoi(e) : 1; }();
       // BatchNorm-backward epilogue on 128-bit views (validated by fdg_conv2d): the instantiation that prefetches its mask rows
       if (bn2_on && p->e_scale && a.a_tile <= 23 * 1024 && a.pair && a.cchunks == 1 && !p->has_affine && p->Cout % 64 == 0)
-        return launch_halo<128, 3, true>(a, st);
+        return cl ? launch_halo<128, 3, true, true>(a, st) : launch_halo<128, 3, true>(a, st);
       return a.a_tile <= 23 * 1024 ? launch_halo<128, 3>(a, st) : launch_halo<128, 2>(a, st);
     }
   }

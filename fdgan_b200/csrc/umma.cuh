@@ -47,6 +47,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// multicast form: the bytes land at the same shared-memory offset in every CTA of `mask`, each one's mbarrier (same offset) counts them
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 |
 // SBO(1024 B >> 4)<<32 | version 1 <<46 | layout SWIZZLE_128B (2) << 61
 __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
