@@ -286,3 +286,31 @@ def test_pytorch_ssim_surface_matches_reference_arithmetic():
     assert tuple(per.shape) == (3,) and maxabs(per, want) <= 2e-6
     with pytest.raises(NotImplementedError):
         PS.ssim(a.cuda(), b.cuda(), window_size=7)
+
+
+def test_fused_norm2_backward_equals_the_reduce_pass(monkeypatch, conv_path):
+    """engine.FUSED_BN2_BWD (norm2 backward inside the conv2 data-gradient epilogue: conv_halo<128,3,BN2,CL>, two epilogue sets, cluster
+    multicast of the weights) against the separate reduce pass: same FDGAN gradients (fp32 summation order only)."""
+    from fdgan_b200 import engine
+    if conv_path != "tcgen05_bf16x3":
+        pytest.skip("the fused form exists on the tensor-core path only")
+    x = seeded((2, 3, 64, 64), 11).cuda()
+    gout = seeded((2, 3, 64, 64), 12, -1, 1).cuda()
+    grads = []
+    for on in (True, False):
+        monkeypatch.setattr(engine, "FUSED_BN2_BWD", on)
+        m = _fdgan(seed=3)
+        xi = x.clone().requires_grad_(True)
+        y = m(xi)
+        y.backward(gout)
+        torch.cuda.synchronize()
+        g = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+        grads.append((y.detach().clone(), xi.grad.clone(), g))
+    (ya, dxa, ga), (yb, dxb, gb) = grads
+    assert maxabs(ya, yb) <= 1e-5                      # same forward; the fp64 atomics of the statistics land in any order
+    edx = float((dxa - dxb).norm() / dxb.norm())
+    assert set(ga) == set(gb)
+    gmax = max(float(v.norm()) for v in gb.values())
+    # (biases in front of a BatchNorm have a zero gradient: both values are rounding noise, hence the absolute term)
+    worst = max((float((ga[k] - gb[k]).norm()) / (float(gb[k].norm()) + 1e-3 * gmax), k) for k in gb)
+    assert edx <= 1e-3 and worst[0] <= 1e-2, (edx, worst)

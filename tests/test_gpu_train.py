@@ -83,6 +83,28 @@ def test_graphed_step_matches_eager_step():
     assert maxabs(pb, pa) <= 2e-3
 
 
+def test_step_is_the_same_with_and_without_stream_overlap(monkeypatch):
+    """The two auxiliary-stream forks of GANTrainer.step (clean-image branch beside the generator forward, perceptual branch beside the
+    discriminator step) only reorder independent work: first step identical up to the fp64-atomics order of the statistics."""
+    from fdgan_b200 import train
+    from fdgan_b200.train import GANTrainer
+    hazy, clean = seeded((2, 3, 64, 64), 5).cuda(), seeded((2, 3, 64, 64), 6).cuda()
+    res = []
+    for on in (True, False):
+        monkeypatch.setattr(train, "OVERLAP_CLEAN_BRANCH", on)
+        monkeypatch.setattr(train, "OVERLAP_PERC_BRANCH", on)
+        G, D, V = _nets()
+        tr = GANTrainer(G, D, V)
+        fake = tr.step(hazy, clean).clone()
+        torch.cuda.synchronize()
+        res.append((fake, dict(tr.last), tr.sG.grad.clone(), tr.sD.grad.clone()))
+    (fa, la, ga, da), (fb, lb, gb, db) = res
+    assert maxabs(fa, fb) <= 1e-6
+    for k in ("loss_d", "l1_weighted", "perc_weighted", "adv_weighted", "loss_g"):
+        assert abs(la[k] - lb[k]) <= 1e-6 * max(1.0, abs(la[k])), k
+    assert float((ga - gb).norm() / gb.norm()) <= 1e-4 and float((da - db).norm() / db.norm()) <= 1e-4
+
+
 def test_trainer_uses_flat_buffers():
     from fdgan_b200.train import GANTrainer
     G, D, V = _nets()
