@@ -48,3 +48,15 @@ def test_product_arm_needs_a_gpu():
         return
     r = _run(["--steps", "1", "--warmup", "1"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_committed_traffic_file_belongs_to_the_committed_kernels():
+    """profiles/r02_traffic.json feeds roofline.traffic; bench.py refuses it (traffic = null) when the kernel sources changed after the ncu
+    launch list was captured.  This test makes a stale file visible on the CPU side before a round closes."""
+    import json
+    import bench
+    with open(os.path.join(ROOT, bench.TRAFFIC_FILE)) as f:
+        js = json.load(f)
+    assert js["src_sha"] == bench.kernel_source_sha(), "re-capture the launch list (tools/r2_final_profiles.sh) after the last kernel change"
+    fam, why = bench.ncu_family_profile("conv_tcgen05")
+    assert fam is not None and fam["dram_bytes_per_launch"] > 0, why
